@@ -1,0 +1,134 @@
+/* asam_host.h -- internal declarations of the host side (C) of aprilsam_b200. */
+#ifndef ASAM_HOST_H
+#define ASAM_HOST_H
+
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "aprilsam.h"
+#include "asam_cuda.h"
+
+#define ASAM_API __attribute__((visibility("default")))
+
+/* ---- small containers ---------------------------------------------------------------- */
+typedef struct {
+    int *p;
+    int n, cap;
+} ivec_t;
+
+static inline void ivec_reserve(ivec_t *v, int cap)
+{
+    if (cap <= v->cap)
+        return;
+    int c = v->cap ? v->cap : 8;
+    while (c < cap)
+        c *= 2;
+    v->p = (int *) realloc(v->p, sizeof(int) * (size_t) c);
+    v->cap = c;
+}
+
+static inline void ivec_push(ivec_t *v, int x)
+{
+    if (v->n == v->cap)
+        ivec_reserve(v, v->n + 1);
+    v->p[v->n++] = x;
+}
+
+static inline void ivec_free(ivec_t *v)
+{
+    free(v->p);
+    v->p = NULL;
+    v->n = v->cap = 0;
+}
+
+/* (lo,hi) node pair -> Hessian off-diagonal slot */
+typedef struct {
+    uint64_t *keys;
+    int *vals;
+    int cap, n; /* cap is a power of two */
+} pairmap_t;
+
+void pairmap_init(pairmap_t *m, int expect);
+void pairmap_free(pairmap_t *m);
+/* returns the slot of (lo,hi); *created = 1 if it was inserted with value `next_slot` */
+int pairmap_get_or_add(pairmap_t *m, int lo, int hi, int next_slot, int *created);
+
+/* ---- ordering (ordering.c) ----------------------------------------------------------- */
+/* Reference-equivalent elimination order; adj lists ascending, no self loops.
+ * Returns malloc'd order[pos] = node. */
+int *asam_ref_ordering(int N, const int *adj_ptr, const int *adj);
+
+/* ---- symbolic plan (plan.c) ----------------------------------------------------------- */
+#define ASAM_TR_FLAG (1 << 30) /* a_rb flag: gather the slot transposed */
+
+typedef struct {
+    ivec_t rows;     /* block rows in q positions, ascending; first cb = own columns  */
+    ivec_t rel;      /* rel[k] = index of rows[k] in the parent's rows (k >= cb)       */
+    ivec_t children; /* supernode ids                                                   */
+    ivec_t a_slot, a_rb, a_cb;
+} sn_host_t;
+
+typedef struct {
+    int N;        /* nodes covered by the plan                                        */
+    int *order;   /* reference elimination position -> node (mirrors param->ordering)  */
+    int *pos;     /* node -> reference position                                        */
+    int *node2q;  /* node -> numeric position (post-order of the block etree)          */
+    int *q2node;
+    int *parent_pos; /* block etree in reference positions (node level), -1 = root     */
+    int node_cap;
+
+    pairmap_t pairs;
+    int n_slots;
+    int *fslot; /* per factor; -1 for unary factors */
+    int fslot_cap;
+    int n_factors; /* factors covered by the plan */
+
+    int nsn, sn_cap;
+    asam_sn_desc_t *desc;
+    sn_host_t *snh;
+    int *sn_of_q;
+
+    ivec_t ipool_host; /* host copy of the device int pool */
+    int64_t ipool_n;  /* ints used in the device pool   */
+    int64_t arena_n;  /* doubles used in the device arena */
+    int max_m;        /* largest front order (scalars)  */
+
+    /* full task lists (batch) */
+    int *tasks, *nwait, *btasks;
+
+    /* statistics of the last build */
+    int64_t nnz_l_blocks; /* sum over nodes of (1 + |below|) */
+    double flops;         /* sum over scalar columns of count^2 */
+    int n_levels;
+
+    /* structure cache */
+    uint64_t struct_hash;
+} plan_t;
+
+void plan_free(plan_t *pl);
+
+/* Build ordering + symbolic factorisation + supernodes + gather lists for the first
+ * n_factors factors over N nodes and upload everything to `dev`.  ftype/fa/fb are the
+ * factor type and node ids.  Returns 0 on success. */
+int plan_build(plan_t *pl, asam_dev_t *dev, int N, int n_factors, const int *ftype, const int *fa, const int *fb);
+
+/* Same, but keep a given elimination order for the first N_keep nodes (order_keep[pos]) and
+ * append the remaining nodes in id order (used by the incremental fallback). */
+int plan_build_with_order(plan_t *pl, asam_dev_t *dev, int N, int n_factors, const int *ftype, const int *fa,
+                          const int *fb, const int *order_keep, int N_keep);
+
+/* Incremental append: nodes [pl->N, N) and factors [pl->n_factors, n_factors) are new and
+ * every new binary factor touches at least one new node.  marked_old = graph-node ids of
+ * old nodes on the root paths (any order).  On return tasks_out/nwait_out (malloc'd, length
+ * *ntasks_out) list the supernodes to re-factor, children first.
+ * Returns 0 ok, 1 error, 2 = not an append-only update (caller falls back). */
+int plan_append(plan_t *pl, asam_dev_t *dev, int N, int n_factors, const int *ftype, const int *fa, const int *fb,
+                const int *marked_old, int n_marked, int **tasks_out, int **nwait_out, int *ntasks_out);
+
+/* ---- solver context (solver.c) --------------------------------------------------------- */
+void asam_graph_forget(april_graph_t *g);
+void asam_set_error(const char *fmt, ...);
+void asam_fatal(const char *fmt, ...);
+
+#endif

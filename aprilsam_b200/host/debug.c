@@ -1,0 +1,94 @@
+/* debug.c -- test-only exports of the host symbolic layer (no GPU needed).
+ *
+ * tests/ (-m "not gpu") build plans through these entry points and replay them with a
+ * numpy emulation of the kernels to check row structures, relative indices, gather lists
+ * and the task schedule without a device.  Nothing here is on the solve path.
+ */
+#include <stdlib.h>
+#include <string.h>
+
+#include "asam_host.h"
+
+ASAM_API void *asam_dbg_plan_create(void) { return calloc(1, sizeof(plan_t)); }
+
+ASAM_API void asam_dbg_plan_destroy(void *p)
+{
+    if (!p)
+        return;
+    plan_free((plan_t *) p);
+    free(p);
+}
+
+ASAM_API int asam_dbg_plan_build(void *p, int N, int F, const int *ftype, const int *fa, const int *fb)
+{
+    return plan_build((plan_t *) p, NULL, N, F, ftype, fa, fb);
+}
+
+ASAM_API int asam_dbg_plan_build_with_order(void *p, int N, int F, const int *ftype, const int *fa, const int *fb,
+                                            const int *order_keep, int N_keep)
+{
+    return plan_build_with_order((plan_t *) p, NULL, N, F, ftype, fa, fb, order_keep, N_keep);
+}
+
+/* returns ntasks (>= 0) or -rc */
+ASAM_API int asam_dbg_plan_append(void *p, int N, int F, const int *ftype, const int *fa, const int *fb,
+                                  const int *marked, int n_marked, int *tasks_out, int *nwait_out, int cap)
+{
+    int *tasks = NULL, *nwait = NULL, nt = 0;
+    int rc = plan_append((plan_t *) p, NULL, N, F, ftype, fa, fb, marked, n_marked, &tasks, &nwait, &nt);
+    if (rc)
+        return -rc;
+    if (nt > cap)
+        nt = cap;
+    memcpy(tasks_out, tasks, sizeof(int) * (size_t) nt);
+    memcpy(nwait_out, nwait, sizeof(int) * (size_t) nt);
+    free(tasks);
+    free(nwait);
+    return nt;
+}
+
+/* info: N, nsn, n_slots, ipool_n, arena_n, max_m, nnz_l_blocks, n_levels, n_factors */
+ASAM_API void asam_dbg_plan_info(void *p, int64_t *info, double *flops)
+{
+    plan_t *pl = (plan_t *) p;
+    info[0] = pl->N;
+    info[1] = pl->nsn;
+    info[2] = pl->n_slots;
+    info[3] = pl->ipool_n;
+    info[4] = pl->arena_n;
+    info[5] = pl->max_m;
+    info[6] = pl->nnz_l_blocks;
+    info[7] = pl->n_levels;
+    info[8] = pl->n_factors;
+    *flops = pl->flops;
+}
+
+/* which: 0 order 1 pos 2 node2q 3 q2node 4 parent_pos 5 fslot 6 sn_of_q 7 ipool 8 tasks 9 nwait
+ * 10 btasks 11 desc (as int32 words, 12 per supernode) */
+ASAM_API const int *asam_dbg_plan_array(void *p, int which, int64_t *count)
+{
+    plan_t *pl = (plan_t *) p;
+    switch (which) {
+    case 0: *count = pl->N; return pl->order;
+    case 1: *count = pl->N; return pl->pos;
+    case 2: *count = pl->N; return pl->node2q;
+    case 3: *count = pl->N; return pl->q2node;
+    case 4: *count = pl->N; return pl->parent_pos;
+    case 5: *count = pl->n_factors; return pl->fslot;
+    case 6: *count = pl->N; return pl->sn_of_q;
+    case 7: *count = pl->ipool_host.n; return pl->ipool_host.p;
+    case 8: *count = pl->tasks ? pl->nsn : 0; return pl->tasks;
+    case 9: *count = pl->nwait ? pl->nsn : 0; return pl->nwait;
+    case 10: *count = pl->btasks ? pl->nsn : 0; return pl->btasks;
+    case 11: *count = 12 * (int64_t) pl->nsn; return (const int *) pl->desc;
+    default: *count = 0; return NULL;
+    }
+}
+
+ASAM_API int asam_dbg_ref_ordering(int N, const int *adj_ptr, const int *adj, int *out)
+{
+    int *o = asam_ref_ordering(N, adj_ptr, adj);
+    memcpy(out, o, sizeof(int) * (size_t) (N > 0 ? N : 0));
+    free(o);
+    return 0;
+}

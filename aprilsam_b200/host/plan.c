@@ -1,0 +1,895 @@
+/* plan.c -- host-side symbolic analysis and numeric plan for the GPU multifrontal solver.
+ *
+ * Replaces, with its own algorithms, the symbolic half of the reference's batch step:
+ *   node adjacency                     aprilsam.c:104-114 (smatd Asym)
+ *   ordering                           aprilsam.c:121       -> ordering.c
+ *   cs_schol (etree, post, counts)     csparse.c:1693-1716  -> block elimination tree + block
+ *                                                             row structures computed directly
+ *   search_tree_create_from_smat       aprilsam.c:613-657   -> parent_pos[] (node-level tree)
+ * and adds what a GPU supernodal method needs: post-ordering, fundamental supernodes, frontal
+ * matrix layout, child->parent relative indices, Hessian gather lists, a level schedule.
+ *
+ * plan_append() is the symbolic side of april_graph_cholesky_inc (aprilsam.c:393-498,
+ * :908-987): new poses are appended at the end of the elimination order and only the
+ * supernodes on root paths of the touched nodes change (they gain the new poses as rows).
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "asam_host.h"
+
+#define MAX_SN_COLS 64 /* block columns per supernode (bounds the single-CTA panel width) */
+
+/* ---- pair map ---------------------------------------------------------------------------- */
+static inline uint64_t mix64(uint64_t x)
+{
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdULL;
+    x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ULL;
+    x ^= x >> 33;
+    return x;
+}
+
+void pairmap_init(pairmap_t *m, int expect)
+{
+    int cap = 64;
+    while (cap < 2 * expect + 16)
+        cap *= 2;
+    m->cap = cap;
+    m->n = 0;
+    m->keys = malloc(sizeof(uint64_t) * cap);
+    m->vals = malloc(sizeof(int) * cap);
+    memset(m->keys, 0xff, sizeof(uint64_t) * cap);
+}
+
+void pairmap_free(pairmap_t *m)
+{
+    free(m->keys);
+    free(m->vals);
+    memset(m, 0, sizeof(*m));
+}
+
+static void pairmap_grow(pairmap_t *m)
+{
+    pairmap_t n;
+    pairmap_init(&n, m->cap);
+    for (int i = 0; i < m->cap; i++) {
+        if (m->keys[i] == UINT64_MAX)
+            continue;
+        uint64_t h = mix64(m->keys[i]) & (uint64_t) (n.cap - 1);
+        while (n.keys[h] != UINT64_MAX)
+            h = (h + 1) & (uint64_t) (n.cap - 1);
+        n.keys[h] = m->keys[i];
+        n.vals[h] = m->vals[i];
+    }
+    n.n = m->n;
+    free(m->keys);
+    free(m->vals);
+    *m = n;
+}
+
+int pairmap_get_or_add(pairmap_t *m, int lo, int hi, int next_slot, int *created)
+{
+    if (2 * (m->n + 1) > m->cap)
+        pairmap_grow(m);
+    uint64_t key = ((uint64_t) (uint32_t) lo << 32) | (uint32_t) hi;
+    uint64_t h = mix64(key) & (uint64_t) (m->cap - 1);
+    while (m->keys[h] != UINT64_MAX) {
+        if (m->keys[h] == key) {
+            *created = 0;
+            return m->vals[h];
+        }
+        h = (h + 1) & (uint64_t) (m->cap - 1);
+    }
+    m->keys[h] = key;
+    m->vals[h] = next_slot;
+    m->n++;
+    *created = 1;
+    return next_slot;
+}
+
+/* ---- helpers ------------------------------------------------------------------------------ */
+static int cmp_int(const void *a, const void *b)
+{
+    int x = *(const int *) a, y = *(const int *) b;
+    return (x > y) - (x < y);
+}
+
+static void sort_ints(int *p, int n)
+{
+    if (n < 2)
+        return;
+    if (n <= 24) { /* insertion sort: most lists are tiny */
+        for (int i = 1; i < n; i++) {
+            int v = p[i], j = i - 1;
+            while (j >= 0 && p[j] > v) {
+                p[j + 1] = p[j];
+                j--;
+            }
+            p[j + 1] = v;
+        }
+        return;
+    }
+    qsort(p, n, sizeof(int), cmp_int);
+}
+
+static int sort_unique(int *p, int n)
+{
+    sort_ints(p, n);
+    int k = 0;
+    for (int i = 0; i < n; i++)
+        if (k == 0 || p[k - 1] != p[i])
+            p[k++] = p[i];
+    return k;
+}
+
+static int find_sorted(const int *p, int n, int v)
+{
+    int lo = 0, hi = n - 1;
+    while (lo <= hi) {
+        int mid = (lo + hi) >> 1;
+        if (p[mid] == v)
+            return mid;
+        if (p[mid] < v)
+            lo = mid + 1;
+        else
+            hi = mid - 1;
+    }
+    return -1;
+}
+
+static void sn_host_free(sn_host_t *h)
+{
+    ivec_free(&h->rows);
+    ivec_free(&h->rel);
+    ivec_free(&h->children);
+    ivec_free(&h->a_slot);
+    ivec_free(&h->a_rb);
+    ivec_free(&h->a_cb);
+}
+
+void plan_free(plan_t *pl)
+{
+    free(pl->order);
+    free(pl->pos);
+    free(pl->node2q);
+    free(pl->q2node);
+    free(pl->parent_pos);
+    if (pl->pairs.keys)
+        pairmap_free(&pl->pairs);
+    free(pl->fslot);
+    for (int s = 0; s < pl->nsn; s++)
+        sn_host_free(&pl->snh[s]);
+    free(pl->desc);
+    free(pl->snh);
+    free(pl->sn_of_q);
+    free(pl->tasks);
+    free(pl->nwait);
+    free(pl->btasks);
+    ivec_free(&pl->ipool_host);
+    memset(pl, 0, sizeof(*pl));
+}
+
+static void node_arrays_reserve(plan_t *pl, int N)
+{
+    if (N <= pl->node_cap)
+        return;
+    int cap = pl->node_cap ? pl->node_cap : 64;
+    while (cap < N)
+        cap *= 2;
+    pl->order = realloc(pl->order, sizeof(int) * cap);
+    pl->pos = realloc(pl->pos, sizeof(int) * cap);
+    pl->node2q = realloc(pl->node2q, sizeof(int) * cap);
+    pl->q2node = realloc(pl->q2node, sizeof(int) * cap);
+    pl->parent_pos = realloc(pl->parent_pos, sizeof(int) * cap);
+    pl->sn_of_q = realloc(pl->sn_of_q, sizeof(int) * cap);
+    pl->node_cap = cap;
+}
+
+static void sn_arrays_reserve(plan_t *pl, int n)
+{
+    if (n <= pl->sn_cap)
+        return;
+    int cap = pl->sn_cap ? pl->sn_cap : 64;
+    while (cap < n)
+        cap *= 2;
+    pl->desc = realloc(pl->desc, sizeof(asam_sn_desc_t) * cap);
+    pl->snh = realloc(pl->snh, sizeof(sn_host_t) * cap);
+    memset(pl->snh + pl->sn_cap, 0, sizeof(sn_host_t) * (cap - pl->sn_cap));
+    memset(pl->desc + pl->sn_cap, 0, sizeof(asam_sn_desc_t) * (cap - pl->sn_cap));
+    pl->sn_cap = cap;
+}
+
+static void fslot_reserve(plan_t *pl, int n)
+{
+    if (n <= pl->fslot_cap)
+        return;
+    int cap = pl->fslot_cap ? pl->fslot_cap : 64;
+    while (cap < n)
+        cap *= 2;
+    pl->fslot = realloc(pl->fslot, sizeof(int) * cap);
+    pl->fslot_cap = cap;
+}
+
+/* rel[k] for k >= cb: index of the child's row in the parent's row list */
+static int compute_rel(plan_t *pl, int s)
+{
+    sn_host_t *h = &pl->snh[s];
+    int cb = pl->desc[s].cb;
+    ivec_reserve(&h->rel, h->rows.n);
+    h->rel.n = h->rows.n;
+    for (int k = 0; k < cb && k < h->rows.n; k++)
+        h->rel.p[k] = -1;
+    int P = pl->desc[s].parent;
+    if (P < 0) {
+        if (h->rows.n != cb) {
+            asam_set_error("plan: supernode %d has rows below but no parent", s);
+            return 1;
+        }
+        return 0;
+    }
+    const ivec_t *pr = &pl->snh[P].rows;
+    int j = 0;
+    for (int k = cb; k < h->rows.n; k++) {
+        int v = h->rows.p[k];
+        while (j < pr->n && pr->p[j] < v)
+            j++;
+        if (j >= pr->n || pr->p[j] != v) {
+            asam_set_error("plan: row %d of supernode %d missing in parent %d", v, s, P);
+            return 1;
+        }
+        h->rel.p[k] = j;
+    }
+    return 0;
+}
+
+/* Serialise the index segment of supernode s at the tail of `buf`; sets desc.seg. */
+static void emit_segment(plan_t *pl, int s, ivec_t *buf, int64_t base)
+{
+    sn_host_t *h = &pl->snh[s];
+    asam_sn_desc_t *d = &pl->desc[s];
+    d->seg = (int32_t) (base + buf->n);
+    d->mb = h->rows.n;
+    d->ch_cnt = h->children.n;
+    d->a_cnt = h->a_slot.n;
+    int need = buf->n + 2 * h->rows.n + h->children.n + 3 * h->a_slot.n;
+    ivec_reserve(buf, need);
+    memcpy(buf->p + buf->n, h->rows.p, sizeof(int) * h->rows.n);
+    buf->n += h->rows.n;
+    memcpy(buf->p + buf->n, h->rel.p, sizeof(int) * h->rows.n);
+    buf->n += h->rows.n;
+    memcpy(buf->p + buf->n, h->children.p, sizeof(int) * h->children.n);
+    buf->n += h->children.n;
+    memcpy(buf->p + buf->n, h->a_slot.p, sizeof(int) * h->a_slot.n);
+    buf->n += h->a_slot.n;
+    memcpy(buf->p + buf->n, h->a_rb.p, sizeof(int) * h->a_slot.n);
+    buf->n += h->a_slot.n;
+    memcpy(buf->p + buf->n, h->a_cb.p, sizeof(int) * h->a_slot.n);
+    buf->n += h->a_slot.n;
+}
+
+static int64_t front_doubles(int mb)
+{
+    int64_t m = 3 * (int64_t) mb;
+    return m * m + m;
+}
+
+/* ---- batch build --------------------------------------------------------------------------- */
+static int plan_build_impl(plan_t *pl, asam_dev_t *dev, int N, int n_factors, const int *ftype, const int *fa,
+                           const int *fb, const int *order_keep, int N_keep)
+{
+    uint64_t keep_hash = pl->struct_hash;
+    plan_free(pl);
+    pl->struct_hash = keep_hash;
+    if (N <= 0)
+        return 0;
+    node_arrays_reserve(pl, N);
+    fslot_reserve(pl, n_factors);
+    pl->N = N;
+    pl->n_factors = n_factors;
+
+    /* 1. unique node pairs -> Hessian slots */
+    pairmap_init(&pl->pairs, n_factors);
+    ivec_t plo = { 0 }, phi = { 0 };
+    for (int f = 0; f < n_factors; f++) {
+        if (ftype[f] == APRIL_GRAPH_FACTOR_XYT_TYPE) {
+            int a = fa[f], b = fb[f];
+            if (a == b || a < 0 || b < 0 || a >= N || b >= N) {
+                asam_set_error("factor %d: bad node ids (%d,%d)", f, a, b);
+                return 1;
+            }
+            int lo = a < b ? a : b, hi = a < b ? b : a, created;
+            int slot = pairmap_get_or_add(&pl->pairs, lo, hi, pl->n_slots, &created);
+            if (created) {
+                ivec_push(&plo, lo);
+                ivec_push(&phi, hi);
+                pl->n_slots++;
+            }
+            pl->fslot[f] = slot;
+        } else if (ftype[f] == APRIL_GRAPH_FACTOR_XYTPOS_TYPE) {
+            if (fa[f] < 0 || fa[f] >= N) {
+                asam_set_error("factor %d: bad node id %d", f, fa[f]);
+                return 1;
+            }
+            pl->fslot[f] = -1;
+        } else {
+            asam_set_error("factor %d: unsupported factor type %d", f, ftype[f]);
+            return 1;
+        }
+    }
+    const int S = pl->n_slots;
+
+    /* 2. adjacency CSR, ascending */
+    int *adj_ptr = calloc((size_t) N + 1, sizeof(int));
+    for (int s = 0; s < S; s++) {
+        adj_ptr[plo.p[s] + 1]++;
+        adj_ptr[phi.p[s] + 1]++;
+    }
+    for (int i = 0; i < N; i++)
+        adj_ptr[i + 1] += adj_ptr[i];
+    int *adj = malloc(sizeof(int) * (size_t) (2 * S + 1));
+    int *fill = malloc(sizeof(int) * (size_t) N);
+    memcpy(fill, adj_ptr, sizeof(int) * (size_t) N);
+    for (int s = 0; s < S; s++) {
+        adj[fill[plo.p[s]]++] = phi.p[s];
+        adj[fill[phi.p[s]]++] = plo.p[s];
+    }
+    for (int i = 0; i < N; i++)
+        sort_ints(adj + adj_ptr[i], adj_ptr[i + 1] - adj_ptr[i]);
+    free(fill);
+
+    /* 3. elimination order */
+    if (order_keep) {
+        for (int p = 0; p < N_keep; p++)
+            pl->order[p] = order_keep[p];
+        for (int p = N_keep; p < N; p++)
+            pl->order[p] = p;
+    } else {
+        int *ord = asam_ref_ordering(N, adj_ptr, adj);
+        memcpy(pl->order, ord, sizeof(int) * (size_t) N);
+        free(ord);
+    }
+    for (int p = 0; p < N; p++)
+        pl->pos[pl->order[p]] = p;
+
+    /* 4. block symbolic factorisation in reference positions */
+    int *parent = pl->parent_pos;
+    int *head = malloc(sizeof(int) * (size_t) N), *tail = malloc(sizeof(int) * (size_t) N);
+    int *next = malloc(sizeof(int) * (size_t) N), *nchild = calloc((size_t) N, sizeof(int));
+    int *stamp = calloc((size_t) N, sizeof(int));
+    int64_t *bptr = malloc(sizeof(int64_t) * ((size_t) N + 1));
+    ivec_t bl = { 0 };
+    for (int p = 0; p < N; p++)
+        head[p] = tail[p] = next[p] = -1;
+    bptr[0] = 0;
+    for (int p = 0; p < N; p++) {
+        int v = pl->order[p], start = bl.n, token = p + 1;
+        stamp[p] = token;
+        for (int e = adj_ptr[v]; e < adj_ptr[v + 1]; e++) {
+            int pu = pl->pos[adj[e]];
+            if (pu > p && stamp[pu] != token) {
+                stamp[pu] = token;
+                ivec_push(&bl, pu);
+            }
+        }
+        for (int c = head[p]; c >= 0; c = next[c]) {
+            for (int64_t e = bptr[c]; e < bptr[c + 1]; e++) {
+                int x = bl.p[e];
+                if (stamp[x] != token) {
+                    stamp[x] = token;
+                    ivec_push(&bl, x);
+                }
+            }
+        }
+        sort_ints(bl.p + start, bl.n - start);
+        bptr[p + 1] = bl.n;
+        parent[p] = bl.n > start ? bl.p[start] : -1;
+        if (parent[p] >= 0) {
+            int P = parent[p];
+            if (tail[P] < 0)
+                head[P] = p;
+            else
+                next[tail[P]] = p;
+            tail[P] = p;
+            nchild[P]++;
+        }
+    }
+    free(stamp);
+    free(adj);
+    free(adj_ptr);
+
+    /* 5. post-order -> numeric positions q */
+    int *qpos = malloc(sizeof(int) * (size_t) N), *pofq = malloc(sizeof(int) * (size_t) N);
+    {
+        int *stack = malloc(sizeof(int) * (size_t) N), *it = malloc(sizeof(int) * (size_t) N);
+        int q = 0;
+        for (int r = 0; r < N; r++) {
+            if (parent[r] >= 0)
+                continue;
+            int sp = 0;
+            stack[sp] = r;
+            it[sp] = head[r];
+            sp++;
+            while (sp > 0) {
+                int c = it[sp - 1];
+                if (c >= 0) {
+                    it[sp - 1] = next[c];
+                    stack[sp] = c;
+                    it[sp] = head[c];
+                    sp++;
+                } else {
+                    int p = stack[--sp];
+                    qpos[p] = q;
+                    pofq[q] = p;
+                    q++;
+                }
+            }
+        }
+        free(stack);
+        free(it);
+    }
+    for (int p = 0; p < N; p++) {
+        pl->node2q[pl->order[p]] = qpos[p];
+        pl->q2node[qpos[p]] = pl->order[p];
+    }
+
+    /* 6. supernodes (fundamental chains, capped width) */
+    pl->nsn = 0;
+    pl->nnz_l_blocks = 0;
+    pl->flops = 0.0;
+    for (int q = 0; q < N; q++) {
+        int p = pofq[q];
+        int nb = (int) (bptr[p + 1] - bptr[p]);
+        pl->nnz_l_blocks += 1 + nb;
+        for (int k = 0; k < 3; k++) {
+            double cnt = 3.0 * nb + 3 - k;
+            pl->flops += cnt * cnt;
+        }
+        int merge = 0;
+        if (q > 0 && pl->nsn > 0) {
+            int pp = pofq[q - 1];
+            int nbp = (int) (bptr[pp + 1] - bptr[pp]);
+            if (parent[pp] == p && nchild[p] == 1 && nbp == nb + 1 && pl->desc[pl->nsn - 1].cb < MAX_SN_COLS)
+                merge = 1;
+        }
+        if (merge) {
+            pl->desc[pl->nsn - 1].cb++;
+        } else {
+            sn_arrays_reserve(pl, pl->nsn + 1);
+            asam_sn_desc_t *d = &pl->desc[pl->nsn];
+            memset(d, 0, sizeof(*d));
+            d->first = q;
+            d->cb = 1;
+            d->parent = -1;
+            pl->nsn++;
+        }
+        pl->sn_of_q[q] = pl->nsn - 1;
+    }
+
+    /* 7. row lists, parents, children, levels */
+    pl->max_m = 0;
+    for (int s = 0; s < pl->nsn; s++) {
+        asam_sn_desc_t *d = &pl->desc[s];
+        sn_host_t *h = &pl->snh[s];
+        int qt = d->first + d->cb - 1, pt = pofq[qt];
+        int nb = (int) (bptr[pt + 1] - bptr[pt]);
+        ivec_reserve(&h->rows, d->cb + nb);
+        for (int k = 0; k < d->cb; k++)
+            ivec_push(&h->rows, d->first + k);
+        for (int64_t e = bptr[pt]; e < bptr[pt + 1]; e++)
+            ivec_push(&h->rows, qpos[bl.p[e]]);
+        /* positions on a root path are ordered alike in both numberings; be safe anyway */
+        sort_ints(h->rows.p + d->cb, nb);
+        d->mb = h->rows.n;
+        if (3 * d->mb > pl->max_m)
+            pl->max_m = 3 * d->mb;
+        d->parent = nb > 0 ? pl->sn_of_q[h->rows.p[d->cb]] : -1;
+    }
+    for (int s = 0; s < pl->nsn; s++) {
+        int P = pl->desc[s].parent;
+        if (P >= 0) {
+            ivec_push(&pl->snh[P].children, s);
+            int lv = pl->desc[s].level + 1;
+            if (lv > pl->desc[P].level)
+                pl->desc[P].level = lv; /* children have smaller ids: final when P is reached */
+        }
+    }
+    pl->n_levels = 0;
+    for (int s = 0; s < pl->nsn; s++) {
+        if (compute_rel(pl, s))
+            return 1;
+        if (pl->desc[s].level + 1 > pl->n_levels)
+            pl->n_levels = pl->desc[s].level + 1;
+    }
+    free(bptr);
+    ivec_free(&bl);
+    free(head);
+    free(tail);
+    free(next);
+    free(nchild);
+    free(qpos);
+    free(pofq);
+
+    /* 8. Hessian gather lists */
+    for (int sl = 0; sl < S; sl++) {
+        int lo = plo.p[sl], hi = phi.p[sl];
+        int qlo = pl->node2q[lo], qhi = pl->node2q[hi];
+        int qe = qlo < qhi ? qlo : qhi, ql = qlo < qhi ? qhi : qlo;
+        int s = pl->sn_of_q[qe];
+        sn_host_t *h = &pl->snh[s];
+        int rb = find_sorted(h->rows.p, h->rows.n, ql);
+        if (rb < 0) {
+            asam_set_error("plan: Hessian block (%d,%d) not in the structure of supernode %d", lo, hi, s);
+            return 1;
+        }
+        ivec_push(&h->a_slot, sl);
+        ivec_push(&h->a_rb, rb | (qe == qlo ? 0 : ASAM_TR_FLAG));
+        ivec_push(&h->a_cb, qe - pl->desc[s].first);
+    }
+    ivec_free(&plo);
+    ivec_free(&phi);
+
+    /* 9. layout + schedule */
+    ivec_t seg = { 0 };
+    pl->arena_n = 0;
+    for (int s = 0; s < pl->nsn; s++) {
+        emit_segment(pl, s, &seg, 0);
+        pl->desc[s].f_off = pl->arena_n;
+        pl->arena_n += front_doubles(pl->desc[s].mb);
+    }
+    pl->ipool_n = seg.n;
+
+    pl->tasks = malloc(sizeof(int) * (size_t) pl->nsn);
+    pl->nwait = malloc(sizeof(int) * (size_t) pl->nsn);
+    pl->btasks = malloc(sizeof(int) * (size_t) pl->nsn);
+    {
+        /* counting sort by level, ids ascending inside a level */
+        int *cnt = calloc((size_t) pl->n_levels + 1, sizeof(int));
+        for (int s = 0; s < pl->nsn; s++)
+            cnt[pl->desc[s].level + 1]++;
+        for (int l = 0; l < pl->n_levels; l++)
+            cnt[l + 1] += cnt[l];
+        for (int s = 0; s < pl->nsn; s++)
+            pl->tasks[cnt[pl->desc[s].level]++] = s;
+        free(cnt);
+        for (int t = 0; t < pl->nsn; t++) {
+            pl->nwait[t] = pl->desc[pl->tasks[t]].ch_cnt;
+            pl->btasks[pl->nsn - 1 - t] = pl->tasks[t];
+        }
+    }
+
+    /* host mirror of the device int pool (debug / tests) */
+    ivec_free(&pl->ipool_host);
+    ivec_reserve(&pl->ipool_host, seg.n);
+    memcpy(pl->ipool_host.p, seg.p, sizeof(int) * (size_t) seg.n);
+    pl->ipool_host.n = seg.n;
+    if (!dev) {
+        ivec_free(&seg);
+        return 0;
+    }
+
+    /* 10. upload */
+    int64_t ipool_cap = pl->ipool_n * 2 + 4096, arena_cap = pl->arena_n + pl->arena_n / 2 + 65536;
+    int rc = asam_reserve(dev, N + N / 2 + 64, n_factors + n_factors / 2 + 64, S + S / 2 + 64,
+                          pl->nsn + N / 2 + 64, ipool_cap, arena_cap);
+    if (rc)
+        return rc;
+    int *ids = malloc(sizeof(int) * (size_t) pl->nsn);
+    for (int s = 0; s < pl->nsn; s++)
+        ids[s] = s;
+    rc |= asam_upload_ipool(dev, 0, seg.n, seg.p);
+    rc |= asam_upload_desc(dev, pl->nsn, ids, pl->desc);
+    rc |= asam_upload_node2q(dev, 0, N, pl->node2q);
+    rc |= asam_upload_q2node(dev, 0, N, pl->q2node);
+    rc |= asam_upload_fslot(dev, 0, n_factors, pl->fslot);
+    rc |= asam_set_full_tasks(dev, pl->nsn, pl->tasks, pl->nwait, pl->btasks);
+    free(ids);
+    ivec_free(&seg);
+    return rc;
+}
+
+int plan_build(plan_t *pl, asam_dev_t *dev, int N, int n_factors, const int *ftype, const int *fa, const int *fb)
+{
+    return plan_build_impl(pl, dev, N, n_factors, ftype, fa, fb, NULL, 0);
+}
+
+int plan_build_with_order(plan_t *pl, asam_dev_t *dev, int N, int n_factors, const int *ftype, const int *fa,
+                          const int *fb, const int *order_keep, int N_keep)
+{
+    int *keep = malloc(sizeof(int) * (size_t) (N_keep > 0 ? N_keep : 1));
+    memcpy(keep, order_keep, sizeof(int) * (size_t) N_keep);
+    int rc = plan_build_impl(pl, dev, N, n_factors, ftype, fa, fb, keep, N_keep);
+    free(keep);
+    return rc;
+}
+
+/* ---- incremental append ------------------------------------------------------------------- */
+int plan_append(plan_t *pl, asam_dev_t *dev, int N, int n_factors, const int *ftype, const int *fa, const int *fb,
+                const int *marked_old, int n_marked, int **tasks_out, int **nwait_out, int *ntasks_out)
+{
+    const int N0 = pl->N, F0 = pl->n_factors, nsn0 = pl->nsn;
+    *tasks_out = *nwait_out = NULL;
+    *ntasks_out = 0;
+    for (int f = F0; f < n_factors; f++) {
+        if (ftype[f] == APRIL_GRAPH_FACTOR_XYT_TYPE) {
+            if (fa[f] == fb[f] || fa[f] < 0 || fb[f] < 0 || fa[f] >= N || fb[f] >= N) {
+                asam_set_error("factor %d: bad node ids (%d,%d)", f, fa[f], fb[f]);
+                return 1;
+            }
+            if (fa[f] < N0 && fb[f] < N0)
+                return 2; /* edge between two old poses: structure of old rows changes */
+        } else if (ftype[f] == APRIL_GRAPH_FACTOR_XYTPOS_TYPE) {
+            if (fa[f] < 0 || fa[f] >= N) {
+                asam_set_error("factor %d: bad node id %d", f, fa[f]);
+                return 1;
+            }
+        } else {
+            asam_set_error("factor %d: unsupported factor type %d", f, ftype[f]);
+            return 1;
+        }
+    }
+
+    /* grow node-indexed arrays: new poses are eliminated last, in id order */
+    node_arrays_reserve(pl, N);
+    fslot_reserve(pl, n_factors);
+    const int nnew = N - N0;
+    sn_arrays_reserve(pl, nsn0 + nnew);
+    for (int i = N0; i < N; i++) {
+        pl->order[i] = i;
+        pl->pos[i] = i;
+        pl->node2q[i] = i;
+        pl->q2node[i] = i;
+        pl->parent_pos[i] = -1;
+        pl->sn_of_q[i] = nsn0 + (i - N0);
+    }
+
+    /* new Hessian slots */
+    const int slot0 = pl->n_slots;
+    ivec_t nlo = { 0 }, nhi = { 0 };
+    for (int f = F0; f < n_factors; f++) {
+        if (ftype[f] != APRIL_GRAPH_FACTOR_XYT_TYPE) {
+            pl->fslot[f] = -1;
+            continue;
+        }
+        int a = fa[f], b = fb[f], lo = a < b ? a : b, hi = a < b ? b : a, created;
+        int slot = pairmap_get_or_add(&pl->pairs, lo, hi, pl->n_slots, &created);
+        if (created) {
+            ivec_push(&nlo, lo);
+            ivec_push(&nhi, hi);
+            pl->n_slots++;
+        }
+        pl->fslot[f] = slot;
+    }
+
+    /* marked supernodes, ascending id (= children first) */
+    int *msn = malloc(sizeof(int) * (size_t) (n_marked + 1));
+    int nm = 0;
+    for (int i = 0; i < n_marked; i++)
+        if (marked_old[i] < N0)
+            msn[nm++] = pl->sn_of_q[pl->node2q[marked_old[i]]];
+    nm = sort_unique(msn, nm);
+    int *mark_idx = malloc(sizeof(int) * (size_t) (nsn0 + nnew + 1)); /* sn -> index in msn or -1 */
+    for (int s = 0; s < nsn0 + nnew; s++)
+        mark_idx[s] = -1;
+    for (int i = 0; i < nm; i++)
+        mark_idx[msn[i]] = i;
+
+    int rc = 0;
+    ivec_t *gain = calloc((size_t) nm + 1, sizeof(ivec_t));
+    ivec_t *pend = calloc((size_t) nnew + 1, sizeof(ivec_t)); /* children of each new supernode */
+    ivec_t *nbelow = calloc((size_t) nnew + 1, sizeof(ivec_t));
+
+    /* seed gains with the new edges (old pose, new pose); new-new edges seed nbelow */
+    for (int k = 0; k < nlo.n; k++) {
+        int lo = nlo.p[k], hi = nhi.p[k];
+        if (lo < N0) {
+            int s = pl->sn_of_q[pl->node2q[lo]];
+            if (mark_idx[s] < 0) {
+                asam_set_error("plan_append: pose %d gets a new factor but is not marked", lo);
+                rc = 1;
+                goto done;
+            }
+            ivec_push(&gain[mark_idx[s]], hi);
+        } else {
+            ivec_push(&nbelow[lo - N0], hi);
+        }
+    }
+
+    /* propagate gains up the marked sub-forest; grow row lists; re-place fronts */
+    for (int i = 0; i < nm; i++) {
+        int s = msn[i];
+        sn_host_t *h = &pl->snh[s];
+        asam_sn_desc_t *d = &pl->desc[s];
+        for (int c = 0; c < h->children.n; c++) {
+            int ci = mark_idx[h->children.p[c]];
+            if (ci >= 0)
+                for (int e = 0; e < gain[ci].n; e++)
+                    ivec_push(&gain[i], gain[ci].p[e]);
+        }
+        gain[i].n = sort_unique(gain[i].p, gain[i].n);
+        int old_mb = h->rows.n;
+        for (int e = 0; e < gain[i].n; e++)
+            ivec_push(&h->rows, gain[i].p[e]); /* new poses sort after every old row */
+        d->mb = h->rows.n;
+        if (3 * d->mb > pl->max_m)
+            pl->max_m = 3 * d->mb;
+        if (d->mb != old_mb) {
+            d->f_off = pl->arena_n;
+            pl->arena_n += front_doubles(d->mb);
+        }
+        if (d->parent < 0 && gain[i].n > 0) { /* old root: hangs under the first new pose */
+            int P = nsn0 + (gain[i].p[0] - N0);
+            d->parent = P;
+            ivec_push(&pend[P - nsn0], s);
+            int top = pl->q2node[d->first + d->cb - 1];
+            pl->parent_pos[pl->pos[top]] = gain[i].p[0]; /* pos == q == id for new poses */
+        }
+    }
+    /* gather-list entries for the new (old,new) blocks */
+    for (int k = 0; k < nlo.n; k++) {
+        int lo = nlo.p[k], hi = nhi.p[k];
+        if (lo >= N0)
+            continue;
+        int s = pl->sn_of_q[pl->node2q[lo]];
+        sn_host_t *h = &pl->snh[s];
+        int rb = find_sorted(h->rows.p, h->rows.n, hi);
+        if (rb < 0) {
+            asam_set_error("plan_append: internal (row %d not in supernode %d)", hi, s);
+            rc = 1;
+            goto done;
+        }
+        ivec_push(&h->a_slot, slot0 + k);
+        ivec_push(&h->a_rb, rb); /* early = lo = lower id: no transpose */
+        ivec_push(&h->a_cb, pl->node2q[lo] - pl->desc[s].first);
+    }
+
+    /* new poses: singleton supernodes, ascending */
+    for (int j = 0; j < nnew; j++) {
+        int n = N0 + j, sid = nsn0 + j;
+        asam_sn_desc_t *d = &pl->desc[sid];
+        sn_host_t *h = &pl->snh[sid];
+        memset(d, 0, sizeof(*d));
+        d->first = n;
+        d->cb = 1;
+        d->parent = -1;
+        ivec_t *bel = &nbelow[j];
+        for (int c = 0; c < pend[j].n; c++) {
+            int X = pend[j].p[c];
+            const sn_host_t *hx = &pl->snh[X];
+            for (int e = pl->desc[X].cb; e < hx->rows.n; e++)
+                if (hx->rows.p[e] != n)
+                    ivec_push(bel, hx->rows.p[e]);
+            int lv = pl->desc[X].level + 1;
+            if (lv > d->level)
+                d->level = lv;
+        }
+        bel->n = sort_unique(bel->p, bel->n);
+        h->rows.n = 0;
+        ivec_push(&h->rows, n);
+        for (int e = 0; e < bel->n; e++)
+            ivec_push(&h->rows, bel->p[e]);
+        h->children.n = 0;
+        for (int c = 0; c < pend[j].n; c++)
+            ivec_push(&h->children, pend[j].p[c]);
+        h->a_slot.n = h->a_rb.n = h->a_cb.n = 0;
+        d->mb = h->rows.n;
+        if (3 * d->mb > pl->max_m)
+            pl->max_m = 3 * d->mb;
+        d->f_off = pl->arena_n;
+        pl->arena_n += front_doubles(d->mb);
+        if (bel->n > 0) {
+            int P = nsn0 + (bel->p[0] - N0);
+            d->parent = P;
+            ivec_push(&pend[P - nsn0], sid);
+            pl->parent_pos[n] = bel->p[0];
+        }
+        if (d->level + 1 > pl->n_levels)
+            pl->n_levels = d->level + 1;
+    }
+    pl->nsn = nsn0 + nnew;
+    for (int k = 0; k < nlo.n; k++) { /* (new,new) blocks */
+        int lo = nlo.p[k], hi = nhi.p[k];
+        if (lo < N0)
+            continue;
+        int s = nsn0 + (lo - N0);
+        sn_host_t *h = &pl->snh[s];
+        int rb = find_sorted(h->rows.p, h->rows.n, hi);
+        if (rb < 0) {
+            asam_set_error("plan_append: internal (row %d not in new supernode %d)", hi, s);
+            rc = 1;
+            goto done;
+        }
+        ivec_push(&h->a_slot, slot0 + k);
+        ivec_push(&h->a_rb, rb);
+        ivec_push(&h->a_cb, 0);
+    }
+
+    /* relative indices + segments of everything that changed */
+    {
+        int nt = nm + nnew;
+        int *tasks = malloc(sizeof(int) * (size_t) (nt + 1)), *nwait = malloc(sizeof(int) * (size_t) (nt + 1));
+        for (int i = 0; i < nm; i++)
+            tasks[i] = msn[i];
+        for (int j = 0; j < nnew; j++) {
+            tasks[nm + j] = nsn0 + j;
+            mark_idx[nsn0 + j] = nm + j;
+        }
+        ivec_t seg = { 0 };
+        for (int t = 0; t < nt && !rc; t++)
+            rc |= compute_rel(pl, tasks[t]);
+        for (int t = 0; t < nt && !rc; t++) {
+            int s = tasks[t], w = 0;
+            for (int c = 0; c < pl->snh[s].children.n; c++)
+                if (mark_idx[pl->snh[s].children.p[c]] >= 0)
+                    w++;
+            nwait[t] = w;
+            emit_segment(pl, s, &seg, pl->ipool_n);
+        }
+        if (!rc) {
+            ivec_reserve(&pl->ipool_host, pl->ipool_host.n + seg.n);
+            memcpy(pl->ipool_host.p + pl->ipool_host.n, seg.p, sizeof(int) * (size_t) seg.n);
+            pl->ipool_host.n += seg.n;
+        }
+        if (!rc && !dev)
+            pl->ipool_n += seg.n;
+        if (!rc && dev) {
+            int64_t ipool_need = pl->ipool_n + seg.n;
+            rc = asam_reserve(dev, N + 64, n_factors + 64, pl->n_slots + 64, pl->nsn + 64, ipool_need + ipool_need / 2,
+                              pl->arena_n + pl->arena_n / 4);
+            asam_sn_desc_t *dd = malloc(sizeof(asam_sn_desc_t) * (size_t) (nt + 1));
+            for (int t = 0; t < nt; t++)
+                dd[t] = pl->desc[tasks[t]];
+            if (!rc)
+                rc |= asam_upload_ipool(dev, pl->ipool_n, seg.n, seg.p);
+            if (!rc)
+                rc |= asam_upload_desc(dev, nt, tasks, dd);
+            if (!rc && nnew > 0) {
+                rc |= asam_upload_node2q(dev, N0, nnew, pl->node2q + N0);
+                rc |= asam_upload_q2node(dev, N0, nnew, pl->q2node + N0);
+            }
+            if (!rc && nnew > 0) { /* new supernodes are ancestors of all older ones */
+                int *pre = malloc(sizeof(int) * (size_t) nnew);
+                for (int j = 0; j < nnew; j++)
+                    pre[j] = nsn0 + nnew - 1 - j;
+                rc |= asam_btasks_prepend(dev, nnew, pre);
+                free(pre);
+            }
+            if (!rc)
+                rc |= asam_upload_fslot(dev, F0, n_factors - F0, pl->fslot + F0);
+            if (!rc)
+                rc |= asam_hessian_clear_range(dev, N0, nnew, slot0, pl->n_slots - slot0);
+            free(dd);
+            pl->ipool_n += seg.n;
+        }
+        ivec_free(&seg);
+        if (rc) {
+            free(tasks);
+            free(nwait);
+        } else {
+            *tasks_out = tasks;
+            *nwait_out = nwait;
+            *ntasks_out = nt;
+        }
+    }
+    pl->N = N;
+    pl->n_factors = n_factors;
+
+done:
+    for (int i = 0; i < nm; i++)
+        ivec_free(&gain[i]);
+    for (int j = 0; j < nnew; j++) {
+        ivec_free(&pend[j]);
+        ivec_free(&nbelow[j]);
+    }
+    free(gain);
+    free(pend);
+    free(nbelow);
+    free(msn);
+    free(mark_idx);
+    ivec_free(&nlo);
+    ivec_free(&nhi);
+    return rc;
+}

@@ -1,0 +1,249 @@
+/* aprilsam.h -- public API of aprilsam_b200 (drop-in for AprilSAM's solver path).
+ *
+ * This header re-declares, from scratch, the part of the reference's public C API
+ * that the Gauss-Newton path touches (reference: aprilsam/aprilsam.h).  Struct layouts
+ * are ABI-identical on x86-64 (checked by the _Static_asserts at the bottom; offsets
+ * from SURVEY.md section 8b) so a program written against the reference re-links against
+ * libaprilsam_b200.so unchanged.  Each declaration cites the reference line it replaces.
+ *
+ * What runs where: every entry point below is host C; all arithmetic of
+ * april_graph_cholesky{,_inc}() and april_graph_chi2() -- linearisation, J'WJ assembly,
+ * sparse Cholesky, triangular solves -- runs in sm_100a CUDA kernels behind the C-ABI in
+ * include/asam_cuda.h.  There is no CPU fallback: without a CUDA device the solver entry
+ * points abort with a message.
+ */
+#ifndef APRILSAM_B200_APRILSAM_H
+#define APRILSAM_B200_APRILSAM_H
+
+#include <stdint.h>
+#include <stdlib.h>
+
+#include "common/doubles.h"
+#include "common/matd.h"
+#include "common/zarray.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Types the reference exposes through pointers only; opaque here. */
+typedef struct zhash zhash_t;
+typedef struct stype stype_t;
+typedef struct smatd smatd_t;
+
+/* reference: aprilsam/common/smatd.h:62-67.  In this library `u` is unused and the
+ * object is the owner of the opaque GPU solver context (see aprilsam_b200/host). */
+typedef struct {
+    smatd_t *u;
+    int is_spd;
+} smatd_chol_t;
+
+void APRILSAM_VERSION(void); /* aprilsam.h:44 */
+
+/* ---- attributes (aprilsam.h:46-61): string -> (stype, value) table ---------------- */
+typedef struct april_graph_attr april_graph_attr_t;
+struct april_graph_attr {
+    zhash_t *hash;
+    const stype_t *stype;
+};
+
+/* ---- graph (aprilsam.h:64-72) ------------------------------------------------------ */
+typedef struct april_graph april_graph_t;
+struct april_graph {
+    zarray_t *factors; /* of april_graph_factor_t*  */
+    zarray_t *nodes;   /* of april_graph_node_t*    */
+    april_graph_attr_t *attr;
+    const stype_t *stype;
+};
+
+/* ---- factor evaluation record (aprilsam.h:75-89) ----------------------------------- */
+typedef struct april_graph_factor_eval april_graph_factor_eval_t;
+struct april_graph_factor_eval {
+    double chi2;
+    matd_t **jacobians; /* one per connected node, NULL-terminated */
+    int length;
+    double *r; /* residual, length x 1   */
+    matd_t *W; /* information, length^2  */
+};
+
+#define APRIL_GRAPH_FACTOR_XYT_TYPE 1    /* aprilsam.h:91 */
+#define APRIL_GRAPH_FACTOR_XYTPOS_TYPE 2 /* aprilsam.h:92 */
+#define APRIL_GRAPH_NODE_XYT_TYPE 100    /* aprilsam.h:94 */
+
+/* ---- factor (aprilsam.h:98-146) ---------------------------------------------------- */
+typedef struct april_graph_factor april_graph_factor_t;
+struct april_graph_factor {
+    int type;
+    int nnodes;
+    int *nodes; /* indices into graph->nodes */
+    int length; /* residual DOF */
+    april_graph_attr_t *attr;
+
+    april_graph_factor_t *(*copy)(april_graph_factor_t *factor);
+    /* Host-side plug-in hooks kept for API compatibility.  The GPU solver does NOT call
+     * them: it dispatches on `type` and evaluates xyt / xytpos factors in-kernel. */
+    april_graph_factor_eval_t *(*eval)(april_graph_factor_t *factor, april_graph_t *graph,
+                                       april_graph_factor_eval_t *eval);
+    april_graph_factor_eval_t *(*state_eval)(april_graph_factor_t *factor, april_graph_t *graph,
+                                             april_graph_factor_eval_t *eval);
+    void (*destroy)(april_graph_factor_t *factor);
+
+    union {
+        struct {
+            double *z;
+            double *ztruth;
+            matd_t *W;
+            void *impl;
+        } common;
+        struct {
+            april_graph_factor_t **factors;
+            double *logw;
+            int nfactors;
+        } max;
+        struct {
+            void *impl;
+        } impl;
+    } u;
+
+    const stype_t *stype;
+};
+
+/* ---- node (aprilsam.h:151-179) ----------------------------------------------------- */
+typedef struct april_graph_node april_graph_node_t;
+struct april_graph_node {
+    int UID;
+    int type;
+    int length; /* DOF */
+
+    double *state;   /* current estimate                      */
+    double *init;
+    double *truth;
+    double *l_point; /* linearisation point                   */
+    double *delta_X; /* last solved offset from l_point        */
+
+    april_graph_attr_t *attr;
+
+    april_graph_node_t *(*copy)(april_graph_node_t *node);
+    void (*update)(april_graph_node_t *node, double *dstate); /* state = l_point + dstate */
+    void (*relinearize)(april_graph_node_t *node);            /* l_point = state         */
+    void (*destroy)(april_graph_node_t *node);
+
+    void *impl;
+    const stype_t *stype;
+};
+
+/* ---- graph lifecycle (aprilsam.h:184-188) ------------------------------------------ */
+april_graph_t *april_graph_create(void);
+void april_graph_destroy(april_graph_t *graph);
+void april_graph_factor_eval_destroy(april_graph_factor_eval_t *eval);
+
+/* ---- block elimination tree (aprilsam.h:190-228) ----------------------------------- */
+typedef struct search_tree_node search_tree_node_t;
+struct search_tree_node {
+    int *children; /* graph-node ids */
+    int parent;    /* graph-node id, -1 = none */
+    int nalloc;
+    int nchildren;
+    int id; /* position in the elimination order */
+    april_graph_node_t *g_node;
+    int label_changed;      /* on a root path of a factor added this step */
+    int label_relinearized; /* counted towards start_over since the last batch */
+};
+
+typedef struct search_tree search_tree_t;
+struct search_tree {
+    int nnodes;
+    int nalloc;
+    search_tree_node_t *root;
+    search_tree_node_t *nodes; /* indexed by graph-node id */
+    int start_over;
+    int nlinearized_nodes;
+    int *linearized_nodes;
+    int isam1_cnt;
+    int naffected;
+    double delta_xy;
+    double delta_theta;
+    double total_delta_xy;
+    double total_delta_theta;
+};
+
+void search_tree_destroy(search_tree_t *tr);
+
+/* ---- solver parameters + persistent state (aprilsam.h:231-265) --------------------- */
+typedef struct april_graph_cholesky_param april_graph_cholesky_param_t;
+struct april_graph_cholesky_param {
+    double tikhanov; /* lambda added to every diagonal entry at each batch solve */
+
+    smatd_chol_t *chol; /* non-NULL once a batch solve has run (owns the GPU context) */
+    int factor_num;     /* factors consumed so far */
+
+    int *ordering;   /* ordering[pos] = graph-node id; owned by the param */
+    int nreordering; /* non-zero = enabled; after a solve: node count at that solve */
+    int show_timing;
+
+    double *delta_x; /* unused (reference leaves it dangling, aprilsam.c:360-366) */
+    double *B;       /* unused here: rhs lives in HBM */
+    double *y;       /* unused here */
+    smatd_t *A;      /* unused here: the block Hessian lives in HBM */
+
+    search_tree_t *tr;
+
+    double l_thresh;     /* unused by the reference solver */
+    double delta_thresh; /* unused by the reference solver */
+    int nthreshold;      /* batch re-solve when more than this many nodes moved */
+
+    double batch_time;
+
+    double delta_xy;    /* relinearisation thresholds */
+    double delta_theta;
+};
+
+/* aprilsam.h:268-269 (the spelling "destory" is the reference's) */
+void april_graph_cholesky_param_init(april_graph_cholesky_param_t *param);
+void april_graph_cholesky_param_destory(april_graph_cholesky_param_t *param);
+
+/* aprilsam.h:274-276 */
+void april_graph_cholesky(april_graph_t *graph, april_graph_cholesky_param_t *param);
+void april_graph_cholesky_inc(april_graph_t *graph, april_graph_cholesky_param_t *param);
+void april_graph_cholesky_inc_solver(april_graph_t *graph, april_graph_cholesky_param_t *param, int *idxs);
+
+/* aprilsam.h:280-281 */
+int april_graph_dof(april_graph_t *graph);
+double april_graph_chi2(april_graph_t *graph);
+
+/* aprilsam.h:283-286 */
+april_graph_node_t *april_graph_node_xyt_create(const double *state, const double *init, const double *truth);
+april_graph_factor_t *april_graph_factor_xyt_create(int a, int b, const double *z, const double *ztruth, const matd_t *W);
+april_graph_factor_t *april_graph_factor_xytpos_create(int a, double *z, double *ztruth, matd_t *W);
+
+/* Last error text of this library on the calling thread ("" if none).  Extension: the
+ * reference reports nothing (void returns, asserts, NULL dereference on non-SPD). */
+const char *aprilsam_b200_last_error(void);
+
+/* ---- ABI checks against the reference layout ------------------ */
+#if defined(__x86_64__) && !defined(__cplusplus)
+#include <stddef.h>
+_Static_assert(sizeof(zarray_t) == 24, "zarray_t");
+_Static_assert(sizeof(april_graph_t) == 32, "april_graph_t");
+_Static_assert(sizeof(april_graph_node_t) == 112 && offsetof(april_graph_node_t, state) == 16 &&
+                   offsetof(april_graph_node_t, l_point) == 40 && offsetof(april_graph_node_t, delta_X) == 48 &&
+                   offsetof(april_graph_node_t, update) == 72 && offsetof(april_graph_node_t, relinearize) == 80,
+               "april_graph_node_t");
+_Static_assert(sizeof(april_graph_factor_t) == 104 && offsetof(april_graph_factor_t, nodes) == 8 &&
+                   offsetof(april_graph_factor_t, eval) == 40 && offsetof(april_graph_factor_t, u.common.z) == 64 &&
+                   offsetof(april_graph_factor_t, u.common.W) == 80 && offsetof(april_graph_factor_t, stype) == 96,
+               "april_graph_factor_t");
+_Static_assert(sizeof(search_tree_node_t) == 40 && sizeof(search_tree_t) == 80, "search_tree");
+_Static_assert(sizeof(april_graph_cholesky_param_t) == 128 && offsetof(april_graph_cholesky_param_t, chol) == 8 &&
+                   offsetof(april_graph_cholesky_param_t, ordering) == 24 &&
+                   offsetof(april_graph_cholesky_param_t, nreordering) == 32 &&
+                   offsetof(april_graph_cholesky_param_t, tr) == 72 &&
+                   offsetof(april_graph_cholesky_param_t, nthreshold) == 96 &&
+                   offsetof(april_graph_cholesky_param_t, delta_xy) == 112,
+               "april_graph_cholesky_param_t");
+#endif
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,127 @@
+/* asam_cuda.h -- C-ABI between the host solver (C) and the sm_100a CUDA kernels.
+ *
+ * Plain pointers and sizes only.  Every entry point returns 0 on success, non-zero on
+ * failure (text via asam_last_error()).  All calls on one asam_dev_t must come from one
+ * host thread (the reference library is single-threaded).
+ *
+ * Data model in HBM (all indices 32-bit, all arithmetic IEEE double):
+ *   node i        graph->nodes index                         (reference: aprilsam.h:151-179)
+ *   q = node2q[i] elimination position of node i (post-ordered block elimination tree)
+ *   lp[3i], st[3i]        linearisation point / state mirrors   (april_graph_node_t.l_point/.state)
+ *   factor f      type, node ids, z[3], W[9] mirrors            (april_graph_factor_t, aprilsam.h:98-146)
+ *   Adiag[9i]     diagonal 3x3 block of node i of A = J'WJ (+lambda I), row-major, entries r<=c valid
+ *   Aoff[9s]      off-diagonal block of node-pair slot s, stored [lower node id][higher node id]
+ *   Bq[3i]        B = J'W r of node i                             (aprilsam.c:154-204)
+ *   supernode s   consecutive positions first..first+cb-1 sharing one dense frontal matrix
+ *                 F (m x m, column-major, m = 3*mb) + m rhs doubles at arena[f_off]:
+ *                 columns [0,3cb) hold L after factorisation, the trailing block holds the
+ *                 Schur complement ("update matrix") handed to the parent supernode.
+ *   y[3q], x[3q]  forward-solve result and solution in elimination order (aprilsam.c:298)
+ */
+#ifndef ASAM_CUDA_H
+#define ASAM_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct asam_dev asam_dev_t;
+
+/* Supernode descriptor as stored in HBM (48 bytes). `seg` is the offset into the int pool
+ * of this supernode's index segment, laid out as
+ *   rows[mb] | rel[mb] | children[ch_cnt] | a_slot[a_cnt] | a_rb[a_cnt] | a_cb[a_cnt]
+ * rows = block-row list in q positions (first cb entries are the supernode's own columns),
+ * rel[k] = index of rows[k] in the PARENT's row list (k >= cb), children = supernode ids,
+ * (a_slot, a_rb, a_cb) = off-diagonal A blocks gathered into block (row a_rb, col a_cb);
+ * bit 30 of a_rb is set when the column node is the higher node id (gather transposed). */
+typedef struct asam_sn_desc {
+    int32_t first, cb, mb, parent;
+    int32_t seg, ch_cnt, a_cnt, level;
+    int64_t f_off;
+    int64_t reserved;
+} asam_sn_desc_t;
+
+const char *asam_last_error(void);
+
+/* Context on the current CUDA device (env ASAM_DEVICE or LOCAL_RANK selects it). */
+int asam_dev_create(asam_dev_t **out);
+void asam_dev_destroy(asam_dev_t *d);
+int asam_device_count(void);
+
+/* Capacity management (grow-only; contents preserved). */
+int asam_reserve(asam_dev_t *d, int n_nodes, int n_factors, int n_slots, int n_sn, int64_t ipool_ints,
+                 int64_t arena_doubles);
+
+/* Graph mirror.  Factors are append-only (reference API has no removal). */
+int asam_upload_factors(asam_dev_t *d, int first, int count, const int32_t *type, const int32_t *na,
+                        const int32_t *nb, const double *z3, const double *W9);
+/* which: 0 = l_point, 1 = state */
+int asam_upload_points(asam_dev_t *d, int which, int first, int count, const double *p3);
+
+/* Symbolic plan pieces. */
+int asam_upload_node2q(asam_dev_t *d, int first, int count, const int32_t *node2q);
+int asam_upload_q2node(asam_dev_t *d, int first, int count, const int32_t *q2node);
+int asam_upload_fslot(asam_dev_t *d, int first, int count, const int32_t *fslot);
+int asam_upload_ipool(asam_dev_t *d, int64_t first, int64_t count, const int32_t *data);
+int asam_upload_desc(asam_dev_t *d, int n, const int32_t *sn_ids, const asam_sn_desc_t *desc);
+
+/* A = 0 (diag = lambda on positions [0, n_lambda)), B = 0 for positions [0, n_nodes) and
+ * slots [0, n_slots).  (aprilsam.c:152-153,197-204) */
+int asam_hessian_reset(asam_dev_t *d, int n_nodes, int n_slots, int n_lambda, double lambda);
+/* Zero a range of newly created positions / slots (incremental growth, no lambda). */
+int asam_hessian_clear_range(asam_dev_t *d, int q_first, int q_count, int slot_first, int slot_count);
+
+/* Kernel 1: linearise factors [f_first, f_first+f_count) and scatter J'WJ / J'Wr into
+ * Adiag/Aoff/Bq (replaces xyt_factor_eval + the assembly loop: april_graph_xyt.c:62-124,
+ * april_graph_xytpos.c:63-102, aprilsam.c:154-195 and :508-542).  If pts6 != NULL it holds
+ * per-factor evaluation points (a then b, host memory) overriding the lp/st mirrors. */
+int asam_linearize(asam_dev_t *d, int f_first, int f_count, const double *pts6);
+
+/* Kernel 2: multifrontal supernodal Cholesky + fused forward solve over the given
+ * supernodes (children before parents).  nwait[t] = number of children of tasks[t] that are
+ * themselves in the task list.  Replaces cs_schol/cs_chol + forward solve
+ * (csparse.c:462-513, smatd.c:1051-1073) and, with a subset, the un-eliminate /
+ * re-eliminate of the incremental path (aprilsam.c:791-906). */
+int asam_factor(asam_dev_t *d, int ntasks, const int32_t *tasks, const int32_t *nwait);
+/* Same, re-using the task list of the previous asam_factor_full upload. */
+int asam_set_full_tasks(asam_dev_t *d, int ntasks, const int32_t *tasks, const int32_t *nwait,
+                        const int32_t *btasks);
+int asam_factor_full(asam_dev_t *d);
+/* Supernodes created after asam_set_full_tasks (poses appended by incremental steps) are
+ * ancestors of everything older: prepend them (parents first) to the full back-solve list. */
+int asam_btasks_prepend(asam_dev_t *d, int n, const int32_t *ids);
+
+/* Kernel 3: back-substitution over the given supernodes (parents before children; the
+ * list must be closed under ancestors).  (smatd.c:1075-1097, aprilsam.c:721-779) */
+int asam_backsolve(asam_dev_t *d, int ntasks, const int32_t *btasks);
+int asam_backsolve_full(asam_dev_t *d);
+
+/* Solution read-back: x in elimination order, positions [q_first, q_first+q_count). */
+int asam_download_x(asam_dev_t *d, int q_first, int q_count, double *x3);
+int asam_download_y(asam_dev_t *d, int q_first, int q_count, double *y3);
+
+/* chi2 = sum 0.5 r'Wr (xyt, at state) + sum r'Wr (xytpos) over factors [0, n_factors)
+ * using the st mirror (april_graph.c:79-98). Deterministic reduction. */
+int asam_chi2(asam_dev_t *d, int n_factors, double *chi2_out);
+
+/* Status of the last factorisation: 0 ok, >0 = 1 + supernode id with a non-positive pivot,
+ * <0 = internal dependency timeout. */
+int asam_factor_status(asam_dev_t *d, int *status_out);
+
+/* Debug / test access (not used on the solve path). */
+int asam_debug_read_hessian(asam_dev_t *d, int n_nodes, int n_slots, double *Adiag9, double *Aoff9, double *Bq3);
+int asam_debug_read_front(asam_dev_t *d, int64_t f_off, int64_t count, double *out);
+int asam_sync(asam_dev_t *d);
+/* Counters: [0] kernel launches since creation, [1] bytes H2D, [2] bytes D2H. */
+int asam_counters(asam_dev_t *d, int64_t *out3);
+/* Device-side time (ms) of the kernels launched by the last linearize / factor / backsolve
+ * calls, measured with CUDA events on the library's stream (0 if timing disabled). */
+int asam_set_timing(asam_dev_t *d, int enabled);
+int asam_last_kernel_ms(asam_dev_t *d, float *lin_ms, float *fac_ms, float *bs_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
