@@ -100,6 +100,9 @@ struct asam_dev {
     int timing = 0;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int ev_set[3] = {0, 0, 0};
+    cudaEvent_t tev[2] = {nullptr, nullptr};
+    Buf flush;
+    int flush_val = 0;
 };
 
 static int buf_reserve(asam_dev *d, Buf &b, size_t bytes, bool keep, bool zero_new)
@@ -769,7 +772,7 @@ ASAM_EXPORT int asam_dev_create(asam_dev_t **out)
     // launch geometry: k_factor keeps a whole front in shared memory when it fits
     int max_optin = 0;
     CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    int want = 100 * 1024;
+    int want = 200 * 1024; // fronts up to m = 159 stay on chip (M3500's largest is 147)
     const char *es = getenv("ASAM_FACTOR_SMEM_KB");
     if (es)
         want = atoi(es) * 1024;
@@ -802,7 +805,10 @@ ASAM_EXPORT void asam_dev_destroy(asam_dev_t *d)
     Buf *all[] = { &d->f_type, &d->f_a, &d->f_b, &d->f_z, &d->f_W, &d->f_slot, &d->lp, &d->st, &d->node2q, &d->q2node,
                    &d->Adiag, &d->Aoff, &d->Bq, &d->y, &d->x, &d->sn, &d->ipool, &d->arena, &d->arrive,
                    &d->xdone, &d->tasks_full, &d->nwait_full, &d->btasks_full, &d->tasks_tmp, &d->nwait_tmp,
-                   &d->btasks_tmp, &d->ctrl, &d->partial, &d->patch_ids, &d->patch_desc, &d->pts };
+                   &d->btasks_tmp, &d->ctrl, &d->partial, &d->patch_ids, &d->patch_desc, &d->pts, &d->flush };
+    for (int i = 0; i < 2; i++)
+        if (d->tev[i])
+            cudaEventDestroy(d->tev[i]);
     for (Buf *b : all)
         if (b->p)
             cudaFree(b->p);
@@ -1216,6 +1222,49 @@ ASAM_EXPORT int asam_counters(asam_dev_t *d, int64_t *out3)
     out3[0] = d->n_launch;
     out3[1] = d->n_h2d;
     out3[2] = d->n_d2h;
+    return 0;
+}
+
+// Generic device-side stopwatch on the library's stream (bench.py): asam_timer_start /
+// asam_timer_stop bracket any sequence of asam_* calls; _stop synchronises and returns ms.
+ASAM_EXPORT int asam_timer_start(asam_dev_t *d)
+{
+    CK(cudaSetDevice(d->device));
+    if (!d->tev[0]) {
+        CK(cudaEventCreate(&d->tev[0]));
+        CK(cudaEventCreate(&d->tev[1]));
+    }
+    CK(cudaEventRecord(d->tev[0], d->stream));
+    return 0;
+}
+
+ASAM_EXPORT int asam_timer_stop(asam_dev_t *d, float *ms)
+{
+    CK(cudaSetDevice(d->device));
+    CK(cudaEventRecord(d->tev[1], d->stream));
+    CK(cudaEventSynchronize(d->tev[1]));
+    CK(cudaEventElapsedTime(ms, d->tev[0], d->tev[1]));
+    return 0;
+}
+
+// Evict the working set from L2 between timed iterations: overwrite a buffer larger than L2.
+ASAM_EXPORT int asam_l2_flush(asam_dev_t *d)
+{
+    CK(cudaSetDevice(d->device));
+    const size_t bytes = (size_t) 384 << 20;
+    if (buf_reserve(d, d->flush, bytes, false, false))
+        return 1;
+    d->flush_val ^= 0x5a;
+    CK(cudaMemsetAsync(d->flush.p, d->flush_val, bytes, d->stream));
+    return 0;
+}
+
+ASAM_EXPORT int asam_device_info(asam_dev_t *d, int *n_sm, int *fac_grid, int *fac_smem, int *bs_grid)
+{
+    *n_sm = d->n_sm;
+    *fac_grid = d->fac_grid;
+    *fac_smem = d->fac_smem;
+    *bs_grid = d->bs_grid;
     return 0;
 }
 

@@ -75,6 +75,10 @@ def _load(impl: str) -> C.CDLL:
     lib.h_replay.argtypes = [C.c_void_p, C.c_int, _dp, _ip, _ip, _ip, _dp, _dp, C.c_int,
                              C.c_int, C.c_int, _dp, _dp, _ip]
     lib.h_replay.restype = C.c_int
+    lib.h_graph.argtypes = [C.c_void_p]
+    lib.h_graph.restype = C.c_void_p
+    lib.h_param.argtypes = [C.c_void_p]
+    lib.h_param.restype = C.c_void_p
     lib.h_load_full.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int, _ip, _ip, _dp, _dp]
     _LIBS[impl] = lib
     return lib
@@ -227,6 +231,12 @@ class Harness:
         out = np.zeros(max(self.n_nodes, 1), dtype=np.int32)
         n = self.lib.h_get_tree_parents(self.h, _i(out), out.size)
         return out[:n]
+
+    def graph_ptr(self) -> int:
+        return self.lib.h_graph(self.h)
+
+    def param_ptr(self) -> int:
+        return self.lib.h_param(self.h)
 
     # -- demo-protocol replay ------------------------------------------------------------
     def replay_begin(self, d: PoseGraphData):

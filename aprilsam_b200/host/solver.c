@@ -775,3 +775,18 @@ ASAM_API void april_graph_cholesky_inc_solver(april_graph_t *graph, april_graph_
     apply_solution(s, param->tr, x, 0);
     param->tr->naffected = keep;
 }
+
+/* ---- test-only accessors (tools/gpu_diag.py, tests/) ------------------------------------------ */
+ASAM_API void *asam_dbg_dev_of_graph(april_graph_t *g)
+{
+    for (gctx_t *c = g_ctx_list; c; c = c->next)
+        if (c->graph == g)
+            return c->dev;
+    return NULL;
+}
+
+ASAM_API void *asam_dbg_plan_of_param(april_graph_cholesky_param_t *param)
+{
+    solver_t *s = param && param->chol ? solver_of(param) : NULL;
+    return s ? (void *) &s->plan : NULL;
+}

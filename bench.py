@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py -- Gauss-Newton solves/sec of the april_graph_cholesky{,_inc} path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--workload m3500_batch|manhattan_batch|m3500_replay|manhattan_replay] [--poses P]
+
+One "step" is one pass of the hot path over one batch of synthetic/fixture input:
+  *_batch   one april_graph_cholesky() call on the full graph (relinearise -> assemble ->
+            factor -> 2 triangular solves -> state update), node states reset to the VERTEX2
+            initial estimate before every call so each call does identical work;
+  *_replay  one april_graph_cholesky_inc() call of the demo-protocol pose-by-pose replay
+            (includes any batch escalation it triggers).
+Default workload: BASELINE.json configs[1] = "M3500 batch Cholesky on 1xB200".
+
+JSON line (rank 0):
+  value        solves/s with every input already resident in HBM: the GPU pipeline
+               (reset + k_linearize + k_factor + k_backsolve) timed per step with CUDA events on
+               the library's stream, L2 flushed between steps (outside the timed events)
+  e2e.value    solves/s through the public C API (april_graph_cholesky on HOST structs): host
+               pose gather, H2D, kernels, D2H of the solution, host state update all inside
+  roofline     dominant kernel k_factor: algorithmic bytes 8*nnz(A_upper)+16*nnz(L) per launch
+                / measured launch time, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline the reference's own CPU implementation (oracle/_ref) on this box, 1 thread
+Multi-GPU: M3500 and every incremental workload do not shard ("replicas
+only"): each rank solves its own replica, value = total solves of all ranks / max rank time.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from aprilsam_b200 import capi, datasets  # noqa: E402
+from aprilsam_b200 import harness as H  # noqa: E402
+
+METRIC = "Gauss-Newton solves/sec (batch + incremental) on M3500 & 100k-pose graph"
+
+
+def load_workload(name: str, poses: int):
+    if name.startswith("m3500"):
+        d = H.PoseGraphData.load(os.path.join(ROOT, "tests", "golden", "m3500.npz"))
+        label = "M3500 (3500 poses, 5453 xyt + 1 xytpos factors)"
+    elif name == "manhattan_batch":
+        d = datasets.manhattan_dense(poses, seed=1)
+        label = f"synthetic Manhattan seed 1, {d.n_nodes} poses, {d.n_edges} xyt + 1 xytpos factors"
+    elif name == "manhattan_replay":
+        d = datasets.manhattan_sparse(poses, seed=1)
+        label = f"synthetic Manhattan 5% closures seed 1, {d.n_nodes} poses, {d.n_edges} xyt + 1 xytpos factors"
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    return d, label
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    def __init__(self, device: int):
+        self.p = None
+        self.device = device
+        self.path = os.path.join("/tmp", f"asam_clocks_{os.getpid()}.csv")
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.f = open(self.path, "w")
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.device)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.p:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                t = [x.strip() for x in line.split(",")]
+                if len(t) < 9:
+                    continue
+                sm.append(float(t[1]))
+                mx.append(float(t[2]))
+                for nm, v in zip(names, t[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+def dist_setup(ngpus: int):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        return world, rank, local, dist
+    return 1, 0, local, None
+
+
+def barrier_max(dist, local, value: float) -> float:
+    if dist is None:
+        return value
+    import torch
+    t = torch.tensor([value], dtype=torch.float64, device=torch.device("cuda", local))
+    dist.barrier()
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    torch.cuda.synchronize()
+    return float(t.item())
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm / cpu baseline
+# ----------------------------------------------------------------------------------------------
+def time_reference_batch(d, calls: int, warm: int = 1):
+    h = H.Harness("reference")
+    h.load_full(d)
+    init = d.init.copy()
+    ms = []
+    for i in range(warm + calls):
+        h.set_states(init)
+        t = h.batch()
+        if i >= warm:
+            ms.append(t)
+    h.close()
+    return np.array(ms)
+
+
+def time_reference_replay(d, s_begin: int, steps: int):
+    h = H.Harness("reference")
+    h.replay_begin(d)
+    h.replay_to(s_begin, want_chi2=False)
+    _, ms, _ = h.replay_to(s_begin + steps, want_chi2=False)
+    h.close()
+    return ms
+
+
+def run_reference(args, d, label, world, rank):
+    if rank != 0:
+        return
+    if not H.available("reference"):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (needs /root/reference at build time)"}))
+        return
+    if args.workload.endswith("_batch"):
+        ms = time_reference_batch(d, args.steps, args.warmup)
+        sample = f"{args.steps} april_graph_cholesky calls on the full graph after {args.warmup} warm-up"
+    else:
+        s0 = replay_start(args, d)
+        ms = time_reference_replay(d, s0, args.steps)
+        sample = f"demo replay steps [{s0}, {s0 + len(ms)})"
+    total_s = float(ms.sum()) / 1e3
+    val = len(ms) / total_s
+    line = {"metric": METRIC, "value": val, "unit": "solves/s", "impl": "reference", "n_gpus": args.gpus,
+            "steps": int(len(ms)), "warmup": args.warmup, "ms_per_step": float(ms.mean()), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic" if "manhattan" in args.workload else "fixture M3500 (public dataset) + synthetic prior",
+            "config": {"workload": args.workload, "graph": label},
+            "cpu_baseline": {"value": val, "unit": "solves/s", "cores": 1, "kind": "reference", "sample": sample},
+            "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def replay_start(args, d) -> int:
+    return max(1, min(args.replay_from, d.n_nodes - 1))
+
+
+# ----------------------------------------------------------------------------------------------
+# b200 arm
+# ----------------------------------------------------------------------------------------------
+def run_b200(args, d, label, world, rank, local, dist):
+    L = capi.lib()
+    if L.asam_device_count() <= 0:
+        raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU fallback")
+    hbm_peak, peak_src = peaks()
+    is_batch = args.workload.endswith("_batch")
+    sampler = ClockSampler(local)
+
+    h = H.Harness("b200")
+    init = d.init.copy()
+    if is_batch:
+        h.load_full(d)
+        t0 = time.perf_counter()
+        h.batch()  # cold call: ordering + symbolic analysis + plan upload
+        cold_ms = (time.perf_counter() - t0) * 1e3
+    else:
+        s0 = replay_start(args, d)
+        h.replay_begin(d)
+        h.replay_to(s0, want_chi2=False)
+        cold_ms = None
+    dev = L.asam_dbg_dev_of_graph(h.graph_ptr())
+    pinfo = capi.plan_info(L.asam_dbg_plan_of_param(h.param_ptr()))
+    L.asam_set_timing(dev, 1)
+
+    # ---- e2e: through the public API, host structs in, host structs out ----------------------
+    K, W = args.steps, args.warmup
+    e2e_ms, kern = [], []
+    launches0 = h2d0 = d2h0 = 0
+    if rank == 0:
+        sampler.start()
+    if is_batch:
+        for i in range(W + K):
+            h.set_states(init)
+            if i == W:
+                barrier_max(dist, local, 0.0)
+                launches0, h2d0, d2h0 = capi.counters(dev)
+            e2e_t = h.batch()
+            if i >= W:
+                e2e_ms.append(e2e_t)
+                kern.append(capi.kernel_ms(dev))
+    else:
+        h.replay_to(s0 + W, want_chi2=False)
+        barrier_max(dist, local, 0.0)
+        launches0, h2d0, d2h0 = capi.counters(dev)
+        _, ms, info = h.replay_to(s0 + W + K, want_chi2=False)
+        e2e_ms = list(ms)
+    launches1, h2d1, d2h1 = capi.counters(dev)
+    e2e_total_s = barrier_max(dist, local, float(np.sum(e2e_ms)) / 1e3)
+    nsteps = len(e2e_ms)
+    e2e_val = world * nsteps / e2e_total_s
+
+    # ---- device-resident: same pipeline, inputs already in HBM, CUDA events per step ----------
+    dev_ms = []
+    fac_ms = []
+    if is_batch:
+        h.set_states(init)
+        h.batch()
+        N, S, F = pinfo["N"], pinfo["n_slots"], pinfo["n_factors"]
+        ms = C.c_float()
+        for i in range(W + K):
+            capi.check(L.asam_l2_flush(dev), "l2_flush")
+            capi.check(L.asam_timer_start(dev), "timer")
+            capi.check(L.asam_hessian_reset(dev, N, S, N, 1e-4), "reset")
+            capi.check(L.asam_linearize(dev, 0, F, None), "linearize")
+            capi.check(L.asam_factor_full(dev), "factor")
+            capi.check(L.asam_backsolve_full(dev), "backsolve")
+            capi.check(L.asam_timer_stop(dev, C.byref(ms)), "timer")
+            if i >= W:
+                dev_ms.append(ms.value)
+                fac_ms.append(capi.kernel_ms(dev)[1])
+        st = C.c_int()
+        L.asam_factor_status(dev, C.byref(st))
+        if st.value != 0:
+            raise SystemExit(f"bench.py: factorisation status {st.value}")
+        dev_total_s = barrier_max(dist, local, float(np.sum(dev_ms)) / 1e3)
+        value = world * len(dev_ms) / dev_total_s
+        ms_per_step = float(np.mean(dev_ms))
+        gpu_launches = 4 * len(dev_ms)
+    else:
+        value = e2e_val
+        ms_per_step = float(np.mean(e2e_ms))
+        gpu_launches = launches1 - launches0
+    clocks = sampler.stop() if rank == 0 else {}
+
+    # ---- roofline of the dominant kernel (k_factor) -------------------------------------------
+    nnz_l = 9 * (pinfo["nnz_l_blocks"] - pinfo["N"]) + 6 * pinfo["N"]
+    nnz_a = 6 * pinfo["N"] + 9 * pinfo["n_slots"]
+    alg_bytes = 8 * nnz_a + 16 * nnz_l
+    if is_batch and fac_ms:
+        t_fac = float(np.mean(fac_ms)) * 1e-3
+        achieved = alg_bytes / t_fac / 1e9
+        roof = {"kernel": "k_factor", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": t_fac * 1e3,
+                "fp64_gflops": pinfo["flops"] / t_fac / 1e9, "flops_per_launch": pinfo["flops"]}
+    else:
+        roof = {"kernel": "k_factor", "bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None,
+                "traffic": None, "peak_source": peak_src}
+
+    # ---- cpu baseline (rank 0, N=1): the reference on this box's host cores -------------------
+    cpu = None
+    if rank == 0 and world == 1 and H.available("reference") and not args.no_cpu_baseline:
+        if is_batch:
+            probe = time_reference_batch(d, 1, 0)
+            calls = int(max(1, min(300, 10e3 / max(probe[0], 1e-3))))
+            ms = time_reference_batch(d, calls, 0)
+            cpu = {"value": calls / (float(ms.sum()) / 1e3), "unit": "solves/s", "cores": 1, "kind": "reference",
+                   "sample": f"{calls} april_graph_cholesky calls of the same graph (oracle/_ref, 1 thread: the reference has no threads)"}
+        else:
+            ms = time_reference_replay(d, s0 + W, min(K, 2000))
+            cpu = {"value": len(ms) / (float(ms.sum()) / 1e3), "unit": "solves/s", "cores": 1, "kind": "reference",
+                   "sample": f"replay steps [{s0 + W}, {s0 + W + len(ms)}) (oracle/_ref, deterministic clock)"}
+    h.close()
+
+    if rank != 0:
+        return
+    per_step = max(nsteps, 1)
+    line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64",
+            "data": "synthetic" if "manhattan" in args.workload else "fixture M3500 (public dataset) + synthetic prior",
+            "config": {"workload": args.workload, "graph": label, "parallelism": f"replicas x{world}",
+                       "cache": "L2 flushed (384 MiB overwrite) between timed steps" if is_batch else "working set grows each step",
+                       "plan": {k: pinfo[k] for k in ("N", "nsn", "n_slots", "n_levels", "max_m", "nnz_l_blocks")},
+                       "cold_first_call_ms": cold_ms},
+            "e2e": {"value": e2e_val, "unit": "solves/s", "ms_per_step": float(np.mean(e2e_ms)),
+                    "h2d_bytes_per_step": (h2d1 - h2d0) // per_step, "d2h_bytes_per_step": (d2h1 - d2h0) // per_step},
+            "gpu_launches": int(gpu_launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks}
+    if kern:
+        k = np.array(kern)
+        line["kernel_ms"] = {"k_linearize": float(np.median(k[:, 0])), "k_factor": float(np.median(k[:, 1])),
+                             "k_backsolve": float(np.median(k[:, 2]))}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="m3500_batch",
+                    choices=["m3500_batch", "manhattan_batch", "m3500_replay", "manhattan_replay"])
+    ap.add_argument("--poses", type=int, default=100000)
+    ap.add_argument("--replay-from", type=int, default=1, help="replay workloads: first timed step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200" and args.workload.endswith("_batch"):
+        args.warmup = 3
+    d, label = load_workload(args.workload, args.poses)
+    if args.impl == "reference":
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        rank = int(os.environ.get("RANK", "0"))
+        run_reference(args, d, label, world, rank)
+        return
+    world, rank, local, dist = dist_setup(args.gpus)
+    try:
+        run_b200(args, d, label, world, rank, local, dist)
+    finally:
+        if dist is not None:
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

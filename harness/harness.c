@@ -289,3 +289,6 @@ H_EXPORT void h_load_full(hctx_t *h, int N, const double *init, int E, const int
         h_add_xyt(h, ea[e], eb[e], &ez[3 * e], &eW[9 * e]);
     h->next_step = N;
 }
+
+H_EXPORT void *h_graph(hctx_t *h) { return h->g; }
+H_EXPORT void *h_param(hctx_t *h) { return h->p; }

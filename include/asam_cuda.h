@@ -119,6 +119,12 @@ int asam_counters(asam_dev_t *d, int64_t *out3);
 /* Device-side time (ms) of the kernels launched by the last linearize / factor / backsolve
  * calls, measured with CUDA events on the library's stream (0 if timing disabled). */
 int asam_set_timing(asam_dev_t *d, int enabled);
+/* Device stopwatch on the library's stream around any sequence of calls; an L2 flush
+ * (384 MiB overwrite) for cold-cache timing; launch geometry of the persistent kernels. */
+int asam_timer_start(asam_dev_t *d);
+int asam_timer_stop(asam_dev_t *d, float *ms);
+int asam_l2_flush(asam_dev_t *d);
+int asam_device_info(asam_dev_t *d, int *n_sm, int *fac_grid, int *fac_smem, int *bs_grid);
 int asam_last_kernel_ms(asam_dev_t *d, float *lin_ms, float *fac_ms, float *bs_ms);
 
 #ifdef __cplusplus

@@ -1,0 +1,289 @@
+"""CPU-only tests (-m "not gpu"): ABI surface, host symbolic layer, oracle vs golden vectors.
+
+The numeric checks replay the plan that would be uploaded to HBM with tests/support/emul.py (a
+numpy emulation of the kernels' index arithmetic) -- that validates ordering, elimination tree,
+supernode row lists, relative indices, gather lists and task order without a device.
+"""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spl
+
+from aprilsam_b200 import datasets
+from aprilsam_b200 import harness as H
+from conftest import ROOT, golden
+from support import emul
+from support.hostplan import HostPlan
+
+
+def factor_arrays(d, n_edges=None):
+    E = d.n_edges if n_edges is None else n_edges
+    ftype = np.r_[2, np.ones(E, dtype=np.int32)].astype(np.int32)
+    fa = np.r_[0, d.ea[:E]].astype(np.int32)
+    fb = np.r_[-1, d.eb[:E]].astype(np.int32)
+    fz = np.vstack([[0, 0, 0], d.ez[:E]])
+    fW = np.vstack([[1e4, 0, 0, 0, 1e4, 0, 0, 0, 1e3], d.eW[:E]])
+    return ftype, fa, fb, fz, fW
+
+
+# ---------------------------------------------------------------------------------------------
+# ABI
+# ---------------------------------------------------------------------------------------------
+def declared_functions(header):
+    src = open(header).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"^\s*#.*$", "", src, flags=re.M)
+    src = re.sub(r"static inline[^{;]*\{", "{", src)
+    names = set()
+    skip = {"defined", "_Static_assert", "sizeof", "offsetof", "void", "int", "double", "char", "float"}
+    for m in re.finditer(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{}]*\)\s*;", src):
+        n = m.group(1)
+        if n not in skip and not n.startswith("__"):
+            names.add(n)
+    return names
+
+
+def test_library_exports_every_declared_symbol(built):
+    lib = C.CDLL(built)
+    missing = []
+    for hdr in ("include/asam_cuda.h", "include/aprilsam/aprilsam.h", "include/aprilsam/common/matd.h"):
+        for name in sorted(declared_functions(os.path.join(ROOT, hdr))):
+            if "(*" in name:
+                continue
+            try:
+                getattr(lib, name)
+            except AttributeError:
+                missing.append(f"{hdr}:{name}")
+    assert not missing, missing
+
+
+def test_struct_abi_matches_reference_layout(built, tmp_path):
+    """Offsets from SURVEY.md section 8b (measured against the reference headers)."""
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "aprilsam.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(zarray_t), sizeof(april_graph_t), sizeof(april_graph_node_t),
+         sizeof(april_graph_factor_t), sizeof(search_tree_node_t), sizeof(search_tree_t), sizeof(april_graph_cholesky_param_t));
+  printf("%zu %zu %zu %zu %zu %zu %zu\n", offsetof(april_graph_node_t, state), offsetof(april_graph_node_t, l_point),
+         offsetof(april_graph_node_t, delta_X), offsetof(april_graph_factor_t, u.common.z), offsetof(april_graph_factor_t, u.common.W),
+         offsetof(april_graph_cholesky_param_t, tr), offsetof(april_graph_cholesky_param_t, delta_theta));
+  return 0; }''')
+    exe = tmp_path / "abi"
+    subprocess.check_call(["gcc", "-std=gnu99", "-I" + os.path.join(ROOT, "include", "aprilsam"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)]).decode().split()
+    assert [int(x) for x in out] == [24, 32, 112, 104, 40, 80, 128, 16, 40, 48, 64, 80, 72, 120]
+
+
+def test_solver_fails_loudly_without_gpu(built):
+    """No CPU fallback: on a box without a CUDA device the solver entry points abort."""
+    from aprilsam_b200 import capi
+    if capi.lib().asam_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from aprilsam_b200 import harness as H\n"
+            "h = H.Harness('b200'); h.add_node([0,0,0]); h.add_xytpos(0,[0,0,0],[1,0,0,0,1,0,0,0,1]); h.batch()\n"
+            "print('SOLVED')\n") % ROOT
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert p.returncode != 0 and "SOLVED" not in p.stdout
+    assert "no usable CUDA device" in p.stderr
+
+
+# ---------------------------------------------------------------------------------------------
+# ordering + elimination tree == reference
+# ---------------------------------------------------------------------------------------------
+def node_parents(plan, n):
+    order, ppos = plan.array("order"), plan.array("parent_pos")
+    par = np.full(n, -1, dtype=np.int32)
+    for ui in range(n):
+        if ppos[ui] >= 0:
+            par[order[ui]] = order[ppos[ui]]
+    return par
+
+
+def test_m3500_ordering_and_tree_match_golden(m3500):
+    g = golden("m3500_batch.npz")
+    ftype, fa, fb, _, _ = factor_arrays(m3500)
+    p = HostPlan().build(m3500.n_nodes, ftype, fa, fb)
+    assert np.array_equal(p.array("order"), g["ordering"])
+    assert np.array_equal(node_parents(p, m3500.n_nodes), g["tree_parents"])
+    info = p.info()
+    assert info["nsn"] <= info["N"] and info["n_slots"] == 5453
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 7, 13, 64, 257, 900])
+def test_subgraph_ordering_matches_reference(m3500, n):
+    if not H.available("reference"):
+        pytest.skip("reference oracle not built")
+    sub = m3500.head(n)
+    with H.Harness("reference") as h:
+        h.load_full(sub)
+        h.batch()
+        ref_order, ref_par = h.ordering(), h.tree_parents()
+    ftype, fa, fb, _, _ = factor_arrays(sub)
+    p = HostPlan().build(n, ftype, fa, fb)
+    assert np.array_equal(p.array("order"), ref_order)
+    assert np.array_equal(node_parents(p, n), ref_par)
+
+
+def test_synthetic_ordering_matches_reference():
+    if not H.available("reference"):
+        pytest.skip("reference oracle not built")
+    d = datasets.manhattan_dense(1500, seed=3)
+    with H.Harness("reference") as h:
+        h.load_full(d)
+        h.batch()
+        ref_order = h.ordering()
+    ftype, fa, fb, _, _ = factor_arrays(d)
+    p = HostPlan().build(d.n_nodes, ftype, fa, fb)
+    assert np.array_equal(p.array("order"), ref_order)
+
+
+# ---------------------------------------------------------------------------------------------
+# plan + emulated kernels == reference solution
+# ---------------------------------------------------------------------------------------------
+def emulate_batch(d):
+    n = d.n_nodes
+    ftype, fa, fb, fz, fW = factor_arrays(d)
+    p = HostPlan().build(n, ftype, fa, fb)
+    info = p.info()
+    Hs = emul.Hessian(n, info["n_slots"])
+    Hs.reset(n, 1e-4)
+    lp = d.init.copy()
+    node2q = p.array("node2q")
+    Hs.linearize(range(len(ftype)), ftype, fa, fb, fz, fW, lp, lp, node2q, p.array("fslot"))
+    fr = emul.Fronts()
+    fr.ensure(n)
+    desc, ipool = p.descs(), p.array("ipool")
+    emul.factor(fr, Hs, desc, ipool, p.array("q2node"), p.array("tasks"), p.array("nwait"))
+    emul.backsolve(fr, desc, ipool, p.array("btasks"))
+    x = np.stack([fr.x[3 * node2q[i]:3 * node2q[i] + 3] for i in range(n)])
+    st = lp + x
+    st[:, 2] = emul.mod2pi(st[:, 2])
+    return st
+
+
+def test_emulated_batch_matches_golden_m3500(m3500):
+    g = golden("m3500_batch.npz")
+    st = emulate_batch(m3500)
+    assert np.abs(st - g["states"][0]).max() < 1e-7
+
+
+def test_emulated_batch_synthetic_vs_reference():
+    if not H.available("reference"):
+        pytest.skip("reference oracle not built")
+    d = datasets.manhattan_dense(600, seed=2)
+    with H.Harness("reference") as h:
+        h.load_full(d)
+        h.batch()
+        ref = h.states()
+    assert np.abs(emulate_batch(d) - ref).max() < 1e-6 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("n0,n1,step", [(1, 40, 1), (120, 200, 1), (300, 330, 3)])
+def test_emulated_incremental_append(m3500, n0, n1, step):
+    """plan_append: re-factoring only the marked supernodes reproduces the full solution."""
+    db, estart = m3500.bucketed()
+    ftype, fa, fb, fz, fW = factor_arrays(db, estart[n0])
+    p = HostPlan().build(n0, ftype, fa, fb)
+    Hs = emul.Hessian(n0, p.info()["n_slots"])
+    Hs.reset(n0, 1e-4)
+    lp = m3500.init.copy()
+    Hs.linearize(range(len(ftype)), ftype, fa, fb, fz, fW, lp, lp, p.array("node2q"), p.array("fslot"))
+    fr = emul.Fronts()
+    fr.ensure(n0)
+    emul.factor(fr, Hs, p.descs(), p.array("ipool"), p.array("q2node"), p.array("tasks"), p.array("nwait"))
+    F0, N0 = len(ftype), n0
+    for n in range(n0 + step, n1 + 1, step):
+        ftype, fa, fb, fz, fW = factor_arrays(db, estart[n])
+        order, pos, ppos = p.array("order"), p.array("pos"), p.array("parent_pos")
+        marked = set()
+        for f in range(F0, len(ftype)):
+            for v in ([fa[f], fb[f]] if ftype[f] == 1 else [fa[f]]):
+                while v < N0 and v not in marked:
+                    marked.add(int(v))
+                    pp = ppos[pos[v]]
+                    if pp < 0:
+                        break
+                    v = order[pp]
+        r = p.append(n, ftype, fa, fb, sorted(marked))
+        assert r is not None
+        tasks, nwait = r
+        info = p.info()
+        Hs.grow(n, info["n_slots"])
+        fr.ensure(n)
+        node2q = p.array("node2q")
+        Hs.linearize(range(F0, len(ftype)), ftype, fa, fb, fz, fW, lp, lp, node2q, p.array("fslot"))
+        desc, ipool = p.descs(), p.array("ipool")
+        emul.factor(fr, Hs, desc, ipool, p.array("q2node"), tasks, nwait)
+        F0, N0 = len(ftype), n
+    emul.backsolve(fr, desc, ipool, np.arange(info["nsn"] - 1, -1, -1))
+    fslot = p.array("fslot")
+    pairs = {}
+    for f in range(len(ftype)):
+        if ftype[f] == 1:
+            pairs[fslot[f]] = (min(fa[f], fb[f]), max(fa[f], fb[f]))
+    A = Hs.dense([pairs[s] for s in range(info["n_slots"])])
+    xs = spl.spsolve(A.tocsc(), Hs.B.reshape(-1))
+    x_node = np.concatenate([fr.x[3 * node2q[i]:3 * node2q[i] + 3] for i in range(N0)])
+    assert np.abs(x_node - xs).max() < 1e-8 * max(1.0, np.abs(xs).max())
+
+
+def test_append_rejects_edge_between_old_poses(m3500):
+    sub = m3500.head(50)
+    ftype, fa, fb, _, _ = factor_arrays(sub)
+    p = HostPlan().build(50, ftype, fa, fb)
+    ftype2 = np.r_[ftype, 1].astype(np.int32)
+    fa2 = np.r_[fa, 3].astype(np.int32)
+    fb2 = np.r_[fb, 40].astype(np.int32)
+    assert p.append(50, ftype2, fa2, fb2, [3, 40]) is None  # rc == 2: caller falls back
+
+
+# ---------------------------------------------------------------------------------------------
+# oracle pinned against the golden vectors; data generators
+# ---------------------------------------------------------------------------------------------
+def test_reference_oracle_reproduces_golden(m3500):
+    if not H.available("reference"):
+        pytest.skip("reference oracle not built")
+    g = golden("m3500_batch.npz")
+    with H.Harness("reference") as h:
+        h.load_full(m3500)
+        assert abs(h.chi2() - g["chi2"][0]) < 1e-9 * g["chi2"][0]
+        h.batch()
+        assert np.array_equal(h.states(), g["states"][0])
+    r = golden("m3500_replay.npz")
+    with H.Harness("reference") as h:
+        h.replay_begin(m3500)
+        chi2, _, info = h.replay_to(150)
+        assert np.array_equal(chi2, r["chi2"][:150])
+        assert np.array_equal(info[:, 0], r["naffected"][:150])
+
+
+def test_golden_known_answers():
+    """Values quoted in SURVEY.md section 8c."""
+    g = golden("m3500_batch.npz")
+    assert abs(g["chi2"][0] - 1283333.8296) < 1e-3
+    assert abs(g["chi2"][1] - 127723.205936) < 1e-5
+    assert abs(g["chi2"][6] - 70.1644936267) < 1e-8
+    r = golden("m3500_replay.npz")
+    assert abs(r["chi2"][-1] - 68.965607796) < 1e-8
+    assert abs(r["chi2"][499] - 8.330019947) < 1e-8
+
+
+def test_generators_are_seeded():
+    a, b = datasets.manhattan_dense(800, 1), datasets.manhattan_dense(800, 1)
+    assert np.array_equal(a.ea, b.ea) and np.array_equal(a.ez, b.ez) and np.array_equal(a.init, b.init)
+    c = datasets.manhattan_dense(800, 2)
+    assert not np.array_equal(a.ez[:10], c.ez[:10])
+    assert 3.5 * 800 < a.n_edges < 4.5 * 800
+    s = datasets.manhattan_sparse(2000, 1)
+    assert 2000 - 1 < s.n_edges < 2000 * 1.1
+    key = np.maximum(s.ea, s.eb)
+    assert np.all(np.diff(key) >= 0) and np.all(s.ea < s.eb)
