@@ -1,18 +1,6 @@
-// asam_cuda.cu -- sm_100a CUDA kernels + C-ABI for the AprilSAM Gauss-Newton path.
-//
-// Kernels (see DESIGN.md for the roofline of each):
-//   k_linearize   one thread per factor: residual, Jacobians, J'WJ / J'Wr, atomically
-//                 scattered into the block Hessian (Adiag / Aoff / Bq).
-//                 reference: april_graph_xyt.c:62-124, april_graph_xytpos.c:63-102,
-//                            aprilsam.c:154-195 (batch), :508-542 (incremental)
-//   k_factor      persistent, dependency-driven multifrontal supernodal Cholesky with the
-//                 forward solve fused in (rhs carried as an extra front column).
-//                 reference: csparse.c:462-513 (cs_chol), smatd.c:1051-1073, and for a
-//                 subset of supernodes aprilsam.c:791-906 (reconstruct + re-eliminate)
-//   k_backsolve   persistent, dependency-driven back-substitution L' x = y.
-//                 reference: smatd.c:1075-1097, aprilsam.c:721-779
-//   k_chi2*       deterministic reduction of the factor energies at `state`.
-//                 reference: april_graph.c:79-98, april_graph_xyt.c:126-188
+// asam_cuda.cu -- C-ABI (include/asam_cuda.h) of the sm_100a CUDA implementation of the AprilSAM
+// Gauss-Newton path: device context, HBM buffers, uploads/downloads, kernel launches.
+// The kernels themselves are in asam_kernels.cuh.
 //
 // There is no CPU implementation of any of this in the product: if the CUDA runtime or a
 // device is missing, asam_dev_create() fails and the host API aborts.
@@ -29,7 +17,6 @@
 #include "asam_cuda.h"
 
 #define ASAM_EXPORT extern "C" __attribute__((visibility("default")))
-#define ASAM_TR_FLAG (1 << 30)
 
 // ------------------------------------------------------------------------------------------
 // error plumbing
@@ -103,6 +90,9 @@ struct asam_dev {
     cudaEvent_t tev[2] = {nullptr, nullptr};
     Buf flush;
     int flush_val = 0;
+    int trace_on = 0;
+    Buf trace_fac, trace_bs;
+    int trace_nfac = 0, trace_nbs = 0;
 };
 
 static int buf_reserve(asam_dev *d, Buf &b, size_t bytes, bool keep, bool zero_new)
@@ -167,569 +157,7 @@ static int download(asam_dev *d, void *dst, const void *src, size_t bytes)
     return 0;
 }
 
-// ------------------------------------------------------------------------------------------
-// device helpers
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ double d_mod2pi(double v)
-{
-    // reference: common/math_util.h:113-122 (same constants, same operation order)
-    const double twopi = 6.2831853071795862319959;
-    const double pi = 3.141592653589793238462643383279502884196;
-    double w = v + pi;
-    return (w - twopi * floor(w / twopi)) - pi;
-}
-
-// C = A' * B for row-major 3x3 (matd_op("M'*M"): transpose then naive triple loop,
-// reference common/matd.c:230-254)
-__device__ __forceinline__ void d_atb(const double *A, const double *B, double *C)
-{
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-            double acc = 0.0;
-#pragma unroll
-            for (int k = 0; k < 3; k++)
-                acc += A[k * 3 + i] * B[k * 3 + j];
-            C[i * 3 + j] = acc;
-        }
-}
-
-__device__ __forceinline__ void d_ab(const double *A, const double *B, double *C)
-{
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-            double acc = 0.0;
-#pragma unroll
-            for (int k = 0; k < 3; k++)
-                acc += A[i * 3 + k] * B[k * 3 + j];
-            C[i * 3 + j] = acc;
-        }
-}
-
-__device__ __forceinline__ void d_av(const double *A, const double *v, double *r)
-{
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-        r[i] = A[i * 3 + 0] * v[0] + A[i * 3 + 1] * v[1] + A[i * 3 + 2] * v[2];
-}
-
-// Residual + Jacobians of an xyt factor at (pa, pb)   (april_graph_xyt.c:62-124)
-__device__ __forceinline__ void d_xyt_eval(const double *pa, const double *pb, const double *z, double *Ja,
-                                           double *Jb, double *r)
-{
-    double ca, sa;
-    sincos(pa[2], &sa, &ca);
-    double dx = pb[0] - pa[0], dy = pb[1] - pa[1];
-    double zh0 = ca * dx + sa * dy;
-    double zh1 = -sa * dx + ca * dy;
-    double zh2 = pb[2] - pa[2];
-    Ja[0] = -ca; Ja[1] = -sa; Ja[2] = -sa * dx + ca * dy;
-    Ja[3] = sa;  Ja[4] = -ca; Ja[5] = -ca * dx - sa * dy;
-    Ja[6] = 0.0; Ja[7] = 0.0; Ja[8] = -1.0;
-    Jb[0] = ca;  Jb[1] = sa;  Jb[2] = 0.0;
-    Jb[3] = -sa; Jb[4] = ca;  Jb[5] = 0.0;
-    Jb[6] = 0.0; Jb[7] = 0.0; Jb[8] = 1.0;
-    r[0] = z[0] - zh0;
-    r[1] = z[1] - zh1;
-    r[2] = d_mod2pi(z[2] - zh2);
-}
-
-// ------------------------------------------------------------------------------------------
-// kernel 1: linearise + scatter
-// ------------------------------------------------------------------------------------------
-struct LinArgs {
-    const int *f_type, *f_a, *f_b, *f_slot;
-    const double *f_z, *f_W;
-    const double *lp, *st;
-    const double *pts; // optional, indexed from f_first
-    const int *node2q;
-    double *Adiag, *Aoff, *Bq;
-    int f_first, f_count;
-};
-
-__global__ void __launch_bounds__(128) k_linearize(LinArgs a)
-{
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.f_count)
-        return;
-    int f = a.f_first + t;
-    int type = a.f_type[f];
-    int na = a.f_a[f];
-    double z[3], W[9];
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-        z[i] = a.f_z[3 * (size_t) f + i];
-#pragma unroll
-    for (int i = 0; i < 9; i++)
-        W[i] = a.f_W[9 * (size_t) f + i];
-    if (type == 2) { // xytpos: J = I, r = z - state   (april_graph_xytpos.c:63-102)
-        double p[3];
-        const double *src = a.pts ? (a.pts + 6 * (size_t) t) : (a.st + 3 * (size_t) na);
-        p[0] = src[0]; p[1] = src[1]; p[2] = src[2];
-        double r[3] = { z[0] - p[0], z[1] - p[1], d_mod2pi(z[2] - p[2]) };
-        // J'W = W ; (J'W) J = W ; keep scalar row <= col  (aprilsam.c:171-172)
-#pragma unroll
-        for (int i = 0; i < 3; i++)
-#pragma unroll
-            for (int j = i; j < 3; j++)
-                atomicAdd(&a.Adiag[9 * (size_t) na + i * 3 + j], W[i * 3 + j]);
-        double g[3];
-        d_av(W, r, g);
-#pragma unroll
-        for (int i = 0; i < 3; i++)
-            atomicAdd(&a.Bq[3 * (size_t) na + i], g[i]);
-        return;
-    }
-
-    // xyt factor
-    int nb = a.f_b[f];
-    int qa = a.node2q[na], qb = a.node2q[nb];
-    double pa[3], pb[3];
-    if (a.pts) {
-        const double *src = a.pts + 6 * (size_t) t;
-#pragma unroll
-        for (int i = 0; i < 3; i++) { pa[i] = src[i]; pb[i] = src[3 + i]; }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 3; i++) { pa[i] = a.lp[3 * (size_t) na + i]; pb[i] = a.lp[3 * (size_t) nb + i]; }
-    }
-    double Ja[9], Jb[9], r[3];
-    d_xyt_eval(pa, pb, z, Ja, Jb, r);
-
-    double JatW[9], JbtW[9], H[9], g[3];
-    d_atb(Ja, W, JatW); // J_a' W
-    d_atb(Jb, W, JbtW); // J_b' W
-
-    // diagonal blocks: entries with scalar row <= col only (aprilsam.c:171-172)
-    d_ab(JatW, Ja, H);
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = i; j < 3; j++)
-            atomicAdd(&a.Adiag[9 * (size_t) na + i * 3 + j], H[i * 3 + j]);
-    d_ab(JbtW, Jb, H);
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = i; j < 3; j++)
-            atomicAdd(&a.Adiag[9 * (size_t) nb + i * 3 + j], H[i * 3 + j]);
-
-    // off-diagonal block: the reference keeps (J_early' W J_late) where "early" is the node
-    // eliminated first; the mirrored block is dropped (matters for non-symmetric W).
-    // The slot is stored as S[lower node id][higher node id]; H is [early][late].
-    int slot = a.f_slot[f];
-    int early;
-    if (qa < qb) {
-        d_ab(JatW, Jb, H);
-        early = na;
-    } else {
-        d_ab(JbtW, Ja, H);
-        early = nb;
-    }
-    const bool early_is_lo = early == (na < nb ? na : nb);
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++)
-            atomicAdd(&a.Aoff[9 * (size_t) slot + (early_is_lo ? i * 3 + j : j * 3 + i)], H[i * 3 + j]);
-
-    d_av(JatW, r, g);
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-        atomicAdd(&a.Bq[3 * (size_t) na + i], g[i]);
-    d_av(JbtW, r, g);
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-        atomicAdd(&a.Bq[3 * (size_t) nb + i], g[i]);
-}
-
-__global__ void k_hessian_reset(double *Adiag, double *Aoff, double *Bq, int n_nodes, int n_slots, int n_lambda,
-                                double lambda)
-{
-    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-    size_t nd = 9 * (size_t) n_nodes, no = 9 * (size_t) n_slots, nb = 3 * (size_t) n_nodes;
-    if (i < nd) {
-        int e = (int) (i % 9);
-        int q = (int) (i / 9);
-        Adiag[i] = ((e == 0 || e == 4 || e == 8) && q < n_lambda) ? lambda : 0.0;
-    } else if (i < nd + no) {
-        Aoff[i - nd] = 0.0;
-    } else if (i < nd + no + nb) {
-        Bq[i - nd - no] = 0.0;
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// kernel 2: persistent multifrontal factorisation (+ fused forward solve)
-// ------------------------------------------------------------------------------------------
-struct FacArgs {
-    const asam_sn_desc_t *sn;
-    const int *ipool;
-    double *arena;
-    const double *Adiag, *Aoff, *Bq;
-    const int *q2node;
-    double *y;
-    int *arrive;
-    const int *tasks, *nwait;
-    int ntasks;
-    int *ctrl; // [0] ticket, [1] err
-    int smem_doubles;
-    long long spin_limit;
-};
-
-__device__ __forceinline__ int ld_volatile(const int *p) { return *((const volatile int *) p); }
-
-// Dense partial Cholesky of the first c columns of the m x m lower-triangular front F
-// (column-major, leading dimension m), right-looking, all threads of the CTA.  rhs (m)
-// is carried as an extra column: on exit rhs[0..c) = L11^-1 b1, rhs[c..m) = b2 - L21 y1.
-__device__ void front_partial_cholesky(double *F, double *rhs, int m, int c, int sn_id, int *err)
-{
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
-    for (int k = 0; k < c; ++k) {
-        __syncthreads();
-        double dkk = F[k + (size_t) k * m];
-        if (!(dkk > 0.0)) {
-            if (tid == 0)
-                atomicCAS(err, 0, 1 + sn_id);
-        }
-        double piv = sqrt(dkk);
-        __syncthreads(); // everyone has read F[k,k]
-        double *col = F + (size_t) k * m;
-        for (int i = k + tid; i < m; i += nt)
-            col[i] = (i == k) ? piv : col[i] / piv;
-        if (tid == 0)
-            rhs[k] = rhs[k] / piv;
-        __syncthreads();
-        const int n = m - k - 1;
-        const double *lk = col + k + 1; // L[k+1.., k]
-        for (int j = warp; j < n; j += nwarps) {
-            double ljk = lk[j];
-            double *cj = F + (size_t) (k + 1 + j) * m + (k + 1);
-            for (int i = j + lane; i < n; i += 32)
-                cj[i] -= lk[i] * ljk;
-        }
-        double yk = rhs[k];
-        for (int i = tid; i < n; i += nt)
-            rhs[k + 1 + i] -= lk[i] * yk;
-    }
-    __syncthreads();
-}
-
-__global__ void __launch_bounds__(256) k_factor(FacArgs a)
-{
-    extern __shared__ double sm[];
-    __shared__ int s_task;
-    __shared__ int s_abort;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    int *err = a.ctrl + 1;
-
-    for (;;) {
-        if (tid == 0) {
-            s_task = atomicAdd(&a.ctrl[0], 1);
-            s_abort = 0;
-        }
-        __syncthreads();
-        const int t = s_task;
-        if (t >= a.ntasks)
-            break;
-        const int s = a.tasks[t];
-        const int nw = a.nwait[t];
-        const asam_sn_desc_t d = a.sn[s];
-        const int m = 3 * d.mb, c = 3 * d.cb;
-        const int *seg = a.ipool + d.seg;
-        const int *children = seg + 2 * d.mb;
-        const int *a_slot = children + d.ch_cnt;
-        const int *a_rb = a_slot + d.a_cnt;
-        const int *a_cb = a_rb + d.a_cnt;
-        double *Fg = a.arena + d.f_off;
-        const bool use_sm = ((long long) m * m + m) <= (long long) a.smem_doubles;
-        double *F = use_sm ? sm : Fg;
-        double *rhs = F + (size_t) m * m;
-
-        // ---- 1. zero the front, gather original entries ---------------------------------
-        for (size_t i = tid; i < (size_t) m * m + m; i += nt)
-            F[i] = 0.0;
-        __syncthreads();
-        for (int e = tid; e < d.cb * 9; e += nt) {
-            int k = e / 9, p = (e % 9) / 3, q = e % 3; // F[row 3k+p, col 3k+q], p >= q
-            if (p >= q)
-                F[(3 * k + p) + (size_t) (3 * k + q) * m] =
-                    a.Adiag[9 * (size_t) a.q2node[d.first + k] + q * 3 + p];
-        }
-        for (int e = tid; e < c; e += nt)
-            rhs[e] = a.Bq[3 * (size_t) a.q2node[d.first + e / 3] + e % 3];
-        for (int e = tid; e < d.a_cnt * 9; e += nt) {
-            int i = e / 9, p = (e % 9) / 3, q = e % 3; // late-node component p (row), early q (col)
-            const int rbf = a_rb[i];
-            const int rb = rbf & ~ASAM_TR_FLAG;
-            // slot is S[lo id][hi id]; flag set when the early (column) node is the higher id
-            const int si = (rbf & ASAM_TR_FLAG) ? (p * 3 + q) : (q * 3 + p);
-            F[(3 * rb + p) + (size_t) (3 * a_cb[i] + q) * m] = a.Aoff[9 * (size_t) a_slot[i] + si];
-        }
-
-        // ---- 2. wait for the children that are being re-factored in this launch ---------
-        if (nw > 0) {
-            if (tid == 0) {
-                long long spins = 0;
-                while (ld_volatile(&a.arrive[s]) < nw) {
-                    __nanosleep(64);
-                    if (++spins > a.spin_limit || ld_volatile(err) < 0) {
-                        atomicCAS(err, 0, -(1 + s));
-                        s_abort = 1;
-                        break;
-                    }
-                }
-                a.arrive[s] = 0;
-                __threadfence();
-            }
-        }
-        __syncthreads();
-        if (s_abort)
-            break;
-
-        // ---- 3. extend-add the children's update matrices --------------------------------
-        for (int ci = 0; ci < d.ch_cnt; ++ci) {
-            const int cs = children[ci];
-            const asam_sn_desc_t cd = a.sn[cs];
-            const int cm = 3 * cd.mb, cc = 3 * cd.cb, cr = cm - cc;
-            const double *CF = a.arena + cd.f_off;
-            const int *crel = a.ipool + cd.seg + cd.mb; // rel[]
-            const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
-            for (int j = warp; j < cr; j += nwarps) {
-                const int dj = 3 * crel[(cc + j) / 3] + (cc + j) % 3;
-                const double *ccol = CF + (size_t) (cc + j) * cm + cc;
-                double *fcol = F + (size_t) dj * m;
-                for (int i = j + lane; i < cr; i += 32) {
-                    const int di = 3 * crel[(cc + i) / 3] + (cc + i) % 3;
-                    fcol[di] += __ldcg(ccol + i);
-                }
-            }
-            const double *crhs = CF + (size_t) cm * cm + cc;
-            for (int i = tid; i < cr; i += nt) {
-                const int di = 3 * crel[(cc + i) / 3] + (cc + i) % 3;
-                rhs[di] += __ldcg(crhs + i);
-            }
-            __syncthreads();
-        }
-
-        // ---- 4. eliminate this supernode's columns ---------------------------------------
-        front_partial_cholesky(F, rhs, m, c, s, err);
-
-        // ---- 5. publish: y, L panel + update matrix ---------------------------------------
-        for (int e = tid; e < c; e += nt)
-            a.y[3 * (size_t) d.first + e] = rhs[e];
-        if (use_sm) {
-            for (size_t i = tid; i < (size_t) m * m + m; i += nt)
-                Fg[i] = F[i];
-        }
-        __syncthreads();
-        if (tid == 0 && d.parent >= 0) {
-            __threadfence();
-            atomicAdd(&a.arrive[d.parent], 1);
-        }
-        __syncthreads();
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// kernel 3: persistent back-substitution
-// ------------------------------------------------------------------------------------------
-struct BsArgs {
-    const asam_sn_desc_t *sn;
-    const int *ipool;
-    const double *arena;
-    const double *y;
-    double *x;
-    int *xdone;
-    const int *btasks;
-    int ntasks;
-    int *ctrl; // [2] ticket, [1] err
-    int epoch;
-    int smem_doubles;
-    long long spin_limit;
-};
-
-__global__ void __launch_bounds__(128) k_backsolve(BsArgs a)
-{
-    extern __shared__ double sm[]; // xs[r] | w[c]
-    __shared__ int s_task;
-    __shared__ int s_abort;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
-    int *err = a.ctrl + 1;
-
-    for (;;) {
-        if (tid == 0) {
-            s_task = atomicAdd(&a.ctrl[2], 1);
-            s_abort = 0;
-        }
-        __syncthreads();
-        const int t = s_task;
-        if (t >= a.ntasks)
-            break;
-        const int s = a.btasks[t];
-        const asam_sn_desc_t d = a.sn[s];
-        const int m = 3 * d.mb, c = 3 * d.cb, r = m - c;
-        const int *rows = a.ipool + d.seg;
-        const double *L = a.arena + d.f_off;
-        const bool use_sm = (m <= a.smem_doubles);
-        if (!use_sm) { // cannot happen: host sizes smem for the largest front
-            if (tid == 0)
-                atomicCAS(err, 0, -(1 + s));
-            break;
-        }
-        double *xs = sm;     // r
-        double *w = sm + r;  // c
-
-        if (d.parent >= 0) {
-            if (tid == 0) {
-                long long spins = 0;
-                while (ld_volatile(&a.xdone[d.parent]) != a.epoch) {
-                    __nanosleep(64);
-                    if (++spins > a.spin_limit || ld_volatile(err) < 0) {
-                        atomicCAS(err, 0, -(1 + s));
-                        s_abort = 1;
-                        break;
-                    }
-                }
-                __threadfence();
-            }
-        }
-        __syncthreads();
-        if (s_abort)
-            break;
-
-        for (int i = tid; i < r; i += nt)
-            xs[i] = __ldcg(&a.x[3 * (size_t) rows[d.cb + i / 3] + i % 3]);
-        __syncthreads();
-        // w_k = y_k - sum_i L[c+i, k] * xs[i]
-        for (int k = warp; k < c; k += nwarps) {
-            const double *lk = L + (size_t) k * m + c;
-            double acc = 0.0;
-            for (int i = lane; i < r; i += 32)
-                acc += lk[i] * xs[i];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
-                acc += __shfl_down_sync(0xffffffffu, acc, o);
-            if (lane == 0)
-                w[k] = a.y[3 * (size_t) d.first + k] - acc;
-        }
-        __syncthreads();
-        // L11' x1 = w  (warp 0, column k descending)
-        if (warp == 0) {
-            for (int k = c - 1; k >= 0; --k) {
-                const double *lk = L + (size_t) k * m;
-                double acc = 0.0;
-                for (int j = k + 1 + lane; j < c; j += 32)
-                    acc += lk[j] * w[j];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1)
-                    acc += __shfl_down_sync(0xffffffffu, acc, o);
-                if (lane == 0)
-                    w[k] = (w[k] - acc) / lk[k];
-                __syncwarp();
-            }
-            for (int k = lane; k < c; k += 32)
-                a.x[3 * (size_t) d.first + k] = w[k];
-            __syncwarp();
-            if (lane == 0) {
-                __threadfence();
-                atomicExch(&a.xdone[s], a.epoch);
-            }
-        }
-        __syncthreads();
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// chi2
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_chi2_partial(const int *f_type, const int *f_a, const int *f_b,
-                                                      const double *f_z, const double *f_W, const double *st,
-                                                      int n_factors, double *partial)
-{
-    __shared__ double red[256];
-    int f = blockIdx.x * blockDim.x + threadIdx.x;
-    double v = 0.0;
-    if (f < n_factors) {
-        int type = f_type[f];
-        int na = f_a[f];
-        double z[3], W[9], r[3];
-#pragma unroll
-        for (int i = 0; i < 3; i++)
-            z[i] = f_z[3 * (size_t) f + i];
-#pragma unroll
-        for (int i = 0; i < 9; i++)
-            W[i] = f_W[9 * (size_t) f + i];
-        double scale;
-        if (type == 1) { // xyt at `state`, weight 0.5   (april_graph.c:86-89)
-            int nb = f_b[f];
-            double pa[3], pb[3], Ja[9], Jb[9];
-#pragma unroll
-            for (int i = 0; i < 3; i++) { pa[i] = st[3 * (size_t) na + i]; pb[i] = st[3 * (size_t) nb + i]; }
-            d_xyt_eval(pa, pb, z, Ja, Jb, r);
-            scale = 0.5;
-        } else { // weight 1.0   (april_graph.c:90-93)
-            r[0] = z[0] - st[3 * (size_t) na + 0];
-            r[1] = z[1] - st[3 * (size_t) na + 1];
-            r[2] = d_mod2pi(z[2] - st[3 * (size_t) na + 2]);
-            scale = 1.0;
-        }
-        double X[3];
-        d_av(W, r, X);
-        v = scale * (r[0] * X[0] + r[1] * X[1] + r[2] * X[2]);
-    }
-    red[threadIdx.x] = v;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if (threadIdx.x < o)
-            red[threadIdx.x] += red[threadIdx.x + o];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0)
-        partial[blockIdx.x] = red[0];
-}
-
-__global__ void __launch_bounds__(256) k_chi2_final(const double *partial, int n, double *out)
-{
-    __shared__ double red[256];
-    double v = 0.0;
-    for (int i = threadIdx.x; i < n; i += 256)
-        v += partial[i];
-    red[threadIdx.x] = v;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if (threadIdx.x < o)
-            red[threadIdx.x] += red[threadIdx.x + o];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0)
-        out[0] = red[0];
-}
-
-__global__ void k_apply_desc(asam_sn_desc_t *sn, const int *ids, const asam_sn_desc_t *desc, int n)
-{
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n)
-        sn[ids[i]] = desc[i];
-}
-
-__global__ void k_clear_range(double *Adiag, double *Bq, double *Aoff, int q_first, int q_count, int s_first,
-                              int s_count)
-{
-    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-    size_t nd = 9 * (size_t) q_count, nb = 3 * (size_t) q_count, no = 9 * (size_t) s_count;
-    if (i < nd)
-        Adiag[9 * (size_t) q_first + i] = 0.0;
-    else if (i < nd + nb)
-        Bq[3 * (size_t) q_first + (i - nd)] = 0.0;
-    else if (i < nd + nb + no)
-        Aoff[9 * (size_t) s_first + (i - nd - nb)] = 0.0;
-}
+#include "asam_kernels.cuh"
 
 // ------------------------------------------------------------------------------------------
 // C-ABI
@@ -805,7 +233,7 @@ ASAM_EXPORT void asam_dev_destroy(asam_dev_t *d)
     Buf *all[] = { &d->f_type, &d->f_a, &d->f_b, &d->f_z, &d->f_W, &d->f_slot, &d->lp, &d->st, &d->node2q, &d->q2node,
                    &d->Adiag, &d->Aoff, &d->Bq, &d->y, &d->x, &d->sn, &d->ipool, &d->arena, &d->arrive,
                    &d->xdone, &d->tasks_full, &d->nwait_full, &d->btasks_full, &d->tasks_tmp, &d->nwait_tmp,
-                   &d->btasks_tmp, &d->ctrl, &d->partial, &d->patch_ids, &d->patch_desc, &d->pts, &d->flush };
+                   &d->btasks_tmp, &d->ctrl, &d->partial, &d->patch_ids, &d->patch_desc, &d->pts, &d->flush, &d->trace_fac, &d->trace_bs };
     for (int i = 0; i < 2; i++)
         if (d->tev[i])
             cudaEventDestroy(d->tev[i]);
@@ -1021,6 +449,13 @@ static int launch_factor(asam_dev *d, int ntasks, const int *tasks_dev, const in
     a.ctrl = (int *) d->ctrl.p;
     a.smem_doubles = d->fac_smem / (int) sizeof(double);
     a.spin_limit = 4000000LL; // a few seconds; a dependency bug must not hang the GPU
+    a.trace = nullptr;
+    if (d->trace_on) {
+        if (buf_reserve(d, d->trace_fac, (size_t) ntasks * 8 * sizeof(unsigned long long), false, false))
+            return 1;
+        a.trace = (unsigned long long *) d->trace_fac.p;
+        d->trace_nfac = ntasks;
+    }
     int grid = d->fac_grid < ntasks ? d->fac_grid : ntasks;
     if (d->timing)
         CK(cudaEventRecord(d->ev[2], d->stream));
@@ -1053,6 +488,13 @@ static int launch_backsolve(asam_dev *d, int ntasks, const int *btasks_dev)
     a.epoch = d->epoch;
     a.smem_doubles = d->bs_smem / (int) sizeof(double);
     a.spin_limit = 4000000LL;
+    a.trace = nullptr;
+    if (d->trace_on) {
+        if (buf_reserve(d, d->trace_bs, (size_t) ntasks * 8 * sizeof(unsigned long long), false, false))
+            return 1;
+        a.trace = (unsigned long long *) d->trace_bs.p;
+        d->trace_nbs = ntasks;
+    }
     int grid = d->bs_grid < ntasks ? d->bs_grid : ntasks;
     if (d->timing)
         CK(cudaEventRecord(d->ev[4], d->stream));
@@ -1265,6 +707,28 @@ ASAM_EXPORT int asam_device_info(asam_dev_t *d, int *n_sm, int *fac_grid, int *f
     *fac_grid = d->fac_grid;
     *fac_smem = d->fac_smem;
     *bs_grid = d->bs_grid;
+    return 0;
+}
+
+// Per-task timestamps (globaltimer ns) of the last k_factor (which=0) / k_backsolve (which=1)
+// launch: 8 words per task (see asam_kernels.cuh).  Diagnostics only.
+ASAM_EXPORT int asam_set_trace(asam_dev_t *d, int enabled)
+{
+    d->trace_on = enabled;
+    return 0;
+}
+
+ASAM_EXPORT int asam_download_trace(asam_dev_t *d, int which, unsigned long long *out, int max_tasks)
+{
+    CK(cudaSetDevice(d->device));
+    int n = which == 0 ? d->trace_nfac : d->trace_nbs;
+    Buf &b = which == 0 ? d->trace_fac : d->trace_bs;
+    if (n > max_tasks)
+        n = max_tasks;
+    if (n <= 0 || !b.p)
+        return 0;
+    CK(cudaMemcpyAsync(out, b.p, (size_t) n * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d->stream));
+    CK(cudaStreamSynchronize(d->stream));
     return 0;
 }
 

@@ -1,0 +1,733 @@
+// asam_kernels.cuh -- device code of the AprilSAM Gauss-Newton path for sm_100a.
+//
+//   k_linearize   one thread per factor: residual, Jacobians, J'WJ / J'Wr, atomically
+//                 scattered into the block Hessian (Adiag / Aoff / Bq).
+//                 reference: april_graph_xyt.c:62-124, april_graph_xytpos.c:63-102,
+//                            aprilsam.c:154-195 (batch), :508-542 (incremental)
+//   k_factor      persistent, dependency-driven multifrontal supernodal Cholesky with the
+//                 forward solve fused in (the rhs is carried as an extra ROW of each front).
+//                 reference: csparse.c:462-513 (cs_chol), smatd.c:1051-1073, and for a
+//                 subset of supernodes aprilsam.c:791-906 (reconstruct + re-eliminate)
+//   k_backsolve   persistent, dependency-driven back-substitution L' x = y.
+//                 reference: smatd.c:1075-1097, aprilsam.c:721-779
+//   k_chi2_*      deterministic reduction of the factor energies at `state`.
+//                 reference: april_graph.c:79-98, april_graph_xyt.c:126-188
+//
+// Front layout (arena[f_off ...], (m+1)*m doubles): column-major, leading dimension
+// ld = m+1, m = 3*mb.  Rows 0..m-1 are the supernode's block rows, ROW m is the right-hand
+// side.  After elimination of the first c = 3*cb columns: columns [0,c) hold L (L11 on top of
+// L21) and, in row m, y1 = L11^-1 b1; the trailing (m-c) x (m-c) lower triangle holds the
+// update matrix (Schur complement) and row m, columns [c,m), the updated rhs b2 - L21 y1 --
+// both are scatter-added into the parent's front ("extend-add").
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "asam_cuda.h"
+
+#define ASAM_TR_FLAG (1 << 30)
+#define ASAM_MAX_CACHED_CHILDREN 24
+
+// ------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double d_mod2pi(double v)
+{
+    // reference: common/math_util.h:113-122 (same constants, same operation order)
+    const double twopi = 6.2831853071795862319959;
+    const double pi = 3.141592653589793238462643383279502884196;
+    double w = v + pi;
+    return (w - twopi * floor(w / twopi)) - pi;
+}
+
+// C = A' * B for row-major 3x3 (matd_op("M'*M"): transpose then naive triple loop,
+// reference common/matd.c:230-254)
+__device__ __forceinline__ void d_atb(const double *A, const double *B, double *C)
+{
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+                acc += A[k * 3 + i] * B[k * 3 + j];
+            C[i * 3 + j] = acc;
+        }
+}
+
+__device__ __forceinline__ void d_ab(const double *A, const double *B, double *C)
+{
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+                acc += A[i * 3 + k] * B[k * 3 + j];
+            C[i * 3 + j] = acc;
+        }
+}
+
+__device__ __forceinline__ void d_av(const double *A, const double *v, double *r)
+{
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+        r[i] = A[i * 3 + 0] * v[0] + A[i * 3 + 1] * v[1] + A[i * 3 + 2] * v[2];
+}
+
+// Residual + Jacobians of an xyt factor at (pa, pb)   (april_graph_xyt.c:62-124)
+__device__ __forceinline__ void d_xyt_eval(const double *pa, const double *pb, const double *z, double *Ja,
+                                           double *Jb, double *r)
+{
+    double ca, sa;
+    sincos(pa[2], &sa, &ca);
+    double dx = pb[0] - pa[0], dy = pb[1] - pa[1];
+    double zh0 = ca * dx + sa * dy;
+    double zh1 = -sa * dx + ca * dy;
+    double zh2 = pb[2] - pa[2];
+    Ja[0] = -ca; Ja[1] = -sa; Ja[2] = -sa * dx + ca * dy;
+    Ja[3] = sa;  Ja[4] = -ca; Ja[5] = -ca * dx - sa * dy;
+    Ja[6] = 0.0; Ja[7] = 0.0; Ja[8] = -1.0;
+    Jb[0] = ca;  Jb[1] = sa;  Jb[2] = 0.0;
+    Jb[3] = -sa; Jb[4] = ca;  Jb[5] = 0.0;
+    Jb[6] = 0.0; Jb[7] = 0.0; Jb[8] = 1.0;
+    r[0] = z[0] - zh0;
+    r[1] = z[1] - zh1;
+    r[2] = d_mod2pi(z[2] - zh2);
+}
+
+__device__ __forceinline__ int ld_volatile(const int *p) { return *((const volatile int *) p); }
+
+__device__ __forceinline__ unsigned long long d_now()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel 1: linearise + scatter
+// ------------------------------------------------------------------------------------------
+struct LinArgs {
+    const int *f_type, *f_a, *f_b, *f_slot;
+    const double *f_z, *f_W;
+    const double *lp, *st;
+    const double *pts; // optional, indexed from f_first
+    const int *node2q;
+    double *Adiag, *Aoff, *Bq;
+    int f_first, f_count;
+};
+
+__global__ void __launch_bounds__(128) k_linearize(LinArgs a)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.f_count)
+        return;
+    int f = a.f_first + t;
+    int type = a.f_type[f];
+    int na = a.f_a[f];
+    double z[3], W[9];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+        z[i] = a.f_z[3 * (size_t) f + i];
+#pragma unroll
+    for (int i = 0; i < 9; i++)
+        W[i] = a.f_W[9 * (size_t) f + i];
+
+    if (type == 2) { // xytpos: J = I, r = z - state   (april_graph_xytpos.c:63-102)
+        double p[3];
+        const double *src = a.pts ? (a.pts + 6 * (size_t) t) : (a.st + 3 * (size_t) na);
+        p[0] = src[0]; p[1] = src[1]; p[2] = src[2];
+        double r[3] = { z[0] - p[0], z[1] - p[1], d_mod2pi(z[2] - p[2]) };
+        // J'W = W ; (J'W) J = W ; keep scalar row <= col  (aprilsam.c:171-172)
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = i; j < 3; j++)
+                atomicAdd(&a.Adiag[9 * (size_t) na + i * 3 + j], W[i * 3 + j]);
+        double g[3];
+        d_av(W, r, g);
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            atomicAdd(&a.Bq[3 * (size_t) na + i], g[i]);
+        return;
+    }
+
+    // xyt factor
+    int nb = a.f_b[f];
+    int qa = a.node2q[na], qb = a.node2q[nb];
+    double pa[3], pb[3];
+    if (a.pts) {
+        const double *src = a.pts + 6 * (size_t) t;
+#pragma unroll
+        for (int i = 0; i < 3; i++) { pa[i] = src[i]; pb[i] = src[3 + i]; }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 3; i++) { pa[i] = a.lp[3 * (size_t) na + i]; pb[i] = a.lp[3 * (size_t) nb + i]; }
+    }
+    double Ja[9], Jb[9], r[3];
+    d_xyt_eval(pa, pb, z, Ja, Jb, r);
+
+    double JatW[9], JbtW[9], H[9], g[3];
+    d_atb(Ja, W, JatW); // J_a' W
+    d_atb(Jb, W, JbtW); // J_b' W
+
+    // diagonal blocks: entries with scalar row <= col only (aprilsam.c:171-172)
+    d_ab(JatW, Ja, H);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = i; j < 3; j++)
+            atomicAdd(&a.Adiag[9 * (size_t) na + i * 3 + j], H[i * 3 + j]);
+    d_ab(JbtW, Jb, H);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = i; j < 3; j++)
+            atomicAdd(&a.Adiag[9 * (size_t) nb + i * 3 + j], H[i * 3 + j]);
+
+    // off-diagonal block: the reference keeps (J_early' W J_late) where "early" is the node
+    // eliminated first; the mirrored block is dropped (matters for non-symmetric W).
+    // The slot is stored as S[lower node id][higher node id]; H is [early][late].
+    int slot = a.f_slot[f];
+    int early;
+    if (qa < qb) {
+        d_ab(JatW, Jb, H);
+        early = na;
+    } else {
+        d_ab(JbtW, Ja, H);
+        early = nb;
+    }
+    const bool early_is_lo = early == (na < nb ? na : nb);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+            atomicAdd(&a.Aoff[9 * (size_t) slot + (early_is_lo ? i * 3 + j : j * 3 + i)], H[i * 3 + j]);
+
+    d_av(JatW, r, g);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+        atomicAdd(&a.Bq[3 * (size_t) na + i], g[i]);
+    d_av(JbtW, r, g);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+        atomicAdd(&a.Bq[3 * (size_t) nb + i], g[i]);
+}
+
+__global__ void k_hessian_reset(double *Adiag, double *Aoff, double *Bq, int n_nodes, int n_slots, int n_lambda,
+                                double lambda)
+{
+    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    size_t nd = 9 * (size_t) n_nodes, no = 9 * (size_t) n_slots, nb = 3 * (size_t) n_nodes;
+    if (i < nd) {
+        int e = (int) (i % 9);
+        int q = (int) (i / 9);
+        Adiag[i] = ((e == 0 || e == 4 || e == 8) && q < n_lambda) ? lambda : 0.0;
+    } else if (i < nd + no) {
+        Aoff[i - nd] = 0.0;
+    } else if (i < nd + no + nb) {
+        Bq[i - nd - no] = 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel 2: persistent multifrontal factorisation (+ fused forward solve)
+// ------------------------------------------------------------------------------------------
+struct FacArgs {
+    const asam_sn_desc_t *sn;
+    const int *ipool;
+    double *arena;
+    const double *Adiag, *Aoff, *Bq;
+    const int *q2node;
+    double *y;
+    int *arrive;
+    const int *tasks, *nwait;
+    int ntasks;
+    int *ctrl; // [0] ticket, [1] err
+    int smem_doubles;
+    long long spin_limit;
+    unsigned long long *trace; // optional: 8 words per task
+};
+
+// Trailing update  C[i,j] -= sum_{p<pb} P[i,p] * P[j,p]  for j in [j0, m), i in [j, m]
+// (row m = rhs row).  P holds the pb factored panel columns (leading dim ldp, row index =
+// front row); C is the front (leading dim ld).  One warp per tile of 4 columns, each lane
+// R rows spaced 32 apart (conflict-free shared-memory reads, b values broadcast).
+template <int R>
+__device__ __forceinline__ void trailing_update(double *C, int ld, const double *P, int ldp, int pb, int j0, int m)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int tj = j0 + 4 * warp; tj < m; tj += 4 * nwarps) {
+        for (int ib = tj; ib <= m; ib += 32 * R) {
+            double acc[R][4];
+            int irow[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                irow[r] = ib + lane + 32 * r;
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    acc[r][q] = 0.0;
+            }
+            for (int p = 0; p < pb; p++) {
+                const double *pc = P + (size_t) p * ldp;
+                double b[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    b[q] = (tj + q < m) ? pc[tj + q] : 0.0;
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    double av = (irow[r] <= m) ? pc[irow[r]] : 0.0;
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        acc[r][q] += av * b[q];
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < R; r++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    int i = irow[r], j = tj + q;
+                    if (i <= m && j < m && i >= j)
+                        C[i + (size_t) j * ld] -= acc[r][q];
+                }
+        }
+    }
+}
+
+// Left-looking factorisation of panel columns [k0, k0+pb) of the front held in P (column p of
+// the panel at P + p*ldp, rows indexed by front row; rows k0..m valid).  Each thread owns rows;
+// one barrier per column.  On exit P holds L (and y in row m).
+__device__ __forceinline__ void panel_factor(double *P, int ldp, int k0, int pb, int m, int sn_id, int *err)
+{
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int kk = 0; kk < pb; kk++) {
+        const int k = k0 + kk;
+        // pivot (every thread recomputes it: <= pb terms)
+        double d = P[k + (size_t) kk * ldp];
+        for (int p = 0; p < kk; p++) {
+            double v = P[k + (size_t) p * ldp];
+            d -= v * v;
+        }
+        if (!(d > 0.0) && tid == 0)
+            atomicCAS(err, 0, 1 + sn_id);
+        const double piv = sqrt(d);
+        __syncthreads(); // all threads have read P[k, kk] before its owner overwrites it
+        for (int i = k + tid; i <= m; i += nt) {
+            if (i == k) {
+                P[i + (size_t) kk * ldp] = piv;
+            } else {
+                double v = P[i + (size_t) kk * ldp];
+                for (int p = 0; p < kk; p++)
+                    v -= P[i + (size_t) p * ldp] * P[k + (size_t) p * ldp];
+                P[i + (size_t) kk * ldp] = v / piv;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) k_factor(FacArgs a)
+{
+    extern __shared__ double sm[];
+    __shared__ int s_task, s_abort;
+    __shared__ asam_sn_desc_t s_cd[ASAM_MAX_CACHED_CHILDREN];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    int *err = a.ctrl + 1;
+
+    for (;;) {
+        if (tid == 0) {
+            s_task = atomicAdd(&a.ctrl[0], 1);
+            s_abort = 0;
+        }
+        __syncthreads();
+        const int t = s_task;
+        if (t >= a.ntasks)
+            break;
+        unsigned long long tr0 = 0, tr1 = 0, tr2 = 0, tr3 = 0, tr4 = 0;
+        if (a.trace && tid == 0)
+            tr0 = d_now();
+        const int s = a.tasks[t];
+        const int nw = a.nwait[t];
+        const asam_sn_desc_t d = a.sn[s];
+        const int m = 3 * d.mb, c = 3 * d.cb, ld = m + 1;
+        const int *seg = a.ipool + d.seg;
+        const int *children = seg + 2 * d.mb;
+        const int *a_slot = children + d.ch_cnt;
+        const int *a_rb = a_slot + d.a_cnt;
+        const int *a_cb = a_rb + d.a_cnt;
+        double *Fg = a.arena + d.f_off;
+        // shared-memory budget: front + destination map (ld ints) when the front fits
+        const long long fsz = (long long) ld * m;
+        const bool use_sm = fsz + (ld + 1) / 2 + 2 <= (long long) a.smem_doubles;
+        double *F = use_sm ? sm : Fg;
+        int *dmap = (int *) (sm + (use_sm ? fsz : 0)); // ld ints
+        double *Pbuf = sm + (ld + 1) / 2 + 1;           // big mode only: staged panel
+
+        // ---- 1. zero the lower trapezoid (+ rhs row), gather the original entries ---------
+        if (use_sm) {
+            for (int i = tid; i < (int) fsz; i += nt)
+                F[i] = 0.0;
+        } else {
+            for (int j = warp; j < m; j += nwarps)
+                for (int i = j + lane; i <= m; i += 32)
+                    F[i + (size_t) j * ld] = 0.0;
+        }
+        for (int e = tid; e < d.ch_cnt && e < ASAM_MAX_CACHED_CHILDREN; e += nt)
+            s_cd[e] = a.sn[children[e]];
+        __syncthreads();
+        for (int e = tid; e < d.cb * 9; e += nt) {
+            int k = e / 9, p = (e % 9) / 3, q = e % 3; // F[row 3k+p, col 3k+q], p >= q
+            if (p >= q)
+                F[(3 * k + p) + (size_t) (3 * k + q) * ld] =
+                    a.Adiag[9 * (size_t) a.q2node[d.first + k] + q * 3 + p];
+        }
+        for (int e = tid; e < c; e += nt) // rhs row
+            F[m + (size_t) e * ld] = a.Bq[3 * (size_t) a.q2node[d.first + e / 3] + e % 3];
+        for (int e = tid; e < d.a_cnt * 9; e += nt) {
+            int i = e / 9, p = (e % 9) / 3, q = e % 3; // late-node component p (row), early q (col)
+            const int rbf = a_rb[i];
+            const int rb = rbf & ~ASAM_TR_FLAG;
+            // slot is S[lo id][hi id]; flag set when the early (column) node is the higher id
+            const int si = (rbf & ASAM_TR_FLAG) ? (p * 3 + q) : (q * 3 + p);
+            F[(3 * rb + p) + (size_t) (3 * a_cb[i] + q) * ld] = a.Aoff[9 * (size_t) a_slot[i] + si];
+        }
+        if (a.trace && tid == 0)
+            tr1 = d_now();
+
+        // ---- 2. wait for the children that are being re-factored in this launch ---------
+        if (nw > 0 && tid == 0) {
+            long long spins = 0;
+            while (ld_volatile(&a.arrive[s]) < nw) {
+                __nanosleep(32);
+                if (++spins > a.spin_limit || ld_volatile(err) < 0) {
+                    atomicCAS(err, 0, -(1 + s));
+                    s_abort = 1;
+                    break;
+                }
+            }
+            a.arrive[s] = 0;
+            __threadfence();
+        }
+        __syncthreads();
+        if (s_abort)
+            break;
+        if (a.trace && tid == 0)
+            tr2 = d_now();
+
+        // ---- 3. extend-add the children's update matrices (fixed order: deterministic) ----
+        for (int ci = 0; ci < d.ch_cnt; ++ci) {
+            const asam_sn_desc_t cd = ci < ASAM_MAX_CACHED_CHILDREN ? s_cd[ci] : a.sn[children[ci]];
+            const int cm = 3 * cd.mb, cc = 3 * cd.cb, cr = cm - cc, cld = cm + 1;
+            const double *CF = a.arena + cd.f_off;
+            const int *crel = a.ipool + cd.seg + cd.mb; // rel[]
+            // destination row of child row cc+i (i in [0,cr]); the child's rhs row -> ours
+            for (int i = tid; i <= cr; i += nt)
+                dmap[i] = (i < cr) ? 3 * crel[(cc + i) / 3] + (cc + i) % 3 : m;
+            __syncthreads();
+            for (int j = warp; j < cr; j += nwarps) {
+                const double *ccol = CF + (size_t) (cc + j) * cld + cc;
+                double *fcol = F + (size_t) dmap[j] * ld;
+                for (int i = j + lane; i <= cr; i += 32)
+                    fcol[dmap[i]] += __ldcg(ccol + i);
+            }
+            __syncthreads();
+        }
+        if (a.trace && tid == 0)
+            tr3 = d_now();
+
+        // ---- 4. eliminate this supernode's columns, panel by panel ------------------------
+        if (use_sm) {
+            const int PB = 12;
+            for (int k0 = 0; k0 < c; k0 += PB) {
+                const int pb = min(PB, c - k0);
+                double *P = F + (size_t) k0 * ld; // panel columns live inside the front
+                panel_factor(P, ld, k0, pb, m, s, err);
+                const int n = m - (k0 + pb);
+                if (n > 0 || true) {
+                    if (n > 96)
+                        trailing_update<4>(F, ld, P, ld, pb, k0 + pb, m);
+                    else if (n > 40)
+                        trailing_update<2>(F, ld, P, ld, pb, k0 + pb, m);
+                    else
+                        trailing_update<1>(F, ld, P, ld, pb, k0 + pb, m);
+                }
+                __syncthreads();
+            }
+        } else {
+            // big front: stage each panel (rows k0..m, pb columns) in shared memory
+            const int avail = a.smem_doubles - ((ld + 1) / 2 + 2);
+            int PB = avail / ld;
+            PB = PB > 32 ? 32 : PB;
+            PB = PB - (PB % 4);
+            if (PB < 4) { // front too tall for even a 4-column panel (cannot happen below m ~ 6000)
+                if (tid == 0)
+                    atomicCAS(err, 0, -(1 + s));
+                break;
+            }
+            for (int k0 = 0; k0 < c; k0 += PB) {
+                const int pb = min(PB, c - k0);
+                for (int p = warp; p < pb; p += nwarps)
+                    for (int i = k0 + lane; i <= m; i += 32)
+                        Pbuf[i + (size_t) p * ld] = F[i + (size_t) (k0 + p) * ld];
+                __syncthreads();
+                panel_factor(Pbuf, ld, k0, pb, m, s, err);
+                for (int p = warp; p < pb; p += nwarps)
+                    for (int i = k0 + lane; i <= m; i += 32)
+                        F[i + (size_t) (k0 + p) * ld] = Pbuf[i + (size_t) p * ld];
+                trailing_update<4>(F, ld, Pbuf, ld, pb, k0 + pb, m);
+                __syncthreads();
+            }
+        }
+        if (a.trace && tid == 0)
+            tr4 = d_now();
+
+        // ---- 5. publish: y, L panel + update matrix ---------------------------------------
+        for (int e = tid; e < c; e += nt)
+            a.y[3 * (size_t) d.first + e] = F[m + (size_t) e * ld];
+        if (use_sm) {
+            for (int j = warp; j < m; j += nwarps)
+                for (int i = j + lane; i <= m; i += 32)
+                    Fg[i + (size_t) j * ld] = F[i + (size_t) j * ld];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            if (d.parent >= 0) {
+                __threadfence();
+                atomicAdd(&a.arrive[d.parent], 1);
+            }
+            if (a.trace) {
+                unsigned smid;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                unsigned long long *tr = a.trace + 8 * (size_t) t;
+                tr[0] = tr0; tr[1] = tr1; tr[2] = tr2; tr[3] = tr3; tr[4] = tr4; tr[5] = d_now();
+                tr[6] = (unsigned long long) s;
+                tr[7] = ((unsigned long long) smid << 32) | (unsigned) m;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel 3: persistent back-substitution
+// ------------------------------------------------------------------------------------------
+struct BsArgs {
+    const asam_sn_desc_t *sn;
+    const int *ipool;
+    const double *arena;
+    const double *y;
+    double *x;
+    int *xdone;
+    const int *btasks;
+    int ntasks;
+    int *ctrl; // [2] ticket, [1] err
+    int epoch;
+    int smem_doubles;
+    long long spin_limit;
+    unsigned long long *trace;
+};
+
+__global__ void __launch_bounds__(128) k_backsolve(BsArgs a)
+{
+    extern __shared__ double sm[]; // xs[r] | w[c] | staged L panel (optional)
+    __shared__ int s_task, s_abort;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    int *err = a.ctrl + 1;
+
+    for (;;) {
+        if (tid == 0) {
+            s_task = atomicAdd(&a.ctrl[2], 1);
+            s_abort = 0;
+        }
+        __syncthreads();
+        const int t = s_task;
+        if (t >= a.ntasks)
+            break;
+        unsigned long long tr0 = 0, tr1 = 0, tr2 = 0;
+        if (a.trace && tid == 0)
+            tr0 = d_now();
+        const int s = a.btasks[t];
+        const asam_sn_desc_t d = a.sn[s];
+        const int m = 3 * d.mb, c = 3 * d.cb, r = m - c, ld = m + 1;
+        const int *rows = a.ipool + d.seg;
+        const double *Lg = a.arena + d.f_off;
+        if (m + 2 > a.smem_doubles) { // host sizes shared memory for the largest front
+            if (tid == 0)
+                atomicCAS(err, 0, -(1 + s));
+            break;
+        }
+        double *xs = sm;    // r
+        double *w = sm + r; // c
+        // everything that does not depend on the parent is fetched before waiting
+        const bool staged = (long long) m + (long long) m * c <= (long long) a.smem_doubles;
+        double *Ls = sm + m; // m x c, leading dim m
+        if (staged) {
+            for (int k = warp; k < c; k += nwarps)
+                for (int i = k + lane; i < m; i += 32)
+                    Ls[i + (size_t) k * m] = Lg[i + (size_t) k * ld];
+        }
+        for (int k = tid; k < c; k += nt)
+            w[k] = a.y[3 * (size_t) d.first + k];
+        const double *L = staged ? Ls : Lg;
+        const int ll = staged ? m : ld;
+        if (a.trace && tid == 0)
+            tr1 = d_now();
+
+        if (d.parent >= 0 && tid == 0) {
+            long long spins = 0;
+            while (ld_volatile(&a.xdone[d.parent]) != a.epoch) {
+                __nanosleep(32);
+                if (++spins > a.spin_limit || ld_volatile(err) < 0) {
+                    atomicCAS(err, 0, -(1 + s));
+                    s_abort = 1;
+                    break;
+                }
+            }
+            __threadfence();
+        }
+        __syncthreads();
+        if (s_abort)
+            break;
+        if (a.trace && tid == 0)
+            tr2 = d_now();
+
+        for (int i = tid; i < r; i += nt)
+            xs[i] = __ldcg(&a.x[3 * (size_t) rows[d.cb + i / 3] + i % 3]);
+        __syncthreads();
+        // w_k = y_k - sum_i L[c+i, k] * xs[i]
+        for (int k = warp; k < c; k += nwarps) {
+            const double *lk = L + (size_t) k * ll + c;
+            double acc = 0.0;
+            for (int i = lane; i < r; i += 32)
+                acc += lk[i] * xs[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+                acc += __shfl_down_sync(0xffffffffu, acc, o);
+            if (lane == 0)
+                w[k] -= acc;
+        }
+        __syncthreads();
+        // L11' x1 = w  (warp 0, column k descending)
+        if (warp == 0) {
+            for (int k = c - 1; k >= 0; --k) {
+                const double *lk = L + (size_t) k * ll;
+                double acc = 0.0;
+                for (int j = k + 1 + lane; j < c; j += 32)
+                    acc += lk[j] * w[j];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+                    acc += __shfl_down_sync(0xffffffffu, acc, o);
+                if (lane == 0)
+                    w[k] = (w[k] - acc) / lk[k];
+                __syncwarp();
+            }
+            for (int k = lane; k < c; k += 32)
+                a.x[3 * (size_t) d.first + k] = w[k];
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence();
+                atomicExch(&a.xdone[s], a.epoch);
+                if (a.trace) {
+                    unsigned long long *tr = a.trace + 8 * (size_t) t;
+                    tr[0] = tr0; tr[1] = tr1; tr[2] = tr2; tr[3] = d_now();
+                    tr[6] = (unsigned long long) s;
+                    tr[7] = (unsigned) m;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// chi2
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_chi2_partial(const int *f_type, const int *f_a, const int *f_b,
+                                                      const double *f_z, const double *f_W, const double *st,
+                                                      int n_factors, double *partial)
+{
+    __shared__ double red[256];
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    double v = 0.0;
+    if (f < n_factors) {
+        int type = f_type[f];
+        int na = f_a[f];
+        double z[3], W[9], r[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            z[i] = f_z[3 * (size_t) f + i];
+#pragma unroll
+        for (int i = 0; i < 9; i++)
+            W[i] = f_W[9 * (size_t) f + i];
+        double scale;
+        if (type == 1) { // xyt at `state`, weight 0.5   (april_graph.c:86-89)
+            int nb = f_b[f];
+            double pa[3], pb[3], Ja[9], Jb[9];
+#pragma unroll
+            for (int i = 0; i < 3; i++) { pa[i] = st[3 * (size_t) na + i]; pb[i] = st[3 * (size_t) nb + i]; }
+            d_xyt_eval(pa, pb, z, Ja, Jb, r);
+            scale = 0.5;
+        } else { // weight 1.0   (april_graph.c:90-93)
+            r[0] = z[0] - st[3 * (size_t) na + 0];
+            r[1] = z[1] - st[3 * (size_t) na + 1];
+            r[2] = d_mod2pi(z[2] - st[3 * (size_t) na + 2]);
+            scale = 1.0;
+        }
+        double X[3];
+        d_av(W, r, X);
+        v = scale * (r[0] * X[0] + r[1] * X[1] + r[2] * X[2]);
+    }
+    red[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o)
+            red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+        partial[blockIdx.x] = red[0];
+}
+
+__global__ void __launch_bounds__(256) k_chi2_final(const double *partial, int n, double *out)
+{
+    __shared__ double red[256];
+    double v = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256)
+        v += partial[i];
+    red[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o)
+            red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+        out[0] = red[0];
+}
+
+__global__ void k_apply_desc(asam_sn_desc_t *sn, const int *ids, const asam_sn_desc_t *desc, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        sn[ids[i]] = desc[i];
+}
+
+__global__ void k_clear_range(double *Adiag, double *Bq, double *Aoff, int q_first, int q_count, int s_first,
+                              int s_count)
+{
+    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    size_t nd = 9 * (size_t) q_count, nb = 3 * (size_t) q_count, no = 9 * (size_t) s_count;
+    if (i < nd)
+        Adiag[9 * (size_t) q_first + i] = 0.0;
+    else if (i < nd + nb)
+        Bq[3 * (size_t) q_first + (i - nd)] = 0.0;
+    else if (i < nd + nb + no)
+        Aoff[9 * (size_t) s_first + (i - nd - nb)] = 0.0;
+}

@@ -50,6 +50,29 @@ void asam_fatal(const char *fmt, ...)
 
 ASAM_API const char *aprilsam_b200_last_error(void) { return g_error; }
 
+/* ---- host phase profile (diagnostics; read with asam_dbg_profile) ----------------------------- */
+static double g_prof[24];
+static inline double prof_now(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+#define PROF_BEGIN() double prof_t_ = prof_now()
+#define PROF_LAP(idx)                   \
+    do {                                \
+        double n_ = prof_now();         \
+        g_prof[idx] += n_ - prof_t_;    \
+        prof_t_ = n_;                   \
+    } while (0)
+
+ASAM_API void asam_dbg_profile(double *out, int reset)
+{
+    memcpy(out, g_prof, sizeof(g_prof));
+    if (reset)
+        memset(g_prof, 0, sizeof(g_prof));
+}
+
 #define DEV_OK(call)                                                                       \
     do {                                                                                   \
         if ((call) != 0)                                                                   \
@@ -398,6 +421,8 @@ ASAM_API void april_graph_cholesky(april_graph_t *graph, april_graph_cholesky_pa
     if (!param->nreordering)
         asam_fatal("april_graph_cholesky: param->nreordering == 0 is not supported (the reference asserts)");
 
+    PROF_BEGIN();
+    g_prof[9] += 1;
     solver_t *s = solver_get(graph, param);
     gctx_t *c = s->gc;
     asam_dev_t *dev = c->dev;
@@ -412,6 +437,7 @@ ASAM_API void april_graph_cholesky(april_graph_t *graph, april_graph_cholesky_pa
         memcpy(lp + 3 * (size_t) i, n->state, 3 * sizeof(double));
     }
 
+    PROF_LAP(11);
     /* ordering + symbolic analysis: cached while the factor structure is unchanged */
     uint64_t h = structure_hash(N, F, c->ftype, c->fa, c->fb);
     if (!(s->plan_valid && s->plan.N == N && s->plan.n_factors == F && s->plan.struct_hash == h)) {
@@ -421,6 +447,7 @@ ASAM_API void april_graph_cholesky(april_graph_t *graph, april_graph_cholesky_pa
         s->plan_valid = 1;
     }
     plan_t *pl = &s->plan;
+    PROF_LAP(12);
 
     DEV_OK(asam_upload_points(dev, 0, 0, N, lp));
     DEV_OK(asam_upload_points(dev, 1, 0, N, lp));
@@ -428,9 +455,12 @@ ASAM_API void april_graph_cholesky(april_graph_t *graph, april_graph_cholesky_pa
     DEV_OK(asam_linearize(dev, 0, F, NULL));
     DEV_OK(asam_factor_full(dev));
     DEV_OK(asam_backsolve_full(dev));
+    PROF_LAP(13);
     double *x = solver_x(s, N);
     DEV_OK(asam_download_x(dev, 0, N, x));
+    PROF_LAP(14);
     check_factor_status(s, "april_graph_cholesky");
+    PROF_LAP(15);
 
     /* persistent state the incremental path continues from (:260-288) */
     if (param->tr)
@@ -447,6 +477,7 @@ ASAM_API void april_graph_cholesky(april_graph_t *graph, april_graph_cholesky_pa
     /* state = l_point + x (:311-315) */
     for (int i = N - 1; i >= 0; i--)
         apply_update(node_at(graph, i), x + 3 * (size_t) pl->node2q[i]);
+    PROF_LAP(16);
 }
 
 /* ---- incremental step ---------------------------------------------------------------------------- */
@@ -559,6 +590,8 @@ ASAM_API void april_graph_cholesky_inc(april_graph_t *graph, april_graph_cholesk
     if (pl->N != N0 || pl->n_factors != F0)
         asam_fatal("april_graph_cholesky_inc: solver state out of sync (%d/%d nodes, %d/%d factors)", pl->N, N0,
                    pl->n_factors, F0);
+    PROF_BEGIN();
+    g_prof[8] += 1;
     check_nodes(graph, N0, N);
     gctx_sync_factors(c, graph);
 
@@ -635,6 +668,7 @@ ASAM_API void april_graph_cholesky_inc(april_graph_t *graph, april_graph_cholesk
 
     /* symbolic append + numeric re-factorisation of the marked supernodes */
     int *tasks = NULL, *nwait = NULL, ntasks = 0;
+    PROF_LAP(0);
     int rc = plan_append(pl, dev, N, F, c->ftype, c->fa, c->fb, marked, n_marked, &tasks, &nwait, &ntasks);
     if (rc == 2) {
         inc_general_fallback(graph, param, s, N, F, F0);
@@ -642,13 +676,16 @@ ASAM_API void april_graph_cholesky_inc(april_graph_t *graph, april_graph_cholesk
     }
     if (rc != 0)
         asam_fatal("april_graph_cholesky_inc: %s %s", g_error, asam_last_error());
+    PROF_LAP(1);
     DEV_OK(asam_linearize(dev, F0, nf, pts));
     DEV_OK(asam_factor(dev, ntasks, tasks, nwait));
     param->factor_num = F;
+    PROF_LAP(2);
 
     /* tree append (:550) */
     tree_append_from_plan(tr, pl, marked, n_marked, old_root_pos, N);
     param->nreordering = N;
+    PROF_LAP(3);
 
     /* solve (:563, :578-597): which supernodes does the traversal need? */
     {
@@ -691,8 +728,13 @@ ASAM_API void april_graph_cholesky_inc(april_graph_t *graph, april_graph_cholesk
             free(stamp);
             free(bt);
         }
+        PROF_LAP(4);
         check_factor_status(s, "april_graph_cholesky_inc");
+        PROF_LAP(5);
         apply_solution(s, tr, x, qbase);
+        PROF_LAP(6);
+        if (tr->naffected > 5)
+            g_prof[17] += 1;
     }
     free(tasks);
     free(nwait);
@@ -707,6 +749,8 @@ escalate:
         april_graph_cholesky(graph, param);
         clock_gettime(CLOCK_MONOTONIC, &t1);
         param->batch_time = (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6;
+        g_prof[7] += param->batch_time;
+        g_prof[10] += 1;
         param->tr->start_over = 0;
         param->tr->nlinearized_nodes = 0;
     }

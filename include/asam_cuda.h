@@ -119,6 +119,10 @@ int asam_counters(asam_dev_t *d, int64_t *out3);
 /* Device-side time (ms) of the kernels launched by the last linearize / factor / backsolve
  * calls, measured with CUDA events on the library's stream (0 if timing disabled). */
 int asam_set_timing(asam_dev_t *d, int enabled);
+/* Per-task globaltimer stamps of the last k_factor (which=0) / k_backsolve (which=1) launch,
+ * 8 x uint64 per task in task-list order (diagnostics only). */
+int asam_set_trace(asam_dev_t *d, int enabled);
+int asam_download_trace(asam_dev_t *d, int which, unsigned long long *out, int max_tasks);
 /* Device stopwatch on the library's stream around any sequence of calls; an L2 flush
  * (384 MiB overwrite) for cold-cache timing; launch geometry of the persistent kernels. */
 int asam_timer_start(asam_dev_t *d);

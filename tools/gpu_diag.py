@@ -22,6 +22,7 @@ from support import emul  # noqa: E402
 from support.hostplan import HostPlan, lib as hostlib  # noqa: E402
 
 _dp = C.POINTER(C.c_double)
+DUMP = {}
 
 
 def log(*a):
@@ -42,7 +43,41 @@ def dev_api():
     L.asam_set_timing.argtypes = [C.c_void_p, C.c_int]
     L.asam_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.asam_counters.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+    L.asam_set_trace.argtypes = [C.c_void_p, C.c_int]
+    L.asam_download_trace.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64), C.c_int]
     return L
+
+
+def trace_report(L, dev, ntasks, label):
+    for which, name in ((0, "k_factor"), (1, "k_backsolve")):
+        tr = np.zeros((ntasks, 8), dtype=np.uint64)
+        L.asam_download_trace(dev, which, tr.ctypes.data_as(C.POINTER(C.c_uint64)), ntasks)
+        tr = tr[tr[:, 0] > 0]
+        if len(tr) == 0:
+            continue
+        t = tr[:, :6].astype(np.int64)
+        t0 = t[:, 0].min()
+        if which == 0:
+            end = t[:, 5]
+            ph = np.stack([t[:, 1] - t[:, 0], t[:, 2] - t[:, 1], t[:, 3] - t[:, 2], t[:, 4] - t[:, 3], t[:, 5] - t[:, 4]], 1)
+            names = ["gather", "wait", "extend-add", "eliminate", "publish"]
+            mm = (tr[:, 7] & np.uint64(0xffffffff)).astype(np.int64)
+        else:
+            end = t[:, 3]
+            ph = np.stack([t[:, 1] - t[:, 0], t[:, 2] - t[:, 1], t[:, 3] - t[:, 2]], 1)
+            names = ["prefetch", "wait", "solve"]
+            mm = tr[:, 7].astype(np.int64)
+        span = (end.max() - t0) / 1e3
+        log(f"    [{label}] {name}: {len(tr)} tasks, span {span:.1f} us; per-task phase medians (us): " +
+            ", ".join(f"{n} {np.median(ph[:, i]) / 1e3:.2f}" for i, n in enumerate(names)) +
+            "; phase sums (ms): " + ", ".join(f"{n} {ph[:, i].sum() / 1e6:.2f}" for i, n in enumerate(names)))
+        dur = (end - t[:, 0])
+        top = np.argsort(-dur)[:6]
+        log("      longest tasks (us, m): " + ", ".join(f"{dur[i] / 1e3:.1f}/m={mm[i]}" for i in top))
+        busy = ph.sum() - ph[:, 1].sum()
+        log(f"      non-wait busy time {busy / 1e6:.2f} ms over {len(tr)} tasks -> {busy / 1e3 / len(tr):.2f} us per task")
+        if DUMP is not None:
+            DUMP[f"{label}:{name}"] = tr
 
 
 def borrowed_plan(L, param_ptr):
@@ -102,7 +137,7 @@ def check_batch(L, d, n, have_ref):
                 m = 3 * int(desc["mb"][s])
                 Fd = np.zeros(m * m + m)
                 L.asam_debug_read_front(dev, int(desc["f_off"][s]), m * m + m, Fd.ctypes.data_as(_dp))
-                Fd_m = Fd[:m * m].reshape(m, m).T  # column-major -> [row, col]
+                Fd_m = Fd.reshape(m, m + 1).T[:m, :]  # column-major, ld = m+1 -> [row, col]
                 Fe = fr.F[int(desc["f_off"][s])]
                 log(f"    first bad supernode {s}: first={first} cb={cb} mb={desc['mb'][s]} level={desc['level'][s]} "
                     f"ch={desc['ch_cnt'][s]} a_cnt={desc['a_cnt'][s]}")
@@ -165,14 +200,93 @@ def timing(L, d):
     ks = np.array(ks)
     log(f"    wall ms median {np.median(walls):.3f} min {np.min(walls):.3f}; kernels ms median lin {np.median(ks[:,0]):.4f} "
         f"factor {np.median(ks[:,1]):.4f} backsolve {np.median(ks[:,2]):.4f}")
+    L.asam_set_trace(dev, 1)
+    h.set_states(init)
+    h.batch()
+    trace_report(L, dev, 8192, "M3500 batch")
+    plan = borrowed_plan(L, h.param_ptr())
+    DUMP["M3500 batch:desc"] = plan.array("desc")
+    L.asam_set_trace(dev, 0)
+    h.close()
+
+
+def replay_profile(L, d, nsteps):
+    """Host-phase breakdown of the incremental path over a replay (no reference)."""
+    L.asam_dbg_profile.argtypes = [_dp, C.c_int]
+    prof = np.zeros(24)
+    h = H.Harness("b200")
+    h.replay_begin(d)
+    h.replay_to(2, want_chi2=False)
+    L.asam_dbg_profile(prof.ctypes.data_as(_dp), 1)
+    t0 = time.perf_counter()
+    _, ms, info = h.replay_to(nsteps, want_chi2=False)
+    wall = (time.perf_counter() - t0) * 1e3
+    L.asam_dbg_profile(prof.ctypes.data_as(_dp), 1)
+    ninc, nbatch = prof[8], prof[10]
+    log(f"--- replay profile: {len(ms)} steps in {wall:.1f} ms (sum of api calls {ms.sum():.1f} ms), inc calls {ninc:.0f}, "
+        f"full-traversal steps {prof[17]:.0f}, batch escalations {nbatch:.0f} taking {prof[7]:.1f} ms")
+    names = ["pre(sync factors, tree grow, mark)", "plan_append(+uploads)", "linearize+factor launch", "tree append",
+             "backsolve launch + x download (GPU wait)", "status download", "apply_solution"]
+    for i, nm in enumerate(names):
+        log(f"    inc phase {nm}: total {prof[i]:.1f} ms, per call {1e3 * prof[i] / max(ninc, 1):.1f} us")
+    bn = ["host gather", "plan (cache check/build)", "uploads+launches", "x download (GPU wait)", "status", "tree+update"]
+    for i, nm in enumerate(bn):
+        log(f"    batch phase {nm}: total {prof[11 + i]:.1f} ms, per call {prof[11 + i] / max(prof[9], 1):.3f} ms")
+    naff = info[:, 0]
+    for lo, hi in ((0, 5), (6, 20), (21, 100), (101, 10000)):
+        sel = (naff >= lo) & (naff <= hi)
+        if sel.any():
+            log(f"    steps with naffected in [{lo},{hi}]: {sel.sum()} steps, median {np.median(ms[sel]):.3f} ms, mean {ms[sel].mean():.3f} ms")
+    h.close()
+
+
+def check_synth(L, N, have_ref, iters=2):
+    """Synthetic Manhattan graph: exercises the big-front (global-memory) path of k_factor."""
+    from aprilsam_b200 import datasets
+    d = datasets.manhattan_dense(N, seed=1)
+    log(f"--- synthetic manhattan_dense N={N} edges={d.n_edges}")
+    h = H.Harness("b200")
+    h.load_full(d)
+    t0 = time.perf_counter()
+    ms = h.batch()
+    log(f"    cold batch wall {ms:.1f} ms (python {1e3 * (time.perf_counter() - t0):.1f})")
+    dev = L.asam_dbg_dev_of_graph(h.graph_ptr())
+    plan = borrowed_plan(L, h.param_ptr())
+    log("    plan", plan.info())
+    L.asam_set_timing(dev, 1)
+    st1 = h.states()
+    r = None
+    if have_ref and N <= 30000:
+        r = H.Harness("reference"); r.load_full(d)
+        tr = r.batch()
+        err = np.abs(st1 - r.states())
+        log(f"    iter 1 vs reference ({tr:.1f} ms): max abs state diff {err.max():.3e}, chi2 {h.chi2():.9g} vs {r.chi2():.9g}")
+    for it in range(iters):
+        ms = h.batch()
+        lin = C.c_float(); fac = C.c_float(); bs = C.c_float()
+        L.asam_last_kernel_ms(dev, C.byref(lin), C.byref(fac), C.byref(bs))
+        msg = f"    warm batch {it}: wall {ms:.2f} ms; kernels lin {lin.value:.3f} factor {fac.value:.3f} backsolve {bs.value:.3f} ms"
+        if r is not None:
+            r.batch()
+            msg += f"; max abs state diff {np.abs(h.states() - r.states()).max():.3e}"
+        log(msg)
+    L.asam_set_trace(dev, 1)
+    h.batch()
+    trace_report(L, dev, 200000, f"manhattan {N}")
+    DUMP[f"manhattan {N}:desc"] = plan.array("desc")
+    L.asam_set_trace(dev, 0)
+    if r is not None:
+        r.close()
     h.close()
 
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
+    ap.add_argument("--synth", default="", help="comma list of synthetic graph sizes")
     ap.add_argument("--sizes", default="1,2,10,100,3500")
     ap.add_argument("--replay", type=int, default=300)
     ap.add_argument("--time", action="store_true")
+    ap.add_argument("--profile-replay", type=int, default=0)
     args = ap.parse_args()
     d = H.PoseGraphData.load(os.path.join(ROOT, "tests", "golden", "m3500.npz"))
     L = dev_api()
@@ -184,4 +298,11 @@ if __name__ == "__main__":
         check_replay(d, args.replay, have_ref)
     if args.time:
         timing(L, d)
+    if args.profile_replay > 0:
+        replay_profile(L, d, args.profile_replay)
+    for n in [int(s) for s in args.synth.split(",") if s]:
+        check_synth(L, n, have_ref)
+    if DUMP:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        np.savez_compressed(os.path.join(ROOT, "gpurun_out", "traces.npz"), **{k.replace(" ", "_").replace(":", "__"): v for k, v in DUMP.items()})
     log(f"done in {time.time() - t0:.1f}s")
