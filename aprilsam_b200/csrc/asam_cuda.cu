@@ -58,7 +58,7 @@ struct asam_dev {
     Buf f_type, f_a, f_b, f_z, f_W, f_slot;
     Buf lp, st, node2q, q2node;
     // hessian
-    Buf Adiag, Aoff, Bq, y, x;
+    Buf Adiag, Aoff, Bq, y, x, dinv;
     // plan
     Buf sn, ipool, arena;
     Buf arrive, xdone;
@@ -214,7 +214,7 @@ ASAM_EXPORT int asam_dev_create(asam_dev_t **out)
         return set_err("k_factor does not fit on an SM");
     d->fac_grid = occ * d->n_sm;
 
-    d->bs_smem = 64 * 1024;
+    d->bs_smem = 100 * 1024; // two CTAs per SM; L11 of a 96-column supernode stays on chip
     CK(cudaFuncSetAttribute(k_backsolve, cudaFuncAttributeMaxDynamicSharedMemorySize, d->bs_smem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_backsolve, d->bs_threads, d->bs_smem));
     if (occ < 1)
@@ -231,7 +231,7 @@ ASAM_EXPORT void asam_dev_destroy(asam_dev_t *d)
     cudaSetDevice(d->device);
     cudaStreamSynchronize(d->stream);
     Buf *all[] = { &d->f_type, &d->f_a, &d->f_b, &d->f_z, &d->f_W, &d->f_slot, &d->lp, &d->st, &d->node2q, &d->q2node,
-                   &d->Adiag, &d->Aoff, &d->Bq, &d->y, &d->x, &d->sn, &d->ipool, &d->arena, &d->arrive,
+                   &d->Adiag, &d->Aoff, &d->Bq, &d->y, &d->x, &d->dinv, &d->sn, &d->ipool, &d->arena, &d->arrive,
                    &d->xdone, &d->tasks_full, &d->nwait_full, &d->btasks_full, &d->tasks_tmp, &d->nwait_tmp,
                    &d->btasks_tmp, &d->ctrl, &d->partial, &d->patch_ids, &d->patch_desc, &d->pts, &d->flush, &d->trace_fac, &d->trace_bs };
     for (int i = 0; i < 2; i++)
@@ -270,6 +270,7 @@ ASAM_EXPORT int asam_reserve(asam_dev_t *d, int n_nodes, int n_factors, int n_sl
     rc |= buf_reserve(d, d->Bq, N * 3 * sizeof(double), true, true);
     rc |= buf_reserve(d, d->y, N * 3 * sizeof(double), true, true);
     rc |= buf_reserve(d, d->x, N * 3 * sizeof(double), true, true);
+    rc |= buf_reserve(d, d->dinv, N * 3 * sizeof(double), true, true);
     rc |= buf_reserve(d, d->Aoff, S * 9 * sizeof(double), true, true);
     rc |= buf_reserve(d, d->sn, SN * sizeof(asam_sn_desc_t), true, false);
     rc |= buf_reserve(d, d->arrive, SN * sizeof(int), true, true);
@@ -442,6 +443,7 @@ static int launch_factor(asam_dev *d, int ntasks, const int *tasks_dev, const in
     a.Bq = (const double *) d->Bq.p;
     a.q2node = (const int *) d->q2node.p;
     a.y = (double *) d->y.p;
+    a.dinv = (double *) d->dinv.p;
     a.arrive = (int *) d->arrive.p;
     a.tasks = tasks_dev;
     a.nwait = nwait_dev;
@@ -480,6 +482,7 @@ static int launch_backsolve(asam_dev *d, int ntasks, const int *btasks_dev)
     a.ipool = (const int *) d->ipool.p;
     a.arena = (const double *) d->arena.p;
     a.y = (const double *) d->y.p;
+    a.dinv = (const double *) d->dinv.p;
     a.x = (double *) d->x.p;
     a.xdone = (int *) d->xdone.p;
     a.btasks = btasks_dev;

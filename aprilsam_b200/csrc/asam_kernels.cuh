@@ -245,6 +245,7 @@ struct FacArgs {
     const double *Adiag, *Aoff, *Bq;
     const int *q2node;
     double *y;
+    double *dinv; // 1/L_kk in elimination order (used by k_backsolve)
     int *arrive;
     const int *tasks, *nwait;
     int ntasks;
@@ -299,36 +300,72 @@ __device__ __forceinline__ void trailing_update(double *C, int ld, const double 
     }
 }
 
-// Left-looking factorisation of panel columns [k0, k0+pb) of the front held in P (column p of
-// the panel at P + p*ldp, rows indexed by front row; rows k0..m valid).  Each thread owns rows;
-// one barrier per column.  On exit P holds L (and y in row m).
-__device__ __forceinline__ void panel_factor(double *P, int ldp, int k0, int pb, int m, int sn_id, int *err)
+#define ASAM_PB 16 // panel width of the dense partial Cholesky
+
+// Panel step of the dense partial Cholesky: columns [k0, k0+pb) of the front held in P (panel
+// column p at P + p*ldp, indexed by front row; rows k0..m valid, row m = rhs).
+//   A. warp 0 factors the pb x pb diagonal block in place (right-looking, reciprocal square
+//      roots, lanes = block rows, l_j broadcast by shuffle) and leaves 1/L_jj in s_rinv;
+//   B. every thread solves whole rows below the block against L11' (registers, broadcast reads).
+// Two block barriers per panel instead of two per column.
+__device__ __forceinline__ void panel_factor(double *P, int ldp, int k0, int pb, int m, int sn_id, int *err,
+                                             double *s_rinv, double *dinv_out)
+{
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    if (tid < 32) {
+        const int i = lane; // row inside the diagonal block
+        for (int kk = 0; kk < pb; kk++) {
+            const double d = P[(k0 + kk) + (size_t) kk * ldp];
+            if (!(d > 0.0) && lane == 0)
+                atomicCAS(err, 0, 1 + sn_id);
+            const double rinv = rsqrt(d);
+            double l = 0.0;
+            if (i > kk && i < pb)
+                l = P[(k0 + i) + (size_t) kk * ldp] * rinv;
+            __syncwarp();
+            if (i == kk) {
+                P[(k0 + kk) + (size_t) kk * ldp] = d * rinv;
+                s_rinv[kk] = rinv;
+                if (dinv_out)
+                    dinv_out[k0 + kk] = rinv;
+            } else if (i > kk && i < pb) {
+                P[(k0 + i) + (size_t) kk * ldp] = l;
+            }
+            for (int j = kk + 1; j < pb; j++) {
+                const double lj = __shfl_sync(0xffffffffu, l, j);
+                if (i >= j && i < pb)
+                    P[(k0 + i) + (size_t) j * ldp] -= l * lj;
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void panel_trsm(double *P, int ldp, int k0, int pb, int m, const double *s_rinv)
 {
     const int tid = threadIdx.x, nt = blockDim.x;
-    for (int kk = 0; kk < pb; kk++) {
-        const int k = k0 + kk;
-        // pivot (every thread recomputes it: <= pb terms)
-        double d = P[k + (size_t) kk * ldp];
-        for (int p = 0; p < kk; p++) {
-            double v = P[k + (size_t) p * ldp];
-            d -= v * v;
-        }
-        if (!(d > 0.0) && tid == 0)
-            atomicCAS(err, 0, 1 + sn_id);
-        const double piv = sqrt(d);
-        __syncthreads(); // all threads have read P[k, kk] before its owner overwrites it
-        for (int i = k + tid; i <= m; i += nt) {
-            if (i == k) {
-                P[i + (size_t) kk * ldp] = piv;
-            } else {
-                double v = P[i + (size_t) kk * ldp];
-                for (int p = 0; p < kk; p++)
-                    v -= P[i + (size_t) p * ldp] * P[k + (size_t) p * ldp];
-                P[i + (size_t) kk * ldp] = v / piv;
+    for (int i = k0 + pb + tid; i <= m; i += nt) {
+        double x[ASAM_PB];
+#pragma unroll
+        for (int j = 0; j < ASAM_PB; j++)
+            x[j] = (j < pb) ? P[i + (size_t) j * ldp] : 0.0;
+#pragma unroll
+        for (int j = 0; j < ASAM_PB; j++) {
+            if (j < pb) {
+                x[j] *= s_rinv[j];
+#pragma unroll
+                for (int j2 = j + 1; j2 < ASAM_PB; j2++)
+                    if (j2 < pb)
+                        x[j2] -= x[j] * P[(k0 + j2) + (size_t) j * ldp];
             }
         }
-        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < ASAM_PB; j++)
+            if (j < pb)
+                P[i + (size_t) j * ldp] = x[j];
     }
+    __syncthreads();
 }
 
 __global__ void __launch_bounds__(256) k_factor(FacArgs a)
@@ -336,6 +373,7 @@ __global__ void __launch_bounds__(256) k_factor(FacArgs a)
     extern __shared__ double sm[];
     __shared__ int s_task, s_abort;
     __shared__ asam_sn_desc_t s_cd[ASAM_MAX_CACHED_CHILDREN];
+    __shared__ double s_rinv[ASAM_PB];
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     int *err = a.ctrl + 1;
@@ -349,7 +387,7 @@ __global__ void __launch_bounds__(256) k_factor(FacArgs a)
         const int t = s_task;
         if (t >= a.ntasks)
             break;
-        unsigned long long tr0 = 0, tr1 = 0, tr2 = 0, tr3 = 0, tr4 = 0;
+        unsigned long long tr0 = 0, tr1 = 0, tr2 = 0, tr3 = 0, tr4 = 0, accA = 0, accB = 0;
         if (a.trace && tid == 0)
             tr0 = d_now();
         const int s = a.tasks[t];
@@ -368,6 +406,7 @@ __global__ void __launch_bounds__(256) k_factor(FacArgs a)
         double *F = use_sm ? sm : Fg;
         int *dmap = (int *) (sm + (use_sm ? fsz : 0)); // ld ints
         double *Pbuf = sm + (ld + 1) / 2 + 1;           // big mode only: staged panel
+        double *dinv = a.dinv + 3 * (size_t) d.first;   // 1/L_kk of this supernode's columns
 
         // ---- 1. zero the lower trapezoid (+ rhs row), gather the original entries ---------
         if (use_sm) {
@@ -433,7 +472,16 @@ __global__ void __launch_bounds__(256) k_factor(FacArgs a)
             for (int j = warp; j < cr; j += nwarps) {
                 const double *ccol = CF + (size_t) (cc + j) * cld + cc;
                 double *fcol = F + (size_t) dmap[j] * ld;
-                for (int i = j + lane; i <= cr; i += 32)
+                int i = j + lane;
+                for (; i + 96 <= cr; i += 128) { // four independent loads in flight per lane
+                    const double v0 = __ldcg(ccol + i), v1 = __ldcg(ccol + i + 32);
+                    const double v2 = __ldcg(ccol + i + 64), v3 = __ldcg(ccol + i + 96);
+                    fcol[dmap[i]] += v0;
+                    fcol[dmap[i + 32]] += v1;
+                    fcol[dmap[i + 64]] += v2;
+                    fcol[dmap[i + 96]] += v3;
+                }
+                for (; i <= cr; i += 32)
                     fcol[dmap[i]] += __ldcg(ccol + i);
             }
             __syncthreads();
@@ -443,27 +491,34 @@ __global__ void __launch_bounds__(256) k_factor(FacArgs a)
 
         // ---- 4. eliminate this supernode's columns, panel by panel ------------------------
         if (use_sm) {
-            const int PB = 12;
-            for (int k0 = 0; k0 < c; k0 += PB) {
-                const int pb = min(PB, c - k0);
+            for (int k0 = 0; k0 < c; k0 += ASAM_PB) {
+                const int pb = min(ASAM_PB, c - k0);
                 double *P = F + (size_t) k0 * ld; // panel columns live inside the front
-                panel_factor(P, ld, k0, pb, m, s, err);
-                const int n = m - (k0 + pb);
-                if (n > 0 || true) {
-                    if (n > 96)
-                        trailing_update<4>(F, ld, P, ld, pb, k0 + pb, m);
-                    else if (n > 40)
-                        trailing_update<2>(F, ld, P, ld, pb, k0 + pb, m);
-                    else
-                        trailing_update<1>(F, ld, P, ld, pb, k0 + pb, m);
+                unsigned long long ta = 0, tb = 0;
+                if (a.trace && tid == 0)
+                    ta = d_now();
+                panel_factor(P, ld, k0, pb, m, s, err, s_rinv, dinv);
+                if (a.trace && tid == 0)
+                    tb = d_now();
+                panel_trsm(P, ld, k0, pb, m, s_rinv);
+                if (a.trace && tid == 0) {
+                    accA += tb - ta;
+                    accB += d_now() - tb;
                 }
+                const int n = m - (k0 + pb);
+                if (n > 96)
+                    trailing_update<4>(F, ld, P, ld, pb, k0 + pb, m);
+                else if (n > 40)
+                    trailing_update<2>(F, ld, P, ld, pb, k0 + pb, m);
+                else
+                    trailing_update<1>(F, ld, P, ld, pb, k0 + pb, m);
                 __syncthreads();
             }
         } else {
             // big front: stage each panel (rows k0..m, pb columns) in shared memory
             const int avail = a.smem_doubles - ((ld + 1) / 2 + 2);
             int PB = avail / ld;
-            PB = PB > 32 ? 32 : PB;
+            PB = PB > ASAM_PB ? ASAM_PB : PB;
             PB = PB - (PB % 4);
             if (PB < 4) { // front too tall for even a 4-column panel (cannot happen below m ~ 6000)
                 if (tid == 0)
@@ -476,7 +531,8 @@ __global__ void __launch_bounds__(256) k_factor(FacArgs a)
                     for (int i = k0 + lane; i <= m; i += 32)
                         Pbuf[i + (size_t) p * ld] = F[i + (size_t) (k0 + p) * ld];
                 __syncthreads();
-                panel_factor(Pbuf, ld, k0, pb, m, s, err);
+                panel_factor(Pbuf, ld, k0, pb, m, s, err, s_rinv, dinv);
+                panel_trsm(Pbuf, ld, k0, pb, m, s_rinv);
                 for (int p = warp; p < pb; p += nwarps)
                     for (int i = k0 + lane; i <= m; i += 32)
                         F[i + (size_t) (k0 + p) * ld] = Pbuf[i + (size_t) p * ld];
@@ -506,8 +562,9 @@ __global__ void __launch_bounds__(256) k_factor(FacArgs a)
                 asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
                 unsigned long long *tr = a.trace + 8 * (size_t) t;
                 tr[0] = tr0; tr[1] = tr1; tr[2] = tr2; tr[3] = tr3; tr[4] = tr4; tr[5] = d_now();
-                tr[6] = (unsigned long long) s;
-                tr[7] = ((unsigned long long) smid << 32) | (unsigned) m;
+                (void) smid;
+                tr[6] = (unsigned long long) s | (accB << 32); // low: supernode, high: ns in panel TRSM
+                tr[7] = (unsigned long long) (unsigned) m | (accA << 32); // low: m, high: ns in diag blocks
             }
         }
         __syncthreads();
@@ -522,6 +579,7 @@ struct BsArgs {
     const int *ipool;
     const double *arena;
     const double *y;
+    const double *dinv; // 1/L_kk written by k_factor
     double *x;
     int *xdone;
     const int *btasks;
@@ -533,9 +591,12 @@ struct BsArgs {
     unsigned long long *trace;
 };
 
+// One supernode: x1 = L11^-T (y1 - L21' x2), x2 gathered from the ancestors' solution.
+// Everything that does not depend on the parent (descriptor, row list, y1, 1/diag and the L
+// panel when it fits in shared memory) is fetched BEFORE waiting on the parent's flag.
 __global__ void __launch_bounds__(128) k_backsolve(BsArgs a)
 {
-    extern __shared__ double sm[]; // xs[r] | w[c] | staged L panel (optional)
+    extern __shared__ double sm[]; // xs[r] | w[c] | rd[c] | staged L (panel or L11)
     __shared__ int s_task, s_abort;
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
@@ -558,25 +619,33 @@ __global__ void __launch_bounds__(128) k_backsolve(BsArgs a)
         const int m = 3 * d.mb, c = 3 * d.cb, r = m - c, ld = m + 1;
         const int *rows = a.ipool + d.seg;
         const double *Lg = a.arena + d.f_off;
-        if (m + 2 > a.smem_doubles) { // host sizes shared memory for the largest front
+        if (m + c + 2 > a.smem_doubles) { // host sizes shared memory for the largest front
             if (tid == 0)
                 atomicCAS(err, 0, -(1 + s));
             break;
         }
-        double *xs = sm;    // r
-        double *w = sm + r; // c
-        // everything that does not depend on the parent is fetched before waiting
-        const bool staged = (long long) m + (long long) m * c <= (long long) a.smem_doubles;
-        double *Ls = sm + m; // m x c, leading dim m
-        if (staged) {
+        double *xs = sm;        // r
+        double *w = sm + r;     // c
+        double *rd = sm + m;    // c
+        double *Ls = sm + m + c;
+        const long long room = (long long) a.smem_doubles - (m + c);
+        // staging mode: 2 = whole panel (m x c, ld m), 1 = L11 only (c x c, ld c), 0 = none
+        const int mode = ((long long) m * c <= room) ? 2 : (((long long) c * c <= room) ? 1 : 0);
+        const int ll = mode == 2 ? m : (mode == 1 ? c : ld);
+        if (mode == 2) {
             for (int k = warp; k < c; k += nwarps)
                 for (int i = k + lane; i < m; i += 32)
                     Ls[i + (size_t) k * m] = Lg[i + (size_t) k * ld];
+        } else if (mode == 1) {
+            for (int k = warp; k < c; k += nwarps)
+                for (int i = k + lane; i < c; i += 32)
+                    Ls[i + (size_t) k * c] = Lg[i + (size_t) k * ld];
         }
-        for (int k = tid; k < c; k += nt)
+        for (int k = tid; k < c; k += nt) {
             w[k] = a.y[3 * (size_t) d.first + k];
-        const double *L = staged ? Ls : Lg;
-        const int ll = staged ? m : ld;
+            rd[k] = a.dinv[3 * (size_t) d.first + k];
+        }
+        const double *L11 = mode ? Ls : Lg; // (row, col) at L11[row + col*ll]
         if (a.trace && tid == 0)
             tr1 = d_now();
 
@@ -601,31 +670,36 @@ __global__ void __launch_bounds__(128) k_backsolve(BsArgs a)
         for (int i = tid; i < r; i += nt)
             xs[i] = __ldcg(&a.x[3 * (size_t) rows[d.cb + i / 3] + i % 3]);
         __syncthreads();
-        // w_k = y_k - sum_i L[c+i, k] * xs[i]
-        for (int k = warp; k < c; k += nwarps) {
-            const double *lk = L + (size_t) k * ll + c;
-            double acc = 0.0;
-            for (int i = lane; i < r; i += 32)
-                acc += lk[i] * xs[i];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
-                acc += __shfl_down_sync(0xffffffffu, acc, o);
-            if (lane == 0)
-                w[k] -= acc;
-        }
-        __syncthreads();
-        // L11' x1 = w  (warp 0, column k descending)
-        if (warp == 0) {
-            for (int k = c - 1; k >= 0; --k) {
-                const double *lk = L + (size_t) k * ll;
-                double acc = 0.0;
-                for (int j = k + 1 + lane; j < c; j += 32)
-                    acc += lk[j] * w[j];
+        // w_k -= sum_i L21[i, k] * xs[i]   (one warp per column, two accumulators)
+        if (r > 0) {
+            for (int k = warp; k < c; k += nwarps) {
+                const double *lk = (mode == 2) ? (Ls + (size_t) k * m + c) : (Lg + (size_t) k * ld + c);
+                double acc0 = 0.0, acc1 = 0.0;
+                int i = lane;
+                for (; i + 32 < r; i += 64) {
+                    acc0 += lk[i] * xs[i];
+                    acc1 += lk[i + 32] * xs[i + 32];
+                }
+                if (i < r)
+                    acc0 += lk[i] * xs[i];
+                acc0 += acc1;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1)
-                    acc += __shfl_down_sync(0xffffffffu, acc, o);
+                    acc0 += __shfl_down_sync(0xffffffffu, acc0, o);
                 if (lane == 0)
-                    w[k] = (w[k] - acc) / lk[k];
+                    w[k] -= acc0;
+            }
+            __syncthreads();
+        }
+        // L11' x1 = w, right-looking: x_k = w_k / L_kk, then w_j -= L[k, j] * x_k for j < k
+        if (warp == 0) {
+            for (int k = c - 1; k >= 0; --k) {
+                const double xk = w[k] * rd[k];
+                __syncwarp();
+                if (lane == 0)
+                    w[k] = xk;
+                for (int j = lane; j < k; j += 32)
+                    w[j] -= L11[k + (size_t) j * ll] * xk;
                 __syncwarp();
             }
             for (int k = lane; k < c; k += 32)

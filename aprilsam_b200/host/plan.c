@@ -20,7 +20,7 @@
 
 #include "asam_host.h"
 
-#define MAX_SN_COLS 64 /* block columns per supernode (bounds the single-CTA panel width) */
+#define MAX_SN_COLS 32 /* block columns per supernode: L11 (96x96) fits k_backsolve shared memory */
 
 /* ---- pair map ---------------------------------------------------------------------------- */
 static inline uint64_t mix64(uint64_t x)
@@ -538,7 +538,8 @@ static int plan_build_impl(plan_t *pl, asam_dev_t *dev, int N, int n_factors, co
     for (int s = 0; s < pl->nsn; s++) {
         emit_segment(pl, s, &seg, 0);
         pl->desc[s].f_off = pl->arena_n;
-        pl->arena_n += front_doubles(pl->desc[s].mb);
+        pl->desc[s].reserved = front_doubles(pl->desc[s].mb); /* capacity of this allocation */
+        pl->arena_n += pl->desc[s].reserved;
     }
     pl->ipool_n = seg.n;
 
@@ -716,9 +717,13 @@ int plan_append(plan_t *pl, asam_dev_t *dev, int N, int n_factors, const int *ft
         d->mb = h->rows.n;
         if (3 * d->mb > pl->max_m)
             pl->max_m = 3 * d->mb;
-        if (d->mb != old_mb) {
+        if (d->mb != old_mb && front_doubles(d->mb) > d->reserved) {
+            /* the front outgrew its allocation: move it, with head-room for the poses that
+             * later steps will append (the old space is reclaimed at the next batch) */
+            int slack = d->mb / 4 > 4 ? d->mb / 4 : 4;
+            d->reserved = front_doubles(d->mb + slack);
             d->f_off = pl->arena_n;
-            pl->arena_n += front_doubles(d->mb);
+            pl->arena_n += d->reserved;
         }
         if (d->parent < 0 && gain[i].n > 0) { /* old root: hangs under the first new pose */
             int P = nsn0 + (gain[i].p[0] - N0);
@@ -778,8 +783,9 @@ int plan_append(plan_t *pl, asam_dev_t *dev, int N, int n_factors, const int *ft
         d->mb = h->rows.n;
         if (3 * d->mb > pl->max_m)
             pl->max_m = 3 * d->mb;
+        d->reserved = front_doubles(d->mb + 4);
         d->f_off = pl->arena_n;
-        pl->arena_n += front_doubles(d->mb);
+        pl->arena_n += d->reserved;
         if (bel->n > 0) {
             int P = nsn0 + (bel->p[0] - N0);
             d->parent = P;

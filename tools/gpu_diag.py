@@ -62,6 +62,14 @@ def trace_report(L, dev, ntasks, label):
             ph = np.stack([t[:, 1] - t[:, 0], t[:, 2] - t[:, 1], t[:, 3] - t[:, 2], t[:, 4] - t[:, 3], t[:, 5] - t[:, 4]], 1)
             names = ["gather", "wait", "extend-add", "eliminate", "publish"]
             mm = (tr[:, 7] & np.uint64(0xffffffff)).astype(np.int64)
+            accA = (tr[:, 7] >> np.uint64(32)).astype(np.int64)
+            accB = (tr[:, 6] >> np.uint64(32)).astype(np.int64)
+            tr = tr.copy()
+            tr[:, 6] = tr[:, 6] & np.uint64(0xffffffff)
+            big = np.argsort(-ph[:, 3])[:4]
+            log("      slowest eliminations: " + "; ".join(
+                f"m={mm[i]} elim {ph[i, 3] / 1e3:.1f}us (diag {accA[i] / 1e3:.1f}, trsm {accB[i] / 1e3:.1f}, trailing {(ph[i, 3] - accA[i] - accB[i]) / 1e3:.1f})"
+                for i in big))
         else:
             end = t[:, 3]
             ph = np.stack([t[:, 1] - t[:, 0], t[:, 2] - t[:, 1], t[:, 3] - t[:, 2]], 1)
