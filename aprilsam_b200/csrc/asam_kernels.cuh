@@ -257,42 +257,52 @@ struct FacArgs {
 
 // Trailing update  C[i,j] -= sum_{p<pb} P[i,p] * P[j,p]  for j in [j0, m), i in [j, m]
 // (row m = rhs row).  P holds the pb factored panel columns (leading dim ldp, row index =
-// front row); C is the front (leading dim ld).  One warp per tile of 4 columns, each lane
-// R rows spaced 32 apart (conflict-free shared-memory reads, b values broadcast).
-template <int R>
+// front row); C is the front (leading dim ld).  One warp per tile of TN columns, each lane R
+// rows spaced 32 apart: conflict-free shared-memory reads for the row values, broadcast reads
+// for the column values; R*TN accumulators per lane keep the FP64 pipe, not the shared-memory
+// pipe, the limiter (2R + TN wavefronts feed R*TN warp-wide DFMAs per panel column).
+// Out-of-range rows/columns are clamped for the loads and masked at the store.
+template <int R, int TN>
 __device__ __forceinline__ void trailing_update(double *C, int ld, const double *P, int ldp, int pb, int j0, int m)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    for (int tj = j0 + 4 * warp; tj < m; tj += 4 * nwarps) {
+    for (int tj = j0 + TN * warp; tj < m; tj += TN * nwarps) {
+        int jc[TN];
+#pragma unroll
+        for (int q = 0; q < TN; q++)
+            jc[q] = min(tj + q, m - 1);
         for (int ib = tj; ib <= m; ib += 32 * R) {
-            double acc[R][4];
-            int irow[R];
+            double acc[R][TN];
+            int irow[R], ic[R];
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 irow[r] = ib + lane + 32 * r;
+                ic[r] = min(irow[r], m);
 #pragma unroll
-                for (int q = 0; q < 4; q++)
+                for (int q = 0; q < TN; q++)
                     acc[r][q] = 0.0;
             }
+#pragma unroll 2
             for (int p = 0; p < pb; p++) {
                 const double *pc = P + (size_t) p * ldp;
-                double b[4];
+                double b[TN], av[R];
 #pragma unroll
-                for (int q = 0; q < 4; q++)
-                    b[q] = (tj + q < m) ? pc[tj + q] : 0.0;
+                for (int q = 0; q < TN; q++)
+                    b[q] = pc[jc[q]];
 #pragma unroll
-                for (int r = 0; r < R; r++) {
-                    double av = (irow[r] <= m) ? pc[irow[r]] : 0.0;
+                for (int r = 0; r < R; r++)
+                    av[r] = pc[ic[r]];
 #pragma unroll
-                    for (int q = 0; q < 4; q++)
-                        acc[r][q] += av * b[q];
-                }
+                for (int r = 0; r < R; r++)
+#pragma unroll
+                    for (int q = 0; q < TN; q++)
+                        acc[r][q] += av[r] * b[q];
             }
 #pragma unroll
             for (int r = 0; r < R; r++)
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    int i = irow[r], j = tj + q;
+                for (int q = 0; q < TN; q++) {
+                    const int i = irow[r], j = tj + q;
                     if (i <= m && j < m && i >= j)
                         C[i + (size_t) j * ld] -= acc[r][q];
                 }
@@ -300,84 +310,79 @@ __device__ __forceinline__ void trailing_update(double *C, int ld, const double 
     }
 }
 
-#define ASAM_PB 16 // panel width of the dense partial Cholesky
+#define ASAM_PB 12 // panel width of the dense partial Cholesky (a multiple of 3)
 
-// Panel step of the dense partial Cholesky: columns [k0, k0+pb) of the front held in P (panel
-// column p at P + p*ldp, indexed by front row; rows k0..m valid, row m = rhs).
-//   A. warp 0 factors the pb x pb diagonal block in place (right-looking, reciprocal square
-//      roots, lanes = block rows, l_j broadcast by shuffle) and leaves 1/L_jj in s_rinv;
-//   B. every thread solves whole rows below the block against L11' (registers, broadcast reads).
-// Two block barriers per panel instead of two per column.
+// Dense partial Cholesky of one panel of pb (multiple of 3, <= ASAM_PB) columns [k0, k0+pb) of
+// the front held in P (panel column p at P + p*ldp, indexed by front row; rows k0..m valid,
+// row m = rhs).  Every pose contributes a 3x3 block column, so the panel is processed in
+// 3-column steps with a CLOSED-FORM 3x3 Cholesky that every thread evaluates redundantly in
+// registers (three chained reciprocal square roots, no warp/block hand-off), followed by the
+// row TRSM (each thread owns rows) and the rank-3 update of the remaining panel columns.
+// Two block barriers per 3 columns; the code stays small (this kernel executes straight-line
+// code once per task, so instruction-cache footprint matters more than unrolling).
 __device__ __forceinline__ void panel_factor(double *P, int ldp, int k0, int pb, int m, int sn_id, int *err,
-                                             double *s_rinv, double *dinv_out)
-{
-    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
-    if (tid < 32) {
-        const int i = lane; // row inside the diagonal block
-        for (int kk = 0; kk < pb; kk++) {
-            const double d = P[(k0 + kk) + (size_t) kk * ldp];
-            if (!(d > 0.0) && lane == 0)
-                atomicCAS(err, 0, 1 + sn_id);
-            const double rinv = rsqrt(d);
-            double l = 0.0;
-            if (i > kk && i < pb)
-                l = P[(k0 + i) + (size_t) kk * ldp] * rinv;
-            __syncwarp();
-            if (i == kk) {
-                P[(k0 + kk) + (size_t) kk * ldp] = d * rinv;
-                s_rinv[kk] = rinv;
-                if (dinv_out)
-                    dinv_out[k0 + kk] = rinv;
-            } else if (i > kk && i < pb) {
-                P[(k0 + i) + (size_t) kk * ldp] = l;
-            }
-            for (int j = kk + 1; j < pb; j++) {
-                const double lj = __shfl_sync(0xffffffffu, l, j);
-                if (i >= j && i < pb)
-                    P[(k0 + i) + (size_t) j * ldp] -= l * lj;
-            }
-            __syncwarp();
-        }
-    }
-    __syncthreads();
-}
-
-__device__ __forceinline__ void panel_trsm(double *P, int ldp, int k0, int pb, int m, const double *s_rinv)
+                                             double *dinv_out)
 {
     const int tid = threadIdx.x, nt = blockDim.x;
-    for (int i = k0 + pb + tid; i <= m; i += nt) {
-        double x[ASAM_PB];
-#pragma unroll
-        for (int j = 0; j < ASAM_PB; j++)
-            x[j] = (j < pb) ? P[i + (size_t) j * ldp] : 0.0;
-#pragma unroll
-        for (int j = 0; j < ASAM_PB; j++) {
-            if (j < pb) {
-                x[j] *= s_rinv[j];
-#pragma unroll
-                for (int j2 = j + 1; j2 < ASAM_PB; j2++)
-                    if (j2 < pb)
-                        x[j2] -= x[j] * P[(k0 + j2) + (size_t) j * ldp];
+    for (int c0 = 0; c0 < pb; c0 += 3) {
+        const int rb = k0 + c0; // front row of this 3x3 diagonal block
+        double *p0 = P + (size_t) c0 * ldp, *p1 = p0 + ldp, *p2 = p1 + ldp;
+        __syncthreads(); // previous in-panel update (or trailing update) is complete
+        const double a00 = p0[rb], a10 = p0[rb + 1], a20 = p0[rb + 2];
+        const double a11 = p1[rb + 1], a21 = p1[rb + 2], a22 = p2[rb + 2];
+        const double r0 = rsqrt(a00);
+        const double l10 = a10 * r0, l20 = a20 * r0;
+        const double d1 = a11 - l10 * l10;
+        const double r1 = rsqrt(d1);
+        const double l21 = (a21 - l20 * l10) * r1;
+        const double d2 = a22 - l20 * l20 - l21 * l21;
+        const double r2 = rsqrt(d2);
+        if (tid == 0 && !(a00 > 0.0 && d1 > 0.0 && d2 > 0.0))
+            atomicCAS(err, 0, 1 + sn_id);
+        // rows below the block: x = row * L11^-T  (the thread keeps x for the update below)
+        const int i_first = rb + 3 + tid;
+        for (int i = i_first; i <= m; i += nt) {
+            const double x0 = p0[i] * r0;
+            const double x1 = (p1[i] - x0 * l10) * r1;
+            const double x2 = (p2[i] - x0 * l20 - x1 * l21) * r2;
+            p0[i] = x0;
+            p1[i] = x1;
+            p2[i] = x2;
+        }
+        __syncthreads(); // every thread has read the diagonal block; L rows are visible
+        if (tid == 0) {
+            p0[rb] = a00 * r0; p0[rb + 1] = l10; p0[rb + 2] = l20;
+            p1[rb + 1] = d1 * r1; p1[rb + 2] = l21;
+            p2[rb + 2] = d2 * r2;
+            if (dinv_out) {
+                dinv_out[rb] = r0; dinv_out[rb + 1] = r1; dinv_out[rb + 2] = r2;
             }
         }
-#pragma unroll
-        for (int j = 0; j < ASAM_PB; j++)
-            if (j < pb)
-                P[i + (size_t) j * ldp] = x[j];
+        // rank-3 update of the remaining panel columns jc in (c0+2, pb): rows i >= k0 + jc
+        const int nrem = pb - (c0 + 3);
+        if (nrem > 0) {
+            for (int i = i_first; i <= m; i += nt) {
+                const double x0 = p0[i], x1 = p1[i], x2 = p2[i];
+                const int jmax = min(nrem, i - (rb + 3) + 1); // columns whose diagonal row <= i
+                for (int jj = 0; jj < jmax; jj++) {
+                    const int jr = rb + 3 + jj; // front row (= column) of panel column c0+3+jj
+                    double *pj = P + (size_t) (c0 + 3 + jj) * ldp;
+                    pj[i] -= x0 * p0[jr] + x1 * p1[jr] + x2 * p2[jr];
+                }
+            }
+        }
     }
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) k_factor(FacArgs a)
+__global__ void __launch_bounds__(256, 1) k_factor(FacArgs a)
 {
     extern __shared__ double sm[];
     __shared__ int s_task, s_abort;
     __shared__ asam_sn_desc_t s_cd[ASAM_MAX_CACHED_CHILDREN];
-    __shared__ double s_rinv[ASAM_PB];
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     int *err = a.ctrl + 1;
-
     for (;;) {
         if (tid == 0) {
             s_task = atomicAdd(&a.ctrl[0], 1);
@@ -472,17 +477,16 @@ __global__ void __launch_bounds__(256) k_factor(FacArgs a)
             for (int j = warp; j < cr; j += nwarps) {
                 const double *ccol = CF + (size_t) (cc + j) * cld + cc;
                 double *fcol = F + (size_t) dmap[j] * ld;
-                int i = j + lane;
-                for (; i + 96 <= cr; i += 128) { // four independent loads in flight per lane
-                    const double v0 = __ldcg(ccol + i), v1 = __ldcg(ccol + i + 32);
-                    const double v2 = __ldcg(ccol + i + 64), v3 = __ldcg(ccol + i + 96);
-                    fcol[dmap[i]] += v0;
-                    fcol[dmap[i + 32]] += v1;
-                    fcol[dmap[i + 64]] += v2;
-                    fcol[dmap[i + 96]] += v3;
+                for (int i0 = j + lane; i0 <= cr; i0 += 256) { // eight independent loads in flight per lane
+                    double v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++)
+                        v[u] = (i0 + 32 * u <= cr) ? __ldcg(ccol + i0 + 32 * u) : 0.0;
+#pragma unroll
+                    for (int u = 0; u < 8; u++)
+                        if (i0 + 32 * u <= cr)
+                            fcol[dmap[i0 + 32 * u]] += v[u];
                 }
-                for (; i <= cr; i += 32)
-                    fcol[dmap[i]] += __ldcg(ccol + i);
             }
             __syncthreads();
         }
@@ -497,21 +501,16 @@ __global__ void __launch_bounds__(256) k_factor(FacArgs a)
                 unsigned long long ta = 0, tb = 0;
                 if (a.trace && tid == 0)
                     ta = d_now();
-                panel_factor(P, ld, k0, pb, m, s, err, s_rinv, dinv);
-                if (a.trace && tid == 0)
-                    tb = d_now();
-                panel_trsm(P, ld, k0, pb, m, s_rinv);
+                panel_factor(P, ld, k0, pb, m, s, err, dinv);
                 if (a.trace && tid == 0) {
+                    tb = d_now();
                     accA += tb - ta;
-                    accB += d_now() - tb;
                 }
                 const int n = m - (k0 + pb);
-                if (n > 96)
-                    trailing_update<4>(F, ld, P, ld, pb, k0 + pb, m);
-                else if (n > 40)
-                    trailing_update<2>(F, ld, P, ld, pb, k0 + pb, m);
+                if (n > 48)
+                    trailing_update<2, 8>(F, ld, P, ld, pb, k0 + pb, m);
                 else
-                    trailing_update<1>(F, ld, P, ld, pb, k0 + pb, m);
+                    trailing_update<1, 4>(F, ld, P, ld, pb, k0 + pb, m);
                 __syncthreads();
             }
         } else {
@@ -519,8 +518,8 @@ __global__ void __launch_bounds__(256) k_factor(FacArgs a)
             const int avail = a.smem_doubles - ((ld + 1) / 2 + 2);
             int PB = avail / ld;
             PB = PB > ASAM_PB ? ASAM_PB : PB;
-            PB = PB - (PB % 4);
-            if (PB < 4) { // front too tall for even a 4-column panel (cannot happen below m ~ 6000)
+            PB = PB - (PB % 3);
+            if (PB < 3) { // front too tall for even a 4-column panel (cannot happen below m ~ 6000)
                 if (tid == 0)
                     atomicCAS(err, 0, -(1 + s));
                 break;
@@ -531,12 +530,11 @@ __global__ void __launch_bounds__(256) k_factor(FacArgs a)
                     for (int i = k0 + lane; i <= m; i += 32)
                         Pbuf[i + (size_t) p * ld] = F[i + (size_t) (k0 + p) * ld];
                 __syncthreads();
-                panel_factor(Pbuf, ld, k0, pb, m, s, err, s_rinv, dinv);
-                panel_trsm(Pbuf, ld, k0, pb, m, s_rinv);
+                panel_factor(Pbuf, ld, k0, pb, m, s, err, dinv);
                 for (int p = warp; p < pb; p += nwarps)
                     for (int i = k0 + lane; i <= m; i += 32)
                         F[i + (size_t) (k0 + p) * ld] = Pbuf[i + (size_t) p * ld];
-                trailing_update<4>(F, ld, Pbuf, ld, pb, k0 + pb, m);
+                trailing_update<4, 8>(F, ld, Pbuf, ld, pb, k0 + pb, m);
                 __syncthreads();
             }
         }
