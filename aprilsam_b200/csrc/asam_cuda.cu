@@ -61,7 +61,7 @@ struct asam_dev {
     Buf Adiag, Aoff, Bq, y, x, dinv;
     // plan
     Buf sn, ipool, arena;
-    Buf arrive, xdone;
+    Buf arrive, xdone, tbar;
     // task lists
     Buf tasks_full, nwait_full, btasks_full;
     int ntasks_full = 0;
@@ -232,7 +232,7 @@ ASAM_EXPORT void asam_dev_destroy(asam_dev_t *d)
     cudaStreamSynchronize(d->stream);
     Buf *all[] = { &d->f_type, &d->f_a, &d->f_b, &d->f_z, &d->f_W, &d->f_slot, &d->lp, &d->st, &d->node2q, &d->q2node,
                    &d->Adiag, &d->Aoff, &d->Bq, &d->y, &d->x, &d->dinv, &d->sn, &d->ipool, &d->arena, &d->arrive,
-                   &d->xdone, &d->tasks_full, &d->nwait_full, &d->btasks_full, &d->tasks_tmp, &d->nwait_tmp,
+                   &d->xdone, &d->tbar, &d->tasks_full, &d->nwait_full, &d->btasks_full, &d->tasks_tmp, &d->nwait_tmp,
                    &d->btasks_tmp, &d->ctrl, &d->partial, &d->patch_ids, &d->patch_desc, &d->pts, &d->flush, &d->trace_fac, &d->trace_bs };
     for (int i = 0; i < 2; i++)
         if (d->tev[i])
@@ -275,6 +275,7 @@ ASAM_EXPORT int asam_reserve(asam_dev_t *d, int n_nodes, int n_factors, int n_sl
     rc |= buf_reserve(d, d->sn, SN * sizeof(asam_sn_desc_t), true, false);
     rc |= buf_reserve(d, d->arrive, SN * sizeof(int), true, true);
     rc |= buf_reserve(d, d->xdone, SN * sizeof(int), true, true);
+    rc |= buf_reserve(d, d->tbar, SN * sizeof(int), true, true);
     rc |= buf_reserve(d, d->ipool, (size_t) ipool_ints * sizeof(int), true, false);
     rc |= buf_reserve(d, d->arena, (size_t) arena_doubles * sizeof(double), true, false);
     return rc;
@@ -434,6 +435,8 @@ static int launch_factor(asam_dev *d, int ntasks, const int *tasks_dev, const in
     if (ntasks <= 0)
         return 0;
     CK(cudaMemsetAsync(d->ctrl.p, 0, 2 * sizeof(int), d->stream)); // ticket, err
+    if (d->tbar.p)
+        CK(cudaMemsetAsync(d->tbar.p, 0, d->tbar.cap, d->stream)); // team barrier counters
     FacArgs a;
     a.sn = (const asam_sn_desc_t *) d->sn.p;
     a.ipool = (const int *) d->ipool.p;
@@ -445,6 +448,7 @@ static int launch_factor(asam_dev *d, int ntasks, const int *tasks_dev, const in
     a.y = (double *) d->y.p;
     a.dinv = (double *) d->dinv.p;
     a.arrive = (int *) d->arrive.p;
+    a.tbar = (int *) d->tbar.p;
     a.tasks = tasks_dev;
     a.nwait = nwait_dev;
     a.ntasks = ntasks;
@@ -512,19 +516,19 @@ static int launch_backsolve(asam_dev *d, int ntasks, const int *btasks_dev)
 }
 
 ASAM_EXPORT int asam_set_full_tasks(asam_dev_t *d, int ntasks, const int32_t *tasks, const int32_t *nwait,
-                                    const int32_t *btasks)
+                                    int nbtasks, const int32_t *btasks)
 {
     CK(cudaSetDevice(d->device));
-    size_t b = (size_t) ntasks * sizeof(int);
-    int headroom = ntasks / 2 + 1024; // room to prepend supernodes of poses appended later
+    size_t b = (size_t) ntasks * sizeof(int), bb = (size_t) nbtasks * sizeof(int);
+    int headroom = nbtasks / 2 + 1024; // room to prepend supernodes of poses appended later
     if (buf_reserve(d, d->tasks_full, b, false, false) || buf_reserve(d, d->nwait_full, b, false, false) ||
-        buf_reserve(d, d->btasks_full, b + (size_t) headroom * sizeof(int), false, false))
+        buf_reserve(d, d->btasks_full, bb + (size_t) headroom * sizeof(int), false, false))
         return 1;
     d->bt_cap = (int) (d->btasks_full.cap / sizeof(int));
-    d->bt_start = d->bt_cap - ntasks;
-    d->bt_count = ntasks;
+    d->bt_start = d->bt_cap - nbtasks;
+    d->bt_count = nbtasks;
     if (upload(d, d->tasks_full.p, tasks, b) || upload(d, d->nwait_full.p, nwait, b) ||
-        upload(d, (int *) d->btasks_full.p + d->bt_start, btasks, b))
+        upload(d, (int *) d->btasks_full.p + d->bt_start, btasks, bb))
         return 1;
     d->ntasks_full = ntasks;
     return 0;

@@ -247,7 +247,8 @@ struct FacArgs {
     double *y;
     double *dinv; // 1/L_kk in elimination order (used by k_backsolve)
     int *arrive;
-    const int *tasks, *nwait;
+    int *tbar; // team barrier counters, zeroed before the launch
+    const int *tasks, *nwait; // nwait: bits 0-19 children in this launch, 20-25 worker, 26-30 team size
     int ntasks;
     int *ctrl; // [0] ticket, [1] err
     int smem_doubles;
@@ -375,6 +376,276 @@ __device__ __forceinline__ void panel_factor(double *P, int ldp, int k0, int pb,
     __syncthreads();
 }
 
+// ------------------------------------------------------------------------------------------
+// Big fronts: a TEAM of G CTAs (consecutive tickets of the same supernode) factors one front that
+// does not fit in shared memory.  The front stays in HBM/L2; phases are separated by a team
+// barrier on a per-supernode counter (tbar, zeroed by the host before the launch):
+//   assemble own columns -> [barrier] -> extend-add into own columns -> [barrier] ->
+//   per panel of <= ASAM_TPB columns: { every worker factors the diagonal block redundantly in
+//   shared memory, TRSMs its 256-row chunks of the panel } -> [barrier] -> { 256 x 64 tiles of
+//   the trailing update, L operands staged in shared memory, round-robin over workers } -> [barrier]
+// Column / chunk / tile ownership is a fixed function of (worker, team size): deterministic.
+// All reads of front data written by other workers bypass L1 (ld.global.cg).
+// ------------------------------------------------------------------------------------------
+#define ASAM_TPB 48   // panel width of the team path
+#define ASAM_TROWS 256
+#define ASAM_TCOLS 64
+
+struct TeamCtx {
+    int *tbar_s;
+    int G, w, phase;
+    long long spin_limit;
+    int *err;
+    int sn;
+};
+
+__device__ __forceinline__ bool team_barrier(TeamCtx &tc, int *s_flag)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(tc.tbar_s, 1);
+        const int target = (++tc.phase) * tc.G;
+        long long spins = 0;
+        int ok = 1;
+        while (ld_volatile(tc.tbar_s) < target) {
+            __nanosleep(32);
+            if (++spins > tc.spin_limit || ld_volatile(tc.err) < 0) {
+                atomicCAS(tc.err, 0, -(1 + tc.sn));
+                ok = 0;
+                break;
+            }
+        }
+        __threadfence();
+        *s_flag = ok;
+    } else {
+        tc.phase++;
+    }
+    __syncthreads();
+    return *s_flag != 0;
+}
+
+__device__ __forceinline__ bool team_owns(int col, int w, int G) { return ((col >> 2) % G) == w; }
+
+// returns false on abort
+__device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int nw, int w, int G, double *sm,
+                           int *s_flag)
+{
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    const int m = 3 * d.mb, c = 3 * d.cb, ld = m + 1;
+    const int *seg = a.ipool + d.seg;
+    const int *children = seg + 2 * d.mb;
+    const int *a_slot = children + d.ch_cnt;
+    const int *a_rb = a_slot + d.a_cnt;
+    const int *a_cb = a_rb + d.a_cnt;
+    double *F = a.arena + d.f_off;
+    int *err = a.ctrl + 1;
+    TeamCtx tc;
+    tc.tbar_s = a.tbar + s;
+    tc.G = G;
+    tc.w = w;
+    tc.phase = 0;
+    tc.spin_limit = a.spin_limit;
+    tc.err = err;
+    tc.sn = s;
+
+    // ---- assemble own columns ------------------------------------------------------------
+    for (int j = warp; j < m; j += nwarps) {
+        if (!team_owns(j, w, G))
+            continue;
+        for (int i = j + lane; i <= m; i += 32)
+            F[i + (size_t) j * ld] = 0.0;
+    }
+    __syncthreads();
+    for (int e = tid; e < d.cb * 9; e += nt) {
+        int k = e / 9, p = (e % 9) / 3, q = e % 3;
+        if (p >= q && team_owns(3 * k + q, w, G))
+            F[(3 * k + p) + (size_t) (3 * k + q) * ld] = a.Adiag[9 * (size_t) a.q2node[d.first + k] + q * 3 + p];
+    }
+    for (int e = tid; e < c; e += nt)
+        if (team_owns(e, w, G))
+            F[m + (size_t) e * ld] = a.Bq[3 * (size_t) a.q2node[d.first + e / 3] + e % 3];
+    for (int e = tid; e < d.a_cnt * 9; e += nt) {
+        int i = e / 9, p = (e % 9) / 3, q = e % 3;
+        const int col = 3 * a_cb[i] + q;
+        if (!team_owns(col, w, G))
+            continue;
+        const int rbf = a_rb[i];
+        const int rb = rbf & ~ASAM_TR_FLAG;
+        const int si = (rbf & ASAM_TR_FLAG) ? (p * 3 + q) : (q * 3 + p);
+        F[(3 * rb + p) + (size_t) col * ld] = a.Aoff[9 * (size_t) a_slot[i] + si];
+    }
+    // worker 0 waits for the children re-factored in this launch; the barrier releases the rest
+    if (w == 0 && nw > 0 && tid == 0) {
+        long long spins = 0;
+        while (ld_volatile(&a.arrive[s]) < nw) {
+            __nanosleep(32);
+            if (++spins > a.spin_limit || ld_volatile(err) < 0) {
+                atomicCAS(err, 0, -(1 + s));
+                break;
+            }
+        }
+        a.arrive[s] = 0;
+    }
+    if (!team_barrier(tc, s_flag))
+        return false;
+
+    // ---- extend-add into own columns -------------------------------------------------------
+    int *dmap = (int *) sm; // ld ints
+    for (int ci = 0; ci < d.ch_cnt; ++ci) {
+        const asam_sn_desc_t cd = a.sn[children[ci]];
+        const int cm = 3 * cd.mb, cc = 3 * cd.cb, cr = cm - cc, cld = cm + 1;
+        const double *CF = a.arena + cd.f_off;
+        const int *crel = a.ipool + cd.seg + cd.mb;
+        for (int i = tid; i <= cr; i += nt)
+            dmap[i] = (i < cr) ? 3 * crel[(cc + i) / 3] + (cc + i) % 3 : m;
+        __syncthreads();
+        for (int j = warp; j < cr; j += nwarps) {
+            const int dj = dmap[j];
+            if (!team_owns(dj, w, G))
+                continue;
+            const double *ccol = CF + (size_t) (cc + j) * cld + cc;
+            double *fcol = F + (size_t) dj * ld;
+            for (int i0 = j + lane; i0 <= cr; i0 += 128) {
+                double v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    v[u] = (i0 + 32 * u <= cr) ? __ldcg(ccol + i0 + 32 * u) : 0.0;
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (i0 + 32 * u <= cr)
+                        fcol[dmap[i0 + 32 * u]] += v[u];
+            }
+        }
+        __syncthreads();
+    }
+    if (!team_barrier(tc, s_flag))
+        return false;
+
+    // ---- panels ---------------------------------------------------------------------------------
+    double *D = sm;                              // ASAM_TPB x ASAM_TPB diagonal block, ld = pb
+    double *Li = sm + ASAM_TPB * ASAM_TPB;       // ASAM_TROWS x pb   (row chunk / row tile)
+    double *Lj = Li + ASAM_TROWS * ASAM_TPB;     // ASAM_TCOLS x pb   (column tile)
+    double *dinv = a.dinv + 3 * (size_t) d.first;
+    for (int k0 = 0; k0 < c; k0 += ASAM_TPB) {
+        const int pb = min(ASAM_TPB, c - k0);
+        // diagonal block, factored redundantly by every worker (closed-form 3x3 steps)
+        for (int e = tid; e < pb * pb; e += nt) {
+            const int i = e % pb, j = e / pb;
+            D[e] = (i >= j) ? __ldcg(&F[(k0 + i) + (size_t) (k0 + j) * ld]) : 0.0;
+        }
+        __syncthreads();
+        panel_factor(D, pb, 0, pb, pb - 1, s, err, nullptr);
+        // TRSM: 256-row chunks of the rows below the block (row m = rhs included), round-robin
+        const int r_first = k0 + pb;
+        const int nchunk = (m - r_first + 1 + ASAM_TROWS - 1) / ASAM_TROWS;
+        for (int ch = w; ch < nchunk; ch += G) {
+            const int i = r_first + ch * ASAM_TROWS + tid;
+            __syncthreads();
+            if (i <= m) {
+                for (int j = 0; j < pb; j++) {
+                    double v = __ldcg(&F[i + (size_t) (k0 + j) * ld]);
+                    for (int p = 0; p < j; p++)
+                        v -= Li[tid + p * ASAM_TROWS] * D[j + p * pb];
+                    v /= D[j + j * pb];
+                    Li[tid + j * ASAM_TROWS] = v;
+                    F[i + (size_t) (k0 + j) * ld] = v;
+                }
+            }
+        }
+        if (!team_barrier(tc, s_flag))
+            return false;
+        // every worker has read the unfactored diagonal block by now: worker 0 may overwrite it
+        if (w == 0) {
+            for (int e = tid; e < pb * pb; e += nt) {
+                const int i = e % pb, j = e / pb;
+                if (i >= j)
+                    F[(k0 + i) + (size_t) (k0 + j) * ld] = D[e];
+            }
+            for (int e = tid; e < pb; e += nt)
+                dinv[k0 + e] = 1.0 / D[e + e * pb];
+        }
+
+        // trailing update: tiles of 256 rows x 64 columns over the lower trapezoid
+        const int j0 = k0 + pb;
+        int u = 0;
+        for (int cb0 = j0; cb0 < m; cb0 += ASAM_TCOLS) {
+            for (int rb0 = cb0; rb0 <= m; rb0 += ASAM_TROWS, ++u) {
+                if (u % G != w)
+                    continue;
+                __syncthreads();
+                const int ncol = min(ASAM_TCOLS, m - cb0), nrow = min(ASAM_TROWS, m - rb0 + 1);
+                for (int e = tid; e < ncol * pb; e += nt) {
+                    const int jj = e % ncol, p = e / ncol;
+                    Lj[jj + p * ASAM_TCOLS] = __ldcg(&F[(cb0 + jj) + (size_t) (k0 + p) * ld]);
+                }
+                for (int e = tid; e < nrow * pb; e += nt) {
+                    const int ii = e % nrow, p = e / nrow;
+                    Li[ii + p * ASAM_TROWS] = __ldcg(&F[(rb0 + ii) + (size_t) (k0 + p) * ld]);
+                }
+                __syncthreads();
+                // warp -> 8 columns, lane -> rows lane + 32 r (two passes of 128 rows)
+                const int tj = 8 * warp;
+                if (tj < ncol) {
+                    for (int ib = 0; ib < nrow; ib += 128) {
+                        double acc[4][8];
+                        int ir[4];
+#pragma unroll
+                        for (int r = 0; r < 4; r++) {
+                            ir[r] = min(ib + lane + 32 * r, nrow - 1);
+#pragma unroll
+                            for (int q = 0; q < 8; q++)
+                                acc[r][q] = 0.0;
+                        }
+#pragma unroll 2
+                        for (int p = 0; p < pb; p++) {
+                            double b[8], av[4];
+#pragma unroll
+                            for (int q = 0; q < 8; q++)
+                                b[q] = Lj[min(tj + q, ncol - 1) + p * ASAM_TCOLS];
+#pragma unroll
+                            for (int r = 0; r < 4; r++)
+                                av[r] = Li[ir[r] + p * ASAM_TROWS];
+#pragma unroll
+                            for (int r = 0; r < 4; r++)
+#pragma unroll
+                                for (int q = 0; q < 8; q++)
+                                    acc[r][q] += av[r] * b[q];
+                        }
+#pragma unroll
+                        for (int r = 0; r < 4; r++)
+#pragma unroll
+                            for (int q = 0; q < 8; q++) {
+                                const int ii = ib + lane + 32 * r, jj = tj + q;
+                                const int i = rb0 + ii, j = cb0 + jj;
+                                if (ii < nrow && jj < ncol && i >= j) {
+                                    double *cp = &F[i + (size_t) j * ld];
+                                    *cp = __ldcg(cp) - acc[r][q];
+                                }
+                            }
+                    }
+                }
+            }
+        }
+        if (!team_barrier(tc, s_flag))
+            return false;
+    }
+
+    // ---- publish ------------------------------------------------------------------------------------
+    if (w == 0) {
+        for (int e = tid; e < c; e += nt)
+            a.y[3 * (size_t) d.first + e] = __ldcg(&F[m + (size_t) e * ld]);
+        __syncthreads();
+        if (tid == 0 && d.parent >= 0) {
+            __threadfence();
+            atomicAdd(&a.arrive[d.parent], 1);
+        }
+    }
+    __syncthreads();
+    return true;
+}
+
 __global__ void __launch_bounds__(256, 1) k_factor(FacArgs a)
 {
     extern __shared__ double sm[];
@@ -396,8 +667,21 @@ __global__ void __launch_bounds__(256, 1) k_factor(FacArgs a)
         if (a.trace && tid == 0)
             tr0 = d_now();
         const int s = a.tasks[t];
-        const int nw = a.nwait[t];
+        const int nwp = a.nwait[t];
+        const int nw = nwp & 0xfffff, tw = (nwp >> 20) & 0x3f, tG = (nwp >> 26) & 0x1f;
         const asam_sn_desc_t d = a.sn[s];
+        if (tG > 1) { // one worker of a multi-CTA team
+            if (!team_front(a, d, s, nw, tw, tG, sm, &s_abort))
+                break;
+            if (a.trace && tid == 0) {
+                unsigned long long *tr = a.trace + 8 * (size_t) t;
+                tr[0] = tr0; tr[1] = tr0; tr[2] = tr0; tr[3] = tr0; tr[4] = d_now(); tr[5] = tr[4];
+                tr[6] = (unsigned long long) s;
+                tr[7] = (unsigned long long) (unsigned) (3 * d.mb);
+            }
+            __syncthreads();
+            continue;
+        }
         const int m = 3 * d.mb, c = 3 * d.cb, ld = m + 1;
         const int *seg = a.ipool + d.seg;
         const int *children = seg + 2 * d.mb;

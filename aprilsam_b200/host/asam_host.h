@@ -94,8 +94,9 @@ typedef struct {
     int64_t arena_n;  /* doubles used in the device arena */
     int max_m;        /* largest front order (scalars)  */
 
-    /* full task lists (batch) */
+    /* full task lists (batch): ntasks entries of tasks/nwait (teams expanded), nsn of btasks */
     int *tasks, *nwait, *btasks;
+    int ntasks;
 
     /* statistics of the last build */
     int64_t nnz_l_blocks; /* sum over nodes of (1 + |below|) */

@@ -77,8 +77,8 @@ ASAM_API const int *asam_dbg_plan_array(void *p, int which, int64_t *count)
     case 5: *count = pl->n_factors; return pl->fslot;
     case 6: *count = pl->N; return pl->sn_of_q;
     case 7: *count = pl->ipool_host.n; return pl->ipool_host.p;
-    case 8: *count = pl->tasks ? pl->nsn : 0; return pl->tasks;
-    case 9: *count = pl->nwait ? pl->nsn : 0; return pl->nwait;
+    case 8: *count = pl->tasks ? pl->ntasks : 0; return pl->tasks;
+    case 9: *count = pl->nwait ? pl->ntasks : 0; return pl->nwait;
     case 10: *count = pl->btasks ? pl->nsn : 0; return pl->btasks;
     case 11: *count = 12 * (int64_t) pl->nsn; return (const int *) pl->desc;
     default: *count = 0; return NULL;

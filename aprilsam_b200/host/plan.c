@@ -20,6 +20,8 @@
 
 #include "asam_host.h"
 
+#define RELAX_Z 2     /* relaxed amalgamation: missing block rows tolerated per merge */
+#define RELAX_FILL 24 /* ... and explicit zero blocks (3x3) added per merge */
 #define MAX_SN_COLS 32 /* block columns per supernode: L11 (96x96) fits k_backsolve shared memory */
 
 /* ---- pair map ---------------------------------------------------------------------------- */
@@ -271,6 +273,24 @@ static void emit_segment(plan_t *pl, int s, ivec_t *buf, int64_t base)
     buf->n += h->a_slot.n;
 }
 
+/* CTAs that share one front in k_factor: fronts that fit in shared memory (200 KB) take one;
+ * larger ones get one CTA per ~3 MFLOP of elimination work, at most 31. */
+static int team_size(int mb, int cb)
+{
+    int64_t m = 3 * (int64_t) mb, c = 3 * (int64_t) cb;
+    if ((m + 1) * m + (m + 2) / 2 + 2 <= 25600)
+        return 1;
+    double fl = (double) c * (double) m * (double) m;
+    int G = (int) (fl / 3.0e6) + 1;
+    if (G < 2)
+        G = 2;
+    if (G > 31)
+        G = 31;
+    return G;
+}
+
+static inline int pack_nwait(int nw, int w, int G) { return (nw & 0xfffff) | (w << 20) | (G << 26); }
+
 static int64_t front_doubles(int mb)
 {
     int64_t m = 3 * (int64_t) mb;
@@ -401,7 +421,34 @@ static int plan_build_impl(plan_t *pl, asam_dev_t *dev, int N, int n_factors, co
     free(adj);
     free(adj_ptr);
 
-    /* 5. post-order -> numeric positions q */
+    /* 5. post-order -> numeric positions q.  Children are visited in ascending structure
+     * size so that the child with the largest front is numbered right before its parent and can
+     * share a supernode with it (step 6). */
+    {
+        int *kids = malloc(sizeof(int) * (size_t) N);
+        for (int p = 0; p < N; p++) {
+            int n = 0;
+            for (int c = head[p]; c >= 0; c = next[c])
+                kids[n++] = c;
+            if (n < 2)
+                continue;
+            for (int i = 1; i < n; i++) { /* insertion sort by (|below|, position) */
+                int v = kids[i], j = i - 1;
+                int64_t kv = bptr[v + 1] - bptr[v];
+                while (j >= 0 && (bptr[kids[j] + 1] - bptr[kids[j]]) > kv) {
+                    kids[j + 1] = kids[j];
+                    j--;
+                }
+                kids[j + 1] = v;
+            }
+            head[p] = kids[0];
+            for (int i = 0; i + 1 < n; i++)
+                next[kids[i]] = kids[i + 1];
+            next[kids[n - 1]] = -1;
+            tail[p] = kids[n - 1];
+        }
+        free(kids);
+    }
     int *qpos = malloc(sizeof(int) * (size_t) N), *pofq = malloc(sizeof(int) * (size_t) N);
     {
         int *stack = malloc(sizeof(int) * (size_t) N), *it = malloc(sizeof(int) * (size_t) N);
@@ -436,7 +483,10 @@ static int plan_build_impl(plan_t *pl, asam_dev_t *dev, int N, int n_factors, co
         pl->q2node[qpos[p]] = pl->order[p];
     }
 
-    /* 6. supernodes (fundamental chains, capped width) */
+    /* 6. supernodes: a node joins the supernode of the child numbered right before it when the
+     * child's structure is the node's structure plus itself (fundamental), or misses at most
+     * RELAX_Z block rows of it (relaxed amalgamation: a few explicit zero blocks buy fewer, fatter
+     * fronts and a shorter dependency chain); width capped at MAX_SN_COLS. */
     pl->nsn = 0;
     pl->nnz_l_blocks = 0;
     pl->flops = 0.0;
@@ -452,7 +502,10 @@ static int plan_build_impl(plan_t *pl, asam_dev_t *dev, int N, int n_factors, co
         if (q > 0 && pl->nsn > 0) {
             int pp = pofq[q - 1];
             int nbp = (int) (bptr[pp + 1] - bptr[pp]);
-            if (parent[pp] == p && nchild[p] == 1 && nbp == nb + 1 && pl->desc[pl->nsn - 1].cb < MAX_SN_COLS)
+            int z = nb + 1 - nbp; /* block rows of {p} + below(p) missing from below(pp); >= 0 */
+            int gcb = pl->desc[pl->nsn - 1].cb;
+            if (parent[pp] == p && gcb < MAX_SN_COLS &&
+                (z == 0 || (z <= RELAX_Z && (int64_t) z * gcb <= RELAX_FILL)))
                 merge = 1;
         }
         if (merge) {
@@ -543,23 +596,34 @@ static int plan_build_impl(plan_t *pl, asam_dev_t *dev, int N, int n_factors, co
     }
     pl->ipool_n = seg.n;
 
-    pl->tasks = malloc(sizeof(int) * (size_t) pl->nsn);
-    pl->nwait = malloc(sizeof(int) * (size_t) pl->nsn);
     pl->btasks = malloc(sizeof(int) * (size_t) pl->nsn);
     {
-        /* counting sort by level, ids ascending inside a level */
+        /* counting sort by level, ids ascending inside a level; big fronts expand into teams */
+        int *byl = malloc(sizeof(int) * (size_t) pl->nsn);
         int *cnt = calloc((size_t) pl->n_levels + 1, sizeof(int));
-        for (int s = 0; s < pl->nsn; s++)
+        int64_t total = 0;
+        for (int s = 0; s < pl->nsn; s++) {
             cnt[pl->desc[s].level + 1]++;
+            total += team_size(pl->desc[s].mb, pl->desc[s].cb);
+        }
         for (int l = 0; l < pl->n_levels; l++)
             cnt[l + 1] += cnt[l];
         for (int s = 0; s < pl->nsn; s++)
-            pl->tasks[cnt[pl->desc[s].level]++] = s;
+            byl[cnt[pl->desc[s].level]++] = s;
         free(cnt);
-        for (int t = 0; t < pl->nsn; t++) {
-            pl->nwait[t] = pl->desc[pl->tasks[t]].ch_cnt;
-            pl->btasks[pl->nsn - 1 - t] = pl->tasks[t];
+        pl->ntasks = (int) total;
+        pl->tasks = malloc(sizeof(int) * (size_t) total);
+        pl->nwait = malloc(sizeof(int) * (size_t) total);
+        int t = 0;
+        for (int k = 0; k < pl->nsn; k++) {
+            int s = byl[k], G = team_size(pl->desc[s].mb, pl->desc[s].cb);
+            for (int w = 0; w < G; w++, t++) {
+                pl->tasks[t] = s;
+                pl->nwait[t] = pack_nwait(pl->desc[s].ch_cnt, w, G > 1 ? G : 0);
+            }
+            pl->btasks[pl->nsn - 1 - k] = s;
         }
+        free(byl);
     }
 
     /* host mirror of the device int pool (debug / tests) */
@@ -586,7 +650,7 @@ static int plan_build_impl(plan_t *pl, asam_dev_t *dev, int N, int n_factors, co
     rc |= asam_upload_node2q(dev, 0, N, pl->node2q);
     rc |= asam_upload_q2node(dev, 0, N, pl->q2node);
     rc |= asam_upload_fslot(dev, 0, n_factors, pl->fslot);
-    rc |= asam_set_full_tasks(dev, pl->nsn, pl->tasks, pl->nwait, pl->btasks);
+    rc |= asam_set_full_tasks(dev, pl->ntasks, pl->tasks, pl->nwait, pl->nsn, pl->btasks);
     free(ids);
     ivec_free(&seg);
     return rc;
@@ -875,6 +939,26 @@ int plan_append(plan_t *pl, asam_dev_t *dev, int N, int n_factors, const int *ft
             free(tasks);
             free(nwait);
         } else {
+            /* expand big fronts into teams of consecutive entries */
+            int total = 0;
+            for (int t = 0; t < nt; t++)
+                total += team_size(pl->desc[tasks[t]].mb, pl->desc[tasks[t]].cb);
+            if (total != nt) {
+                int *t2 = malloc(sizeof(int) * (size_t) total), *w2 = malloc(sizeof(int) * (size_t) total);
+                int k = 0;
+                for (int t = 0; t < nt; t++) {
+                    int G = team_size(pl->desc[tasks[t]].mb, pl->desc[tasks[t]].cb);
+                    for (int w = 0; w < G; w++, k++) {
+                        t2[k] = tasks[t];
+                        w2[k] = pack_nwait(nwait[t], w, G > 1 ? G : 0);
+                    }
+                }
+                free(tasks);
+                free(nwait);
+                tasks = t2;
+                nwait = w2;
+                nt = total;
+            }
             *tasks_out = tasks;
             *nwait_out = nwait;
             *ntasks_out = nt;
