@@ -912,16 +912,19 @@ __global__ void __launch_bounds__(128) k_backsolve(BsArgs a)
         double *Ls = sm + m + c;
         const long long room = (long long) a.smem_doubles - (m + c);
         // staging mode: 2 = whole panel (m x c, ld m), 1 = L11 only (c x c, ld c), 0 = none
-        const int mode = ((long long) m * c <= room) ? 2 : (((long long) c * c <= room) ? 1 : 0);
-        const int ll = mode == 2 ? m : (mode == 1 ? c : ld);
+        // staged leading dimensions are ODD: the triangular solve reads row k across columns
+        // (stride ll doubles), an even stride would pile the lanes onto a few banks
+        const int lm = m | 1, lc = c | 1;
+        const int mode = ((long long) lm * c <= room) ? 2 : (((long long) lc * c <= room) ? 1 : 0);
+        const int ll = mode == 2 ? lm : (mode == 1 ? lc : ld);
         if (mode == 2) {
             for (int k = warp; k < c; k += nwarps)
                 for (int i = k + lane; i < m; i += 32)
-                    Ls[i + (size_t) k * m] = Lg[i + (size_t) k * ld];
+                    Ls[i + (size_t) k * lm] = Lg[i + (size_t) k * ld];
         } else if (mode == 1) {
             for (int k = warp; k < c; k += nwarps)
                 for (int i = k + lane; i < c; i += 32)
-                    Ls[i + (size_t) k * c] = Lg[i + (size_t) k * ld];
+                    Ls[i + (size_t) k * lc] = Lg[i + (size_t) k * ld];
         }
         for (int k = tid; k < c; k += nt) {
             w[k] = a.y[3 * (size_t) d.first + k];
@@ -955,15 +958,19 @@ __global__ void __launch_bounds__(128) k_backsolve(BsArgs a)
         // w_k -= sum_i L21[i, k] * xs[i]   (one warp per column, two accumulators)
         if (r > 0) {
             for (int k = warp; k < c; k += nwarps) {
-                const double *lk = (mode == 2) ? (Ls + (size_t) k * m + c) : (Lg + (size_t) k * ld + c);
+                const double *lk = (mode == 2) ? (Ls + (size_t) k * lm + c) : (Lg + (size_t) k * ld + c);
                 double acc0 = 0.0, acc1 = 0.0;
-                int i = lane;
-                for (; i + 32 < r; i += 64) {
-                    acc0 += lk[i] * xs[i];
-                    acc1 += lk[i + 32] * xs[i + 32];
+                for (int i0 = lane; i0 < r; i0 += 256) { // eight independent loads in flight per lane
+                    double v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++)
+                        v[u] = (i0 + 32 * u < r) ? lk[i0 + 32 * u] : 0.0;
+#pragma unroll
+                    for (int u = 0; u < 8; u += 2) {
+                        acc0 += v[u] * xs[min(i0 + 32 * u, r - 1)];
+                        acc1 += v[u + 1] * xs[min(i0 + 32 * (u + 1), r - 1)];
+                    }
                 }
-                if (i < r)
-                    acc0 += lk[i] * xs[i];
                 acc0 += acc1;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1)

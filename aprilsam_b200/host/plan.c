@@ -708,7 +708,7 @@ int plan_append(plan_t *pl, asam_dev_t *dev, int N, int n_factors, const int *ft
         pl->node2q[i] = i;
         pl->q2node[i] = i;
         pl->parent_pos[i] = -1;
-        pl->sn_of_q[i] = nsn0 + (i - N0);
+        pl->sn_of_q[i] = -1; /* assigned below: joins the root supernode or gets a new one */
     }
 
     /* new Hessian slots */
@@ -790,9 +790,7 @@ int plan_append(plan_t *pl, asam_dev_t *dev, int N, int n_factors, const int *ft
             pl->arena_n += d->reserved;
         }
         if (d->parent < 0 && gain[i].n > 0) { /* old root: hangs under the first new pose */
-            int P = nsn0 + (gain[i].p[0] - N0);
-            d->parent = P;
-            ivec_push(&pend[P - nsn0], s);
+            ivec_push(&pend[gain[i].p[0] - N0], s); /* supernode id of that pose: set below */
             int top = pl->q2node[d->first + d->cb - 1];
             pl->parent_pos[pl->pos[top]] = gain[i].p[0]; /* pos == q == id for new poses */
         }
@@ -815,78 +813,117 @@ int plan_append(plan_t *pl, asam_dev_t *dev, int N, int n_factors, const int *ft
         ivec_push(&h->a_cb, pl->node2q[lo] - pl->desc[s].first);
     }
 
-    /* new poses: singleton supernodes, ascending */
+    /* new poses, ascending.  A pose whose predecessor in the order tops a root supernode with
+     * exactly the structure {pose} + below(pose) becomes one more COLUMN of that supernode
+     * (fundamental merge) -- otherwise every step would add one more link to the chain at the top
+     * of the tree; any other pose starts a singleton supernode. */
+    int *nsid = malloc(sizeof(int) * (size_t) (nnew + 1));
+    int ncreated = 0;
     for (int j = 0; j < nnew; j++) {
-        int n = N0 + j, sid = nsn0 + j;
-        asam_sn_desc_t *d = &pl->desc[sid];
-        sn_host_t *h = &pl->snh[sid];
-        memset(d, 0, sizeof(*d));
-        d->first = n;
-        d->cb = 1;
-        d->parent = -1;
+        int n = N0 + j;
         ivec_t *bel = &nbelow[j];
+        int lvl = 0;
         for (int c = 0; c < pend[j].n; c++) {
             int X = pend[j].p[c];
             const sn_host_t *hx = &pl->snh[X];
             for (int e = pl->desc[X].cb; e < hx->rows.n; e++)
                 if (hx->rows.p[e] != n)
                     ivec_push(bel, hx->rows.p[e]);
-            int lv = pl->desc[X].level + 1;
-            if (lv > d->level)
-                d->level = lv;
+            if (pl->desc[X].level + 1 > lvl)
+                lvl = pl->desc[X].level + 1;
         }
         bel->n = sort_unique(bel->p, bel->n);
-        h->rows.n = 0;
-        ivec_push(&h->rows, n);
-        for (int e = 0; e < bel->n; e++)
-            ivec_push(&h->rows, bel->p[e]);
-        h->children.n = 0;
-        for (int c = 0; c < pend[j].n; c++)
-            ivec_push(&h->children, pend[j].p[c]);
-        h->a_slot.n = h->a_rb.n = h->a_cb.n = 0;
-        d->mb = h->rows.n;
-        if (3 * d->mb > pl->max_m)
-            pl->max_m = 3 * d->mb;
-        d->reserved = front_doubles(d->mb + 4);
-        d->f_off = pl->arena_n;
-        pl->arena_n += d->reserved;
+        int R = n > 0 ? pl->sn_of_q[n - 1] : -1, sid = -1;
+        if (R >= 0 && pl->desc[R].cb < MAX_SN_COLS && pl->desc[R].first + pl->desc[R].cb == n &&
+            pl->snh[R].rows.n - pl->desc[R].cb == 1 + bel->n) {
+            for (int c = 0; c < pend[j].n; c++)
+                if (pend[j].p[c] == R)
+                    sid = R;
+        }
+        if (sid >= 0) { /* n joins R: the row list already holds n right after R's columns */
+            asam_sn_desc_t *d = &pl->desc[R];
+            sn_host_t *h = &pl->snh[R];
+            d->cb += 1;
+            for (int c = 0; c < pend[j].n; c++) {
+                int X = pend[j].p[c];
+                if (X == R)
+                    continue;
+                ivec_push(&h->children, X);
+                pl->desc[X].parent = R;
+            }
+            if (lvl > d->level)
+                d->level = lvl;
+            d->parent = -1;
+        } else {
+            sid = pl->nsn++;
+            ncreated++;
+            asam_sn_desc_t *d = &pl->desc[sid];
+            sn_host_t *h = &pl->snh[sid];
+            memset(d, 0, sizeof(*d));
+            d->first = n;
+            d->cb = 1;
+            d->parent = -1;
+            d->level = lvl;
+            h->rows.n = 0;
+            ivec_push(&h->rows, n);
+            for (int e = 0; e < bel->n; e++)
+                ivec_push(&h->rows, bel->p[e]);
+            h->children.n = 0;
+            for (int c = 0; c < pend[j].n; c++) {
+                ivec_push(&h->children, pend[j].p[c]);
+                pl->desc[pend[j].p[c]].parent = sid;
+            }
+            h->a_slot.n = h->a_rb.n = h->a_cb.n = 0;
+            d->mb = h->rows.n;
+            if (3 * d->mb > pl->max_m)
+                pl->max_m = 3 * d->mb;
+            d->reserved = front_doubles(d->mb + 4);
+            d->f_off = pl->arena_n;
+            pl->arena_n += d->reserved;
+        }
+        nsid[j] = sid;
+        pl->sn_of_q[n] = sid;
         if (bel->n > 0) {
-            int P = nsn0 + (bel->p[0] - N0);
-            d->parent = P;
-            ivec_push(&pend[P - nsn0], sid);
+            ivec_push(&pend[bel->p[0] - N0], sid);
             pl->parent_pos[n] = bel->p[0];
         }
-        if (d->level + 1 > pl->n_levels)
-            pl->n_levels = d->level + 1;
+        if (pl->desc[sid].level + 1 > pl->n_levels)
+            pl->n_levels = pl->desc[sid].level + 1;
     }
-    pl->nsn = nsn0 + nnew;
     for (int k = 0; k < nlo.n; k++) { /* (new,new) blocks */
         int lo = nlo.p[k], hi = nhi.p[k];
         if (lo < N0)
             continue;
-        int s = nsn0 + (lo - N0);
+        int s = nsid[lo - N0];
         sn_host_t *h = &pl->snh[s];
         int rb = find_sorted(h->rows.p, h->rows.n, hi);
         if (rb < 0) {
             asam_set_error("plan_append: internal (row %d not in new supernode %d)", hi, s);
             rc = 1;
+            free(nsid);
             goto done;
         }
         ivec_push(&h->a_slot, slot0 + k);
         ivec_push(&h->a_rb, rb);
-        ivec_push(&h->a_cb, 0);
+        ivec_push(&h->a_cb, lo - pl->desc[s].first);
     }
 
     /* relative indices + segments of everything that changed */
     {
-        int nt = nm + nnew;
+        int nt = nm + ncreated;
         int *tasks = malloc(sizeof(int) * (size_t) (nt + 1)), *nwait = malloc(sizeof(int) * (size_t) (nt + 1));
         for (int i = 0; i < nm; i++)
             tasks[i] = msn[i];
-        for (int j = 0; j < nnew; j++) {
-            tasks[nm + j] = nsn0 + j;
-            mark_idx[nsn0 + j] = nm + j;
+        for (int k = 0; k < ncreated; k++) { /* created supernodes have ids nsn0 .. nsn0+ncreated-1 */
+            tasks[nm + k] = nsn0 + k;
+            mark_idx[nsn0 + k] = nm + k;
         }
+        for (int j = 0; j < nnew; j++) /* a pose may have joined a supernode that was not marked */
+            if (mark_idx[nsid[j]] < 0) {
+                asam_set_error("plan_append: pose %d joined unmarked supernode %d", N0 + j, nsid[j]);
+                rc = 1;
+            }
+        free(nsid);
         ivec_t seg = { 0 };
         for (int t = 0; t < nt && !rc; t++)
             rc |= compute_rel(pl, tasks[t]);
@@ -920,11 +957,11 @@ int plan_append(plan_t *pl, asam_dev_t *dev, int N, int n_factors, const int *ft
                 rc |= asam_upload_node2q(dev, N0, nnew, pl->node2q + N0);
                 rc |= asam_upload_q2node(dev, N0, nnew, pl->q2node + N0);
             }
-            if (!rc && nnew > 0) { /* new supernodes are ancestors of all older ones */
-                int *pre = malloc(sizeof(int) * (size_t) nnew);
-                for (int j = 0; j < nnew; j++)
-                    pre[j] = nsn0 + nnew - 1 - j;
-                rc |= asam_btasks_prepend(dev, nnew, pre);
+            if (!rc && ncreated > 0) { /* new supernodes are ancestors of all older ones */
+                int *pre = malloc(sizeof(int) * (size_t) ncreated);
+                for (int k = 0; k < ncreated; k++)
+                    pre[k] = nsn0 + ncreated - 1 - k;
+                rc |= asam_btasks_prepend(dev, ncreated, pre);
                 free(pre);
             }
             if (!rc)

@@ -230,6 +230,7 @@ typedef struct solver {
     int plan_valid;
     double *x; /* solution in elimination (q) order */
     int xcap;
+    int tree_fresh; /* param->tr is exactly the tree of `plan` as built by the last batch */
     int *scratch;
     int scratch_cap;
 } solver_t;
@@ -344,8 +345,7 @@ static search_tree_t *tree_from_plan(const plan_t *pl, april_graph_t *g)
     tr->nodes = calloc((size_t) N, sizeof(search_tree_node_t));
     tr->linearized_nodes = calloc((size_t) N, sizeof(int));
     for (int i = 0; i < N; i++) {
-        tr->nodes[i].nalloc = 8;
-        tr->nodes[i].children = calloc(8, sizeof(int));
+        /* child lists are allocated on first use (leaves never need one) */
         tr->nodes[i].parent = -1;
         tr->nodes[i].g_node = node_at(g, i);
         tr->nodes[i].g_node->UID = i; /* the reference overwrites UIDs too (:627-628) */
@@ -440,7 +440,9 @@ ASAM_API void april_graph_cholesky(april_graph_t *graph, april_graph_cholesky_pa
     PROF_LAP(11);
     /* ordering + symbolic analysis: cached while the factor structure is unchanged */
     uint64_t h = structure_hash(N, F, c->ftype, c->fa, c->fb);
+    int plan_reused = 1;
     if (!(s->plan_valid && s->plan.N == N && s->plan.n_factors == F && s->plan.struct_hash == h)) {
+        plan_reused = 0;
         if (plan_build(&s->plan, dev, N, F, c->ftype, c->fa, c->fb) != 0)
             asam_fatal("april_graph_cholesky: %s %s", g_error, asam_last_error());
         s->plan.struct_hash = h;
@@ -463,13 +465,29 @@ ASAM_API void april_graph_cholesky(april_graph_t *graph, april_graph_cholesky_pa
     PROF_LAP(15);
 
     /* persistent state the incremental path continues from (:260-288) */
-    if (param->tr)
-        search_tree_destroy(param->tr);
-    param->tr = tree_from_plan(pl, graph);
+    if (plan_reused && s->tree_fresh && param->tr && param->tr->nnodes == N) {
+        /* same structure as the previous batch: same tree; only the per-solve labels reset */
+        search_tree_t *tr = param->tr;
+        for (int i = 0; i < N; i++) {
+            tr->nodes[i].label_changed = 0;
+            tr->nodes[i].label_relinearized = 0;
+            tr->nodes[i].g_node = node_at(graph, i);
+            tr->nodes[i].g_node->UID = i;
+        }
+        tr->start_over = tr->nlinearized_nodes = tr->naffected = tr->isam1_cnt = 0;
+        tr->total_delta_xy = tr->total_delta_theta = 0.0;
+    } else {
+        if (param->tr)
+            search_tree_destroy(param->tr);
+        param->tr = tree_from_plan(pl, graph);
+    }
+    s->tree_fresh = 1;
     param->tr->delta_xy = param->delta_xy;
     param->tr->delta_theta = param->delta_theta;
-    free(param->ordering);
-    param->ordering = malloc(sizeof(int) * (size_t) N);
+    if (!(plan_reused && param->ordering && param->nreordering == N)) {
+        free(param->ordering);
+        param->ordering = malloc(sizeof(int) * (size_t) N);
+    }
     memcpy(param->ordering, pl->order, sizeof(int) * (size_t) N);
     param->nreordering = N;
     param->factor_num = F;
@@ -592,6 +610,7 @@ ASAM_API void april_graph_cholesky_inc(april_graph_t *graph, april_graph_cholesk
                    pl->n_factors, F0);
     PROF_BEGIN();
     g_prof[8] += 1;
+    s->tree_fresh = 0;
     check_nodes(graph, N0, N);
     gctx_sync_factors(c, graph);
 
@@ -618,10 +637,6 @@ ASAM_API void april_graph_cholesky_inc(april_graph_t *graph, april_graph_cholesk
     tr->root = &tr->nodes[root_id];
     for (int i = old_nnodes; i < N; i++) {
         search_tree_node_t *tn = &tr->nodes[i];
-        if (!tn->children) {
-            tn->nalloc = 8;
-            tn->children = calloc(8, sizeof(int));
-        }
         tn->nchildren = 0;
         tn->parent = -1;
         tn->g_node = node_at(graph, i);

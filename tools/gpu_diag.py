@@ -248,6 +248,26 @@ def replay_profile(L, d, nsteps):
     h.close()
 
 
+def trace_steps(L, d, steps):
+    """Kernel traces of individual incremental steps (indices into the demo replay)."""
+    h = H.Harness("b200")
+    h.replay_begin(d)
+    for k in sorted(steps):
+        h.replay_to(k, want_chi2=False)          # steps 0..k-1 done
+        dev = L.asam_dbg_dev_of_graph(h.graph_ptr())
+        L.asam_set_trace(dev, 1)
+        L.asam_set_timing(dev, 1)
+        _, ms, info = h.replay_to(k + 1, want_chi2=False)
+        lin = C.c_float(); fac = C.c_float(); bs = C.c_float()
+        L.asam_last_kernel_ms(dev, C.byref(lin), C.byref(fac), C.byref(bs))
+        log(f"--- step {k}: naffected {info[0][0]} api {ms[0]:.3f} ms; kernels lin {lin.value:.4f} factor {fac.value:.4f} backsolve {bs.value:.4f} ms")
+        plan = borrowed_plan(L, h.param_ptr())
+        trace_report(L, dev, 8192, f"step {k}")
+        DUMP[f"step {k}:desc"] = plan.array("desc")
+        L.asam_set_trace(dev, 0)
+    h.close()
+
+
 def check_synth(L, N, have_ref, iters=2):
     """Synthetic Manhattan graph: exercises the big-front (global-memory) path of k_factor."""
     from aprilsam_b200 import datasets
@@ -295,6 +315,7 @@ if __name__ == "__main__":
     ap.add_argument("--replay", type=int, default=300)
     ap.add_argument("--time", action="store_true")
     ap.add_argument("--profile-replay", type=int, default=0)
+    ap.add_argument("--trace-steps", default="")
     args = ap.parse_args()
     d = H.PoseGraphData.load(os.path.join(ROOT, "tests", "golden", "m3500.npz"))
     L = dev_api()
@@ -308,6 +329,8 @@ if __name__ == "__main__":
         timing(L, d)
     if args.profile_replay > 0:
         replay_profile(L, d, args.profile_replay)
+    if args.trace_steps:
+        trace_steps(L, d, [int(x) for x in args.trace_steps.split(",")])
     for n in [int(s) for s in args.synth.split(",") if s]:
         check_synth(L, n, have_ref)
     if DUMP:
