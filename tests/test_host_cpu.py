@@ -287,3 +287,34 @@ def test_generators_are_seeded():
     assert 2000 - 1 < s.n_edges < 2000 * 1.1
     key = np.maximum(s.ea, s.eb)
     assert np.all(np.diff(key) >= 0) and np.all(s.ea < s.eb)
+
+
+# ---------------------------------------------------------------------------------------------
+# the plain-C oracle port, pinned against the golden vectors of the real reference
+# ---------------------------------------------------------------------------------------------
+def test_oracle_port_matches_golden(m3500):
+    sys.path.insert(0, ROOT)
+    from oracle import port
+    g = golden("m3500_batch.npz")
+    assert abs(port.chi2(m3500, m3500.init) - g["chi2"][0]) < 1e-9 * g["chi2"][0]
+    st = m3500.init
+    for it in range(2):
+        st = port.batch_step(m3500, st)
+        assert np.abs(st - g["states"][it]).max() < 1e-7, it
+        assert abs(port.chi2(m3500, st) - g["chi2"][it + 1]) < 1e-7 * g["chi2"][it + 1]
+
+
+def test_oracle_port_small_graphs_vs_reference(m3500):
+    if not H.available("reference"):
+        pytest.skip("reference oracle not built")
+    sys.path.insert(0, ROOT)
+    from oracle import port
+    for n in (1, 2, 3, 11, 150):
+        sub = m3500.head(n)
+        with H.Harness("reference") as h:
+            h.load_full(sub)
+            h.batch()
+            ref, c = h.states(), h.chi2()
+        st = port.batch_step(sub, sub.init)
+        assert np.abs(st - ref).max() < 1e-9, n
+        assert abs(port.chi2(sub, st) - c) <= 1e-9 * max(1.0, c)
