@@ -248,7 +248,7 @@ struct FacArgs {
     double *dinv; // 1/L_kk in elimination order (used by k_backsolve)
     int *arrive;
     int *tbar; // team barrier counters, zeroed before the launch
-    const int *tasks, *nwait; // nwait: bits 0-19 children in this launch, 20-25 worker, 26-30 team size
+    const int *tasks, *nwait; // nwait: bits 0-15 children in this launch, 16-23 worker, 24-30 team size
     int ntasks;
     int *ctrl; // [0] ticket, [1] err
     int smem_doubles;
@@ -429,8 +429,10 @@ __device__ __forceinline__ bool team_owns(int col, int w, int G) { return ((col 
 
 // returns false on abort
 __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int nw, int w, int G, double *sm,
-                           int *s_flag)
+                           int *s_flag, unsigned long long *trow)
 {
+    // trow (worker 0, thread 0 only): [1] children ready, [2] assembled, [3] extend-added,
+    // [4] eliminated; [7] high word: ns spent in the panel (diag + TRSM) phases
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     const int m = 3 * d.mb, c = 3 * d.cb, ld = m + 1;
@@ -487,9 +489,13 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
             }
         }
         a.arrive[s] = 0;
+        if (trow)
+            trow[1] = d_now();
     }
     if (!team_barrier(tc, s_flag))
         return false;
+    if (trow && tid == 0)
+        trow[2] = d_now();
 
     // ---- extend-add into own columns -------------------------------------------------------
     int *dmap = (int *) sm; // ld ints
@@ -507,13 +513,13 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
                 continue;
             const double *ccol = CF + (size_t) (cc + j) * cld + cc;
             double *fcol = F + (size_t) dj * ld;
-            for (int i0 = j + lane; i0 <= cr; i0 += 128) {
-                double v[4];
+            for (int i0 = j + lane; i0 <= cr; i0 += 256) {
+                double v[8];
 #pragma unroll
-                for (int u = 0; u < 4; u++)
+                for (int u = 0; u < 8; u++)
                     v[u] = (i0 + 32 * u <= cr) ? __ldcg(ccol + i0 + 32 * u) : 0.0;
 #pragma unroll
-                for (int u = 0; u < 4; u++)
+                for (int u = 0; u < 8; u++)
                     if (i0 + 32 * u <= cr)
                         fcol[dmap[i0 + 32 * u]] += v[u];
             }
@@ -522,6 +528,9 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
     }
     if (!team_barrier(tc, s_flag))
         return false;
+    unsigned long long t_panel = 0, t_mark = 0;
+    if (trow && tid == 0)
+        trow[3] = d_now();
 
     // ---- panels ---------------------------------------------------------------------------------
     double *D = sm;                              // ASAM_TPB x ASAM_TPB diagonal block, ld = pb
@@ -530,6 +539,8 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
     double *dinv = a.dinv + 3 * (size_t) d.first;
     for (int k0 = 0; k0 < c; k0 += ASAM_TPB) {
         const int pb = min(ASAM_TPB, c - k0);
+        if (trow && tid == 0)
+            t_mark = d_now();
         // diagonal block, factored redundantly by every worker (closed-form 3x3 steps)
         for (int e = tid; e < pb * pb; e += nt) {
             const int i = e % pb, j = e / pb;
@@ -544,8 +555,12 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
             const int i = r_first + ch * ASAM_TROWS + tid;
             __syncthreads();
             if (i <= m) {
+                // fetch the whole row first (pb independent loads in flight), then solve in place
+                for (int j = 0; j < pb; j++)
+                    Li[tid + j * ASAM_TROWS] = __ldcg(&F[i + (size_t) (k0 + j) * ld]);
                 for (int j = 0; j < pb; j++) {
-                    double v = __ldcg(&F[i + (size_t) (k0 + j) * ld]);
+                    double v = Li[tid + j * ASAM_TROWS];
+#pragma unroll 4
                     for (int p = 0; p < j; p++)
                         v -= Li[tid + p * ASAM_TROWS] * D[j + p * pb];
                     v /= D[j + j * pb];
@@ -556,6 +571,8 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
         }
         if (!team_barrier(tc, s_flag))
             return false;
+        if (trow && tid == 0)
+            t_panel += d_now() - t_mark;
         // every worker has read the unfactored diagonal block by now: worker 0 may overwrite it
         if (w == 0) {
             for (int e = tid; e < pb * pb; e += nt) {
@@ -589,14 +606,20 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
                 const int tj = 8 * warp;
                 if (tj < ncol) {
                     for (int ib = 0; ib < nrow; ib += 128) {
-                        double acc[4][8];
+                        double acc[4][8], cv[4][8];
                         int ir[4];
 #pragma unroll
                         for (int r = 0; r < 4; r++) {
                             ir[r] = min(ib + lane + 32 * r, nrow - 1);
 #pragma unroll
-                            for (int q = 0; q < 8; q++)
+                            for (int q = 0; q < 8; q++) {
                                 acc[r][q] = 0.0;
+                                // the C values are fetched now and consumed after the products:
+                                // their L2 latency hides behind the 4x8xpb FMAs
+                                const int ii = ib + lane + 32 * r, jj = tj + q;
+                                const bool ok = ii < nrow && jj < ncol && rb0 + ii >= cb0 + jj;
+                                cv[r][q] = ok ? __ldcg(&F[(rb0 + ii) + (size_t) (cb0 + jj) * ld]) : 0.0;
+                            }
                         }
 #pragma unroll 2
                         for (int p = 0; p < pb; p++) {
@@ -619,10 +642,8 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
                             for (int q = 0; q < 8; q++) {
                                 const int ii = ib + lane + 32 * r, jj = tj + q;
                                 const int i = rb0 + ii, j = cb0 + jj;
-                                if (ii < nrow && jj < ncol && i >= j) {
-                                    double *cp = &F[i + (size_t) j * ld];
-                                    *cp = __ldcg(cp) - acc[r][q];
-                                }
+                                if (ii < nrow && jj < ncol && i >= j)
+                                    F[i + (size_t) j * ld] = cv[r][q] - acc[r][q];
                             }
                     }
                 }
@@ -632,6 +653,10 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
             return false;
     }
 
+    if (trow && tid == 0) {
+        trow[4] = d_now();
+        trow[7] = (unsigned long long) (unsigned) m | (t_panel << 32);
+    }
     // ---- publish ------------------------------------------------------------------------------------
     if (w == 0) {
         for (int e = tid; e < c; e += nt)
@@ -668,16 +693,25 @@ __global__ void __launch_bounds__(256, 1) k_factor(FacArgs a)
             tr0 = d_now();
         const int s = a.tasks[t];
         const int nwp = a.nwait[t];
-        const int nw = nwp & 0xfffff, tw = (nwp >> 20) & 0x3f, tG = (nwp >> 26) & 0x1f;
+        const int nw = nwp & 0xffff, tw = (nwp >> 16) & 0xff, tG = (nwp >> 24) & 0x7f;
         const asam_sn_desc_t d = a.sn[s];
         if (tG > 1) { // one worker of a multi-CTA team
-            if (!team_front(a, d, s, nw, tw, tG, sm, &s_abort))
+            unsigned long long *trow = (a.trace && tw == 0) ? a.trace + 8 * (size_t) t : nullptr;
+            if (trow && tid == 0) {
+                trow[0] = tr0; trow[1] = tr0;
+            }
+            if (!team_front(a, d, s, nw, tw, tG, sm, &s_abort, trow))
                 break;
             if (a.trace && tid == 0) {
                 unsigned long long *tr = a.trace + 8 * (size_t) t;
-                tr[0] = tr0; tr[1] = tr0; tr[2] = tr0; tr[3] = tr0; tr[4] = d_now(); tr[5] = tr[4];
-                tr[6] = (unsigned long long) s;
-                tr[7] = (unsigned long long) (unsigned) (3 * d.mb);
+                if (tw == 0) {
+                    tr[5] = d_now();
+                    tr[6] = (unsigned long long) s | ((unsigned long long) tG << 32);
+                } else { // other workers: only the total
+                    tr[0] = tr0; tr[1] = tr0; tr[2] = tr0; tr[3] = tr0; tr[4] = d_now(); tr[5] = tr[4];
+                    tr[6] = (unsigned long long) s | ((unsigned long long) tG << 32);
+                    tr[7] = (unsigned long long) (unsigned) (3 * d.mb);
+                }
             }
             __syncthreads();
             continue;

@@ -274,22 +274,25 @@ static void emit_segment(plan_t *pl, int s, ivec_t *buf, int64_t base)
 }
 
 /* CTAs that share one front in k_factor: fronts that fit in shared memory (200 KB) take one;
- * larger ones get one CTA per ~3 MFLOP of elimination work, at most 31. */
+ * larger ones get one CTA per ~3 MFLOP of elimination work or per ~40 k front entries (thin
+ * fronts are bound by moving the update matrix, not by flops), at most 120 (the grid is one CTA
+ * per SM, 148 on B200, and a team must be co-resident). */
 static int team_size(int mb, int cb)
 {
     int64_t m = 3 * (int64_t) mb, c = 3 * (int64_t) cb;
     if ((m + 1) * m + (m + 2) / 2 + 2 <= 25600)
         return 1;
-    double fl = (double) c * (double) m * (double) m;
-    int G = (int) (fl / 3.0e6) + 1;
+    double fl = (double) c * (double) m * (double) m, sz = (double) m * (double) m;
+    double g = fl / 3.0e6 > sz / 4.0e4 ? fl / 3.0e6 : sz / 4.0e4;
+    int G = (int) g + 1;
     if (G < 2)
         G = 2;
-    if (G > 31)
-        G = 31;
+    if (G > 120)
+        G = 120;
     return G;
 }
 
-static inline int pack_nwait(int nw, int w, int G) { return (nw & 0xfffff) | (w << 20) | (G << 26); }
+static inline int pack_nwait(int nw, int w, int G) { return (nw & 0xffff) | (w << 16) | (G << 24); }
 
 static int64_t front_doubles(int mb)
 {

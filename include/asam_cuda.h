@@ -80,8 +80,8 @@ int asam_hessian_clear_range(asam_dev_t *d, int q_first, int q_count, int slot_f
 int asam_linearize(asam_dev_t *d, int f_first, int f_count, const double *pts6);
 
 /* Kernel 2: multifrontal supernodal Cholesky + fused forward solve over the given
- * supernodes (children before parents).  nwait[t]: bits 0-19 = number of children of tasks[t]
- * that are themselves in the task list; bits 20-25 / 26-30 = worker index / team size when a
+ * supernodes (children before parents).  nwait[t]: bits 0-15 = number of children of tasks[t]
+ * that are themselves in the task list; bits 16-23 / 24-30 = worker index / team size when a
  * front too large for shared memory is shared by a team of CTAs (the team's entries must be
  * consecutive; 0 or 1 = single CTA).  Replaces cs_schol/cs_chol + forward solve
  * (csparse.c:462-513, smatd.c:1051-1073) and, with a subset, the un-eliminate /

@@ -130,7 +130,7 @@ def factor(fr: Fronts, H: Hessian, desc, ipool, q2node, tasks, nwait=None, check
     for ti, s in enumerate(tasks):
         s = int(s)
         if s in done:  # further workers of a multi-CTA team: same supernode
-            assert (int(nwait[ti]) >> 26) & 0x1f > 1
+            assert (int(nwait[ti]) >> 24) & 0x7f > 1
             continue
         rows, rel, children, a_slot, a_rb, a_cb = seg_views(desc, ipool, s)
         mb, cb, first = int(desc["mb"][s]), int(desc["cb"][s]), int(desc["first"][s])
@@ -171,7 +171,7 @@ def factor(fr: Fronts, H: Hessian, desc, ipool, q2node, tasks, nwait=None, check
             F[np.ix_(idx, idx)] += np.tril(U)
             rhs[idx] += crhs[3 * ccb:]
         if nwait is not None:
-            assert nw == (int(nwait[ti]) & 0xfffff), f"nwait mismatch for supernode {s}: {nw} vs {nwait[ti]}"
+            assert nw == (int(nwait[ti]) & 0xffff), f"nwait mismatch for supernode {s}: {nw} vs {nwait[ti]}"
         # partial Cholesky of the first c columns (right-looking, lower triangle only)
         for k in range(c):
             d = F[k, k]

@@ -55,6 +55,7 @@ def trace_report(L, dev, ntasks, label):
         tr = tr[tr[:, 0] > 0]
         if len(tr) == 0:
             continue
+        raw = tr.copy()
         t = tr[:, :6].astype(np.int64)
         t0 = t[:, 0].min()
         if which == 0:
@@ -85,7 +86,7 @@ def trace_report(L, dev, ntasks, label):
         busy = ph.sum() - ph[:, 1].sum()
         log(f"      non-wait busy time {busy / 1e6:.2f} ms over {len(tr)} tasks -> {busy / 1e3 / len(tr):.2f} us per task")
         if DUMP is not None:
-            DUMP[f"{label}:{name}"] = tr
+            DUMP[f"{label}:{name}"] = raw
 
 
 def borrowed_plan(L, param_ptr):
