@@ -49,6 +49,17 @@ struct Buf {
     size_t cap = 0; // bytes
 };
 
+struct BatchItem {
+    unsigned long long dst;
+    unsigned int off;   // payload offset (copy items)
+    unsigned int bytes; // multiple of 4
+    unsigned int fill;  // 1 = fill with `val`
+    unsigned int val;
+};
+#define ASAM_MAX_ITEMS 1024
+#define ASAM_TABLE_BYTES (ASAM_MAX_ITEMS * sizeof(BatchItem))
+#define ASAM_ITEM_CHUNK (64u << 10)
+
 struct asam_dev {
     int device = 0;
     int n_sm = 0;
@@ -74,9 +85,23 @@ struct asam_dev {
     Buf pts;
     int epoch = 0;
 
-    // pinned staging
-    char *pin = nullptr;
-    size_t pin_cap = 0, pin_off = 0;
+    // host->device traffic is BATCHED: small uploads and fills are queued in one pinned staging
+    // buffer and reach HBM with a single cudaMemcpyAsync + one scatter kernel (k_scatter) right
+    // before the next kernel launch / download -- an incremental step costs two API calls for all
+    // of its ~15 small transfers.
+    char *pin = nullptr;      // [item table | payload]
+    size_t pin_cap = 0, pin_off = 0; // pin_off = payload bytes used
+    char *dstage = nullptr;   // device mirror of the staging buffer
+    struct BatchItem *items = nullptr;
+    int n_items = 0;
+    cudaEvent_t up_ev = nullptr;
+    int up_busy = 0;
+    char *pin_down = nullptr; // separate pinned buffer for downloads
+    size_t pin_down_cap = 0;
+    // deferred launches (asam_step_begin .. asam_step_run): kernels recorded, launched after ONE flush
+    int defer = 0;
+    struct Pending *pend = nullptr;
+    int npend = 0;
 
     // launch config
     int fac_threads = 256, fac_grid = 0, fac_smem = 0;
@@ -95,10 +120,14 @@ struct asam_dev {
     int trace_nfac = 0, trace_nbs = 0;
 };
 
+static int flush_uploads(asam_dev *d);
+
 static int buf_reserve(asam_dev *d, Buf &b, size_t bytes, bool keep, bool zero_new)
 {
     if (bytes <= b.cap)
         return 0;
+    if (flush_uploads(d)) // queued items may point into the buffer that is about to move
+        return 1;
     size_t want = b.cap ? b.cap : 4096;
     while (want < bytes)
         want = want + want / 2 + 4096;
@@ -117,24 +146,105 @@ static int buf_reserve(asam_dev *d, Buf &b, size_t bytes, bool keep, bool zero_n
     return 0;
 }
 
+__global__ void k_scatter(const BatchItem *items, const char *payload)
+{
+    const BatchItem it = items[blockIdx.x];
+    unsigned int *dst = (unsigned int *) it.dst;
+    const unsigned int words = it.bytes >> 2;
+    if (it.fill) {
+        for (unsigned int i = threadIdx.x; i < words; i += blockDim.x)
+            dst[i] = it.val;
+    } else {
+        const unsigned int *src = (const unsigned int *) (payload + it.off);
+        for (unsigned int i = threadIdx.x; i < words; i += blockDim.x)
+            dst[i] = src[i];
+    }
+}
+
+// Push everything queued so far to the device (one H2D copy + one scatter launch).
+static int flush_uploads(asam_dev *d)
+{
+    if (d->n_items == 0)
+        return 0;
+    memcpy(d->pin, d->items, (size_t) d->n_items * sizeof(BatchItem));
+    const size_t total = ASAM_TABLE_BYTES + d->pin_off;
+    CK(cudaMemcpyAsync(d->dstage, d->pin, total, cudaMemcpyHostToDevice, d->stream));
+    CK(cudaEventRecord(d->up_ev, d->stream));
+    k_scatter<<<d->n_items, 256, 0, d->stream>>>((const BatchItem *) d->dstage, d->dstage + ASAM_TABLE_BYTES);
+    CK(cudaGetLastError());
+    d->n_launch++;
+    d->n_items = 0;
+    d->pin_off = 0;
+    d->up_busy = 1;
+    return 0;
+}
+
+static int batch_room(asam_dev *d, size_t bytes, int items)
+{
+    if (d->up_busy) { // the staging buffer is still being copied by the previous flush
+        CK(cudaEventSynchronize(d->up_ev));
+        d->up_busy = 0;
+    }
+    if (d->n_items + items > ASAM_MAX_ITEMS || ASAM_TABLE_BYTES + d->pin_off + bytes > d->pin_cap) {
+        if (flush_uploads(d))
+            return 1;
+        CK(cudaEventSynchronize(d->up_ev));
+        d->up_busy = 0;
+    }
+    return 0;
+}
+
 static int upload(asam_dev *d, void *dst, const void *src, size_t bytes)
 {
     if (bytes == 0)
         return 0;
     d->n_h2d += (int64_t) bytes;
-    if (bytes > d->pin_cap) { // too large to stage: synchronous pageable copy
+    if ((bytes & 3) || bytes > (d->pin_cap - ASAM_TABLE_BYTES) / 2) { // odd size or large: direct copy
+        if (flush_uploads(d))
+            return 1;
         CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, d->stream));
-        CK(cudaStreamSynchronize(d->stream));
-        d->pin_off = 0;
         return 0;
     }
-    if (d->pin_off + bytes > d->pin_cap) {
-        CK(cudaStreamSynchronize(d->stream));
-        d->pin_off = 0;
+    const int nitems = (int) ((bytes + ASAM_ITEM_CHUNK - 1) / ASAM_ITEM_CHUNK);
+    if (batch_room(d, bytes + 16, nitems))
+        return 1;
+    const size_t off = (d->pin_off + 15) & ~(size_t) 15;
+    memcpy(d->pin + ASAM_TABLE_BYTES + off, src, bytes);
+    for (size_t o = 0; o < bytes; o += ASAM_ITEM_CHUNK) {
+        BatchItem &it = d->items[d->n_items++];
+        it.dst = (unsigned long long) ((char *) dst + o);
+        it.off = (unsigned int) (off + o);
+        it.bytes = (unsigned int) (bytes - o < ASAM_ITEM_CHUNK ? bytes - o : ASAM_ITEM_CHUNK);
+        it.fill = 0;
+        it.val = 0;
     }
-    memcpy(d->pin + d->pin_off, src, bytes);
-    CK(cudaMemcpyAsync(dst, d->pin + d->pin_off, bytes, cudaMemcpyHostToDevice, d->stream));
-    d->pin_off += (bytes + 255) & ~(size_t) 255;
+    d->pin_off = off + bytes;
+    return 0;
+}
+
+// Queue a fill of `bytes` (multiple of 4) at dst with the 32-bit pattern `val`.
+static int queue_fill(asam_dev *d, void *dst, unsigned int val, size_t bytes)
+{
+    if (bytes == 0)
+        return 0;
+    const size_t chunk = 4 * ASAM_ITEM_CHUNK;
+    const int nitems = (int) ((bytes + chunk - 1) / chunk);
+    if (nitems > ASAM_MAX_ITEMS / 2) { // huge: plain memset in stream order
+        if (flush_uploads(d))
+            return 1;
+        CK(cudaMemsetAsync(dst, (int) (val & 0xff), bytes, d->stream));
+        return 0;
+    }
+    if (batch_room(d, 0, nitems))
+        return 1;
+    for (size_t o = 0; o < bytes; o += chunk) {
+        BatchItem &it = d->items[d->n_items++];
+        it.dst = (unsigned long long) ((char *) dst + o);
+        it.off = 0;
+        it.bytes = (unsigned int) (bytes - o < chunk ? bytes - o : chunk);
+        it.fill = 1;
+        it.val = val;
+    }
     return 0;
 }
 
@@ -142,22 +252,111 @@ static int download(asam_dev *d, void *dst, const void *src, size_t bytes)
 {
     if (bytes == 0)
         return 0;
+    if (flush_uploads(d))
+        return 1;
     d->n_d2h += (int64_t) bytes;
-    if (bytes <= d->pin_cap) {
-        CK(cudaStreamSynchronize(d->stream)); // staging area is free after this
-        d->pin_off = 0;
-        CK(cudaMemcpyAsync(d->pin, src, bytes, cudaMemcpyDeviceToHost, d->stream));
+    if (bytes <= d->pin_down_cap) {
+        CK(cudaMemcpyAsync(d->pin_down, src, bytes, cudaMemcpyDeviceToHost, d->stream));
         CK(cudaStreamSynchronize(d->stream));
-        memcpy(dst, d->pin, bytes);
+        memcpy(dst, d->pin_down, bytes);
     } else {
         CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, d->stream));
         CK(cudaStreamSynchronize(d->stream));
-        d->pin_off = 0;
     }
     return 0;
 }
 
 #include "asam_kernels.cuh"
+
+struct Pending {
+    int kind; // 0 linearize, 1 factor, 2 backsolve
+    int grid;
+    LinArgs lin;
+    FacArgs fac;
+    BsArgs bs;
+};
+#define ASAM_MAX_PENDING 8
+
+static int run_linearize(asam_dev *d, const LinArgs &a)
+{
+    if (d->timing)
+        CK(cudaEventRecord(d->ev[0], d->stream));
+    k_linearize<<<(a.f_count + 127) / 128, 128, 0, d->stream>>>(a);
+    d->n_launch++;
+    CK(cudaGetLastError());
+    if (d->timing) {
+        CK(cudaEventRecord(d->ev[1], d->stream));
+        d->ev_set[0] = 1;
+    }
+    return 0;
+}
+
+static int run_factor(asam_dev *d, const FacArgs &a, int grid)
+{
+    if (d->timing)
+        CK(cudaEventRecord(d->ev[2], d->stream));
+    k_factor<<<grid, d->fac_threads, d->fac_smem, d->stream>>>(a);
+    d->n_launch++;
+    CK(cudaGetLastError());
+    if (d->timing) {
+        CK(cudaEventRecord(d->ev[3], d->stream));
+        d->ev_set[1] = 1;
+    }
+    return 0;
+}
+
+static int run_backsolve(asam_dev *d, const BsArgs &a, int grid)
+{
+    if (d->timing)
+        CK(cudaEventRecord(d->ev[4], d->stream));
+    k_backsolve<<<grid, d->bs_threads, d->bs_smem, d->stream>>>(a);
+    d->n_launch++;
+    CK(cudaGetLastError());
+    if (d->timing) {
+        CK(cudaEventRecord(d->ev[5], d->stream));
+        d->ev_set[2] = 1;
+    }
+    return 0;
+}
+
+static int defer_push(asam_dev *d, int kind, int grid, const LinArgs *lin, const FacArgs *fac, const BsArgs *bs)
+{
+    if (d->npend >= ASAM_MAX_PENDING)
+        return set_err("too many deferred launches");
+    Pending &p = d->pend[d->npend++];
+    p.kind = kind;
+    p.grid = grid;
+    if (lin) p.lin = *lin;
+    if (fac) p.fac = *fac;
+    if (bs) p.bs = *bs;
+    return 0;
+}
+
+// Record the kernels of one incremental step and launch them after a single upload flush.
+ASAM_EXPORT int asam_step_begin(asam_dev_t *d)
+{
+    if (!d->pend)
+        d->pend = (Pending *) malloc(sizeof(Pending) * ASAM_MAX_PENDING);
+    d->defer = 1;
+    d->npend = 0;
+    return 0;
+}
+
+ASAM_EXPORT int asam_step_run(asam_dev_t *d)
+{
+    CK(cudaSetDevice(d->device));
+    d->defer = 0;
+    if (flush_uploads(d))
+        return 1;
+    for (int i = 0; i < d->npend; i++) {
+        Pending &p = d->pend[i];
+        int rc = p.kind == 0 ? run_linearize(d, p.lin) : p.kind == 1 ? run_factor(d, p.fac, p.grid) : run_backsolve(d, p.bs, p.grid);
+        if (rc)
+            return rc;
+    }
+    d->npend = 0;
+    return 0;
+}
 
 // ------------------------------------------------------------------------------------------
 // C-ABI
@@ -192,6 +391,11 @@ ASAM_EXPORT int asam_dev_create(asam_dev_t **out)
     CK(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
     d->pin_cap = 8u << 20;
     CK(cudaMallocHost((void **) &d->pin, d->pin_cap));
+    CK(cudaMalloc((void **) &d->dstage, d->pin_cap));
+    d->items = (BatchItem *) malloc(ASAM_TABLE_BYTES);
+    CK(cudaEventCreateWithFlags(&d->up_ev, cudaEventDisableTiming));
+    d->pin_down_cap = 8u << 20;
+    CK(cudaMallocHost((void **) &d->pin_down, d->pin_down_cap));
     for (int i = 0; i < 6; i++)
         CK(cudaEventCreate(&d->ev[i]));
     if (buf_reserve(d, d->ctrl, 8 * sizeof(int), false, true))
@@ -242,6 +446,14 @@ ASAM_EXPORT void asam_dev_destroy(asam_dev_t *d)
             cudaFree(b->p);
     if (d->pin)
         cudaFreeHost(d->pin);
+    if (d->pin_down)
+        cudaFreeHost(d->pin_down);
+    if (d->dstage)
+        cudaFree(d->dstage);
+    if (d->up_ev)
+        cudaEventDestroy(d->up_ev);
+    free(d->items);
+    free(d->pend);
     for (int i = 0; i < 6; i++)
         if (d->ev[i])
             cudaEventDestroy(d->ev[i]);
@@ -349,6 +561,12 @@ ASAM_EXPORT int asam_upload_desc(asam_dev_t *d, int n, const int32_t *sn_ids, co
     if (n <= 0)
         return 0;
     CK(cudaSetDevice(d->device));
+    if (n <= 256) { // incremental step: each descriptor is one queued 48-byte copy
+        for (int i = 0; i < n; i++)
+            if (upload(d, (asam_sn_desc_t *) d->sn.p + sn_ids[i], &desc[i], sizeof(asam_sn_desc_t)))
+                return 1;
+        return 0;
+    }
     if (buf_reserve(d, d->patch_ids, (size_t) n * sizeof(int), false, false))
         return 1;
     if (buf_reserve(d, d->patch_desc, (size_t) n * sizeof(asam_sn_desc_t), false, false))
@@ -356,6 +574,8 @@ ASAM_EXPORT int asam_upload_desc(asam_dev_t *d, int n, const int32_t *sn_ids, co
     if (upload(d, d->patch_ids.p, sn_ids, (size_t) n * sizeof(int)))
         return 1;
     if (upload(d, d->patch_desc.p, desc, (size_t) n * sizeof(asam_sn_desc_t)))
+        return 1;
+    if (flush_uploads(d))
         return 1;
     k_apply_desc<<<(n + 127) / 128, 128, 0, d->stream>>>((asam_sn_desc_t *) d->sn.p, (const int *) d->patch_ids.p,
                                                          (const asam_sn_desc_t *) d->patch_desc.p, n);
@@ -370,6 +590,8 @@ ASAM_EXPORT int asam_hessian_reset(asam_dev_t *d, int n_nodes, int n_slots, int 
     size_t total = 9 * (size_t) n_nodes + 9 * (size_t) n_slots + 3 * (size_t) n_nodes;
     if (total == 0)
         return 0;
+    if (flush_uploads(d))
+        return 1;
     k_hessian_reset<<<(unsigned) ((total + 255) / 256), 256, 0, d->stream>>>(
         (double *) d->Adiag.p, (double *) d->Aoff.p, (double *) d->Bq.p, n_nodes, n_slots, n_lambda, lambda);
     d->n_launch++;
@@ -380,14 +602,14 @@ ASAM_EXPORT int asam_hessian_reset(asam_dev_t *d, int n_nodes, int n_slots, int 
 ASAM_EXPORT int asam_hessian_clear_range(asam_dev_t *d, int q_first, int q_count, int slot_first, int slot_count)
 {
     CK(cudaSetDevice(d->device));
-    size_t total = 12 * (size_t) q_count + 9 * (size_t) slot_count;
-    if (total == 0)
-        return 0;
-    k_clear_range<<<(unsigned) ((total + 255) / 256), 256, 0, d->stream>>>(
-        (double *) d->Adiag.p, (double *) d->Bq.p, (double *) d->Aoff.p, q_first, q_count, slot_first, slot_count);
-    d->n_launch++;
-    CK(cudaGetLastError());
-    return 0;
+    int rc = 0;
+    if (q_count > 0) {
+        rc |= queue_fill(d, (double *) d->Adiag.p + 9 * (size_t) q_first, 0, (size_t) q_count * 9 * sizeof(double));
+        rc |= queue_fill(d, (double *) d->Bq.p + 3 * (size_t) q_first, 0, (size_t) q_count * 3 * sizeof(double));
+    }
+    if (slot_count > 0)
+        rc |= queue_fill(d, (double *) d->Aoff.p + 9 * (size_t) slot_first, 0, (size_t) slot_count * 9 * sizeof(double));
+    return rc;
 }
 
 ASAM_EXPORT int asam_linearize(asam_dev_t *d, int f_first, int f_count, const double *pts6)
@@ -418,25 +640,21 @@ ASAM_EXPORT int asam_linearize(asam_dev_t *d, int f_first, int f_count, const do
     a.Bq = (double *) d->Bq.p;
     a.f_first = f_first;
     a.f_count = f_count;
-    if (d->timing)
-        CK(cudaEventRecord(d->ev[0], d->stream));
-    k_linearize<<<(f_count + 127) / 128, 128, 0, d->stream>>>(a);
-    d->n_launch++;
-    CK(cudaGetLastError());
-    if (d->timing) {
-        CK(cudaEventRecord(d->ev[1], d->stream));
-        d->ev_set[0] = 1;
-    }
-    return 0;
+    if (d->defer)
+        return defer_push(d, 0, 0, &a, nullptr, nullptr);
+    if (flush_uploads(d))
+        return 1;
+    return run_linearize(d, a);
 }
 
 static int launch_factor(asam_dev *d, int ntasks, const int *tasks_dev, const int *nwait_dev)
 {
     if (ntasks <= 0)
         return 0;
-    CK(cudaMemsetAsync(d->ctrl.p, 0, 2 * sizeof(int), d->stream)); // ticket, err
-    if (d->tbar.p)
-        CK(cudaMemsetAsync(d->tbar.p, 0, d->tbar.cap, d->stream)); // team barrier counters
+    if (queue_fill(d, d->ctrl.p, 0, 2 * sizeof(int))) // ticket, err
+        return 1;
+    if (d->tbar.p && queue_fill(d, d->tbar.p, 0, d->tbar.cap)) // team barrier counters
+        return 1;
     FacArgs a;
     a.sn = (const asam_sn_desc_t *) d->sn.p;
     a.ipool = (const int *) d->ipool.p;
@@ -463,23 +681,19 @@ static int launch_factor(asam_dev *d, int ntasks, const int *tasks_dev, const in
         d->trace_nfac = ntasks;
     }
     int grid = d->fac_grid < ntasks ? d->fac_grid : ntasks;
-    if (d->timing)
-        CK(cudaEventRecord(d->ev[2], d->stream));
-    k_factor<<<grid, d->fac_threads, d->fac_smem, d->stream>>>(a);
-    d->n_launch++;
-    CK(cudaGetLastError());
-    if (d->timing) {
-        CK(cudaEventRecord(d->ev[3], d->stream));
-        d->ev_set[1] = 1;
-    }
-    return 0;
+    if (d->defer)
+        return defer_push(d, 1, grid, nullptr, &a, nullptr);
+    if (flush_uploads(d))
+        return 1;
+    return run_factor(d, a, grid);
 }
 
 static int launch_backsolve(asam_dev *d, int ntasks, const int *btasks_dev)
 {
     if (ntasks <= 0)
         return 0;
-    CK(cudaMemsetAsync((int *) d->ctrl.p + 2, 0, sizeof(int), d->stream));
+    if (queue_fill(d, (int *) d->ctrl.p + 2, 0, sizeof(int)))
+        return 1;
     d->epoch++;
     BsArgs a;
     a.sn = (const asam_sn_desc_t *) d->sn.p;
@@ -503,16 +717,11 @@ static int launch_backsolve(asam_dev *d, int ntasks, const int *btasks_dev)
         d->trace_nbs = ntasks;
     }
     int grid = d->bs_grid < ntasks ? d->bs_grid : ntasks;
-    if (d->timing)
-        CK(cudaEventRecord(d->ev[4], d->stream));
-    k_backsolve<<<grid, d->bs_threads, d->bs_smem, d->stream>>>(a);
-    d->n_launch++;
-    CK(cudaGetLastError());
-    if (d->timing) {
-        CK(cudaEventRecord(d->ev[5], d->stream));
-        d->ev_set[2] = 1;
-    }
-    return 0;
+    if (d->defer)
+        return defer_push(d, 2, grid, nullptr, nullptr, &a);
+    if (flush_uploads(d))
+        return 1;
+    return run_backsolve(d, a, grid);
 }
 
 ASAM_EXPORT int asam_set_full_tasks(asam_dev_t *d, int ntasks, const int32_t *tasks, const int32_t *nwait,
@@ -540,6 +749,8 @@ ASAM_EXPORT int asam_btasks_prepend(asam_dev_t *d, int n, const int32_t *ids)
         return 0;
     CK(cudaSetDevice(d->device));
     if (d->bt_start < n) { // out of head-room: move the list to the end of a larger buffer
+        if (flush_uploads(d))
+            return 1;
         int newcap = 2 * (d->bt_count + n) + 1024;
         void *np = nullptr;
         CK(cudaMalloc(&np, (size_t) newcap * sizeof(int)));
@@ -618,6 +829,8 @@ ASAM_EXPORT int asam_chi2(asam_dev_t *d, int n_factors, double *chi2_out)
     if (buf_reserve(d, d->partial, ((size_t) nblk + 1) * sizeof(double), false, false))
         return 1;
     double *partial = (double *) d->partial.p;
+    if (flush_uploads(d))
+        return 1;
     k_chi2_partial<<<nblk, 256, 0, d->stream>>>((const int *) d->f_type.p, (const int *) d->f_a.p,
                                                  (const int *) d->f_b.p, (const double *) d->f_z.p,
                                                  (const double *) d->f_W.p, (const double *) d->st.p, n_factors,
@@ -661,8 +874,32 @@ ASAM_EXPORT int asam_debug_read_front(asam_dev_t *d, int64_t f_off, int64_t coun
 ASAM_EXPORT int asam_sync(asam_dev_t *d)
 {
     CK(cudaSetDevice(d->device));
+    if (flush_uploads(d))
+        return 1;
     CK(cudaStreamSynchronize(d->stream));
-    d->pin_off = 0;
+    return 0;
+}
+
+// x[q_first .. q_first+q_count) and the factorisation status with ONE synchronisation.
+ASAM_EXPORT int asam_download_x_status(asam_dev_t *d, int q_first, int q_count, double *x3, int *status_out)
+{
+    CK(cudaSetDevice(d->device));
+    if (flush_uploads(d))
+        return 1;
+    const size_t xb = (size_t) q_count * 3 * sizeof(double);
+    if (xb + 16 > d->pin_down_cap) {
+        if (download(d, x3, (const double *) d->x.p + 3 * (size_t) q_first, xb))
+            return 1;
+        return asam_factor_status(d, status_out);
+    }
+    d->n_d2h += (int64_t) xb + 8;
+    CK(cudaMemcpyAsync(d->pin_down, d->ctrl.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, d->stream));
+    if (xb)
+        CK(cudaMemcpyAsync(d->pin_down + 16, (const double *) d->x.p + 3 * (size_t) q_first, xb, cudaMemcpyDeviceToHost,
+                           d->stream));
+    CK(cudaStreamSynchronize(d->stream));
+    *status_out = ((const int *) d->pin_down)[1];
+    memcpy(x3, d->pin_down + 16, xb);
     return 0;
 }
 
@@ -679,6 +916,8 @@ ASAM_EXPORT int asam_counters(asam_dev_t *d, int64_t *out3)
 ASAM_EXPORT int asam_timer_start(asam_dev_t *d)
 {
     CK(cudaSetDevice(d->device));
+    if (flush_uploads(d))
+        return 1;
     if (!d->tev[0]) {
         CK(cudaEventCreate(&d->tev[0]));
         CK(cudaEventCreate(&d->tev[1]));
@@ -701,7 +940,7 @@ ASAM_EXPORT int asam_l2_flush(asam_dev_t *d)
 {
     CK(cudaSetDevice(d->device));
     const size_t bytes = (size_t) 384 << 20;
-    if (buf_reserve(d, d->flush, bytes, false, false))
+    if (buf_reserve(d, d->flush, bytes, false, false) || flush_uploads(d))
         return 1;
     d->flush_val ^= 0x5a;
     CK(cudaMemsetAsync(d->flush.p, d->flush_val, bytes, d->stream));
@@ -728,6 +967,8 @@ ASAM_EXPORT int asam_set_trace(asam_dev_t *d, int enabled)
 ASAM_EXPORT int asam_download_trace(asam_dev_t *d, int which, unsigned long long *out, int max_tasks)
 {
     CK(cudaSetDevice(d->device));
+    if (flush_uploads(d))
+        return 1;
     int n = which == 0 ? d->trace_nfac : d->trace_nbs;
     Buf &b = which == 0 ? d->trace_fac : d->trace_bs;
     if (n > max_tasks)
@@ -749,6 +990,8 @@ ASAM_EXPORT int asam_set_timing(asam_dev_t *d, int enabled)
 ASAM_EXPORT int asam_last_kernel_ms(asam_dev_t *d, float *lin_ms, float *fac_ms, float *bs_ms)
 {
     CK(cudaSetDevice(d->device));
+    if (flush_uploads(d))
+        return 1;
     CK(cudaStreamSynchronize(d->stream));
     float *outs[3] = { lin_ms, fac_ms, bs_ms };
     for (int i = 0; i < 3; i++) {

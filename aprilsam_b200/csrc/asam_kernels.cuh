@@ -109,6 +109,11 @@ __device__ __forceinline__ unsigned long long d_now()
     return t;
 }
 
+// k_linearize aggregates the per-node contributions inside the warp before touching HBM: lanes
+// whose destination node matches (__match_any_sync) are summed with shuffles and only the lowest
+// such lane issues the atomics.  Factors are listed by (max node id, min node id), so the closures
+// of one pose sit in neighbouring lanes and would otherwise serialise on the same L2 address.
+
 // ------------------------------------------------------------------------------------------
 // kernel 1: linearise + scatter
 // ------------------------------------------------------------------------------------------
@@ -124,99 +129,126 @@ struct LinArgs {
 
 __global__ void __launch_bounds__(128) k_linearize(LinArgs a)
 {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.f_count)
-        return;
-    int f = a.f_first + t;
-    int type = a.f_type[f];
-    int na = a.f_a[f];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = t < a.f_count;
+    const int f = a.f_first + (live ? t : 0);
+    const int type = live ? a.f_type[f] : 0;
+    const int na = live ? a.f_a[f] : -1;
+    const int nb = (live && type == 1) ? a.f_b[f] : -1;
     double z[3], W[9];
 #pragma unroll
     for (int i = 0; i < 3; i++)
-        z[i] = a.f_z[3 * (size_t) f + i];
+        z[i] = live ? a.f_z[3 * (size_t) f + i] : 0.0;
 #pragma unroll
     for (int i = 0; i < 9; i++)
-        W[i] = a.f_W[9 * (size_t) f + i];
+        W[i] = live ? a.f_W[9 * (size_t) f + i] : 0.0;
 
-    if (type == 2) { // xytpos: J = I, r = z - state   (april_graph_xytpos.c:63-102)
-        double p[3];
+    // per-node contributions: packed upper triangle of the 3x3 block (6) + rhs (3)
+    double ca9[9], cb9[9], H[9];
+    bool has_off = false;
+    if (live && type == 2) { // xytpos: J = I, r = z - state   (april_graph_xytpos.c:63-102)
         const double *src = a.pts ? (a.pts + 6 * (size_t) t) : (a.st + 3 * (size_t) na);
-        p[0] = src[0]; p[1] = src[1]; p[2] = src[2];
-        double r[3] = { z[0] - p[0], z[1] - p[1], d_mod2pi(z[2] - p[2]) };
+        const double r[3] = { z[0] - src[0], z[1] - src[1], d_mod2pi(z[2] - src[2]) };
         // J'W = W ; (J'W) J = W ; keep scalar row <= col  (aprilsam.c:171-172)
+        ca9[0] = W[0]; ca9[1] = W[1]; ca9[2] = W[2]; ca9[3] = W[4]; ca9[4] = W[5]; ca9[5] = W[8];
+        d_av(W, r, ca9 + 6);
+    } else if (live) { // xyt factor
+        const int qa = a.node2q[na], qb = a.node2q[nb];
+        double pa[3], pb[3];
+        if (a.pts) {
+            const double *src = a.pts + 6 * (size_t) t;
 #pragma unroll
-        for (int i = 0; i < 3; i++)
+            for (int i = 0; i < 3; i++) { pa[i] = src[i]; pb[i] = src[3 + i]; }
+        } else {
 #pragma unroll
-            for (int j = i; j < 3; j++)
-                atomicAdd(&a.Adiag[9 * (size_t) na + i * 3 + j], W[i * 3 + j]);
-        double g[3];
-        d_av(W, r, g);
-#pragma unroll
-        for (int i = 0; i < 3; i++)
-            atomicAdd(&a.Bq[3 * (size_t) na + i], g[i]);
-        return;
+            for (int i = 0; i < 3; i++) { pa[i] = a.lp[3 * (size_t) na + i]; pb[i] = a.lp[3 * (size_t) nb + i]; }
+        }
+        double Ja[9], Jb[9], r[3], JatW[9], JbtW[9], D[9];
+        d_xyt_eval(pa, pb, z, Ja, Jb, r);
+        d_atb(Ja, W, JatW); // J_a' W
+        d_atb(Jb, W, JbtW); // J_b' W
+        // diagonal blocks: entries with scalar row <= col only (aprilsam.c:171-172)
+        d_ab(JatW, Ja, D);
+        ca9[0] = D[0]; ca9[1] = D[1]; ca9[2] = D[2]; ca9[3] = D[4]; ca9[4] = D[5]; ca9[5] = D[8];
+        d_av(JatW, r, ca9 + 6);
+        d_ab(JbtW, Jb, D);
+        cb9[0] = D[0]; cb9[1] = D[1]; cb9[2] = D[2]; cb9[3] = D[4]; cb9[4] = D[5]; cb9[5] = D[8];
+        d_av(JbtW, r, cb9 + 6);
+        // off-diagonal block: the reference keeps (J_early' W J_late) where "early" is the node
+        // eliminated first; the mirrored block is dropped (matters for non-symmetric W).
+        if (qa < qb)
+            d_ab(JatW, Jb, H);
+        else
+            d_ab(JbtW, Ja, H);
+        const int early = qa < qb ? na : nb;
+        if (early != (na < nb ? na : nb)) { // slot layout is S[lower node id][higher node id]
+            double tsw;
+            tsw = H[1]; H[1] = H[3]; H[3] = tsw;
+            tsw = H[2]; H[2] = H[6]; H[6] = tsw;
+            tsw = H[5]; H[5] = H[7]; H[7] = tsw;
+        }
+        has_off = true;
     }
 
-    // xyt factor
-    int nb = a.f_b[f];
-    int qa = a.node2q[na], qb = a.node2q[nb];
-    double pa[3], pb[3];
-    if (a.pts) {
-        const double *src = a.pts + 6 * (size_t) t;
+    // scatter: diag block entries (r<=c) at offsets {0,1,2,4,5,8} of Adiag[9*node], rhs at Bq[3*node]
+    {
+        const bool act = live;
+        double tmp[9];
 #pragma unroll
-        for (int i = 0; i < 3; i++) { pa[i] = src[i]; pb[i] = src[3 + i]; }
-    } else {
+        for (int i = 0; i < 9; i++)
+            tmp[i] = live ? ca9[i] : 0.0;
+        // aggregate the 9 values per destination node, then the leader writes to the two arrays
+        const unsigned lane = threadIdx.x & 31;
+        const unsigned m1 = __ballot_sync(0xffffffffu, act);
+        if (act) {
+            const unsigned peers = __match_any_sync(m1, na);
+            const int leader = __ffs(peers) - 1;
+            for (unsigned rem = peers & ~(1u << leader); rem; rem &= rem - 1) {
+                const int src = __ffs(rem) - 1;
 #pragma unroll
-        for (int i = 0; i < 3; i++) { pa[i] = a.lp[3 * (size_t) na + i]; pb[i] = a.lp[3 * (size_t) nb + i]; }
+                for (int i = 0; i < 9; i++)
+                    tmp[i] += __shfl_sync(peers, ca9[i], src);
+            }
+            if ((int) lane == leader) {
+                double *Ad = a.Adiag + 9 * (size_t) na;
+                atomicAdd(Ad + 0, tmp[0]); atomicAdd(Ad + 1, tmp[1]); atomicAdd(Ad + 2, tmp[2]);
+                atomicAdd(Ad + 4, tmp[3]); atomicAdd(Ad + 5, tmp[4]); atomicAdd(Ad + 8, tmp[5]);
+                double *Bn = a.Bq + 3 * (size_t) na;
+                atomicAdd(Bn + 0, tmp[6]); atomicAdd(Bn + 1, tmp[7]); atomicAdd(Bn + 2, tmp[8]);
+            }
+        }
     }
-    double Ja[9], Jb[9], r[3];
-    d_xyt_eval(pa, pb, z, Ja, Jb, r);
-
-    double JatW[9], JbtW[9], H[9], g[3];
-    d_atb(Ja, W, JatW); // J_a' W
-    d_atb(Jb, W, JbtW); // J_b' W
-
-    // diagonal blocks: entries with scalar row <= col only (aprilsam.c:171-172)
-    d_ab(JatW, Ja, H);
+    {
+        const bool act = has_off;
+        const unsigned lane = threadIdx.x & 31;
+        const unsigned m1 = __ballot_sync(0xffffffffu, act);
+        if (act) {
+            double tmp[9];
 #pragma unroll
-    for (int i = 0; i < 3; i++)
+            for (int i = 0; i < 9; i++)
+                tmp[i] = cb9[i];
+            const unsigned peers = __match_any_sync(m1, nb);
+            const int leader = __ffs(peers) - 1;
+            for (unsigned rem = peers & ~(1u << leader); rem; rem &= rem - 1) {
+                const int src = __ffs(rem) - 1;
 #pragma unroll
-        for (int j = i; j < 3; j++)
-            atomicAdd(&a.Adiag[9 * (size_t) na + i * 3 + j], H[i * 3 + j]);
-    d_ab(JbtW, Jb, H);
+                for (int i = 0; i < 9; i++)
+                    tmp[i] += __shfl_sync(peers, cb9[i], src);
+            }
+            if ((int) lane == leader) {
+                double *Ad = a.Adiag + 9 * (size_t) nb;
+                atomicAdd(Ad + 0, tmp[0]); atomicAdd(Ad + 1, tmp[1]); atomicAdd(Ad + 2, tmp[2]);
+                atomicAdd(Ad + 4, tmp[3]); atomicAdd(Ad + 5, tmp[4]); atomicAdd(Ad + 8, tmp[5]);
+                double *Bn = a.Bq + 3 * (size_t) nb;
+                atomicAdd(Bn + 0, tmp[6]); atomicAdd(Bn + 1, tmp[7]); atomicAdd(Bn + 2, tmp[8]);
+            }
+            // off-diagonal slots are (almost always) unique per factor: plain atomics
+            double *S = a.Aoff + 9 * (size_t) a.f_slot[f];
 #pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = i; j < 3; j++)
-            atomicAdd(&a.Adiag[9 * (size_t) nb + i * 3 + j], H[i * 3 + j]);
-
-    // off-diagonal block: the reference keeps (J_early' W J_late) where "early" is the node
-    // eliminated first; the mirrored block is dropped (matters for non-symmetric W).
-    // The slot is stored as S[lower node id][higher node id]; H is [early][late].
-    int slot = a.f_slot[f];
-    int early;
-    if (qa < qb) {
-        d_ab(JatW, Jb, H);
-        early = na;
-    } else {
-        d_ab(JbtW, Ja, H);
-        early = nb;
+            for (int i = 0; i < 9; i++)
+                atomicAdd(S + i, H[i]);
+        }
     }
-    const bool early_is_lo = early == (na < nb ? na : nb);
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++)
-            atomicAdd(&a.Aoff[9 * (size_t) slot + (early_is_lo ? i * 3 + j : j * 3 + i)], H[i * 3 + j]);
-
-    d_av(JatW, r, g);
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-        atomicAdd(&a.Bq[3 * (size_t) na + i], g[i]);
-    d_av(JbtW, r, g);
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-        atomicAdd(&a.Bq[3 * (size_t) nb + i], g[i]);
 }
 
 __global__ void k_hessian_reset(double *Adiag, double *Aoff, double *Bq, int n_nodes, int n_slots, int n_lambda,

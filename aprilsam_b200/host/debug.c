@@ -92,3 +92,6 @@ ASAM_API int asam_dbg_ref_ordering(int N, const int *adj_ptr, const int *adj, in
     free(o);
     return 0;
 }
+
+void asam_dbg_plan_profile(double *out, int reset);
+ASAM_API void asam_dbg_plan_profile_get(double *out, int reset) { asam_dbg_plan_profile(out, reset); }

@@ -13,12 +13,29 @@
  * :908-987): new poses are appended at the end of the elimination order and only the
  * supernodes on root paths of the touched nodes change (they gain the new poses as rows).
  */
+#define _POSIX_C_SOURCE 200809L
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "asam_host.h"
+
+/* diagnostics: time spent in the phases of plan_append (ms), read by tools/gpu_diag.py */
+static double g_plan_prof[8];
+static double pp_now(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+void asam_dbg_plan_profile(double *out, int reset)
+{
+    memcpy(out, g_plan_prof, sizeof(g_plan_prof));
+    if (reset)
+        memset(g_plan_prof, 0, sizeof(g_plan_prof));
+}
 
 #define RELAX_Z 2     /* relaxed amalgamation: missing block rows tolerated per merge */
 #define RELAX_FILL 24 /* ... and explicit zero blocks (3x3) added per merge */
@@ -679,6 +696,7 @@ int plan_append(plan_t *pl, asam_dev_t *dev, int N, int n_factors, const int *ft
                 const int *marked_old, int n_marked, int **tasks_out, int **nwait_out, int *ntasks_out)
 {
     const int N0 = pl->N, F0 = pl->n_factors, nsn0 = pl->nsn;
+    double pp_t0 = pp_now();
     *tasks_out = *nwait_out = NULL;
     *ntasks_out = 0;
     for (int f = F0; f < n_factors; f++) {
@@ -945,10 +963,14 @@ int plan_append(plan_t *pl, asam_dev_t *dev, int N, int n_factors, const int *ft
         }
         if (!rc && !dev)
             pl->ipool_n += seg.n;
+        g_plan_prof[0] += pp_now() - pp_t0; /* host symbolic */
+        pp_t0 = pp_now();
         if (!rc && dev) {
             int64_t ipool_need = pl->ipool_n + seg.n;
             rc = asam_reserve(dev, N + 64, n_factors + 64, pl->n_slots + 64, pl->nsn + 64, ipool_need + ipool_need / 2,
                               pl->arena_n + pl->arena_n / 4);
+            g_plan_prof[1] += pp_now() - pp_t0; /* asam_reserve */
+            pp_t0 = pp_now();
             asam_sn_desc_t *dd = malloc(sizeof(asam_sn_desc_t) * (size_t) (nt + 1));
             for (int t = 0; t < nt; t++)
                 dd[t] = pl->desc[tasks[t]];
@@ -973,6 +995,7 @@ int plan_append(plan_t *pl, asam_dev_t *dev, int N, int n_factors, const int *ft
                 rc |= asam_hessian_clear_range(dev, N0, nnew, slot0, pl->n_slots - slot0);
             free(dd);
             pl->ipool_n += seg.n;
+            g_plan_prof[2] += pp_now() - pp_t0; /* uploads */
         }
         ivec_free(&seg);
         if (rc) {

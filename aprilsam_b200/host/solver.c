@@ -399,10 +399,8 @@ static uint64_t structure_hash(int N, int F, const int *ftype, const int *fa, co
     return h ? h : 1;
 }
 
-static void check_factor_status(solver_t *s, const char *where)
+static void report_factor_status(solver_t *s, int status, const char *where)
 {
-    int status = 0;
-    DEV_OK(asam_factor_status(s->gc->dev, &status));
     if (status > 0) {
         s->hdr.is_spd = 0;
         asam_fatal("%s: information matrix is not positive definite (pivot <= 0 in supernode %d)", where,
@@ -410,6 +408,13 @@ static void check_factor_status(solver_t *s, const char *where)
     } else if (status < 0) {
         asam_fatal("%s: internal scheduling error in the factorisation kernel (supernode %d)", where, -status - 1);
     }
+}
+
+static void check_factor_status(solver_t *s, const char *where)
+{
+    int status = 0;
+    DEV_OK(asam_factor_status(s->gc->dev, &status));
+    report_factor_status(s, status, where);
 }
 
 /* ---- batch Gauss-Newton step (aprilsam.c:87-375) ------------------------------------------------ */
@@ -459,9 +464,10 @@ ASAM_API void april_graph_cholesky(april_graph_t *graph, april_graph_cholesky_pa
     DEV_OK(asam_backsolve_full(dev));
     PROF_LAP(13);
     double *x = solver_x(s, N);
-    DEV_OK(asam_download_x(dev, 0, N, x));
+    int fstatus = 0;
+    DEV_OK(asam_download_x_status(dev, 0, N, x, &fstatus));
     PROF_LAP(14);
-    check_factor_status(s, "april_graph_cholesky");
+    report_factor_status(s, fstatus, "april_graph_cholesky");
     PROF_LAP(15);
 
     /* persistent state the incremental path continues from (:260-288) */
@@ -692,6 +698,7 @@ ASAM_API void april_graph_cholesky_inc(april_graph_t *graph, april_graph_cholesk
     if (rc != 0)
         asam_fatal("april_graph_cholesky_inc: %s %s", g_error, asam_last_error());
     PROF_LAP(1);
+    DEV_OK(asam_step_begin(dev)); /* record the step's kernels; one upload flush at asam_step_run */
     DEV_OK(asam_linearize(dev, F0, nf, pts));
     DEV_OK(asam_factor(dev, ntasks, tasks, nwait));
     param->factor_num = F;
@@ -706,9 +713,11 @@ ASAM_API void april_graph_cholesky_inc(april_graph_t *graph, april_graph_cholesk
     {
         double *x = solver_x(s, N);
         int qbase = 0;
+        int fstatus = 0;
         if (tr->naffected > 5) {
             DEV_OK(asam_backsolve_full(dev));
-            DEV_OK(asam_download_x(dev, 0, N, x));
+            DEV_OK(asam_step_run(dev));
+            DEV_OK(asam_download_x_status(dev, 0, N, x, &fstatus));
         } else {
             /* visited = marked nodes + their children; close under ancestors */
             int *stamp = calloc((size_t) pl->nsn, sizeof(int));
@@ -738,13 +747,14 @@ ASAM_API void april_graph_cholesky_inc(april_graph_t *graph, april_graph_cholesk
                 bt[j + 1] = v;
             }
             DEV_OK(asam_backsolve(dev, nbt, bt));
+            DEV_OK(asam_step_run(dev));
             qbase = qmin;
-            DEV_OK(asam_download_x(dev, qbase, N - qbase, x));
+            DEV_OK(asam_download_x_status(dev, qbase, N - qbase, x, &fstatus));
             free(stamp);
             free(bt);
         }
         PROF_LAP(4);
-        check_factor_status(s, "april_graph_cholesky_inc");
+        report_factor_status(s, fstatus, "april_graph_cholesky_inc");
         PROF_LAP(5);
         apply_solution(s, tr, x, qbase);
         PROF_LAP(6);

@@ -100,9 +100,17 @@ int asam_btasks_prepend(asam_dev_t *d, int n, const int32_t *ids);
 int asam_backsolve(asam_dev_t *d, int ntasks, const int32_t *btasks);
 int asam_backsolve_full(asam_dev_t *d);
 
+/* Between asam_step_begin and asam_step_run, asam_linearize / asam_factor* / asam_backsolve* only
+ * record their launch; asam_step_run pushes every queued upload with one copy and then launches
+ * the recorded kernels in order (one incremental step = one H2D transfer). */
+int asam_step_begin(asam_dev_t *d);
+int asam_step_run(asam_dev_t *d);
+
 /* Solution read-back: x in elimination order, positions [q_first, q_first+q_count). */
 int asam_download_x(asam_dev_t *d, int q_first, int q_count, double *x3);
 int asam_download_y(asam_dev_t *d, int q_first, int q_count, double *y3);
+/* x and the factorisation status (see asam_factor_status) with a single synchronisation. */
+int asam_download_x_status(asam_dev_t *d, int q_first, int q_count, double *x3, int *status_out);
 
 /* chi2 = sum 0.5 r'Wr (xyt, at state) + sum r'Wr (xytpos) over factors [0, n_factors)
  * using the st mirror (april_graph.c:79-98). Deterministic reduction. */

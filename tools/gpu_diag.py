@@ -231,6 +231,10 @@ def replay_profile(L, d, nsteps):
     _, ms, info = h.replay_to(nsteps, want_chi2=False)
     wall = (time.perf_counter() - t0) * 1e3
     L.asam_dbg_profile(prof.ctypes.data_as(_dp), 1)
+    pp = np.zeros(8)
+    L.asam_dbg_plan_profile_get.argtypes = [_dp, C.c_int]
+    L.asam_dbg_plan_profile_get(pp.ctypes.data_as(_dp), 1)
+    log(f"    plan_append internals (ms, whole run incl. warm-up steps): host symbolic {pp[0]:.1f}, asam_reserve {pp[1]:.1f}, uploads {pp[2]:.1f}")
     ninc, nbatch = prof[8], prof[10]
     log(f"--- replay profile: {len(ms)} steps in {wall:.1f} ms (sum of api calls {ms.sum():.1f} ms), inc calls {ninc:.0f}, "
         f"full-traversal steps {prof[17]:.0f}, batch escalations {nbatch:.0f} taking {prof[7]:.1f} ms")
