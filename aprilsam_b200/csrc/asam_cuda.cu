@@ -76,6 +76,11 @@ struct asam_dev {
     // task lists
     Buf tasks_full, nwait_full, btasks_full;
     int ntasks_full = 0;
+    Buf leaf_tasks; // supernodes handled by k_factor_leaf before k_factor (batch solves of large graphs)
+    int n_leaf = 0;
+    int leaf_grid = 0, leaf_smem = 0;
+    int bt_nleaf = 0; // the last bt_nleaf entries of btasks_full are back-solved by k_backsolve_leaf
+    int bsl_grid = 0, bsl_smem = 0;
     int bt_start = 0, bt_count = 0, bt_cap = 0; // btasks_full holds [bt_start, bt_start+bt_count)
     Buf tasks_tmp, nwait_tmp, btasks_tmp;
     // misc
@@ -271,6 +276,7 @@ static int download(asam_dev *d, void *dst, const void *src, size_t bytes)
 struct Pending {
     int kind; // 0 linearize, 1 factor, 2 backsolve
     int grid;
+    int nleaf;
     LinArgs lin;
     FacArgs fac;
     BsArgs bs;
@@ -291,12 +297,35 @@ static int run_linearize(asam_dev *d, const LinArgs &a)
     return 0;
 }
 
-static int run_factor(asam_dev *d, const FacArgs &a, int grid)
+static int run_factor(asam_dev *d, const FacArgs &a, int grid, int with_leaves = 0)
 {
     if (d->timing)
         CK(cudaEventRecord(d->ev[2], d->stream));
-    k_factor<<<grid, d->fac_threads, d->fac_smem, d->stream>>>(a);
-    d->n_launch++;
+    if (with_leaves && d->n_leaf > 0) {
+        LeafArgs l;
+        l.sn = a.sn;
+        l.ipool = a.ipool;
+        l.arena = a.arena;
+        l.Adiag = a.Adiag;
+        l.Aoff = a.Aoff;
+        l.Bq = a.Bq;
+        l.q2node = a.q2node;
+        l.y = a.y;
+        l.dinv = a.dinv;
+        l.arrive = a.arrive;
+        l.tasks = (const int *) d->leaf_tasks.p;
+        l.ntasks = d->n_leaf;
+        l.ctrl = a.ctrl;
+        l.spin_limit = a.spin_limit;
+        const int want = (d->n_leaf + ASAM_LEAF_WARPS - 1) / ASAM_LEAF_WARPS;
+        k_factor_leaf<<<want < d->leaf_grid ? want : d->leaf_grid, 32 * ASAM_LEAF_WARPS, d->leaf_smem, d->stream>>>(l);
+        d->n_launch++;
+        CK(cudaGetLastError());
+    }
+    if (grid > 0) {
+        k_factor<<<grid, d->fac_threads, d->fac_smem, d->stream>>>(a);
+        d->n_launch++;
+    }
     CK(cudaGetLastError());
     if (d->timing) {
         CK(cudaEventRecord(d->ev[3], d->stream));
@@ -305,13 +334,24 @@ static int run_factor(asam_dev *d, const FacArgs &a, int grid)
     return 0;
 }
 
-static int run_backsolve(asam_dev *d, const BsArgs &a, int grid)
+static int run_backsolve(asam_dev *d, const BsArgs &a, int grid, int nleaf = 0)
 {
     if (d->timing)
         CK(cudaEventRecord(d->ev[4], d->stream));
-    k_backsolve<<<grid, d->bs_threads, d->bs_smem, d->stream>>>(a);
-    d->n_launch++;
-    CK(cudaGetLastError());
+    if (grid > 0) {
+        k_backsolve<<<grid, d->bs_threads, d->bs_smem, d->stream>>>(a);
+        d->n_launch++;
+        CK(cudaGetLastError());
+    }
+    if (nleaf > 0) { // same epoch: parents outside the leaf set were flagged by the launch above
+        BsArgs l = a;
+        l.btasks = a.btasks + a.ntasks;
+        l.ntasks = nleaf;
+        const int want = (nleaf + ASAM_BSL_WARPS - 1) / ASAM_BSL_WARPS;
+        k_backsolve_leaf<<<want < d->bsl_grid ? want : d->bsl_grid, 32 * ASAM_BSL_WARPS, d->bsl_smem, d->stream>>>(l);
+        d->n_launch++;
+        CK(cudaGetLastError());
+    }
     if (d->timing) {
         CK(cudaEventRecord(d->ev[5], d->stream));
         d->ev_set[2] = 1;
@@ -319,13 +359,15 @@ static int run_backsolve(asam_dev *d, const BsArgs &a, int grid)
     return 0;
 }
 
-static int defer_push(asam_dev *d, int kind, int grid, const LinArgs *lin, const FacArgs *fac, const BsArgs *bs)
+static int defer_push(asam_dev *d, int kind, int grid, const LinArgs *lin, const FacArgs *fac, const BsArgs *bs,
+                      int nleaf = 0)
 {
     if (d->npend >= ASAM_MAX_PENDING)
         return set_err("too many deferred launches");
     Pending &p = d->pend[d->npend++];
     p.kind = kind;
     p.grid = grid;
+    p.nleaf = nleaf;
     if (lin) p.lin = *lin;
     if (fac) p.fac = *fac;
     if (bs) p.bs = *bs;
@@ -350,7 +392,8 @@ ASAM_EXPORT int asam_step_run(asam_dev_t *d)
         return 1;
     for (int i = 0; i < d->npend; i++) {
         Pending &p = d->pend[i];
-        int rc = p.kind == 0 ? run_linearize(d, p.lin) : p.kind == 1 ? run_factor(d, p.fac, p.grid) : run_backsolve(d, p.bs, p.grid);
+        int rc = p.kind == 0 ? run_linearize(d, p.lin) : p.kind == 1 ? run_factor(d, p.fac, p.grid)
+                                                                      : run_backsolve(d, p.bs, p.grid, p.nleaf);
         if (rc)
             return rc;
     }
@@ -418,6 +461,20 @@ ASAM_EXPORT int asam_dev_create(asam_dev_t **out)
         return set_err("k_factor does not fit on an SM");
     d->fac_grid = occ * d->n_sm;
 
+    d->leaf_smem = ASAM_LEAF_WARPS * ASAM_LEAF_STRIDE * (int) sizeof(double);
+    CK(cudaFuncSetAttribute(k_factor_leaf, cudaFuncAttributeMaxDynamicSharedMemorySize, d->leaf_smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_factor_leaf, 32 * ASAM_LEAF_WARPS, d->leaf_smem));
+    if (occ < 1)
+        return set_err("k_factor_leaf does not fit on an SM");
+    d->leaf_grid = occ * d->n_sm;
+
+    d->bsl_smem = ASAM_BSL_WARPS * ASAM_BSL_STRIDE * (int) sizeof(double);
+    CK(cudaFuncSetAttribute(k_backsolve_leaf, cudaFuncAttributeMaxDynamicSharedMemorySize, d->bsl_smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_backsolve_leaf, 32 * ASAM_BSL_WARPS, d->bsl_smem));
+    if (occ < 1)
+        return set_err("k_backsolve_leaf does not fit on an SM");
+    d->bsl_grid = occ * d->n_sm;
+
     d->bs_smem = 100 * 1024; // two CTAs per SM; L11 of a 96-column supernode stays on chip
     CK(cudaFuncSetAttribute(k_backsolve, cudaFuncAttributeMaxDynamicSharedMemorySize, d->bs_smem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_backsolve, d->bs_threads, d->bs_smem));
@@ -437,7 +494,7 @@ ASAM_EXPORT void asam_dev_destroy(asam_dev_t *d)
     Buf *all[] = { &d->f_type, &d->f_a, &d->f_b, &d->f_z, &d->f_W, &d->f_slot, &d->lp, &d->st, &d->node2q, &d->q2node,
                    &d->Adiag, &d->Aoff, &d->Bq, &d->y, &d->x, &d->dinv, &d->sn, &d->ipool, &d->arena, &d->arrive,
                    &d->xdone, &d->tbar, &d->tasks_full, &d->nwait_full, &d->btasks_full, &d->tasks_tmp, &d->nwait_tmp,
-                   &d->btasks_tmp, &d->ctrl, &d->partial, &d->patch_ids, &d->patch_desc, &d->pts, &d->flush, &d->trace_fac, &d->trace_bs };
+                   &d->btasks_tmp, &d->leaf_tasks, &d->ctrl, &d->partial, &d->patch_ids, &d->patch_desc, &d->pts, &d->flush, &d->trace_fac, &d->trace_bs };
     for (int i = 0; i < 2; i++)
         if (d->tev[i])
             cudaEventDestroy(d->tev[i]);
@@ -647,14 +704,12 @@ ASAM_EXPORT int asam_linearize(asam_dev_t *d, int f_first, int f_count, const do
     return run_linearize(d, a);
 }
 
-static int launch_factor(asam_dev *d, int ntasks, const int *tasks_dev, const int *nwait_dev)
+static int launch_factor(asam_dev *d, int ntasks, const int *tasks_dev, const int *nwait_dev, int with_leaves = 0)
 {
-    if (ntasks <= 0)
+    if (ntasks <= 0 && !(with_leaves && d->n_leaf > 0))
         return 0;
-    if (queue_fill(d, d->ctrl.p, 0, 2 * sizeof(int))) // ticket, err
-        return 1;
-    if (d->tbar.p && queue_fill(d, d->tbar.p, 0, d->tbar.cap)) // team barrier counters
-        return 1;
+    // ticket / team-barrier counters are left at zero by the previous launch (ticket_release,
+    // team_leave); err is only ever non-zero on a fatal path (see clear_status)
     FacArgs a;
     a.sn = (const asam_sn_desc_t *) d->sn.p;
     a.ipool = (const int *) d->ipool.p;
@@ -681,19 +736,21 @@ static int launch_factor(asam_dev *d, int ntasks, const int *tasks_dev, const in
         d->trace_nfac = ntasks;
     }
     int grid = d->fac_grid < ntasks ? d->fac_grid : ntasks;
-    if (d->defer)
+    if (d->defer) {
+        if (with_leaves && d->n_leaf > 0)
+            return set_err("asam_factor_full inside asam_step_begin/asam_step_run");
         return defer_push(d, 1, grid, nullptr, &a, nullptr);
+    }
     if (flush_uploads(d))
         return 1;
-    return run_factor(d, a, grid);
+    return run_factor(d, a, grid, with_leaves);
 }
 
-static int launch_backsolve(asam_dev *d, int ntasks, const int *btasks_dev)
+static int launch_backsolve(asam_dev *d, int ntasks, const int *btasks_dev, int nleaf = 0)
 {
     if (ntasks <= 0)
         return 0;
-    if (queue_fill(d, (int *) d->ctrl.p + 2, 0, sizeof(int)))
-        return 1;
+    ntasks -= nleaf; // the leaf part follows the main part in the list
     d->epoch++;
     BsArgs a;
     a.sn = (const asam_sn_desc_t *) d->sn.p;
@@ -718,10 +775,10 @@ static int launch_backsolve(asam_dev *d, int ntasks, const int *btasks_dev)
     }
     int grid = d->bs_grid < ntasks ? d->bs_grid : ntasks;
     if (d->defer)
-        return defer_push(d, 2, grid, nullptr, nullptr, &a);
+        return defer_push(d, 2, grid, nullptr, nullptr, &a, nleaf);
     if (flush_uploads(d))
         return 1;
-    return run_backsolve(d, a, grid);
+    return run_backsolve(d, a, grid, nleaf);
 }
 
 ASAM_EXPORT int asam_set_full_tasks(asam_dev_t *d, int ntasks, const int32_t *tasks, const int32_t *nwait,
@@ -740,6 +797,27 @@ ASAM_EXPORT int asam_set_full_tasks(asam_dev_t *d, int ntasks, const int32_t *ta
         upload(d, (int *) d->btasks_full.p + d->bt_start, btasks, bb))
         return 1;
     d->ntasks_full = ntasks;
+    d->n_leaf = 0;
+    d->bt_nleaf = 0;
+    return 0;
+}
+
+// Supernodes of the batch schedule that k_factor_leaf handles (one warp per front) before
+// k_factor runs the list given to asam_set_full_tasks; call after asam_set_full_tasks.
+ASAM_EXPORT int asam_set_leaf_tasks(asam_dev_t *d, int n, const int32_t *tasks)
+{
+    CK(cudaSetDevice(d->device));
+    d->n_leaf = 0;
+    d->bt_nleaf = 0;
+    if (n <= 0)
+        return 0;
+    if (n > d->bt_count)
+        return set_err("asam_set_leaf_tasks: %d leaf supernodes but only %d in the back-solve list", n, d->bt_count);
+    if (buf_reserve(d, d->leaf_tasks, (size_t) n * sizeof(int), false, false) ||
+        upload(d, d->leaf_tasks.p, tasks, (size_t) n * sizeof(int)))
+        return 1;
+    d->n_leaf = n;
+    d->bt_nleaf = n;
     return 0;
 }
 
@@ -772,7 +850,7 @@ ASAM_EXPORT int asam_btasks_prepend(asam_dev_t *d, int n, const int32_t *ids)
 ASAM_EXPORT int asam_factor_full(asam_dev_t *d)
 {
     CK(cudaSetDevice(d->device));
-    return launch_factor(d, d->ntasks_full, (const int *) d->tasks_full.p, (const int *) d->nwait_full.p);
+    return launch_factor(d, d->ntasks_full, (const int *) d->tasks_full.p, (const int *) d->nwait_full.p, 1);
 }
 
 ASAM_EXPORT int asam_factor(asam_dev_t *d, int ntasks, const int32_t *tasks, const int32_t *nwait)
@@ -791,7 +869,7 @@ ASAM_EXPORT int asam_factor(asam_dev_t *d, int ntasks, const int32_t *tasks, con
 ASAM_EXPORT int asam_backsolve_full(asam_dev_t *d)
 {
     CK(cudaSetDevice(d->device));
-    return launch_backsolve(d, d->bt_count, (const int *) d->btasks_full.p + d->bt_start);
+    return launch_backsolve(d, d->bt_count, (const int *) d->btasks_full.p + d->bt_start, d->bt_nleaf);
 }
 
 ASAM_EXPORT int asam_backsolve(asam_dev_t *d, int ntasks, const int32_t *btasks)
@@ -841,6 +919,18 @@ ASAM_EXPORT int asam_chi2(asam_dev_t *d, int n_factors, double *chi2_out)
     return download(d, chi2_out, partial, sizeof(double));
 }
 
+// A non-zero status is fatal for the solve in flight; the control words (tickets, team barriers,
+// arrival counters) may be mid-way, so put all of them back to their idle state.
+static int clear_status(asam_dev *d)
+{
+    CK(cudaMemsetAsync(d->ctrl.p, 0, 8 * sizeof(int), d->stream));
+    if (d->tbar.p)
+        CK(cudaMemsetAsync(d->tbar.p, 0, d->tbar.cap, d->stream));
+    if (d->arrive.p)
+        CK(cudaMemsetAsync(d->arrive.p, 0, d->arrive.cap, d->stream));
+    return 0;
+}
+
 ASAM_EXPORT int asam_factor_status(asam_dev_t *d, int *status_out)
 {
     CK(cudaSetDevice(d->device));
@@ -848,6 +938,8 @@ ASAM_EXPORT int asam_factor_status(asam_dev_t *d, int *status_out)
     if (download(d, ctrl, d->ctrl.p, 2 * sizeof(int)))
         return 1;
     *status_out = ctrl[1];
+    if (ctrl[1] != 0)
+        return clear_status(d);
     return 0;
 }
 
@@ -900,6 +992,8 @@ ASAM_EXPORT int asam_download_x_status(asam_dev_t *d, int q_first, int q_count, 
     CK(cudaStreamSynchronize(d->stream));
     *status_out = ((const int *) d->pin_down)[1];
     memcpy(x3, d->pin_down + 16, xb);
+    if (*status_out != 0)
+        return clear_status(d);
     return 0;
 }
 

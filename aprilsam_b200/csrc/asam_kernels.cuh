@@ -411,13 +411,16 @@ __device__ __forceinline__ void panel_factor(double *P, int ldp, int k0, int pb,
 // ------------------------------------------------------------------------------------------
 // Big fronts: a TEAM of G CTAs (consecutive tickets of the same supernode) factors one front that
 // does not fit in shared memory.  The front stays in HBM/L2; phases are separated by a team
-// barrier on a per-supernode counter (tbar, zeroed by the host before the launch):
-//   assemble own columns -> [barrier] -> extend-add into own columns -> [barrier] ->
-//   per panel of <= ASAM_TPB columns: { every worker factors the diagonal block redundantly in
-//   shared memory, TRSMs its 256-row chunks of the panel } -> [barrier] -> { 256 x 64 tiles of
-//   the trailing update, L operands staged in shared memory, round-robin over workers } -> [barrier]
+// barrier on a per-supernode counter (tbar; the last worker to leave a front zeroes it again):
+//   every worker: wait for the children, zero + assemble + extend-add its OWN columns
+//   -> [barrier] -> per panel of <= ASAM_TPB columns: { every worker factors the diagonal block
+//   redundantly in shared memory (left-looking 3-column steps), solves its 256-row chunks of the
+//   panel against it (rows in registers, 12 columns at a time) } -> [barrier] -> { tiles of the
+//   trailing update, L operands staged in shared memory, round-robin over workers } -> [barrier]
 // Column / chunk / tile ownership is a fixed function of (worker, team size): deterministic.
 // All reads of front data written by other workers bypass L1 (ld.global.cg).
+// A supernode of this kind may be arbitrarily wide (host: fundamental chains of team-sized
+// fronts are merged without a cap), e.g. the 1383-column root separator of the 100 k graph.
 // ------------------------------------------------------------------------------------------
 #define ASAM_TPB 48   // panel width of the team path
 #define ASAM_TROWS 256
@@ -441,7 +444,7 @@ __device__ __forceinline__ bool team_barrier(TeamCtx &tc, int *s_flag)
         long long spins = 0;
         int ok = 1;
         while (ld_volatile(tc.tbar_s) < target) {
-            __nanosleep(32);
+            __nanosleep(20);
             if (++spins > tc.spin_limit || ld_volatile(tc.err) < 0) {
                 atomicCAS(tc.err, 0, -(1 + tc.sn));
                 ok = 0;
@@ -457,7 +460,117 @@ __device__ __forceinline__ bool team_barrier(TeamCtx &tc, int *s_flag)
     return *s_flag != 0;
 }
 
+// Leaving a front: the counter stands at phase*G; every worker adds one more and the last one
+// to do so zeroes it for the next launch (no host-side reset between launches).
+__device__ __forceinline__ void team_leave(TeamCtx &tc)
+{
+    if (threadIdx.x == 0) {
+        const int v = atomicAdd(tc.tbar_s, 1);
+        if (v == tc.phase * tc.G + tc.G - 1)
+            atomicExch(tc.tbar_s, 0);
+    }
+}
+
 __device__ __forceinline__ bool team_owns(int col, int w, int G) { return ((col >> 2) % G) == w; }
+
+// Cholesky of the pb x pb diagonal block held in shared memory (column-major, leading dimension
+// ASAM_TPB), by all threads of the CTA: left-looking over 3-column steps (one pose each) -- the
+// three columns first receive the contributions of the columns to their left (one thread per
+// entry, a dot product), then a closed-form 3x3 Cholesky (evaluated redundantly, three chained
+// reciprocal square roots) finishes them.  rdv[k] = 1 / L_kk.
+__device__ __forceinline__ void diag_factor(double *D, int pb, double *rdv, int sn_id, int *err)
+{
+    const int tid = threadIdx.x;
+    constexpr int LDD = ASAM_TPB;
+    for (int c0 = 0; c0 < pb; c0 += 3) {
+        if (c0 > 0 && tid < 3 * (pb - c0)) {
+            const int i = c0 + tid / 3, j = c0 + tid % 3;
+            if (i >= j) {
+                double acc0 = D[i + j * LDD], acc1 = 0.0;
+                int p = 0;
+                for (; p + 1 < c0; p += 2) {
+                    acc0 -= D[i + p * LDD] * D[j + p * LDD];
+                    acc1 -= D[i + (p + 1) * LDD] * D[j + (p + 1) * LDD];
+                }
+                if (p < c0)
+                    acc0 -= D[i + p * LDD] * D[j + p * LDD];
+                D[i + j * LDD] = acc0 + acc1;
+            }
+        }
+        __syncthreads();
+        double *p0 = D + c0 * LDD, *p1 = p0 + LDD, *p2 = p1 + LDD;
+        const double a00 = p0[c0], a10 = p0[c0 + 1], a20 = p0[c0 + 2];
+        const double a11 = p1[c0 + 1], a21 = p1[c0 + 2], a22 = p2[c0 + 2];
+        const double r0 = rsqrt(a00);
+        const double l10 = a10 * r0, l20 = a20 * r0;
+        const double d1 = a11 - l10 * l10;
+        const double r1 = rsqrt(d1);
+        const double l21 = (a21 - l20 * l10) * r1;
+        const double d2 = a22 - l20 * l20 - l21 * l21;
+        const double r2 = rsqrt(d2);
+        if (tid == 0 && !(a00 > 0.0 && d1 > 0.0 && d2 > 0.0))
+            atomicCAS(err, 0, 1 + sn_id);
+        const int i = c0 + 3 + tid;
+        if (i < pb) {
+            const double x0 = p0[i] * r0;
+            const double x1 = (p1[i] - x0 * l10) * r1;
+            const double x2 = (p2[i] - x0 * l20 - x1 * l21) * r2;
+            p0[i] = x0;
+            p1[i] = x1;
+            p2[i] = x2;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            p0[c0] = a00 * r0; p0[c0 + 1] = l10; p0[c0 + 2] = l20;
+            p1[c0 + 1] = d1 * r1; p1[c0 + 2] = l21;
+            p2[c0 + 2] = d2 * r2;
+            rdv[c0] = r0; rdv[c0 + 1] = r1; rdv[c0 + 2] = r2;
+        }
+    }
+    __syncthreads();
+}
+
+// One row of the panel per thread: x = row * L11^-T.  The row lives in Li (column p at
+// Li[tid + p*ASAM_TROWS]); it is processed 12 columns at a time in registers -- first the
+// contributions of the columns already solved (L entries fetched two at a time, broadcast), then
+// the 12x12 triangle fully unrolled.  Results go back to Li and to the front in HBM.
+__device__ __forceinline__ void trsm_row(double *Li, const double *D, const double *rdv, int pb, double *Frow, int ld)
+{
+    const int tid = threadIdx.x;
+    constexpr int LDD = ASAM_TPB;
+    for (int b0 = 0; b0 < pb; b0 += 12) {
+        const int nb = min(12, pb - b0);
+        double r[12];
+#pragma unroll
+        for (int q = 0; q < 12; q++)
+            r[q] = (q < nb) ? Li[tid + (b0 + q) * ASAM_TROWS] : 0.0;
+        for (int p = 0; p < b0; p++) {
+            const double xp = Li[tid + p * ASAM_TROWS];
+            const double2 *Dp = reinterpret_cast<const double2 *>(D + p * LDD + b0);
+#pragma unroll
+            for (int q2 = 0; q2 < 6; q2++) {
+                const double2 v = Dp[q2];
+                r[2 * q2] -= xp * v.x;
+                r[2 * q2 + 1] -= xp * v.y;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 12; q++) {
+            if (q < nb) {
+                r[q] *= rdv[b0 + q];
+#pragma unroll
+                for (int q2 = q + 1; q2 < 12; q2++)
+                    r[q2] -= r[q] * D[(b0 + q2) + (b0 + q) * LDD];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 12; q++)
+            if (q < nb) {
+                Li[tid + (b0 + q) * ASAM_TROWS] = r[q];
+                Frow[(size_t) (b0 + q) * ld] = r[q];
+            }
+    }
+}
 
 // returns false on abort
 __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int nw, int w, int G, double *sm,
@@ -484,7 +597,7 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
     tc.err = err;
     tc.sn = s;
 
-    // ---- assemble own columns ------------------------------------------------------------
+    // ---- zero + assemble own columns ---------------------------------------------------------
     for (int j = warp; j < m; j += nwarps) {
         if (!team_owns(j, w, G))
             continue;
@@ -510,24 +623,29 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
         const int si = (rbf & ASAM_TR_FLAG) ? (p * 3 + q) : (q * 3 + p);
         F[(3 * rb + p) + (size_t) col * ld] = a.Aoff[9 * (size_t) a_slot[i] + si];
     }
-    // worker 0 waits for the children re-factored in this launch; the barrier releases the rest
-    if (w == 0 && nw > 0 && tid == 0) {
+    // every worker waits for the children re-factored in this launch (the counter is zeroed by
+    // worker 0 after the first team barrier, when nobody looks at it any more)
+    if (nw > 0 && tid == 0) {
         long long spins = 0;
+        int ok = 1;
         while (ld_volatile(&a.arrive[s]) < nw) {
-            __nanosleep(32);
+            __nanosleep(20);
             if (++spins > a.spin_limit || ld_volatile(err) < 0) {
                 atomicCAS(err, 0, -(1 + s));
+                ok = 0;
                 break;
             }
         }
-        a.arrive[s] = 0;
-        if (trow)
-            trow[1] = d_now();
+        __threadfence();
+        *s_flag = ok;
+    } else if (tid == 0) {
+        *s_flag = 1;
     }
-    if (!team_barrier(tc, s_flag))
+    __syncthreads();
+    if (!*s_flag)
         return false;
     if (trow && tid == 0)
-        trow[2] = d_now();
+        trow[1] = trow[2] = d_now();
 
     // ---- extend-add into own columns -------------------------------------------------------
     int *dmap = (int *) sm; // ld ints
@@ -536,6 +654,7 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
         const int cm = 3 * cd.mb, cc = 3 * cd.cb, cr = cm - cc, cld = cm + 1;
         const double *CF = a.arena + cd.f_off;
         const int *crel = a.ipool + cd.seg + cd.mb;
+        __syncthreads();
         for (int i = tid; i <= cr; i += nt)
             dmap[i] = (i < cr) ? 3 * crel[(cc + i) / 3] + (cc + i) % 3 : m;
         __syncthreads();
@@ -556,50 +675,52 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
                         fcol[dmap[i0 + 32 * u]] += v[u];
             }
         }
-        __syncthreads();
     }
     if (!team_barrier(tc, s_flag))
         return false;
+    if (w == 0 && nw > 0 && tid == 0)
+        a.arrive[s] = 0;
     unsigned long long t_panel = 0, t_mark = 0;
     if (trow && tid == 0)
         trow[3] = d_now();
 
     // ---- panels ---------------------------------------------------------------------------------
-    double *D = sm;                              // ASAM_TPB x ASAM_TPB diagonal block, ld = pb
-    double *Li = sm + ASAM_TPB * ASAM_TPB;       // ASAM_TROWS x pb   (row chunk / row tile)
+    double *D = sm;                              // ASAM_TPB x ASAM_TPB diagonal block
+    double *rdv = D + ASAM_TPB * ASAM_TPB;       // ASAM_TPB reciprocal diagonal entries
+    double *Li = rdv + ASAM_TPB;                 // ASAM_TROWS x pb   (row chunk / row tile)
     double *Lj = Li + ASAM_TROWS * ASAM_TPB;     // ASAM_TCOLS x pb   (column tile)
     double *dinv = a.dinv + 3 * (size_t) d.first;
     for (int k0 = 0; k0 < c; k0 += ASAM_TPB) {
         const int pb = min(ASAM_TPB, c - k0);
         if (trow && tid == 0)
             t_mark = d_now();
-        // diagonal block, factored redundantly by every worker (closed-form 3x3 steps)
-        for (int e = tid; e < pb * pb; e += nt) {
-            const int i = e % pb, j = e / pb;
-            D[e] = (i >= j) ? __ldcg(&F[(k0 + i) + (size_t) (k0 + j) * ld]) : 0.0;
-        }
+        // diagonal block (every worker, redundantly) ...
         __syncthreads();
-        panel_factor(D, pb, 0, pb, pb - 1, s, err, nullptr);
-        // TRSM: 256-row chunks of the rows below the block (row m = rhs included), round-robin
+        for (int e = tid; e < ASAM_TPB * ASAM_TPB; e += nt) {
+            const int i = e % ASAM_TPB, j = e / ASAM_TPB;
+            D[e] = (i >= j && i < pb && j < pb) ? __ldcg(&F[(k0 + i) + (size_t) (k0 + j) * ld]) : 0.0;
+        }
+        // ... while the first row chunk of this worker is already on its way into shared memory
         const int r_first = k0 + pb;
         const int nchunk = (m - r_first + 1 + ASAM_TROWS - 1) / ASAM_TROWS;
-        for (int ch = w; ch < nchunk; ch += G) {
+        int ch = w;
+        {
             const int i = r_first + ch * ASAM_TROWS + tid;
-            __syncthreads();
-            if (i <= m) {
-                // fetch the whole row first (pb independent loads in flight), then solve in place
+            if (ch < nchunk && i <= m)
                 for (int j = 0; j < pb; j++)
                     Li[tid + j * ASAM_TROWS] = __ldcg(&F[i + (size_t) (k0 + j) * ld]);
-                for (int j = 0; j < pb; j++) {
-                    double v = Li[tid + j * ASAM_TROWS];
-#pragma unroll 4
-                    for (int p = 0; p < j; p++)
-                        v -= Li[tid + p * ASAM_TROWS] * D[j + p * pb];
-                    v /= D[j + j * pb];
-                    Li[tid + j * ASAM_TROWS] = v;
-                    F[i + (size_t) (k0 + j) * ld] = v;
-                }
+        }
+        __syncthreads();
+        diag_factor(D, pb, rdv, s, err);
+        for (; ch < nchunk; ch += G) {
+            const int i = r_first + ch * ASAM_TROWS + tid;
+            if (ch != w) { // later chunks of this worker: fetch now
+                if (i <= m)
+                    for (int j = 0; j < pb; j++)
+                        Li[tid + j * ASAM_TROWS] = __ldcg(&F[i + (size_t) (k0 + j) * ld]);
             }
+            if (i <= m)
+                trsm_row(Li, D, rdv, pb, F + i + (size_t) k0 * ld, ld);
         }
         if (!team_barrier(tc, s_flag))
             return false;
@@ -610,36 +731,65 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
             for (int e = tid; e < pb * pb; e += nt) {
                 const int i = e % pb, j = e / pb;
                 if (i >= j)
-                    F[(k0 + i) + (size_t) (k0 + j) * ld] = D[e];
+                    F[(k0 + i) + (size_t) (k0 + j) * ld] = D[i + j * ASAM_TPB];
             }
             for (int e = tid; e < pb; e += nt)
-                dinv[k0 + e] = 1.0 / D[e + e * pb];
+                dinv[k0 + e] = rdv[e];
         }
 
-        // trailing update: tiles of 256 rows x 64 columns over the lower trapezoid
+        // trailing update: tiles of TR rows x 64 columns over the lower trapezoid (TR = 128 when
+        // 256-row tiles would leave workers idle)
         const int j0 = k0 + pb;
+        int n256 = 0;
+        for (int cb0 = j0; cb0 < m; cb0 += ASAM_TCOLS)
+            n256 += (m - cb0 + 1 + 255) / 256;
+        const int TR = (n256 < 2 * G) ? 128 : 256;
         int u = 0;
         for (int cb0 = j0; cb0 < m; cb0 += ASAM_TCOLS) {
-            for (int rb0 = cb0; rb0 <= m; rb0 += ASAM_TROWS, ++u) {
+            for (int rb0 = cb0; rb0 <= m; rb0 += TR, ++u) {
                 if (u % G != w)
                     continue;
                 __syncthreads();
-                const int ncol = min(ASAM_TCOLS, m - cb0), nrow = min(ASAM_TROWS, m - rb0 + 1);
-                for (int e = tid; e < ncol * pb; e += nt) {
-                    const int jj = e % ncol, p = e / ncol;
-                    Lj[jj + p * ASAM_TCOLS] = __ldcg(&F[(cb0 + jj) + (size_t) (k0 + p) * ld]);
-                }
-                for (int e = tid; e < nrow * pb; e += nt) {
-                    const int ii = e % nrow, p = e / nrow;
-                    Li[ii + p * ASAM_TROWS] = __ldcg(&F[(rb0 + ii) + (size_t) (k0 + p) * ld]);
+                const int ncol = min(ASAM_TCOLS, m - cb0), nrow = min(TR, m - rb0 + 1);
+                // two panel columns per warp and pass: 20 independent loads in flight per lane
+                for (int p = warp; p < pb; p += 2 * nwarps) {
+                    double vj[2][2], vi[2][8];
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int pp = p + h * nwarps;
+                        const double *src = F + (size_t) (k0 + min(pp, pb - 1)) * ld;
+#pragma unroll
+                        for (int u = 0; u < 2; u++)
+                            vj[h][u] = (pp < pb && lane + 32 * u < ncol) ? __ldcg(src + cb0 + lane + 32 * u) : 0.0;
+#pragma unroll
+                        for (int u = 0; u < 8; u++)
+                            vi[h][u] = (pp < pb && lane + 32 * u < nrow) ? __ldcg(src + rb0 + lane + 32 * u) : 0.0;
+                    }
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int pp = p + h * nwarps;
+                        if (pp < pb) {
+#pragma unroll
+                            for (int u = 0; u < 2; u++)
+                                if (lane + 32 * u < ncol)
+                                    Lj[lane + 32 * u + pp * ASAM_TCOLS] = vj[h][u];
+#pragma unroll
+                            for (int u = 0; u < 8; u++)
+                                if (lane + 32 * u < nrow)
+                                    Li[lane + 32 * u + pp * ASAM_TROWS] = vi[h][u];
+                        }
+                    }
                 }
                 __syncthreads();
-                // warp -> 8 columns, lane -> rows lane + 32 r (two passes of 128 rows)
+                // warp -> 8 columns, lane -> rows lane + 32 r (passes of 128 rows)
                 const int tj = 8 * warp;
                 if (tj < ncol) {
                     for (int ib = 0; ib < nrow; ib += 128) {
                         double acc[4][8], cv[4][8];
-                        int ir[4];
+                        int ir[4], jc[8];
+#pragma unroll
+                        for (int q = 0; q < 8; q++)
+                            jc[q] = min(tj + q, ncol - 1);
 #pragma unroll
                         for (int r = 0; r < 4; r++) {
                             ir[r] = min(ib + lane + 32 * r, nrow - 1);
@@ -658,7 +808,7 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
                             double b[8], av[4];
 #pragma unroll
                             for (int q = 0; q < 8; q++)
-                                b[q] = Lj[min(tj + q, ncol - 1) + p * ASAM_TCOLS];
+                                b[q] = Lj[jc[q] + p * ASAM_TCOLS];
 #pragma unroll
                             for (int r = 0; r < 4; r++)
                                 av[r] = Li[ir[r] + p * ASAM_TROWS];
@@ -699,13 +849,28 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
             atomicAdd(&a.arrive[d.parent], 1);
         }
     }
+    team_leave(tc);
     __syncthreads();
     return true;
 }
 
+// Persistent kernels take tickets from a counter in a.ctrl; the last CTA to leave zeroes the
+// counter again, so back-to-back launches need no host-side reset (err stays 0 unless fatal).
+__device__ __forceinline__ void ticket_release(int *ticket, int *done)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(done, 1) == (int) gridDim.x - 1) {
+            atomicExch(ticket, 0);
+            atomicExch(done, 0);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256, 1) k_factor(FacArgs a)
 {
-    extern __shared__ double sm[];
+    extern __shared__ __align__(16) double sm[];
     __shared__ int s_task, s_abort;
     __shared__ asam_sn_desc_t s_cd[ASAM_MAX_CACHED_CHILDREN];
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -917,6 +1082,191 @@ __global__ void __launch_bounds__(256, 1) k_factor(FacArgs a)
         }
         __syncthreads();
     }
+    ticket_release(&a.ctrl[0], &a.ctrl[3]);
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel 2a: the leaves.  Large graphs have tens of thousands of supernodes with tiny fronts
+// (100 k Manhattan: 36 k of 47 k have m < 49) at the bottom of the tree; one CTA per front
+// wastes the SM on them.  Here every WARP takes tickets on its own and factors a whole front
+// (m <= ASAM_LEAF_M) in its private slice of shared memory; the host hands this kernel the
+// downward-closed set of supernodes whose whole subtree consists of such fronts, k_factor does
+// the rest afterwards.  Same arithmetic as k_factor's shared-memory path (3-column closed-form
+// steps, right-looking), same front layout, same arrival counters.
+// ------------------------------------------------------------------------------------------
+#define ASAM_LEAF_M 48
+#define ASAM_LEAF_WARPS 8
+#define ASAM_LEAF_STRIDE ((ASAM_LEAF_M + 1) * ASAM_LEAF_M + ASAM_LEAF_M / 2 + 2) // doubles per warp (even)
+
+struct LeafArgs {
+    const asam_sn_desc_t *sn;
+    const int *ipool;
+    double *arena;
+    const double *Adiag, *Aoff, *Bq;
+    const int *q2node;
+    double *y;
+    double *dinv;
+    int *arrive;
+    const int *tasks; // children before parents
+    int ntasks;
+    int *ctrl; // [5] ticket, [6] done, [1] err
+    long long spin_limit;
+};
+
+__global__ void __launch_bounds__(32 * ASAM_LEAF_WARPS, 1) k_factor_leaf(LeafArgs a)
+{
+    extern __shared__ __align__(16) double sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *F = sm + (size_t) warp * ASAM_LEAF_STRIDE;
+    int *dmap = (int *) (F + (ASAM_LEAF_M + 1) * ASAM_LEAF_M);
+    int *err = a.ctrl + 1;
+    for (;;) {
+        int t = 0;
+        if (lane == 0)
+            t = atomicAdd(&a.ctrl[5], 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= a.ntasks)
+            break;
+        const int s = a.tasks[t];
+        const asam_sn_desc_t d = a.sn[s];
+        const int m = 3 * d.mb, c = 3 * d.cb, ld = m + 1;
+        if (m > ASAM_LEAF_M) { // host error
+            if (lane == 0)
+                atomicCAS(err, 0, -(1 + s));
+            break;
+        }
+        const int *seg = a.ipool + d.seg;
+        const int *children = seg + 2 * d.mb;
+        const int *a_slot = children + d.ch_cnt;
+        const int *a_rb = a_slot + d.a_cnt;
+        const int *a_cb = a_rb + d.a_cnt;
+        double *Fg = a.arena + d.f_off;
+        const int fsz = ld * m;
+
+        // ---- 1. zero, gather the original entries ------------------------------------------
+        for (int i = lane; i < fsz; i += 32)
+            F[i] = 0.0;
+        __syncwarp();
+        for (int e = lane; e < d.cb * 9; e += 32) {
+            int k = e / 9, p = (e % 9) / 3, q = e % 3;
+            if (p >= q)
+                F[(3 * k + p) + (3 * k + q) * ld] = a.Adiag[9 * (size_t) a.q2node[d.first + k] + q * 3 + p];
+        }
+        for (int e = lane; e < c; e += 32)
+            F[m + e * ld] = a.Bq[3 * (size_t) a.q2node[d.first + e / 3] + e % 3];
+        for (int e = lane; e < d.a_cnt * 9; e += 32) {
+            int i = e / 9, p = (e % 9) / 3, q = e % 3;
+            const int rbf = a_rb[i];
+            const int rb = rbf & ~ASAM_TR_FLAG;
+            const int si = (rbf & ASAM_TR_FLAG) ? (p * 3 + q) : (q * 3 + p);
+            F[(3 * rb + p) + (3 * a_cb[i] + q) * ld] = a.Aoff[9 * (size_t) a_slot[i] + si];
+        }
+
+        // ---- 2. wait for the children (all of them are tasks of this launch) -----------------
+        int abort_ = 0;
+        if (d.ch_cnt > 0) {
+            if (lane == 0) {
+                long long spins = 0;
+                while (ld_volatile(&a.arrive[s]) < d.ch_cnt) {
+                    __nanosleep(20);
+                    if (++spins > a.spin_limit || ld_volatile(err) < 0) {
+                        atomicCAS(err, 0, -(1 + s));
+                        abort_ = 1;
+                        break;
+                    }
+                }
+                a.arrive[s] = 0;
+                __threadfence();
+            }
+            abort_ = __shfl_sync(0xffffffffu, abort_, 0);
+        }
+        if (abort_)
+            break;
+        __syncwarp();
+
+        // ---- 3. extend-add --------------------------------------------------------------------
+        for (int ci = 0; ci < d.ch_cnt; ++ci) {
+            const asam_sn_desc_t cd = a.sn[children[ci]];
+            const int cm = 3 * cd.mb, cc = 3 * cd.cb, cr = cm - cc, cld = cm + 1;
+            const double *CF = a.arena + cd.f_off + (size_t) cc * cld + cc; // (0,0) of the update matrix
+            const int *crel = a.ipool + cd.seg + cd.mb;
+            for (int i = lane; i <= cr; i += 32)
+                dmap[i] = (i < cr) ? 3 * crel[(cc + i) / 3] + (cc + i) % 3 : m;
+            __syncwarp();
+            const int n = (cr + 1) * cr; // entries (i, j): i in [0, cr] (cr = rhs row), j in [0, cr)
+            for (int e0 = lane; e0 < n; e0 += 128) {
+                double v[4];
+                int dst[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int e = e0 + 32 * u;
+                    const int j = e / (cr + 1), i = e - j * (cr + 1);
+                    const bool ok = e < n && i >= j;
+                    v[u] = ok ? __ldcg(CF + i + (size_t) j * cld) : 0.0;
+                    dst[u] = ok ? dmap[i] + dmap[j] * ld : -1;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (dst[u] >= 0)
+                        F[dst[u]] += v[u];
+            }
+            __syncwarp();
+        }
+
+        // ---- 4. eliminate the c columns, 3 at a time ---------------------------------------
+        double *dinv = a.dinv + 3 * (size_t) d.first;
+        for (int k = 0; k < c; k += 3) {
+            double *p0 = F + k * ld, *p1 = p0 + ld, *p2 = p1 + ld;
+            const double a00 = p0[k], a10 = p0[k + 1], a20 = p0[k + 2];
+            const double a11 = p1[k + 1], a21 = p1[k + 2], a22 = p2[k + 2];
+            const double r0 = rsqrt(a00);
+            const double l10 = a10 * r0, l20 = a20 * r0;
+            const double d1 = a11 - l10 * l10;
+            const double r1 = rsqrt(d1);
+            const double l21 = (a21 - l20 * l10) * r1;
+            const double d2 = a22 - l20 * l20 - l21 * l21;
+            const double r2 = rsqrt(d2);
+            if (lane == 0 && !(a00 > 0.0 && d1 > 0.0 && d2 > 0.0))
+                atomicCAS(err, 0, 1 + s);
+            __syncwarp(); // every lane has read the diagonal block
+            for (int i = k + 3 + lane; i <= m; i += 32) {
+                const double x0 = p0[i] * r0;
+                const double x1 = (p1[i] - x0 * l10) * r1;
+                const double x2 = (p2[i] - x0 * l20 - x1 * l21) * r2;
+                p0[i] = x0;
+                p1[i] = x1;
+                p2[i] = x2;
+            }
+            if (lane == 0) {
+                p0[k] = a00 * r0; p0[k + 1] = l10; p0[k + 2] = l20;
+                p1[k + 1] = d1 * r1; p1[k + 2] = l21;
+                p2[k + 2] = d2 * r2;
+                dinv[k] = r0; dinv[k + 1] = r1; dinv[k + 2] = r2;
+            }
+            __syncwarp();
+#pragma unroll 4
+            for (int j = k + 3; j < m; ++j) {
+                const double y0 = p0[j], y1 = p1[j], y2 = p2[j];
+                double *cj = F + j * ld;
+                for (int i = j + lane; i <= m; i += 32)
+                    cj[i] -= p0[i] * y0 + p1[i] * y1 + p2[i] * y2;
+            }
+            __syncwarp();
+        }
+
+        // ---- 5. publish ------------------------------------------------------------------------
+        for (int e = lane; e < c; e += 32)
+            a.y[3 * (size_t) d.first + e] = F[m + e * ld];
+        for (int i = lane; i < fsz; i += 32)
+            Fg[i] = F[i];
+        __syncwarp();
+        if (lane == 0 && d.parent >= 0) {
+            __threadfence();
+            atomicAdd(&a.arrive[d.parent], 1);
+        }
+        __syncwarp();
+    }
+    ticket_release(&a.ctrl[5], &a.ctrl[6]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -940,11 +1290,41 @@ struct BsArgs {
 };
 
 // One supernode: x1 = L11^-T (y1 - L21' x2), x2 gathered from the ancestors' solution.
-// Everything that does not depend on the parent (descriptor, row list, y1, 1/diag and the L
-// panel when it fits in shared memory) is fetched BEFORE waiting on the parent's flag.
+// The supernode's columns are solved in blocks of <= ASAM_BSW columns, last block first; for a
+// block [b0, be) every row below it (later blocks and L21 alike) is "already known":
+//   w = y[b0:be] - L[be:m, b0:be]' xf[be:m],   L[b0:be, b0:be]' x = w.
+// Supernodes of the shared-memory path have one block (<= 96 columns); the wide supernodes of
+// the team path (merged chains, up to the whole root separator) loop.
+// Everything that does not depend on the parent (descriptor, row list, y, 1/diag and the L
+// panel of the first block when it fits in shared memory) is fetched BEFORE waiting on the
+// parent's flag.
+#define ASAM_BSW 96
+
+template <int U>
+__device__ __forceinline__ double bs_dot(const double *lk, const double *xs, int n, int lane)
+{
+    double acc0 = 0.0, acc1 = 0.0;
+    for (int i0 = lane; i0 < n; i0 += 32 * U) { // U independent loads in flight per lane
+        double v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            v[u] = (i0 + 32 * u < n) ? lk[i0 + 32 * u] : 0.0;
+#pragma unroll
+        for (int u = 0; u < U; u += 2) {
+            acc0 += v[u] * xs[min(i0 + 32 * u, n - 1)];
+            acc1 += v[u + 1] * xs[min(i0 + 32 * (u + 1), n - 1)];
+        }
+    }
+    acc0 += acc1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        acc0 += __shfl_down_sync(0xffffffffu, acc0, o);
+    return acc0;
+}
+
 __global__ void __launch_bounds__(128) k_backsolve(BsArgs a)
 {
-    extern __shared__ double sm[]; // xs[r] | w[c] | rd[c] | staged L (panel or L11)
+    extern __shared__ __align__(16) double sm[]; // xf[m] | w[bw] | rd[bw] | staged L (panel or L11 of one block)
     __shared__ int s_task, s_abort;
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
@@ -967,112 +1347,247 @@ __global__ void __launch_bounds__(128) k_backsolve(BsArgs a)
         const int m = 3 * d.mb, c = 3 * d.cb, r = m - c, ld = m + 1;
         const int *rows = a.ipool + d.seg;
         const double *Lg = a.arena + d.f_off;
-        if (m + c + 2 > a.smem_doubles) { // host sizes shared memory for the largest front
+        const int bwmax = min(c, ASAM_BSW);
+        if (m + 2 * bwmax + 2 > a.smem_doubles) { // host sizes shared memory for the largest front
             if (tid == 0)
                 atomicCAS(err, 0, -(1 + s));
             break;
         }
-        double *xs = sm;        // r
-        double *w = sm + r;     // c
-        double *rd = sm + m;    // c
-        double *Ls = sm + m + c;
-        const long long room = (long long) a.smem_doubles - (m + c);
-        // staging mode: 2 = whole panel (m x c, ld m), 1 = L11 only (c x c, ld c), 0 = none
-        // staged leading dimensions are ODD: the triangular solve reads row k across columns
-        // (stride ll doubles), an even stride would pile the lanes onto a few banks
-        const int lm = m | 1, lc = c | 1;
-        const int mode = ((long long) lm * c <= room) ? 2 : (((long long) lc * c <= room) ? 1 : 0);
-        const int ll = mode == 2 ? lm : (mode == 1 ? lc : ld);
-        if (mode == 2) {
-            for (int k = warp; k < c; k += nwarps)
-                for (int i = k + lane; i < m; i += 32)
-                    Ls[i + (size_t) k * lm] = Lg[i + (size_t) k * ld];
-        } else if (mode == 1) {
-            for (int k = warp; k < c; k += nwarps)
-                for (int i = k + lane; i < c; i += 32)
-                    Ls[i + (size_t) k * lc] = Lg[i + (size_t) k * ld];
-        }
-        for (int k = tid; k < c; k += nt) {
-            w[k] = a.y[3 * (size_t) d.first + k];
-            rd[k] = a.dinv[3 * (size_t) d.first + k];
-        }
-        const double *L11 = mode ? Ls : Lg; // (row, col) at L11[row + col*ll]
-        if (a.trace && tid == 0)
-            tr1 = d_now();
+        double *xf = sm;          // x over the front's rows: [0,c) own columns, [c,m) ancestors
+        double *w = sm + m;       // bwmax
+        double *rd = w + bwmax;   // bwmax
+        double *Ls = rd + bwmax;
+        const long long room = (long long) a.smem_doubles - (m + 2 * bwmax);
+        const int nblk = (c + ASAM_BSW - 1) / ASAM_BSW;
 
-        if (d.parent >= 0 && tid == 0) {
-            long long spins = 0;
-            while (ld_volatile(&a.xdone[d.parent]) != a.epoch) {
-                __nanosleep(32);
-                if (++spins > a.spin_limit || ld_volatile(err) < 0) {
-                    atomicCAS(err, 0, -(1 + s));
-                    s_abort = 1;
-                    break;
-                }
+        for (int blk = nblk - 1; blk >= 0; --blk) {
+            const int b0 = blk * ASAM_BSW, bw = min(ASAM_BSW, c - b0), be = b0 + bw, hb = m - b0;
+            // staging mode: 2 = whole panel of the block (rows b0..m-1, ld lm), 1 = its diagonal
+            // block only (ld lc), 0 = none.  Staged leading dimensions are ODD: the triangular
+            // solve reads row k across columns, an even stride would pile the lanes onto a few banks
+            const int lm = hb | 1, lc = bw | 1;
+            const int mode = ((long long) lm * bw <= room) ? 2 : (((long long) lc * bw <= room) ? 1 : 0);
+            const int ll = mode == 2 ? lm : (mode == 1 ? lc : ld);
+            if (blk != nblk - 1)
+                __syncthreads(); // the previous block is done with w / rd / Ls
+            if (mode == 2) {
+                for (int k = warp; k < bw; k += nwarps)
+                    for (int i = k + lane; i < hb; i += 32)
+                        Ls[i + (size_t) k * lm] = Lg[(b0 + i) + (size_t) (b0 + k) * ld];
+            } else if (mode == 1) {
+                for (int k = warp; k < bw; k += nwarps)
+                    for (int i = k + lane; i < bw; i += 32)
+                        Ls[i + (size_t) k * lc] = Lg[(b0 + i) + (size_t) (b0 + k) * ld];
             }
-            __threadfence();
-        }
-        __syncthreads();
-        if (s_abort)
-            break;
-        if (a.trace && tid == 0)
-            tr2 = d_now();
+            for (int k = tid; k < bw; k += nt) {
+                w[k] = a.y[3 * (size_t) d.first + b0 + k];
+                rd[k] = a.dinv[3 * (size_t) d.first + b0 + k];
+            }
+            const double *L11 = mode ? Ls : (Lg + b0 + (size_t) b0 * ld); // (row, col) at L11[row + col*ll]
 
-        for (int i = tid; i < r; i += nt)
-            xs[i] = __ldcg(&a.x[3 * (size_t) rows[d.cb + i / 3] + i % 3]);
-        __syncthreads();
-        // w_k -= sum_i L21[i, k] * xs[i]   (one warp per column, two accumulators)
-        if (r > 0) {
-            for (int k = warp; k < c; k += nwarps) {
-                const double *lk = (mode == 2) ? (Ls + (size_t) k * lm + c) : (Lg + (size_t) k * ld + c);
-                double acc0 = 0.0, acc1 = 0.0;
-                for (int i0 = lane; i0 < r; i0 += 256) { // eight independent loads in flight per lane
-                    double v[8];
-#pragma unroll
-                    for (int u = 0; u < 8; u++)
-                        v[u] = (i0 + 32 * u < r) ? lk[i0 + 32 * u] : 0.0;
-#pragma unroll
-                    for (int u = 0; u < 8; u += 2) {
-                        acc0 += v[u] * xs[min(i0 + 32 * u, r - 1)];
-                        acc1 += v[u + 1] * xs[min(i0 + 32 * (u + 1), r - 1)];
+            if (blk == nblk - 1) {
+                if (a.trace && tid == 0)
+                    tr1 = d_now();
+                if (d.parent >= 0 && tid == 0) {
+                    long long spins = 0;
+                    while (ld_volatile(&a.xdone[d.parent]) != a.epoch) {
+                        __nanosleep(20);
+                        if (++spins > a.spin_limit || ld_volatile(err) < 0) {
+                            atomicCAS(err, 0, -(1 + s));
+                            s_abort = 1;
+                            break;
+                        }
                     }
+                    __threadfence();
                 }
-                acc0 += acc1;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1)
-                    acc0 += __shfl_down_sync(0xffffffffu, acc0, o);
-                if (lane == 0)
-                    w[k] -= acc0;
+                __syncthreads();
+                if (s_abort)
+                    break;
+                if (a.trace && tid == 0)
+                    tr2 = d_now();
+                for (int i = tid; i < r; i += nt)
+                    xf[c + i] = __ldcg(&a.x[3 * (size_t) rows[d.cb + i / 3] + i % 3]);
             }
             __syncthreads();
-        }
-        // L11' x1 = w, right-looking: x_k = w_k / L_kk, then w_j -= L[k, j] * x_k for j < k
-        if (warp == 0) {
-            for (int k = c - 1; k >= 0; --k) {
-                const double xk = w[k] * rd[k];
-                __syncwarp();
-                if (lane == 0)
-                    w[k] = xk;
-                for (int j = lane; j < k; j += 32)
-                    w[j] -= L11[k + (size_t) j * ll] * xk;
+            // w_k -= sum_{i >= be} L[i, b0+k] * xf[i]   (one warp per column)
+            const int nr = m - be;
+            if (nr > 0) {
+                for (int k = warp; k < bw; k += nwarps) {
+                    const double *lk = (mode == 2) ? (Ls + (size_t) k * lm + bw) : (Lg + (size_t) (b0 + k) * ld + be);
+                    const double acc = nr > 512 ? bs_dot<16>(lk, xf + be, nr, lane) : bs_dot<8>(lk, xf + be, nr, lane);
+                    if (lane == 0)
+                        w[k] -= acc;
+                }
+                __syncthreads();
+            }
+            // L11' x = w, right-looking: x_k = w_k / L_kk, then w_j -= L[k, j] * x_k for j < k.
+            // One warp, w in registers (lane l holds entries l, l+32, l+64), x_k travels by shuffle:
+            // no shared-memory round trip on the dependent chain.
+            if (warp == 0) {
+                double wr[3];
+#pragma unroll
+                for (int t3 = 0; t3 < 3; t3++)
+                    wr[t3] = (lane + 32 * t3 < bw) ? w[lane + 32 * t3] : 0.0;
+#pragma unroll 2
+                for (int k = bw - 1; k >= 0; --k) {
+                    const int ks = k >> 5;
+                    const double mine = ks == 0 ? wr[0] : (ks == 1 ? wr[1] : wr[2]);
+                    const double xk = __shfl_sync(0xffffffffu, mine, k & 31) * rd[k];
+#pragma unroll
+                    for (int t3 = 0; t3 < 3; t3++) {
+                        const int j = lane + 32 * t3;
+                        if (j < k)
+                            wr[t3] -= L11[k + (size_t) j * ll] * xk;
+                        else if (j == k)
+                            wr[t3] = xk;
+                    }
+                }
+#pragma unroll
+                for (int t3 = 0; t3 < 3; t3++) {
+                    const int k = lane + 32 * t3;
+                    if (k < bw) {
+                        a.x[3 * (size_t) d.first + b0 + k] = wr[t3];
+                        xf[b0 + k] = wr[t3];
+                    }
+                }
                 __syncwarp();
             }
-            for (int k = lane; k < c; k += 32)
-                a.x[3 * (size_t) d.first + k] = w[k];
-            __syncwarp();
-            if (lane == 0) {
-                __threadfence();
-                atomicExch(&a.xdone[s], a.epoch);
-                if (a.trace) {
-                    unsigned long long *tr = a.trace + 8 * (size_t) t;
-                    tr[0] = tr0; tr[1] = tr1; tr[2] = tr2; tr[3] = d_now();
-                    tr[6] = (unsigned long long) s;
-                    tr[7] = (unsigned) m;
-                }
+        }
+        if (s_abort)
+            break;
+        if (warp == 0 && lane == 0) {
+            __threadfence();
+            atomicExch(&a.xdone[s], a.epoch);
+            if (a.trace) {
+                unsigned long long *tr = a.trace + 8 * (size_t) t;
+                tr[0] = tr0; tr[1] = tr1; tr[2] = tr2; tr[3] = d_now();
+                tr[6] = (unsigned long long) s;
+                tr[7] = (unsigned) m;
             }
         }
         __syncthreads();
     }
+    ticket_release(&a.ctrl[2], &a.ctrl[4]);
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel 3a: back-substitution of the leaf set (see k_factor_leaf), one WARP per supernode,
+// launched after k_backsolve has solved every other supernode with the same epoch.  The L panel
+// (m x c, usually 48 x 9 or less) is staged in the warp's slice of shared memory when it fits,
+// L21' x2 is one lane per column, the triangular solve runs in registers with shuffles.
+// ------------------------------------------------------------------------------------------
+#define ASAM_BSL_WARPS 8
+#define ASAM_BSL_PANEL 1024                         // staged panel entries per warp
+#define ASAM_BSL_XS 64                              // rows below the supernode (x2) per warp
+#define ASAM_BSL_STRIDE (ASAM_BSL_PANEL + ASAM_BSL_XS) // doubles per warp
+
+__global__ void __launch_bounds__(32 * ASAM_BSL_WARPS) k_backsolve_leaf(BsArgs a)
+{
+    extern __shared__ __align__(16) double sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *Ls = sm + (size_t) warp * ASAM_BSL_STRIDE;
+    double *xs = Ls + ASAM_BSL_PANEL;
+    int *err = a.ctrl + 1;
+    for (;;) {
+        int t = 0;
+        if (lane == 0)
+            t = atomicAdd(&a.ctrl[5], 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= a.ntasks)
+            break;
+        const int s = a.btasks[t];
+        const asam_sn_desc_t d = a.sn[s];
+        const int m = 3 * d.mb, c = 3 * d.cb, r = m - c, ld = m + 1;
+        if (r > ASAM_BSL_XS || c > 64) { // host error: not a leaf-set supernode
+            if (lane == 0)
+                atomicCAS(err, 0, -(1 + s));
+            break;
+        }
+        const int *rows = a.ipool + d.seg;
+        const double *Lg = a.arena + d.f_off;
+        const int lm = m | 1;
+        const bool staged = lm * c <= ASAM_BSL_PANEL;
+        if (staged) {
+            for (int k = 0; k < c; k++)
+                for (int i = k + lane; i < m; i += 32)
+                    Ls[i + k * lm] = Lg[i + (size_t) k * ld];
+        }
+        const double *L = staged ? Ls : Lg;
+        const int ll = staged ? lm : ld;
+        double wr[2], rdv[2];
+#pragma unroll
+        for (int t2 = 0; t2 < 2; t2++) {
+            const int k = lane + 32 * t2;
+            wr[t2] = k < c ? a.y[3 * (size_t) d.first + k] : 0.0;
+            rdv[t2] = k < c ? a.dinv[3 * (size_t) d.first + k] : 0.0;
+        }
+        int abort_ = 0;
+        if (d.parent >= 0) {
+            if (lane == 0) {
+                long long spins = 0;
+                while (ld_volatile(&a.xdone[d.parent]) != a.epoch) {
+                    __nanosleep(20);
+                    if (++spins > a.spin_limit || ld_volatile(err) < 0) {
+                        atomicCAS(err, 0, -(1 + s));
+                        abort_ = 1;
+                        break;
+                    }
+                }
+                __threadfence();
+            }
+            abort_ = __shfl_sync(0xffffffffu, abort_, 0);
+        }
+        if (abort_)
+            break;
+        for (int i = lane; i < r; i += 32)
+            xs[i] = __ldcg(&a.x[3 * (size_t) rows[d.cb + i / 3] + i % 3]);
+        __syncwarp();
+        // w_k -= sum_i L[c+i, k] xs[i]: one lane per column
+#pragma unroll
+        for (int t2 = 0; t2 < 2; t2++) {
+            const int k = lane + 32 * t2;
+            if (k < c) {
+                const double *lk = L + c + (size_t) k * ll;
+                double acc0 = 0.0, acc1 = 0.0;
+                int i = 0;
+#pragma unroll 4
+                for (; i + 1 < r; i += 2) {
+                    acc0 += lk[i] * xs[i];
+                    acc1 += lk[i + 1] * xs[i + 1];
+                }
+                if (i < r)
+                    acc0 += lk[i] * xs[i];
+                wr[t2] -= acc0 + acc1;
+            }
+        }
+        // L11' x = w in registers, x_k by shuffle
+        for (int k = c - 1; k >= 0; --k) {
+            const double mine = (k >> 5) == 0 ? wr[0] : wr[1];
+            const double rk = (k >> 5) == 0 ? rdv[0] : rdv[1];
+            const double xk = __shfl_sync(0xffffffffu, mine * rk, k & 31);
+#pragma unroll
+            for (int t2 = 0; t2 < 2; t2++) {
+                const int j = lane + 32 * t2;
+                if (j < k)
+                    wr[t2] -= L[k + (size_t) j * ll] * xk;
+                else if (j == k)
+                    wr[t2] = xk;
+            }
+        }
+#pragma unroll
+        for (int t2 = 0; t2 < 2; t2++) {
+            const int k = lane + 32 * t2;
+            if (k < c)
+                a.x[3 * (size_t) d.first + k] = wr[t2];
+        }
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence();
+            atomicExch(&a.xdone[s], a.epoch);
+        }
+        __syncwarp();
+    }
+    ticket_release(&a.ctrl[5], &a.ctrl[6]);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -97,6 +97,8 @@ typedef struct {
     /* full task lists (batch): ntasks entries of tasks/nwait (teams expanded), nsn of btasks */
     int *tasks, *nwait, *btasks;
     int ntasks;
+    int *leaf_tasks; /* supernodes factored by k_factor_leaf before `tasks` (large graphs only) */
+    int n_leaf;
 
     /* statistics of the last build */
     int64_t nnz_l_blocks; /* sum over nodes of (1 + |below|) */

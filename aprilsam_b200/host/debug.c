@@ -64,7 +64,7 @@ ASAM_API void asam_dbg_plan_info(void *p, int64_t *info, double *flops)
 }
 
 /* which: 0 order 1 pos 2 node2q 3 q2node 4 parent_pos 5 fslot 6 sn_of_q 7 ipool 8 tasks 9 nwait
- * 10 btasks 11 desc (as int32 words, 12 per supernode) */
+ * 10 btasks 11 desc (as int32 words, 12 per supernode) 12 leaf_tasks */
 ASAM_API const int *asam_dbg_plan_array(void *p, int which, int64_t *count)
 {
     plan_t *pl = (plan_t *) p;
@@ -81,6 +81,7 @@ ASAM_API const int *asam_dbg_plan_array(void *p, int which, int64_t *count)
     case 9: *count = pl->nwait ? pl->ntasks : 0; return pl->nwait;
     case 10: *count = pl->btasks ? pl->nsn : 0; return pl->btasks;
     case 11: *count = 12 * (int64_t) pl->nsn; return (const int *) pl->desc;
+    case 12: *count = pl->leaf_tasks ? pl->n_leaf : 0; return pl->leaf_tasks;
     default: *count = 0; return NULL;
     }
 }

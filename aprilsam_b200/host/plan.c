@@ -39,6 +39,8 @@ void asam_dbg_plan_profile(double *out, int reset)
 
 #define RELAX_Z 2     /* relaxed amalgamation: missing block rows tolerated per merge */
 #define RELAX_FILL 24 /* ... and explicit zero blocks (3x3) added per merge */
+#define ASAM_LEAF_MAX_M 48       /* = ASAM_LEAF_M of k_factor_leaf */
+#define ASAM_LEAF_MIN_COUNT 4096 /* below this one k_factor launch does it all */
 #define MAX_SN_COLS 32 /* block columns per supernode: L11 (96x96) fits k_backsolve shared memory */
 
 /* ---- pair map ---------------------------------------------------------------------------- */
@@ -188,6 +190,7 @@ void plan_free(plan_t *pl)
     free(pl->tasks);
     free(pl->nwait);
     free(pl->btasks);
+    free(pl->leaf_tasks);
     ivec_free(&pl->ipool_host);
     memset(pl, 0, sizeof(*pl));
 }
@@ -290,18 +293,27 @@ static void emit_segment(plan_t *pl, int s, ivec_t *buf, int64_t base)
     buf->n += h->a_slot.n;
 }
 
-/* CTAs that share one front in k_factor: fronts that fit in shared memory (200 KB) take one;
- * larger ones get one CTA per ~3 MFLOP of elimination work or per ~40 k front entries (thin
- * fronts are bound by moving the update matrix, not by flops), at most 120 (the grid is one CTA
- * per SM, 148 on B200, and a team must be co-resident). */
+/* CTAs that share one front in k_factor: fronts that fit in shared memory (200 KB) take one.
+ * Larger ones are bound by the LATENCY of their panel steps (two team barriers, the diagonal
+ * block, one trailing tile per worker), not by throughput: the team gets one CTA per 256 x 64
+ * tile of the first trailing update and no more, so that the fronts of one tree level find room
+ * side by side on the 148 SMs instead of queueing for each other's workers. */
+static int front_fits_smem(int mb)
+{
+    int64_t m = 3 * (int64_t) mb;
+    return (m + 1) * m + (m + 2) / 2 + 2 <= 25600;
+}
+
 static int team_size(int mb, int cb)
 {
     int64_t m = 3 * (int64_t) mb, c = 3 * (int64_t) cb;
-    if ((m + 1) * m + (m + 2) / 2 + 2 <= 25600)
+    if (front_fits_smem(mb))
         return 1;
-    double fl = (double) c * (double) m * (double) m, sz = (double) m * (double) m;
-    double g = fl / 3.0e6 > sz / 4.0e4 ? fl / 3.0e6 : sz / 4.0e4;
-    int G = (int) g + 1;
+    int64_t j0 = c < 48 ? c : 48, tiles = 0;
+    for (int64_t cb0 = j0; cb0 < m; cb0 += 64)
+        tiles += (m - cb0 + 1 + 255) / 256;
+    int64_t chunks = (m - j0 + 1 + 255) / 256; /* row chunks of the panel solve */
+    int G = (int) (tiles > chunks ? tiles : chunks);
     if (G < 2)
         G = 2;
     if (G > 120)
@@ -527,6 +539,11 @@ static int plan_build_impl(plan_t *pl, asam_dev_t *dev, int N, int n_factors, co
             if (parent[pp] == p && gcb < MAX_SN_COLS &&
                 (z == 0 || (z <= RELAX_Z && (int64_t) z * gcb <= RELAX_FILL)))
                 merge = 1;
+            /* a fundamental chain whose front is processed by a CTA team anyway (it does not fit
+             * in shared memory) is not capped: splitting it only adds levels and one full copy of
+             * the update matrix per link */
+            if (!merge && parent[pp] == p && z == 0 && !front_fits_smem(gcb + nbp))
+                merge = 1;
         }
         if (merge) {
             pl->desc[pl->nsn - 1].cb++;
@@ -618,13 +635,30 @@ static int plan_build_impl(plan_t *pl, asam_dev_t *dev, int N, int n_factors, co
 
     pl->btasks = malloc(sizeof(int) * (size_t) pl->nsn);
     {
+        /* leaf set: supernodes whose whole subtree consists of fronts small enough for the
+         * warp-per-front kernel (children have smaller ids).  Only worth a separate launch when
+         * there are thousands of them. */
+        char *leaf = calloc((size_t) pl->nsn + 1, 1);
+        int n_leaf = 0;
+        for (int s = 0; s < pl->nsn; s++) {
+            int ok = 3 * pl->desc[s].mb <= ASAM_LEAF_MAX_M;
+            for (int c = 0; ok && c < pl->snh[s].children.n; c++)
+                ok = leaf[pl->snh[s].children.p[c]];
+            leaf[s] = (char) ok;
+            n_leaf += ok;
+        }
+        if (n_leaf < ASAM_LEAF_MIN_COUNT) {
+            memset(leaf, 0, (size_t) pl->nsn);
+            n_leaf = 0;
+        }
         /* counting sort by level, ids ascending inside a level; big fronts expand into teams */
         int *byl = malloc(sizeof(int) * (size_t) pl->nsn);
         int *cnt = calloc((size_t) pl->n_levels + 1, sizeof(int));
         int64_t total = 0;
         for (int s = 0; s < pl->nsn; s++) {
             cnt[pl->desc[s].level + 1]++;
-            total += team_size(pl->desc[s].mb, pl->desc[s].cb);
+            if (!leaf[s])
+                total += team_size(pl->desc[s].mb, pl->desc[s].cb);
         }
         for (int l = 0; l < pl->n_levels; l++)
             cnt[l + 1] += cnt[l];
@@ -632,18 +666,29 @@ static int plan_build_impl(plan_t *pl, asam_dev_t *dev, int N, int n_factors, co
             byl[cnt[pl->desc[s].level]++] = s;
         free(cnt);
         pl->ntasks = (int) total;
-        pl->tasks = malloc(sizeof(int) * (size_t) total);
-        pl->nwait = malloc(sizeof(int) * (size_t) total);
-        int t = 0;
+        pl->tasks = malloc(sizeof(int) * (size_t) (total + 1));
+        pl->nwait = malloc(sizeof(int) * (size_t) (total + 1));
+        pl->n_leaf = n_leaf;
+        pl->leaf_tasks = malloc(sizeof(int) * (size_t) (n_leaf + 1));
+        /* back-solve list, parents first: everything outside the leaf set, then the leaf set */
+        int t = 0, tl = 0, bm = pl->nsn - n_leaf - 1, bl = pl->nsn - 1;
         for (int k = 0; k < pl->nsn; k++) {
-            int s = byl[k], G = team_size(pl->desc[s].mb, pl->desc[s].cb);
+            int s = byl[k];
+            if (leaf[s]) {
+                pl->btasks[bl--] = s;
+                pl->leaf_tasks[tl++] = s;
+                continue;
+            }
+            pl->btasks[bm--] = s;
+            /* nwait counts ALL children: those of the leaf set arrived in the earlier launch */
+            int G = team_size(pl->desc[s].mb, pl->desc[s].cb);
             for (int w = 0; w < G; w++, t++) {
                 pl->tasks[t] = s;
                 pl->nwait[t] = pack_nwait(pl->desc[s].ch_cnt, w, G > 1 ? G : 0);
             }
-            pl->btasks[pl->nsn - 1 - k] = s;
         }
         free(byl);
+        free(leaf);
     }
 
     /* host mirror of the device int pool (debug / tests) */
@@ -671,6 +716,7 @@ static int plan_build_impl(plan_t *pl, asam_dev_t *dev, int N, int n_factors, co
     rc |= asam_upload_q2node(dev, 0, N, pl->q2node);
     rc |= asam_upload_fslot(dev, 0, n_factors, pl->fslot);
     rc |= asam_set_full_tasks(dev, pl->ntasks, pl->tasks, pl->nwait, pl->nsn, pl->btasks);
+    rc |= asam_set_leaf_tasks(dev, pl->n_leaf, pl->leaf_tasks);
     free(ids);
     ivec_free(&seg);
     return rc;
@@ -716,6 +762,13 @@ int plan_append(plan_t *pl, asam_dev_t *dev, int N, int n_factors, const int *ft
             asam_set_error("factor %d: unsupported factor type %d", f, ftype[f]);
             return 1;
         }
+    }
+
+    /* incremental steps run the whole schedule through k_factor / k_backsolve */
+    if (pl->n_leaf > 0) {
+        pl->n_leaf = 0;
+        if (dev && asam_set_leaf_tasks(dev, 0, NULL))
+            return 1;
     }
 
     /* grow node-indexed arrays: new poses are eliminated last, in id order */

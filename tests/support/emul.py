@@ -123,10 +123,12 @@ def seg_views(desc, ipool, s):
     return rows, rel, children, a_slot, a_rb, a_cb
 
 
-def factor(fr: Fronts, H: Hessian, desc, ipool, q2node, tasks, nwait=None, check_order=True):
-    """k_factor: assemble + eliminate the listed supernodes (children first)."""
+def factor(fr: Fronts, H: Hessian, desc, ipool, q2node, tasks, nwait=None, check_order=True, prior=()):
+    """k_factor: assemble + eliminate the listed supernodes (children first).  `prior` = supernodes
+    factored by an earlier launch of the same solve (k_factor_leaf): their arrivals count too."""
     done = set()
-    intask = set(int(t) for t in tasks)
+    intask = set(int(t) for t in tasks) | set(int(t) for t in prior)
+    done |= set(int(t) for t in prior)
     for ti, s in enumerate(tasks):
         s = int(s)
         if s in done:  # further workers of a multi-CTA team: same supernode

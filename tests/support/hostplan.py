@@ -36,7 +36,7 @@ def _i(a):
 
 
 ARR = dict(order=0, pos=1, node2q=2, q2node=3, parent_pos=4, fslot=5, sn_of_q=6, ipool=7, tasks=8, nwait=9,
-           btasks=10, desc=11)
+           btasks=10, desc=11, leaf_tasks=12)
 TR_FLAG = 1 << 30
 
 

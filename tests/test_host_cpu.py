@@ -162,7 +162,10 @@ def emulate_batch(d):
     fr = emul.Fronts()
     fr.ensure(n)
     desc, ipool = p.descs(), p.array("ipool")
-    emul.factor(fr, Hs, desc, ipool, p.array("q2node"), p.array("tasks"), p.array("nwait"))
+    leaf = p.array("leaf_tasks")  # large graphs: k_factor_leaf runs these first (children first)
+    if len(leaf):
+        emul.factor(fr, Hs, desc, ipool, p.array("q2node"), leaf, None)
+    emul.factor(fr, Hs, desc, ipool, p.array("q2node"), p.array("tasks"), p.array("nwait"), prior=leaf)
     emul.backsolve(fr, desc, ipool, p.array("btasks"))
     x = np.stack([fr.x[3 * node2q[i]:3 * node2q[i] + 3] for i in range(n)])
     st = lp + x
@@ -185,6 +188,44 @@ def test_emulated_batch_synthetic_vs_reference():
         h.batch()
         ref = h.states()
     assert np.abs(emulate_batch(d) - ref).max() < 1e-6 * max(1.0, np.abs(ref).max())
+
+
+def test_large_plan_leaf_set_and_merged_chains():
+    """12 k-pose dense world: the schedule splits into the leaf set (warp-per-front kernel) and the
+    rest, chains of team-sized fronts are merged into wide supernodes; the emulated kernels on that
+    plan still solve the normal equations (checked against a sparse direct solve)."""
+    import scipy.sparse.linalg as spl
+    d = datasets.manhattan_dense(12000, seed=5)
+    n = d.n_nodes
+    ftype, fa, fb, fz, fW = factor_arrays(d)
+    p = HostPlan().build(n, ftype, fa, fb)
+    D = p.descs()
+    leaf, tasks, nwait = p.array("leaf_tasks"), p.array("tasks"), p.array("nwait")
+    assert len(leaf) >= 4096 and (3 * D["mb"][leaf]).max() <= 48
+    in_leaf = np.zeros(len(D["mb"]), bool)
+    in_leaf[leaf] = True
+    par = D["parent"]
+    assert all(in_leaf[c] for c in range(len(par)) if par[c] >= 0 and in_leaf[par[c]]), "leaf set is downward closed"
+    assert sorted(set(leaf) | set(tasks)) == list(range(len(par))) and not (set(leaf) & set(tasks))
+    wide = D["cb"] > 32
+    assert wide.any(), "fundamental chains of team-sized fronts are merged past the 32-pose cap"
+    m = 3 * D["mb"][wide]
+    assert ((m + 1) * m > 25600).all(), "only fronts of the team path may be wider than the cap"
+    st = emulate_batch(d)
+    # exact Gauss-Newton step from the same Hessian
+    Hs = emul.Hessian(n, p.info()["n_slots"])
+    Hs.reset(n, 1e-4)
+    Hs.linearize(range(len(ftype)), ftype, fa, fb, fz, fW, d.init, d.init, p.array("node2q"), p.array("fslot"))
+    fslot = p.array("fslot")
+    pairs = {}
+    for f in range(len(ftype)):
+        if ftype[f] == 1:
+            pairs[fslot[f]] = (min(fa[f], fb[f]), max(fa[f], fb[f]))
+    A = Hs.dense([pairs[s] for s in range(p.info()["n_slots"])])
+    x = spl.spsolve(A.tocsc(), Hs.B.reshape(-1)).reshape(n, 3)
+    want = d.init + x
+    want[:, 2] = emul.mod2pi(want[:, 2])
+    assert np.abs(st - want).max() < 1e-6 * max(1.0, np.abs(want).max())
 
 
 @pytest.mark.parametrize("n0,n1,step", [(1, 40, 1), (120, 200, 1), (300, 330, 3)])
