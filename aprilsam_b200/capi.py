@@ -48,8 +48,30 @@ def lib() -> C.CDLL:
     L.asam_download_y.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp]
     L.asam_debug_read_hessian.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp]
     L.asam_debug_read_front.argtypes = [C.c_void_p, C.c_int64, C.c_int64, _dp]
+    L.asam_comm_unique_id.argtypes = [C.c_void_p]
+    L.asam_comm_init.argtypes = [C.c_int, C.c_int, C.c_void_p]
+    L.asam_comm_destroy.restype = None
+    L.asam_comm_info.argtypes = [_ip, _ip, _ip]
+    L.asam_comm_set_sharding.argtypes = [C.c_int]
     _lib = L
     return L
+
+
+def comm_init_torch(dist, local_rank: int) -> None:
+    """Create the library's NCCL communicator inside a torch.distributed job: rank 0 makes the
+    128-byte id, torch broadcasts it, every rank joins (one process per GPU)."""
+    import torch
+    L = lib()
+    world, rank = dist.get_world_size(), dist.get_rank()
+    buf = (C.c_ubyte * 128)()
+    if rank == 0:
+        check(L.asam_comm_unique_id(buf), "asam_comm_unique_id")
+    cuda = dist.get_backend() == "nccl"
+    t = torch.tensor(list(buf), dtype=torch.uint8, device=torch.device("cuda", local_rank) if cuda else "cpu")
+    dist.broadcast(t, src=0)
+    raw = bytes(t.cpu().tolist())
+    ident = (C.c_ubyte * 128).from_buffer_copy(raw)
+    check(L.asam_comm_init(world, rank, ident), "asam_comm_init")
 
 
 def check(rc: int, what: str = "asam call"):

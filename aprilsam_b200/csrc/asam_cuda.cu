@@ -80,6 +80,13 @@ struct asam_dev {
     int n_leaf = 0;
     int leaf_grid = 0, leaf_smem = 0;
     int bt_nleaf = 0; // the last bt_nleaf entries of btasks_full are back-solved by k_backsolve_leaf
+    // multi-GPU shard schedule (asam_set_shard_schedule)
+    int sharded = 0;
+    Buf top_tasks, top_nwait;
+    int n_top = 0;
+    int n_shards = 0;
+    int *sh_owner = nullptr, *sh_q0 = nullptr, *sh_qn = nullptr;
+    long long *sh_off = nullptr, *sh_cnt = nullptr;
     int bsl_grid = 0, bsl_smem = 0;
     int bt_start = 0, bt_count = 0, bt_cap = 0; // btasks_full holds [bt_start, bt_start+bt_count)
     Buf tasks_tmp, nwait_tmp, btasks_tmp;
@@ -270,6 +277,8 @@ static int download(asam_dev *d, void *dst, const void *src, size_t bytes)
     }
     return 0;
 }
+
+#include <dlfcn.h>
 
 #include "asam_kernels.cuh"
 
@@ -494,7 +503,7 @@ ASAM_EXPORT void asam_dev_destroy(asam_dev_t *d)
     Buf *all[] = { &d->f_type, &d->f_a, &d->f_b, &d->f_z, &d->f_W, &d->f_slot, &d->lp, &d->st, &d->node2q, &d->q2node,
                    &d->Adiag, &d->Aoff, &d->Bq, &d->y, &d->x, &d->dinv, &d->sn, &d->ipool, &d->arena, &d->arrive,
                    &d->xdone, &d->tbar, &d->tasks_full, &d->nwait_full, &d->btasks_full, &d->tasks_tmp, &d->nwait_tmp,
-                   &d->btasks_tmp, &d->leaf_tasks, &d->ctrl, &d->partial, &d->patch_ids, &d->patch_desc, &d->pts, &d->flush, &d->trace_fac, &d->trace_bs };
+                   &d->btasks_tmp, &d->leaf_tasks, &d->top_tasks, &d->top_nwait, &d->ctrl, &d->partial, &d->patch_ids, &d->patch_desc, &d->pts, &d->flush, &d->trace_fac, &d->trace_bs };
     for (int i = 0; i < 2; i++)
         if (d->tev[i])
             cudaEventDestroy(d->tev[i]);
@@ -511,6 +520,7 @@ ASAM_EXPORT void asam_dev_destroy(asam_dev_t *d)
         cudaEventDestroy(d->up_ev);
     free(d->items);
     free(d->pend);
+    free(d->sh_owner); free(d->sh_q0); free(d->sh_qn); free(d->sh_off); free(d->sh_cnt);
     for (int i = 0; i < 6; i++)
         if (d->ev[i])
             cudaEventDestroy(d->ev[i]);
@@ -847,10 +857,238 @@ ASAM_EXPORT int asam_btasks_prepend(asam_dev_t *d, int n, const int32_t *ids)
     return upload(d, (int *) d->btasks_full.p + d->bt_start, ids, (size_t) n * sizeof(int));
 }
 
+// ------------------------------------------------------------------------------------------
+// several GPUs: NCCL through dlopen (no link-time dependency; a copy already loaded by the host
+// application, e.g. PyTorch's, is re-used because it has the same soname)
+// ------------------------------------------------------------------------------------------
+typedef struct ncclComm *nccl_comm_t;
+typedef struct { char internal[128]; } nccl_uid_t;
+struct NcclApi {
+    void *h = nullptr;
+    int (*GetUniqueId)(nccl_uid_t *) = nullptr;
+    int (*CommInitRank)(nccl_comm_t *, int, nccl_uid_t, int) = nullptr;
+    int (*CommDestroy)(nccl_comm_t) = nullptr;
+    int (*Broadcast)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static nccl_comm_t g_comm = nullptr;
+static int g_world = 1, g_rank = 0, g_sharding = 0;
+#define ASAM_NCCL_FLOAT64 8
+#define ASAM_NCCL_INT32 2
+#define ASAM_NCCL_SUM 0
+
+#define NCK(call)                                                                                  \
+    do {                                                                                           \
+        int r_ = (call);                                                                           \
+        if (r_ != 0)                                                                               \
+            return set_err("%s:%d %s -> NCCL error %d (%s)", __FILE__, __LINE__, #call, r_,        \
+                           g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?");               \
+    } while (0)
+
+static int nccl_load()
+{
+    if (g_nccl.h)
+        return 0;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h)
+        h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h)
+        return set_err("cannot load libnccl.so.2: %s", dlerror());
+#define SYM(field, name)                                                  \
+    *(void **) (&g_nccl.field) = dlsym(h, name);                          \
+    if (!g_nccl.field)                                                    \
+        return set_err("libnccl: symbol %s missing", name);
+    SYM(GetUniqueId, "ncclGetUniqueId")
+    SYM(CommInitRank, "ncclCommInitRank")
+    SYM(CommDestroy, "ncclCommDestroy")
+    SYM(Broadcast, "ncclBroadcast")
+    SYM(AllReduce, "ncclAllReduce")
+    SYM(GroupStart, "ncclGroupStart")
+    SYM(GroupEnd, "ncclGroupEnd")
+    SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    g_nccl.h = h;
+    return 0;
+}
+
+static int select_device(int *dev_out)
+{
+    int n = 0;
+    CK(cudaGetDeviceCount(&n));
+    if (n <= 0)
+        return set_err("no CUDA device");
+    int dev = 0;
+    const char *e = getenv("ASAM_DEVICE");
+    if (!e)
+        e = getenv("LOCAL_RANK");
+    if (e)
+        dev = atoi(e) % n;
+    *dev_out = dev;
+    return 0;
+}
+
+ASAM_EXPORT int asam_comm_unique_id(void *id128_out)
+{
+    if (nccl_load())
+        return 1;
+    nccl_uid_t id;
+    NCK(g_nccl.GetUniqueId(&id));
+    memcpy(id128_out, &id, sizeof(id));
+    return 0;
+}
+
+ASAM_EXPORT int asam_comm_init(int world, int rank, const void *id128)
+{
+    if (world < 1 || rank < 0 || rank >= world)
+        return set_err("asam_comm_init: bad world/rank %d/%d", world, rank);
+    if (g_comm)
+        return set_err("asam_comm_init: communicator already initialised");
+    if (world == 1) {
+        g_world = 1;
+        g_rank = 0;
+        return 0;
+    }
+    if (nccl_load())
+        return 1;
+    int dev = 0;
+    if (select_device(&dev))
+        return 1;
+    CK(cudaSetDevice(dev));
+    nccl_uid_t id;
+    memcpy(&id, id128, sizeof(id));
+    NCK(g_nccl.CommInitRank(&g_comm, world, id, rank));
+    g_world = world;
+    g_rank = rank;
+    return 0;
+}
+
+ASAM_EXPORT void asam_comm_destroy(void)
+{
+    if (g_comm && g_nccl.CommDestroy)
+        g_nccl.CommDestroy(g_comm);
+    g_comm = nullptr;
+    g_world = 1;
+    g_rank = 0;
+    g_sharding = 0;
+}
+
+ASAM_EXPORT int asam_comm_info(int *world, int *rank, int *sharding)
+{
+    if (world)
+        *world = g_world;
+    if (rank)
+        *rank = g_rank;
+    if (sharding)
+        *sharding = g_sharding && g_world > 1;
+    return 0;
+}
+
+ASAM_EXPORT int asam_comm_set_sharding(int enabled)
+{
+    if (enabled && (g_world <= 1 || !g_comm))
+        return set_err("asam_comm_set_sharding: no communicator (asam_comm_init)");
+    g_sharding = enabled ? 1 : 0;
+    return 0;
+}
+
+ASAM_EXPORT int asam_set_shard_schedule(asam_dev_t *d, const asam_shard_sched_t *sh)
+{
+    CK(cudaSetDevice(d->device));
+    d->sharded = 0;
+    d->n_top = 0;
+    d->n_shards = 0;
+    free(d->sh_owner); free(d->sh_q0); free(d->sh_qn); free(d->sh_off); free(d->sh_cnt);
+    d->sh_owner = d->sh_q0 = d->sh_qn = nullptr;
+    d->sh_off = d->sh_cnt = nullptr;
+    if (!sh)
+        return 0;
+    if (g_world <= 1 || !g_comm)
+        return set_err("asam_set_shard_schedule: no communicator (asam_comm_init)");
+    size_t b = (size_t) sh->n_top * sizeof(int);
+    if (sh->n_top > 0) {
+        if (buf_reserve(d, d->top_tasks, b, false, false) || buf_reserve(d, d->top_nwait, b, false, false) ||
+            upload(d, d->top_tasks.p, sh->top_tasks, b) || upload(d, d->top_nwait.p, sh->top_nwait, b))
+            return 1;
+    }
+    const int n = sh->n_shards;
+    d->sh_owner = (int *) malloc(sizeof(int) * (size_t) (n + 1));
+    d->sh_q0 = (int *) malloc(sizeof(int) * (size_t) (n + 1));
+    d->sh_qn = (int *) malloc(sizeof(int) * (size_t) (n + 1));
+    d->sh_off = (long long *) malloc(sizeof(long long) * (size_t) (n + 1));
+    d->sh_cnt = (long long *) malloc(sizeof(long long) * (size_t) (n + 1));
+    for (int i = 0; i < n; i++) {
+        d->sh_owner[i] = sh->shard_owner[i];
+        d->sh_q0[i] = sh->shard_q0[i];
+        d->sh_qn[i] = sh->shard_qn[i];
+        d->sh_off[i] = sh->shard_off[i];
+        d->sh_cnt[i] = sh->shard_cnt[i];
+        if (d->sh_owner[i] < 0 || d->sh_owner[i] >= g_world)
+            return set_err("asam_set_shard_schedule: shard %d owner %d", i, d->sh_owner[i]);
+    }
+    d->n_top = sh->n_top;
+    d->n_shards = n;
+    d->sharded = 1;
+    return 0;
+}
+
+// root fronts of the shards (which = 0) or their solution segments (which = 1): one grouped
+// NCCL broadcast per shard on the library's stream, in place (same offsets on every rank)
+static int shard_exchange(asam_dev *d, int which)
+{
+    if (!d->sharded || d->n_shards == 0)
+        return 0;
+    NCK(g_nccl.GroupStart());
+    for (int i = 0; i < d->n_shards; i++) {
+        void *p;
+        size_t count;
+        if (which == 0) {
+            p = (double *) d->arena.p + d->sh_off[i];
+            count = (size_t) d->sh_cnt[i];
+        } else {
+            p = (double *) d->x.p + 3 * (size_t) d->sh_q0[i];
+            count = 3 * (size_t) d->sh_qn[i];
+        }
+        if (count == 0)
+            continue;
+        NCK(g_nccl.Broadcast(p, p, count, ASAM_NCCL_FLOAT64, d->sh_owner[i], g_comm, d->stream));
+    }
+    NCK(g_nccl.GroupEnd());
+    d->n_launch++;
+    return 0;
+}
+
 ASAM_EXPORT int asam_factor_full(asam_dev_t *d)
 {
     CK(cudaSetDevice(d->device));
-    return launch_factor(d, d->ntasks_full, (const int *) d->tasks_full.p, (const int *) d->nwait_full.p, 1);
+    if (!d->sharded)
+        return launch_factor(d, d->ntasks_full, (const int *) d->tasks_full.p, (const int *) d->nwait_full.p, 1);
+    if (d->defer)
+        return set_err("sharded asam_factor_full inside asam_step_begin/asam_step_run");
+    // own shards -> exchange of the shard roots' update matrices -> the supernodes above the cut
+    const int timing = d->timing;
+    if (flush_uploads(d))
+        return 1;
+    if (timing)
+        CK(cudaEventRecord(d->ev[2], d->stream));
+    d->timing = 0;
+    int rc = launch_factor(d, d->ntasks_full, (const int *) d->tasks_full.p, (const int *) d->nwait_full.p, 1);
+    if (!rc)
+        rc = shard_exchange(d, 0);
+    // arrivals of the shard roots at parents above the cut were counted before the exchange
+    if (!rc && d->arrive.p && cudaMemsetAsync(d->arrive.p, 0, d->arrive.cap, d->stream) != cudaSuccess)
+        rc = set_err("cudaMemsetAsync(arrive) failed");
+    if (!rc)
+        rc = launch_factor(d, d->n_top, (const int *) d->top_tasks.p, (const int *) d->top_nwait.p, 0);
+    d->timing = timing;
+    if (!rc && timing) {
+        CK(cudaEventRecord(d->ev[3], d->stream));
+        d->ev_set[1] = 1;
+    }
+    return rc;
 }
 
 ASAM_EXPORT int asam_factor(asam_dev_t *d, int ntasks, const int32_t *tasks, const int32_t *nwait)
@@ -869,7 +1107,13 @@ ASAM_EXPORT int asam_factor(asam_dev_t *d, int ntasks, const int32_t *tasks, con
 ASAM_EXPORT int asam_backsolve_full(asam_dev_t *d)
 {
     CK(cudaSetDevice(d->device));
-    return launch_backsolve(d, d->bt_count, (const int *) d->btasks_full.p + d->bt_start, d->bt_nleaf);
+    int rc = launch_backsolve(d, d->bt_count, (const int *) d->btasks_full.p + d->bt_start, d->bt_nleaf);
+    if (!rc && d->sharded) {
+        if (d->defer)
+            return set_err("sharded asam_backsolve_full inside asam_step_begin/asam_step_run");
+        rc = shard_exchange(d, 1); // every rank ends up with the whole solution
+    }
+    return rc;
 }
 
 ASAM_EXPORT int asam_backsolve(asam_dev_t *d, int ntasks, const int32_t *btasks)

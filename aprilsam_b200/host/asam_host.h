@@ -99,6 +99,16 @@ typedef struct {
     int ntasks;
     int *leaf_tasks; /* supernodes factored by k_factor_leaf before `tasks` (large graphs only) */
     int n_leaf;
+    int n_btasks;    /* entries of btasks (= nsn on a single GPU) */
+
+    /* multi-GPU sharding (world > 1): tasks / leaf_tasks / btasks then cover this rank's shards
+     * (+ the top in btasks); see build_schedule() in plan.c */
+    int world, rank;
+    int *top_tasks, *top_nwait;
+    int n_top, n_top_sn;
+    int n_shards;
+    int *shard_owner, *shard_q0, *shard_qn;
+    int64_t *shard_off, *shard_cnt;
 
     /* statistics of the last build */
     int64_t nnz_l_blocks; /* sum over nodes of (1 + |below|) */

@@ -24,6 +24,16 @@ ASAM_API int asam_dbg_plan_build(void *p, int N, int F, const int *ftype, const 
     return plan_build((plan_t *) p, NULL, N, F, ftype, fa, fb);
 }
 
+/* multi-GPU schedule of rank `rank` of `world` (no device, no communicator needed) */
+ASAM_API int asam_dbg_plan_build_sharded(void *p, int world, int rank, int N, int F, const int *ftype, const int *fa,
+                                         const int *fb)
+{
+    plan_t *pl = (plan_t *) p;
+    pl->world = world;
+    pl->rank = rank;
+    return plan_build(pl, NULL, N, F, ftype, fa, fb);
+}
+
 ASAM_API int asam_dbg_plan_build_with_order(void *p, int N, int F, const int *ftype, const int *fa, const int *fb,
                                             const int *order_keep, int N_keep)
 {
@@ -64,7 +74,8 @@ ASAM_API void asam_dbg_plan_info(void *p, int64_t *info, double *flops)
 }
 
 /* which: 0 order 1 pos 2 node2q 3 q2node 4 parent_pos 5 fslot 6 sn_of_q 7 ipool 8 tasks 9 nwait
- * 10 btasks 11 desc (as int32 words, 12 per supernode) 12 leaf_tasks */
+ * 10 btasks 11 desc (as int32 words, 12 per supernode) 12 leaf_tasks 13 top_tasks 14 top_nwait
+ * 15 shard_owner 16 shard_q0 17 shard_qn 18 shard_off (int64 as 2 words) 19 shard_cnt (int64) */
 ASAM_API const int *asam_dbg_plan_array(void *p, int which, int64_t *count)
 {
     plan_t *pl = (plan_t *) p;
@@ -79,9 +90,16 @@ ASAM_API const int *asam_dbg_plan_array(void *p, int which, int64_t *count)
     case 7: *count = pl->ipool_host.n; return pl->ipool_host.p;
     case 8: *count = pl->tasks ? pl->ntasks : 0; return pl->tasks;
     case 9: *count = pl->nwait ? pl->ntasks : 0; return pl->nwait;
-    case 10: *count = pl->btasks ? pl->nsn : 0; return pl->btasks;
+    case 10: *count = pl->btasks ? pl->n_btasks : 0; return pl->btasks;
     case 11: *count = 12 * (int64_t) pl->nsn; return (const int *) pl->desc;
     case 12: *count = pl->leaf_tasks ? pl->n_leaf : 0; return pl->leaf_tasks;
+    case 13: *count = pl->top_tasks ? pl->n_top : 0; return pl->top_tasks;
+    case 14: *count = pl->top_nwait ? pl->n_top : 0; return pl->top_nwait;
+    case 15: *count = pl->shard_owner ? pl->n_shards : 0; return pl->shard_owner;
+    case 16: *count = pl->shard_q0 ? pl->n_shards : 0; return pl->shard_q0;
+    case 17: *count = pl->shard_qn ? pl->n_shards : 0; return pl->shard_qn;
+    case 18: *count = pl->shard_off ? 2 * (int64_t) pl->n_shards : 0; return (const int *) pl->shard_off;
+    case 19: *count = pl->shard_cnt ? 2 * (int64_t) pl->n_shards : 0; return (const int *) pl->shard_cnt;
     default: *count = 0; return NULL;
     }
 }

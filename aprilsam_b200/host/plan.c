@@ -191,6 +191,13 @@ void plan_free(plan_t *pl)
     free(pl->nwait);
     free(pl->btasks);
     free(pl->leaf_tasks);
+    free(pl->top_tasks);
+    free(pl->top_nwait);
+    free(pl->shard_owner);
+    free(pl->shard_off);
+    free(pl->shard_cnt);
+    free(pl->shard_q0);
+    free(pl->shard_qn);
     ivec_free(&pl->ipool_host);
     memset(pl, 0, sizeof(*pl));
 }
@@ -329,13 +336,233 @@ static int64_t front_doubles(int mb)
     return m * m + m;
 }
 
+/* ---- schedule: task lists of one batch solve ------------------------------------------------
+ * Single GPU (world == 1): leaf set -> k_factor_leaf, everything else -> k_factor (level order,
+ * teams expanded), back-solve list = [rest | leaf set], parents first.
+ *
+ * Several GPUs (world > 1, one process each): the elimination tree is cut into
+ * disjoint subtrees ("shards") that are dealt to the ranks; a rank factors its own shards (same
+ * two kernels), the shard roots' update matrices are exchanged (NCCL broadcast of the trailing
+ * columns of each root front, same arena offsets on every rank), and every rank then factors the
+ * supernodes above the cut ("top") redundantly.  The back-solve runs top + own shards; the
+ * solution segments of the shards (contiguous q intervals: positions are a post-order) are
+ * exchanged the same way.  Supernodes of other ranks' shards appear in no list of this rank. */
+static double sn_work(const asam_sn_desc_t *d)
+{
+    double m = 3.0 * d->mb, c = 3.0 * d->cb;
+    return c * m * m + 3.0e4; /* flops + a per-front latency floor */
+}
+
+static void build_schedule(plan_t *pl)
+{
+    const int nsn = pl->nsn, W = pl->world > 1 ? pl->world : 1, me = pl->world > 1 ? pl->rank : 0;
+    free(pl->tasks); free(pl->nwait); free(pl->btasks); free(pl->leaf_tasks);
+    free(pl->top_tasks); free(pl->top_nwait);
+    free(pl->shard_owner); free(pl->shard_off); free(pl->shard_cnt); free(pl->shard_q0); free(pl->shard_qn);
+    pl->top_tasks = pl->top_nwait = pl->shard_owner = pl->shard_q0 = pl->shard_qn = NULL;
+    pl->shard_off = pl->shard_cnt = NULL;
+    pl->n_top = pl->n_top_sn = pl->n_shards = 0;
+
+    /* owner[s]: rank that factors s, -1 = top (every rank) */
+    int *owner = malloc(sizeof(int) * (size_t) (nsn + 1));
+    for (int s = 0; s < nsn; s++)
+        owner[s] = 0;
+    if (W > 1 && nsn > 0) {
+        double *sub = malloc(sizeof(double) * (size_t) nsn); /* work of the subtree rooted at s */
+        for (int s = 0; s < nsn; s++)
+            sub[s] = sn_work(&pl->desc[s]);
+        for (int s = 0; s < nsn; s++) /* children have smaller ids */
+            if (pl->desc[s].parent >= 0)
+                sub[pl->desc[s].parent] += sub[s];
+        /* frontier of subtree roots; split the heaviest until the shards can be balanced */
+        int *fr = malloc(sizeof(int) * (size_t) (nsn + 1)), nfr = 0;
+        double total = 0.0;
+        for (int s = 0; s < nsn; s++)
+            if (pl->desc[s].parent < 0) {
+                fr[nfr++] = s;
+                total += sub[s];
+            }
+        for (int s = 0; s < nsn; s++)
+            owner[s] = -2; /* undecided */
+        const int max_shards = 16 * W;
+        double *load = malloc(sizeof(double) * (size_t) W);
+        for (;;) {
+            /* heaviest-first dealing (LPT) of the current frontier */
+            for (int i = 1; i < nfr; i++) { /* insertion sort by (work desc, id asc): deterministic */
+                int v = fr[i], j = i - 1;
+                while (j >= 0 && (sub[fr[j]] < sub[v] || (sub[fr[j]] == sub[v] && fr[j] > v))) {
+                    fr[j + 1] = fr[j];
+                    j--;
+                }
+                fr[j + 1] = v;
+            }
+            for (int r = 0; r < W; r++)
+                load[r] = 0.0;
+            double shard_sum = 0.0;
+            for (int i = 0; i < nfr; i++) {
+                int best = 0;
+                for (int r = 1; r < W; r++)
+                    if (load[r] < load[best])
+                        best = r;
+                load[best] += sub[fr[i]];
+                shard_sum += sub[fr[i]];
+            }
+            double mx = 0.0;
+            for (int r = 0; r < W; r++)
+                if (load[r] > mx)
+                    mx = load[r];
+            /* stop when balanced within 10 %, when there are plenty of shards, or when the heaviest
+             * shard cannot be split (no children) */
+            int h = fr[0];
+            if (nfr >= W && mx <= 1.10 * shard_sum / W)
+                break;
+            if (nfr >= max_shards || pl->snh[h].children.n == 0)
+                break;
+            owner[h] = -1; /* the root of the heaviest shard moves above the cut */
+            fr[0] = fr[nfr - 1];
+            nfr--;
+            for (int c = 0; c < pl->snh[h].children.n; c++)
+                fr[nfr++] = pl->snh[h].children.p[c];
+        }
+        /* final dealing + shard descriptors */
+        for (int r = 0; r < W; r++)
+            load[r] = 0.0;
+        pl->n_shards = nfr;
+        pl->shard_owner = malloc(sizeof(int) * (size_t) (nfr + 1));
+        pl->shard_off = malloc(sizeof(int64_t) * (size_t) (nfr + 1));
+        pl->shard_cnt = malloc(sizeof(int64_t) * (size_t) (nfr + 1));
+        pl->shard_q0 = malloc(sizeof(int) * (size_t) (nfr + 1));
+        pl->shard_qn = malloc(sizeof(int) * (size_t) (nfr + 1));
+        int *npose = calloc((size_t) nsn + 1, sizeof(int)); /* poses in the subtree of s */
+        for (int s = 0; s < nsn; s++) {
+            npose[s] += pl->desc[s].cb;
+            if (pl->desc[s].parent >= 0)
+                npose[pl->desc[s].parent] += npose[s];
+        }
+        for (int i = 0; i < nfr; i++) {
+            int best = 0, s = fr[i];
+            for (int r = 1; r < W; r++)
+                if (load[r] < load[best])
+                    best = r;
+            load[best] += sub[s];
+            owner[s] = best;
+            const asam_sn_desc_t *d = &pl->desc[s];
+            int64_t m = 3 * (int64_t) d->mb, c = 3 * (int64_t) d->cb, ld = m + 1;
+            pl->shard_owner[i] = best;
+            pl->shard_off[i] = d->f_off + c * ld;   /* trailing columns: update matrix + rhs row */
+            pl->shard_cnt[i] = (m - c) * ld;
+            pl->shard_qn[i] = npose[s];
+            pl->shard_q0[i] = d->first + d->cb - npose[s];
+        }
+        /* push ownership down the shards (parents have larger ids) */
+        for (int s = nsn - 1; s >= 0; s--)
+            if (owner[s] == -2)
+                owner[s] = pl->desc[s].parent >= 0 ? owner[pl->desc[s].parent] : -1;
+        free(npose);
+        free(load);
+        free(fr);
+        free(sub);
+    }
+
+    /* leaf set: supernodes whose whole subtree consists of fronts small enough for the
+     * warp-per-front kernels (children have smaller ids).  Only worth separate launches when
+     * there are thousands of them. */
+    char *leaf = calloc((size_t) nsn + 1, 1);
+    int n_leaf_all = 0;
+    for (int s = 0; s < nsn; s++) {
+        int ok = 3 * pl->desc[s].mb <= ASAM_LEAF_MAX_M;
+        for (int c = 0; ok && c < pl->snh[s].children.n; c++)
+            ok = leaf[pl->snh[s].children.p[c]];
+        leaf[s] = (char) ok;
+        n_leaf_all += ok;
+    }
+    if (n_leaf_all < ASAM_LEAF_MIN_COUNT)
+        memset(leaf, 0, (size_t) nsn);
+
+    /* counting sort by level, ids ascending inside a level */
+    int *byl = malloc(sizeof(int) * (size_t) (nsn + 1));
+    int *cnt = calloc((size_t) pl->n_levels + 2, sizeof(int));
+    for (int s = 0; s < nsn; s++)
+        cnt[pl->desc[s].level + 1]++;
+    for (int l = 0; l < pl->n_levels; l++)
+        cnt[l + 1] += cnt[l];
+    for (int s = 0; s < nsn; s++)
+        byl[cnt[pl->desc[s].level]++] = s;
+    free(cnt);
+
+    int64_t n_local = 0, n_top = 0;
+    int n_leaf = 0, n_main_sn = 0, n_top_sn = 0;
+    for (int s = 0; s < nsn; s++) {
+        if (owner[s] == me) {
+            if (leaf[s])
+                n_leaf++;
+            else {
+                n_local += team_size(pl->desc[s].mb, pl->desc[s].cb);
+                n_main_sn++;
+            }
+        } else if (owner[s] == -1) {
+            n_top += team_size(pl->desc[s].mb, pl->desc[s].cb);
+            n_top_sn++;
+        }
+    }
+    pl->ntasks = (int) n_local;
+    pl->tasks = malloc(sizeof(int) * (size_t) (n_local + 1));
+    pl->nwait = malloc(sizeof(int) * (size_t) (n_local + 1));
+    pl->n_leaf = n_leaf;
+    pl->leaf_tasks = malloc(sizeof(int) * (size_t) (n_leaf + 1));
+    pl->n_top = (int) n_top;
+    pl->n_top_sn = n_top_sn;
+    pl->top_tasks = malloc(sizeof(int) * (size_t) (n_top + 1));
+    pl->top_nwait = malloc(sizeof(int) * (size_t) (n_top + 1));
+    pl->n_btasks = n_top_sn + n_main_sn + n_leaf;
+    pl->btasks = malloc(sizeof(int) * (size_t) (pl->n_btasks + 1));
+    /* back-solve list, parents first: [top | own shards outside the leaf set | own leaf set] */
+    int t = 0, tl = 0, tt = 0;
+    int bt = n_top_sn - 1, bm = n_top_sn + n_main_sn - 1, bl = pl->n_btasks - 1;
+    for (int k = 0; k < nsn; k++) {
+        int s = byl[k];
+        if (owner[s] == -1) {
+            pl->btasks[bt--] = s;
+            int nw = 0; /* children above the cut: the others were exchanged before this launch */
+            for (int c = 0; c < pl->snh[s].children.n; c++)
+                nw += owner[pl->snh[s].children.p[c]] == -1;
+            int G = team_size(pl->desc[s].mb, pl->desc[s].cb);
+            for (int w = 0; w < G; w++, tt++) {
+                pl->top_tasks[tt] = s;
+                pl->top_nwait[tt] = pack_nwait(nw, w, G > 1 ? G : 0);
+            }
+            continue;
+        }
+        if (owner[s] != me)
+            continue;
+        if (leaf[s]) {
+            pl->btasks[bl--] = s;
+            pl->leaf_tasks[tl++] = s;
+            continue;
+        }
+        pl->btasks[bm--] = s;
+        /* nwait counts ALL children: those of the leaf set arrived in the earlier launch */
+        int G = team_size(pl->desc[s].mb, pl->desc[s].cb);
+        for (int w = 0; w < G; w++, t++) {
+            pl->tasks[t] = s;
+            pl->nwait[t] = pack_nwait(pl->desc[s].ch_cnt, w, G > 1 ? G : 0);
+        }
+    }
+    free(byl);
+    free(leaf);
+    free(owner);
+}
+
 /* ---- batch build --------------------------------------------------------------------------- */
 static int plan_build_impl(plan_t *pl, asam_dev_t *dev, int N, int n_factors, const int *ftype, const int *fa,
                            const int *fb, const int *order_keep, int N_keep)
 {
     uint64_t keep_hash = pl->struct_hash;
+    int keep_world = pl->world, keep_rank = pl->rank;
     plan_free(pl);
     pl->struct_hash = keep_hash;
+    pl->world = keep_world;
+    pl->rank = keep_rank;
     if (N <= 0)
         return 0;
     node_arrays_reserve(pl, N);
@@ -633,63 +860,7 @@ static int plan_build_impl(plan_t *pl, asam_dev_t *dev, int N, int n_factors, co
     }
     pl->ipool_n = seg.n;
 
-    pl->btasks = malloc(sizeof(int) * (size_t) pl->nsn);
-    {
-        /* leaf set: supernodes whose whole subtree consists of fronts small enough for the
-         * warp-per-front kernel (children have smaller ids).  Only worth a separate launch when
-         * there are thousands of them. */
-        char *leaf = calloc((size_t) pl->nsn + 1, 1);
-        int n_leaf = 0;
-        for (int s = 0; s < pl->nsn; s++) {
-            int ok = 3 * pl->desc[s].mb <= ASAM_LEAF_MAX_M;
-            for (int c = 0; ok && c < pl->snh[s].children.n; c++)
-                ok = leaf[pl->snh[s].children.p[c]];
-            leaf[s] = (char) ok;
-            n_leaf += ok;
-        }
-        if (n_leaf < ASAM_LEAF_MIN_COUNT) {
-            memset(leaf, 0, (size_t) pl->nsn);
-            n_leaf = 0;
-        }
-        /* counting sort by level, ids ascending inside a level; big fronts expand into teams */
-        int *byl = malloc(sizeof(int) * (size_t) pl->nsn);
-        int *cnt = calloc((size_t) pl->n_levels + 1, sizeof(int));
-        int64_t total = 0;
-        for (int s = 0; s < pl->nsn; s++) {
-            cnt[pl->desc[s].level + 1]++;
-            if (!leaf[s])
-                total += team_size(pl->desc[s].mb, pl->desc[s].cb);
-        }
-        for (int l = 0; l < pl->n_levels; l++)
-            cnt[l + 1] += cnt[l];
-        for (int s = 0; s < pl->nsn; s++)
-            byl[cnt[pl->desc[s].level]++] = s;
-        free(cnt);
-        pl->ntasks = (int) total;
-        pl->tasks = malloc(sizeof(int) * (size_t) (total + 1));
-        pl->nwait = malloc(sizeof(int) * (size_t) (total + 1));
-        pl->n_leaf = n_leaf;
-        pl->leaf_tasks = malloc(sizeof(int) * (size_t) (n_leaf + 1));
-        /* back-solve list, parents first: everything outside the leaf set, then the leaf set */
-        int t = 0, tl = 0, bm = pl->nsn - n_leaf - 1, bl = pl->nsn - 1;
-        for (int k = 0; k < pl->nsn; k++) {
-            int s = byl[k];
-            if (leaf[s]) {
-                pl->btasks[bl--] = s;
-                pl->leaf_tasks[tl++] = s;
-                continue;
-            }
-            pl->btasks[bm--] = s;
-            /* nwait counts ALL children: those of the leaf set arrived in the earlier launch */
-            int G = team_size(pl->desc[s].mb, pl->desc[s].cb);
-            for (int w = 0; w < G; w++, t++) {
-                pl->tasks[t] = s;
-                pl->nwait[t] = pack_nwait(pl->desc[s].ch_cnt, w, G > 1 ? G : 0);
-            }
-        }
-        free(byl);
-        free(leaf);
-    }
+    build_schedule(pl);
 
     /* host mirror of the device int pool (debug / tests) */
     ivec_free(&pl->ipool_host);
@@ -715,8 +886,25 @@ static int plan_build_impl(plan_t *pl, asam_dev_t *dev, int N, int n_factors, co
     rc |= asam_upload_node2q(dev, 0, N, pl->node2q);
     rc |= asam_upload_q2node(dev, 0, N, pl->q2node);
     rc |= asam_upload_fslot(dev, 0, n_factors, pl->fslot);
-    rc |= asam_set_full_tasks(dev, pl->ntasks, pl->tasks, pl->nwait, pl->nsn, pl->btasks);
+    rc |= asam_set_full_tasks(dev, pl->ntasks, pl->tasks, pl->nwait, pl->n_btasks, pl->btasks);
     rc |= asam_set_leaf_tasks(dev, pl->n_leaf, pl->leaf_tasks);
+    if (pl->world > 1) {
+        asam_shard_sched_t sh;
+        memset(&sh, 0, sizeof(sh));
+        sh.n_top = pl->n_top;
+        sh.top_tasks = pl->top_tasks;
+        sh.top_nwait = pl->top_nwait;
+        sh.n_top_sn = pl->n_top_sn;
+        sh.n_shards = pl->n_shards;
+        sh.shard_owner = pl->shard_owner;
+        sh.shard_off = pl->shard_off;
+        sh.shard_cnt = pl->shard_cnt;
+        sh.shard_q0 = pl->shard_q0;
+        sh.shard_qn = pl->shard_qn;
+        rc |= asam_set_shard_schedule(dev, &sh);
+    } else {
+        rc |= asam_set_shard_schedule(dev, NULL);
+    }
     free(ids);
     ivec_free(&seg);
     return rc;
@@ -764,6 +952,10 @@ int plan_append(plan_t *pl, asam_dev_t *dev, int N, int n_factors, const int *ft
         }
     }
 
+    if (pl->world > 1) {
+        asam_set_error("a batch solve sharded over %d GPUs cannot be continued incrementally (replicas only)", pl->world);
+        return 1;
+    }
     /* incremental steps run the whole schedule through k_factor / k_backsolve */
     if (pl->n_leaf > 0) {
         pl->n_leaf = 0;

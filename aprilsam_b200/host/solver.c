@@ -446,8 +446,17 @@ ASAM_API void april_graph_cholesky(april_graph_t *graph, april_graph_cholesky_pa
     /* ordering + symbolic analysis: cached while the factor structure is unchanged */
     uint64_t h = structure_hash(N, F, c->ftype, c->fa, c->fb);
     int plan_reused = 1;
-    if (!(s->plan_valid && s->plan.N == N && s->plan.n_factors == F && s->plan.struct_hash == h)) {
+    /* several GPUs (asam_comm_init + asam_comm_set_sharding): this rank factors its shards of the
+     * elimination tree and the part above the cut; every rank calls april_graph_cholesky on its
+     * own copy of the same graph */
+    int cw = 1, cr = 0, csh = 0;
+    asam_comm_info(&cw, &cr, &csh);
+    const int want_world = csh ? cw : 1;
+    if (!(s->plan_valid && s->plan.N == N && s->plan.n_factors == F && s->plan.struct_hash == h &&
+          (s->plan.world > 1 ? s->plan.world : 1) == want_world && (want_world == 1 || s->plan.rank == cr))) {
         plan_reused = 0;
+        s->plan.world = want_world;
+        s->plan.rank = want_world > 1 ? cr : 0;
         if (plan_build(&s->plan, dev, N, F, c->ftype, c->fa, c->fb) != 0)
             asam_fatal("april_graph_cholesky: %s %s", g_error, asam_last_error());
         s->plan.struct_hash = h;

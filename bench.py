@@ -237,6 +237,10 @@ def run_b200(args, d, label, world, rank, local, dist):
     is_batch = args.workload.endswith("_batch")
     sampler = ClockSampler(local, period_ms=int(os.environ.get("ASAM_CLOCK_PERIOD_MS", "500")))
 
+    sharded = world > 1 and is_batch and (args.shard == "on" or (args.shard == "auto" and args.workload == "manhattan_batch"))
+    if sharded:
+        capi.comm_init_torch(dist, local)
+        capi.check(L.asam_comm_set_sharding(1), "asam_comm_set_sharding")
     h = H.Harness("b200")
     init = d.init.copy()
     if is_batch:
@@ -276,7 +280,9 @@ def run_b200(args, d, label, world, rank, local, dist):
         e2e_ms = list(ms)
     launches1, h2d1, d2h1 = capi.counters(dev)
     nsteps = len(e2e_ms)
-    e2e_val = aggregate_rate(dist, local, world, nsteps, float(np.sum(e2e_ms)) / 1e3)
+    # replicas: every rank solved its own copy; sharded: all ranks worked on the SAME solves
+    jobs = 1 if sharded else world
+    e2e_val = aggregate_rate(dist, local, jobs, nsteps, float(np.sum(e2e_ms)) / 1e3)
 
     # ---- device-resident: same pipeline, inputs already in HBM, CUDA events per step ----------
     dev_ms = []
@@ -286,7 +292,10 @@ def run_b200(args, d, label, world, rank, local, dist):
         h.batch()
         N, S, F = pinfo["N"], pinfo["n_slots"], pinfo["n_factors"]
         ms = C.c_float()
+        launches_a = capi.counters(dev)[0]
         for i in range(W + K):
+            if i == W:
+                launches_a = capi.counters(dev)[0]
             capi.check(L.asam_l2_flush(dev), "l2_flush")
             capi.check(L.asam_timer_start(dev), "timer")
             capi.check(L.asam_hessian_reset(dev, N, S, N, 1e-4), "reset")
@@ -297,13 +306,14 @@ def run_b200(args, d, label, world, rank, local, dist):
             if i >= W:
                 dev_ms.append(ms.value)
                 fac_ms.append(capi.kernel_ms(dev)[1])
+        launches_dev = capi.counters(dev)[0] - launches_a
         st = C.c_int()
         L.asam_factor_status(dev, C.byref(st))
         if st.value != 0:
             raise SystemExit(f"bench.py: factorisation status {st.value}")
-        value = aggregate_rate(dist, local, world, len(dev_ms), float(np.sum(dev_ms)) / 1e3)
+        value = aggregate_rate(dist, local, jobs, len(dev_ms), float(np.sum(dev_ms)) / 1e3)
         ms_per_step = float(np.mean(dev_ms))
-        gpu_launches = 4 * len(dev_ms)
+        gpu_launches = launches_dev
     else:
         value = e2e_val
         ms_per_step = float(np.mean(e2e_ms))
@@ -345,10 +355,12 @@ def run_b200(args, d, label, world, rank, local, dist):
         return
     per_step = max(nsteps, 1)
     line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
             "dtype": "f64",
             "data": "synthetic" if "manhattan" in args.workload else "fixture M3500 (public dataset) + synthetic prior",
-            "config": {"workload": args.workload, "graph": label, "parallelism": f"replicas x{world}",
+            "config": {"workload": args.workload, "graph": label,
+                       "parallelism": (f"elimination-tree shards x{world}, top of the tree replicated, NCCL broadcast of shard "
+                                       f"root fronts and solution segments") if sharded else f"replicas x{world}",
                        "cache": "L2 flushed (384 MiB overwrite) between timed steps" if is_batch else "working set grows each step",
                        "plan": {k: pinfo[k] for k in ("N", "nsn", "n_slots", "n_levels", "max_m", "nnz_l_blocks")},
                        "cold_first_call_ms": cold_ms},
@@ -373,6 +385,9 @@ def main():
     ap.add_argument("--poses", type=int, default=100000)
     ap.add_argument("--replay-from", type=int, default=1, help="replay workloads: first timed step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", choices=["auto", "on", "off"], default="auto",
+                    help="--gpus N > 1: shard the elimination tree of ONE solve over the GPUs (NCCL) instead of "
+                         "running N replicas; auto = on for manhattan_batch (SURVEY.md section 8e)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200" and args.workload.endswith("_batch"):
         args.warmup = 3

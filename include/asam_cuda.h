@@ -102,6 +102,36 @@ int asam_factor_full(asam_dev_t *d);
  * ancestors of everything older: prepend them (parents first) to the full back-solve list. */
 int asam_btasks_prepend(asam_dev_t *d, int n, const int32_t *ids);
 
+/* ---- several GPUs, one process per GPU ---------------------------------
+ * The communicator is process-wide (a process drives one GPU): rank 0 obtains a 128-byte id with
+ * asam_comm_unique_id and ships it to the other ranks by any means (bench.py: torch.distributed),
+ * every rank then calls asam_comm_init.  NCCL is loaded with dlopen("libnccl.so.2") -- the copy a
+ * host application (PyTorch) already loaded is re-used.  With a communicator in place a batch solve
+ * (april_graph_cholesky) may shard the elimination tree: asam_comm_set_sharding(1). */
+int asam_comm_unique_id(void *id128_out);
+int asam_comm_init(int world, int rank, const void *id128);
+void asam_comm_destroy(void);
+/* world = 1 without a communicator; *sharding = 1 if batch solves are to be sharded */
+int asam_comm_info(int *world, int *rank, int *sharding);
+int asam_comm_set_sharding(int enabled);
+
+/* Schedule of a sharded batch solve on this rank.  The lists given to asam_set_full_tasks /
+ * asam_set_leaf_tasks then cover this rank's shards only (btasks: top, then own shards, then own
+ * leaf set); here come the supernodes above the cut (factored by every rank after the exchange)
+ * and what is exchanged: for shard i, owner rank, the arena range holding the trailing columns of
+ * its root front (update matrix + rhs row) and its interval of elimination positions (solution
+ * segment).  asam_factor_full = own shards -> broadcast of the root fronts -> top;
+ * asam_backsolve_full = top + own shards -> broadcast of the solution segments. */
+typedef struct asam_shard_sched {
+    int32_t n_top, n_top_sn;
+    const int32_t *top_tasks, *top_nwait;
+    int32_t n_shards;
+    const int32_t *shard_owner;
+    const int64_t *shard_off, *shard_cnt; /* arena doubles */
+    const int32_t *shard_q0, *shard_qn;   /* positions */
+} asam_shard_sched_t;
+int asam_set_shard_schedule(asam_dev_t *d, const asam_shard_sched_t *sched /* NULL: not sharded */);
+
 /* Kernel 3: back-substitution over the given supernodes (parents before children; the
  * list must be closed under ancestors).  (smatd.c:1075-1097, aprilsam.c:721-779) */
 int asam_backsolve(asam_dev_t *d, int ntasks, const int32_t *btasks);

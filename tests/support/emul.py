@@ -123,11 +123,13 @@ def seg_views(desc, ipool, s):
     return rows, rel, children, a_slot, a_rb, a_cb
 
 
-def factor(fr: Fronts, H: Hessian, desc, ipool, q2node, tasks, nwait=None, check_order=True, prior=()):
+def factor(fr: Fronts, H: Hessian, desc, ipool, q2node, tasks, nwait=None, check_order=True, prior=(),
+           count_prior=True):
     """k_factor: assemble + eliminate the listed supernodes (children first).  `prior` = supernodes
-    factored by an earlier launch of the same solve (k_factor_leaf): their arrivals count too."""
+    factored by an earlier launch of the same solve; count_prior: their arrivals are part of nwait
+    (k_factor_leaf before k_factor) or not (arrival counters zeroed in between: the multi-GPU top)."""
     done = set()
-    intask = set(int(t) for t in tasks) | set(int(t) for t in prior)
+    intask = set(int(t) for t in tasks) | (set(int(t) for t in prior) if count_prior else set())
     done |= set(int(t) for t in prior)
     for ti, s in enumerate(tasks):
         s = int(s)

@@ -20,6 +20,7 @@ def lib():
         L.asam_dbg_plan_create.restype = C.c_void_p
         L.asam_dbg_plan_destroy.argtypes = [C.c_void_p]
         L.asam_dbg_plan_build.argtypes = [C.c_void_p, C.c_int, C.c_int, _ip, _ip, _ip]
+        L.asam_dbg_plan_build_sharded.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, _ip]
         L.asam_dbg_plan_build_with_order.argtypes = [C.c_void_p, C.c_int, C.c_int, _ip, _ip, _ip, _ip, C.c_int]
         L.asam_dbg_plan_append.argtypes = [C.c_void_p, C.c_int, C.c_int, _ip, _ip, _ip, _ip, C.c_int, _ip, _ip, C.c_int]
         L.asam_dbg_plan_info.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double)]
@@ -36,7 +37,8 @@ def _i(a):
 
 
 ARR = dict(order=0, pos=1, node2q=2, q2node=3, parent_pos=4, fslot=5, sn_of_q=6, ipool=7, tasks=8, nwait=9,
-           btasks=10, desc=11, leaf_tasks=12)
+           btasks=10, desc=11, leaf_tasks=12, top_tasks=13, top_nwait=14, shard_owner=15,
+           shard_q0=16, shard_qn=17, shard_off=18, shard_cnt=19)
 TR_FLAG = 1 << 30
 
 
@@ -55,11 +57,14 @@ class HostPlan:
     def __del__(self):
         self.close()
 
-    def build(self, N, ftype, fa, fb, order_keep=None):
+    def build(self, N, ftype, fa, fb, order_keep=None, world=1, rank=0):
         self.ftype = np.ascontiguousarray(ftype, dtype=np.int32)
         self.fa = np.ascontiguousarray(fa, dtype=np.int32)
         self.fb = np.ascontiguousarray(fb, dtype=np.int32)
-        if order_keep is None:
+        if world > 1:
+            rc = self.L.asam_dbg_plan_build_sharded(self.p, world, rank, N, len(self.ftype), _i(self.ftype),
+                                                    _i(self.fa), _i(self.fb))
+        elif order_keep is None:
             rc = self.L.asam_dbg_plan_build(self.p, N, len(self.ftype), _i(self.ftype), _i(self.fa), _i(self.fb))
         else:
             ok = np.ascontiguousarray(order_keep, dtype=np.int32)
@@ -100,6 +105,9 @@ class HostPlan:
         if n.value == 0:
             return np.zeros(0, dtype=np.int32)
         return np.ctypeslib.as_array(ptr, shape=(n.value,)).copy()
+
+    def array64(self, name):
+        return self.array(name).view(np.int64)
 
     def descs(self):
         """Structured view of asam_sn_desc_t[]."""

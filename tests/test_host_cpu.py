@@ -228,6 +228,77 @@ def test_large_plan_leaf_set_and_merged_chains():
     assert np.abs(st - want).max() < 1e-6 * max(1.0, np.abs(want).max())
 
 
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_sharded_schedule_emulated(world):
+    """Multi-GPU schedule: every rank factors its shards, the shard roots' trailing
+    columns are exchanged, every rank factors the top, back-solves top + own shards, solution segments
+    are exchanged.  Emulated with one numpy arena per rank; the result must equal the single-rank one."""
+    d = datasets.manhattan_dense(6000, seed=7)
+    n = d.n_nodes
+    ftype, fa, fb, fz, fW = factor_arrays(d)
+    ref = emulate_batch(d)
+    plans = [HostPlan().build(n, ftype, fa, fb, world=world, rank=r) for r in range(world)]
+    desc, ipool, q2node, node2q = plans[0].descs(), plans[0].array("ipool"), plans[0].array("q2node"), plans[0].array("node2q")
+    nsn = len(desc["mb"])
+    own = plans[0].array("shard_owner")
+    q0, qn = plans[0].array("shard_q0"), plans[0].array("shard_qn")
+    off, cnt = plans[0].array64("shard_off"), plans[0].array64("shard_cnt")
+    assert len(own) >= world and set(own) == set(range(world)), "every rank gets work"
+    for p in plans[1:]:  # the cut is the same on every rank
+        assert np.array_equal(p.array("shard_owner"), own) and np.array_equal(p.array64("shard_off"), off)
+        assert np.array_equal(p.array("top_tasks"), plans[0].array("top_tasks"))
+    top = set(int(t) for t in plans[0].array("top_tasks"))
+    seen = set(top)
+    for r, p in enumerate(plans):
+        mine = set(int(t) for t in p.array("tasks")) | set(int(t) for t in p.array("leaf_tasks"))
+        assert not (mine & seen), "shards are disjoint from each other and from the top"
+        seen |= mine
+        assert set(int(t) for t in p.array("btasks")) == mine | top
+    assert seen == set(range(nsn)), "top + shards cover the tree"
+    # shard intervals are disjoint position ranges
+    iv = sorted(zip(q0, q0 + qn))
+    assert all(a[1] <= b[0] for a, b in zip(iv, iv[1:]))
+    root_of = {}  # shard root front offset -> shard
+    for s_ in range(nsn):
+        m_, c_ = 3 * int(desc["mb"][s_]), 3 * int(desc["cb"][s_])
+        for i in range(len(own)):
+            if int(desc["f_off"][s_]) + c_ * (m_ + 1) == off[i] and (m_ - c_) * (m_ + 1) == cnt[i]:
+                root_of[s_] = i
+    assert len(root_of) == len(own), "every exchanged range is the trailing part of one root front"
+
+    Hs = emul.Hessian(n, plans[0].info()["n_slots"])
+    Hs.reset(n, 1e-4)
+    Hs.linearize(range(len(ftype)), ftype, fa, fb, fz, fW, d.init, d.init, node2q, plans[0].array("fslot"))
+    arenas = []
+    for r, p in enumerate(plans):  # phase 1: own shards
+        fr = emul.Fronts()
+        fr.ensure(n)
+        leaf = p.array("leaf_tasks")
+        if len(leaf):
+            emul.factor(fr, Hs, desc, ipool, q2node, leaf, None)
+        emul.factor(fr, Hs, desc, ipool, q2node, p.array("tasks"), p.array("nwait"), prior=leaf)
+        arenas.append(fr)
+    for s_, i in root_of.items():  # exchange: root fronts of the shards
+        o = int(desc["f_off"][s_])
+        for r in range(world):
+            if r != own[i]:
+                arenas[r].F[o] = arenas[own[i]].F[o]
+                arenas[r].rhs[o] = arenas[own[i]].rhs[o]
+    xs = []
+    for r, p in enumerate(plans):  # phase 2: top (redundantly) + back-solve of top and own shards
+        done_before = [s_ for s_ in range(nsn) if s_ not in top]
+        emul.factor(arenas[r], Hs, desc, ipool, q2node, p.array("top_tasks"), p.array("top_nwait"), prior=done_before,
+                    count_prior=False)
+        emul.backsolve(arenas[r], desc, ipool, p.array("btasks"))
+        xs.append(arenas[r].x.copy())
+    x = xs[0].copy()
+    for i in range(len(own)):  # exchange: solution segments
+        x[3 * q0[i]:3 * (q0[i] + qn[i])] = xs[own[i]][3 * q0[i]:3 * (q0[i] + qn[i])]
+    st = d.init + np.stack([x[3 * node2q[i]:3 * node2q[i] + 3] for i in range(n)])
+    st[:, 2] = emul.mod2pi(st[:, 2])
+    assert np.abs(st - ref).max() < 1e-9 * max(1.0, np.abs(ref).max())
+
+
 @pytest.mark.parametrize("n0,n1,step", [(1, 40, 1), (120, 200, 1), (300, 330, 3)])
 def test_emulated_incremental_append(m3500, n0, n1, step):
     """plan_append: re-factoring only the marked supernodes reproduces the full solution."""
