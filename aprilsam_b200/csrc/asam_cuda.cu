@@ -554,7 +554,7 @@ ASAM_EXPORT int asam_reserve(asam_dev_t *d, int n_nodes, int n_factors, int n_sl
     rc |= buf_reserve(d, d->sn, SN * sizeof(asam_sn_desc_t), true, false);
     rc |= buf_reserve(d, d->arrive, SN * sizeof(int), true, true);
     rc |= buf_reserve(d, d->xdone, SN * sizeof(int), true, true);
-    rc |= buf_reserve(d, d->tbar, SN * sizeof(int), true, true);
+    rc |= buf_reserve(d, d->tbar, 2 * SN * sizeof(int), true, true);
     rc |= buf_reserve(d, d->ipool, (size_t) ipool_ints * sizeof(int), true, false);
     rc |= buf_reserve(d, d->arena, (size_t) arena_doubles * sizeof(double), true, false);
     return rc;

@@ -589,7 +589,7 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
     double *F = a.arena + d.f_off;
     int *err = a.ctrl + 1;
     TeamCtx tc;
-    tc.tbar_s = a.tbar + s;
+    tc.tbar_s = a.tbar + 2 * (size_t) s; // [2s] team barrier, [2s+1] crew barrier of the look-ahead
     tc.G = G;
     tc.w = w;
     tc.phase = 0;
@@ -684,156 +684,213 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
     if (trow && tid == 0)
         trow[3] = d_now();
 
-    // ---- panels ---------------------------------------------------------------------------------
+    // ---- panels, with one panel of look-ahead ---------------------------------------------------
+    // Panel k+1 is factored by a small CREW (the workers that own its 256-row chunks) while the
+    // other workers are still applying panel k to the rest of the trailing matrix: in iteration k
+    //   crew worker w:  update rows chunk w of the NEXT panel's columns with panel k
+    //                   -> [crew barrier] -> diagonal block (redundantly) + TRSM of chunk w
+    //   everybody:      tiles of the trailing update with panel k right of the next panel
+    //   -> [team barrier]
+    // so the dependent chain per panel is one chunk update + the panel factorisation + one
+    // barrier instead of panel factorisation + barrier + a whole trailing update + barrier.
     double *D = sm;                              // ASAM_TPB x ASAM_TPB diagonal block
     double *rdv = D + ASAM_TPB * ASAM_TPB;       // ASAM_TPB reciprocal diagonal entries
     double *Li = rdv + ASAM_TPB;                 // ASAM_TROWS x pb   (row chunk / row tile)
     double *Lj = Li + ASAM_TROWS * ASAM_TPB;     // ASAM_TCOLS x pb   (column tile)
     double *dinv = a.dinv + 3 * (size_t) d.first;
-    for (int k0 = 0; k0 < c; k0 += ASAM_TPB) {
-        const int pb = min(ASAM_TPB, c - k0);
-        if (trow && tid == 0)
-            t_mark = d_now();
-        // diagonal block (every worker, redundantly) ...
+    int *crew_bar = a.tbar + 2 * (size_t) s + 1;
+    int crew_cum = 0;
+
+    // C[rb0.., cb0..] -= L[rb0.., k0..k0+pb) * L[cb0.., k0..k0+pb)'  (lower trapezoid only)
+    auto tile = [&](int k0, int pb, int cb0, int ncol, int rb0, int nrow) {
+        __syncthreads();
+        // two panel columns per warp and pass: 20 independent loads in flight per lane
+        for (int p = warp; p < pb; p += 2 * nwarps) {
+            double vj[2][2], vi[2][8];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int pp = p + h * nwarps;
+                const double *src = F + (size_t) (k0 + min(pp, pb - 1)) * ld;
+#pragma unroll
+                for (int u = 0; u < 2; u++)
+                    vj[h][u] = (pp < pb && lane + 32 * u < ncol) ? __ldcg(src + cb0 + lane + 32 * u) : 0.0;
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                    vi[h][u] = (pp < pb && lane + 32 * u < nrow) ? __ldcg(src + rb0 + lane + 32 * u) : 0.0;
+            }
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int pp = p + h * nwarps;
+                if (pp < pb) {
+#pragma unroll
+                    for (int u = 0; u < 2; u++)
+                        if (lane + 32 * u < ncol)
+                            Lj[lane + 32 * u + pp * ASAM_TCOLS] = vj[h][u];
+#pragma unroll
+                    for (int u = 0; u < 8; u++)
+                        if (lane + 32 * u < nrow)
+                            Li[lane + 32 * u + pp * ASAM_TROWS] = vi[h][u];
+                }
+            }
+        }
+        __syncthreads();
+        // warp -> 8 columns, lane -> rows lane + 32 r (passes of 128 rows)
+        const int tj = 8 * warp;
+        if (tj < ncol) {
+            for (int ib = 0; ib < nrow; ib += 128) {
+                double acc[4][8], cv[4][8];
+                int ir[4], jc[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++)
+                    jc[q] = min(tj + q, ncol - 1);
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    ir[r] = min(ib + lane + 32 * r, nrow - 1);
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        acc[r][q] = 0.0;
+                        // the C values are fetched now and consumed after the products:
+                        // their L2 latency hides behind the 4x8xpb FMAs
+                        const int ii = ib + lane + 32 * r, jj = tj + q;
+                        const bool ok = ii < nrow && jj < ncol && rb0 + ii >= cb0 + jj;
+                        cv[r][q] = ok ? __ldcg(&F[(rb0 + ii) + (size_t) (cb0 + jj) * ld]) : 0.0;
+                    }
+                }
+#pragma unroll 2
+                for (int p = 0; p < pb; p++) {
+                    double bq[8], av[4];
+#pragma unroll
+                    for (int q = 0; q < 8; q++)
+                        bq[q] = Lj[jc[q] + p * ASAM_TCOLS];
+#pragma unroll
+                    for (int r = 0; r < 4; r++)
+                        av[r] = Li[ir[r] + p * ASAM_TROWS];
+#pragma unroll
+                    for (int r = 0; r < 4; r++)
+#pragma unroll
+                        for (int q = 0; q < 8; q++)
+                            acc[r][q] += av[r] * bq[q];
+                }
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        const int ii = ib + lane + 32 * r, jj = tj + q;
+                        const int i = rb0 + ii, j = cb0 + jj;
+                        if (ii < nrow && jj < ncol && i >= j)
+                            F[i + (size_t) j * ld] = cv[r][q] - acc[r][q];
+                    }
+            }
+        }
+    };
+    // diagonal block of the panel at k0 into D (every caller redundantly), the caller's row chunk
+    // [rb0, rb0+256) below the block into Li while the block is being factored, then the rows
+    auto panel = [&](int k0, int pb, int rb0) {
         __syncthreads();
         for (int e = tid; e < ASAM_TPB * ASAM_TPB; e += nt) {
             const int i = e % ASAM_TPB, j = e / ASAM_TPB;
             D[e] = (i >= j && i < pb && j < pb) ? __ldcg(&F[(k0 + i) + (size_t) (k0 + j) * ld]) : 0.0;
         }
-        // ... while the first row chunk of this worker is already on its way into shared memory
-        const int r_first = k0 + pb;
-        const int nchunk = (m - r_first + 1 + ASAM_TROWS - 1) / ASAM_TROWS;
-        int ch = w;
-        {
-            const int i = r_first + ch * ASAM_TROWS + tid;
-            if (ch < nchunk && i <= m)
-                for (int j = 0; j < pb; j++)
-                    Li[tid + j * ASAM_TROWS] = __ldcg(&F[i + (size_t) (k0 + j) * ld]);
-        }
+        const int i = rb0 + tid;
+        const bool row = rb0 >= 0 && i >= k0 + pb && i <= m;
+        if (row)
+            for (int j = 0; j < pb; j++)
+                Li[tid + j * ASAM_TROWS] = __ldcg(&F[i + (size_t) (k0 + j) * ld]);
         __syncthreads();
         diag_factor(D, pb, rdv, s, err);
-        for (; ch < nchunk; ch += G) {
-            const int i = r_first + ch * ASAM_TROWS + tid;
-            if (ch != w) { // later chunks of this worker: fetch now
-                if (i <= m)
-                    for (int j = 0; j < pb; j++)
-                        Li[tid + j * ASAM_TROWS] = __ldcg(&F[i + (size_t) (k0 + j) * ld]);
-            }
-            if (i <= m)
-                trsm_row(Li, D, rdv, pb, F + i + (size_t) k0 * ld, ld);
+        if (row)
+            trsm_row(Li, D, rdv, pb, F + i + (size_t) k0 * ld, ld);
+    };
+    auto writeback = [&](int k0, int pb) { // worker 0, after a team barrier: nobody reads the raw block any more
+        for (int e = tid; e < pb * pb; e += nt) {
+            const int i = e % pb, j = e / pb;
+            if (i >= j)
+                F[(k0 + i) + (size_t) (k0 + j) * ld] = D[i + j * ASAM_TPB];
+        }
+        for (int e = tid; e < pb; e += nt)
+            dinv[k0 + e] = rdv[e];
+    };
+
+    // prologue: panel 0 by everybody (row chunks of 256 from the panel's first row, round-robin)
+    {
+        const int pb = min(ASAM_TPB, c);
+        if (trow && tid == 0)
+            t_mark = d_now();
+        const int nchunk = (m + 1 + ASAM_TROWS - 1) / ASAM_TROWS;
+        bool first = true;
+        for (int ch = w; ch < nchunk || first; ch += G) {
+            panel(0, pb, ch < nchunk ? ch * ASAM_TROWS : -1);
+            first = false;
         }
         if (!team_barrier(tc, s_flag))
             return false;
         if (trow && tid == 0)
             t_panel += d_now() - t_mark;
-        // every worker has read the unfactored diagonal block by now: worker 0 may overwrite it
-        if (w == 0) {
-            for (int e = tid; e < pb * pb; e += nt) {
-                const int i = e % pb, j = e / pb;
-                if (i >= j)
-                    F[(k0 + i) + (size_t) (k0 + j) * ld] = D[i + j * ASAM_TPB];
+        if (w == 0)
+            writeback(0, pb);
+    }
+    for (int k0 = 0; k0 < c; k0 += ASAM_TPB) {
+        const int pb = min(ASAM_TPB, c - k0);
+        const int kn0 = k0 + pb;                       // first trailing column = next panel
+        const bool has_next = kn0 < c;
+        const int pbn = has_next ? min(ASAM_TPB, c - kn0) : 0;
+        const int ncrew = has_next ? (m - kn0 + 1 + ASAM_TROWS - 1) / ASAM_TROWS : 0;
+        if (w < ncrew) {
+            if (trow && tid == 0)
+                t_mark = d_now();
+            const int rb0 = kn0 + w * ASAM_TROWS;
+            tile(k0, pb, kn0, pbn, rb0, min(ASAM_TROWS, m - rb0 + 1));
+            // crew barrier: the next panel's columns have received panel k on all their rows
+            __syncthreads();
+            if (tid == 0) {
+                __threadfence();
+                atomicAdd(crew_bar, 1);
+                long long spins = 0;
+                int ok = 1;
+                while (ld_volatile(crew_bar) < crew_cum + ncrew) {
+                    __nanosleep(20);
+                    if (++spins > a.spin_limit || ld_volatile(err) < 0) {
+                        atomicCAS(err, 0, -(1 + s));
+                        ok = 0;
+                        break;
+                    }
+                }
+                __threadfence();
+                *s_flag = ok;
             }
-            for (int e = tid; e < pb; e += nt)
-                dinv[k0 + e] = rdv[e];
+            __syncthreads();
+            if (!*s_flag)
+                return false;
+            panel(kn0, pbn, rb0);
+            if (trow && tid == 0)
+                t_panel += d_now() - t_mark;
         }
+        crew_cum += ncrew;
 
-        // trailing update: tiles of TR rows x 64 columns over the lower trapezoid (TR = 128 when
-        // 256-row tiles would leave workers idle)
-        const int j0 = k0 + pb;
+        // trailing update with panel k right of the next panel: tiles of TR rows x 64 columns over
+        // the lower trapezoid (TR = 128 when 256-row tiles would leave workers idle).  The crew is
+        // on the critical path already (its chain is longer than two tiles): the tiles go to the
+        // other workers only, unless the team is all crew
+        const int j0 = kn0 + pbn;
+        const int nfree = (G - ncrew >= 2) ? G - ncrew : G, wfree = (G - ncrew >= 2) ? w - ncrew : w;
         int n256 = 0;
         for (int cb0 = j0; cb0 < m; cb0 += ASAM_TCOLS)
             n256 += (m - cb0 + 1 + 255) / 256;
-        const int TR = (n256 < 2 * G) ? 128 : 256;
-        int u = 0;
-        for (int cb0 = j0; cb0 < m; cb0 += ASAM_TCOLS) {
-            for (int rb0 = cb0; rb0 <= m; rb0 += TR, ++u) {
-                if (u % G != w)
-                    continue;
-                __syncthreads();
-                const int ncol = min(ASAM_TCOLS, m - cb0), nrow = min(TR, m - rb0 + 1);
-                // two panel columns per warp and pass: 20 independent loads in flight per lane
-                for (int p = warp; p < pb; p += 2 * nwarps) {
-                    double vj[2][2], vi[2][8];
-#pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        const int pp = p + h * nwarps;
-                        const double *src = F + (size_t) (k0 + min(pp, pb - 1)) * ld;
-#pragma unroll
-                        for (int u = 0; u < 2; u++)
-                            vj[h][u] = (pp < pb && lane + 32 * u < ncol) ? __ldcg(src + cb0 + lane + 32 * u) : 0.0;
-#pragma unroll
-                        for (int u = 0; u < 8; u++)
-                            vi[h][u] = (pp < pb && lane + 32 * u < nrow) ? __ldcg(src + rb0 + lane + 32 * u) : 0.0;
-                    }
-#pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        const int pp = p + h * nwarps;
-                        if (pp < pb) {
-#pragma unroll
-                            for (int u = 0; u < 2; u++)
-                                if (lane + 32 * u < ncol)
-                                    Lj[lane + 32 * u + pp * ASAM_TCOLS] = vj[h][u];
-#pragma unroll
-                            for (int u = 0; u < 8; u++)
-                                if (lane + 32 * u < nrow)
-                                    Li[lane + 32 * u + pp * ASAM_TROWS] = vi[h][u];
-                        }
-                    }
-                }
-                __syncthreads();
-                // warp -> 8 columns, lane -> rows lane + 32 r (passes of 128 rows)
-                const int tj = 8 * warp;
-                if (tj < ncol) {
-                    for (int ib = 0; ib < nrow; ib += 128) {
-                        double acc[4][8], cv[4][8];
-                        int ir[4], jc[8];
-#pragma unroll
-                        for (int q = 0; q < 8; q++)
-                            jc[q] = min(tj + q, ncol - 1);
-#pragma unroll
-                        for (int r = 0; r < 4; r++) {
-                            ir[r] = min(ib + lane + 32 * r, nrow - 1);
-#pragma unroll
-                            for (int q = 0; q < 8; q++) {
-                                acc[r][q] = 0.0;
-                                // the C values are fetched now and consumed after the products:
-                                // their L2 latency hides behind the 4x8xpb FMAs
-                                const int ii = ib + lane + 32 * r, jj = tj + q;
-                                const bool ok = ii < nrow && jj < ncol && rb0 + ii >= cb0 + jj;
-                                cv[r][q] = ok ? __ldcg(&F[(rb0 + ii) + (size_t) (cb0 + jj) * ld]) : 0.0;
-                            }
-                        }
-#pragma unroll 2
-                        for (int p = 0; p < pb; p++) {
-                            double b[8], av[4];
-#pragma unroll
-                            for (int q = 0; q < 8; q++)
-                                b[q] = Lj[jc[q] + p * ASAM_TCOLS];
-#pragma unroll
-                            for (int r = 0; r < 4; r++)
-                                av[r] = Li[ir[r] + p * ASAM_TROWS];
-#pragma unroll
-                            for (int r = 0; r < 4; r++)
-#pragma unroll
-                                for (int q = 0; q < 8; q++)
-                                    acc[r][q] += av[r] * b[q];
-                        }
-#pragma unroll
-                        for (int r = 0; r < 4; r++)
-#pragma unroll
-                            for (int q = 0; q < 8; q++) {
-                                const int ii = ib + lane + 32 * r, jj = tj + q;
-                                const int i = rb0 + ii, j = cb0 + jj;
-                                if (ii < nrow && jj < ncol && i >= j)
-                                    F[i + (size_t) j * ld] = cv[r][q] - acc[r][q];
-                            }
-                    }
-                }
-            }
+        const int TR = (n256 < 2 * nfree) ? 128 : 256;
+        if (wfree >= 0) {
+            int u = 0;
+            for (int cb0 = j0; cb0 < m; cb0 += ASAM_TCOLS)
+                for (int rb0 = cb0; rb0 <= m; rb0 += TR, ++u)
+                    if (u % nfree == wfree)
+                        tile(k0, pb, cb0, min(ASAM_TCOLS, m - cb0), rb0, min(TR, m - rb0 + 1));
         }
         if (!team_barrier(tc, s_flag))
             return false;
+        if (w == 0 && has_next)
+            writeback(kn0, pbn);
     }
+    if (w == 0 && tid == 0)
+        atomicExch(crew_bar, 0); // everybody is past its last crew barrier (team barrier above)
 
     if (trow && tid == 0) {
         trow[4] = d_now();

@@ -79,7 +79,8 @@ def _finish(truth, ea, eb, rng) -> PoseGraphData:
         p = init[i]
         c, s = np.cos(p[2]), np.sin(p[2])
         init[i + 1] = (p[0] + c * z[k, 0] - s * z[k, 1], p[1] + s * z[k, 0] + c * z[k, 1], p[2] + z[k, 2])
-    return PoseGraphData(init, ea, eb, np.ascontiguousarray(z), W)
+    t0 = truth - np.array([truth[0, 0], truth[0, 1], 0.0])  # pose 0 sits at the origin (heading 0), like the prior
+    return PoseGraphData(init, ea, eb, np.ascontiguousarray(z), W, t0)
 
 
 def _candidates(xy, side):

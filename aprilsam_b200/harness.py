@@ -92,6 +92,7 @@ class PoseGraphData:
     eb: np.ndarray     # (E,) int32     EDGE2 IDin
     ez: np.ndarray     # (E,3) float64  dx dy dth
     eW: np.ndarray     # (E,9) float64  row-major 3x3 as the demo loader fills it
+    truth: np.ndarray | None = None  # (N,3) ground-truth poses in the frame of pose 0 (synthetic graphs only)
 
     @property
     def n_nodes(self) -> int:
@@ -106,7 +107,7 @@ class PoseGraphData:
         key = np.maximum(self.ea, self.eb)
         order = np.argsort(key, kind="stable")
         d = PoseGraphData(self.init, self.ea[order].copy(), self.eb[order].copy(),
-                          self.ez[order].copy(), self.eW[order].copy())
+                          self.ez[order].copy(), self.eW[order].copy(), self.truth)
         estart = np.searchsorted(key[order], np.arange(self.n_nodes + 1), side="left").astype(np.int32)
         return d, estart
 
@@ -126,7 +127,8 @@ class PoseGraphData:
         """Sub-graph induced by the first n poses."""
         keep = (self.ea < n) & (self.eb < n)
         return PoseGraphData(self.init[:n].copy(), self.ea[keep].copy(), self.eb[keep].copy(),
-                             self.ez[keep].copy(), self.eW[keep].copy())
+                             self.ez[keep].copy(), self.eW[keep].copy(),
+                             None if self.truth is None else self.truth[:n].copy())
 
 
 class Harness:

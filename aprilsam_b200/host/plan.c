@@ -320,7 +320,7 @@ static int team_size(int mb, int cb)
     for (int64_t cb0 = j0; cb0 < m; cb0 += 64)
         tiles += (m - cb0 + 1 + 255) / 256;
     int64_t chunks = (m - j0 + 1 + 255) / 256; /* row chunks of the panel solve */
-    int G = (int) (tiles > chunks ? tiles : chunks);
+    int G = (int) (tiles + chunks); /* the look-ahead crew (one CTA per chunk) takes no tiles */
     if (G < 2)
         G = 2;
     if (G > 120)

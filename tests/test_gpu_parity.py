@@ -198,6 +198,35 @@ def test_sparse_replay_lockstep():
             assert err < RTOL, (k, err)
 
 
+def test_sparse_bulk_then_incremental_lockstep():
+    """Incremental steps on a LARGE sparse graph (fronts of the multi-CTA team path are re-factored
+    by incremental steps): the first 29 700 poses are loaded at once at the generator's ground truth and
+    batch-solved twice, then 200 poses are appended one by one on both arms."""
+    if not have_ref():
+        pytest.skip("reference oracle not built on this box")
+    from aprilsam_b200 import datasets
+    d = datasets.manhattan_sparse(30000, seed=1)
+    s0 = 29700
+    sub = d.head(s0)
+    with H.Harness("b200") as a, H.Harness("reference") as b:
+        for h in (a, b):
+            h.replay_begin(d)
+            h.load_full(sub)
+            h.set_states(sub.truth)
+            h.batch()
+            h.batch()
+        assert rel_state_err(a.states(), b.states()) < RTOL
+        for k in range(s0 + 25, s0 + 201, 25):
+            _, _, ia = a.replay_to(k, want_chi2=False)
+            _, _, ib = b.replay_to(k, want_chi2=False)
+            assert np.array_equal(ia[:, 0], ib[:, 0]), f"naffected differs before step {k}"
+            assert np.array_equal(ia[:, 1], ib[:, 1]), f"start_over differs before step {k}"
+            err = rel_state_err(a.states(), b.states())
+            assert err < RTOL, (k, err)
+        ca, cb = a.chi2(), b.chi2()
+        assert abs(ca - cb) <= RTOL * max(1.0, cb)
+
+
 def test_multi_pose_append_per_call(m3500):
     """Several poses appended between two incremental calls (aprilsam.c:887-904 path)."""
     if not have_ref():

@@ -96,6 +96,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--chunk", type=int, default=20)
     ap.add_argument("--dense", action="store_true")
+    ap.add_argument("--dead-reckoned", action="store_true", help="start the bulk load at the dead-reckoned VERTEX2 estimate")
     ap.add_argument("--exact", action="store_true",
                     help="after the steps: solve the Hessian held in HBM with scipy (SuperLU) and compare both arms")
     args = ap.parse_args()
@@ -110,7 +111,11 @@ def main():
             continue
         h.replay_begin(d)
         t0 = time.time()
-        h.load_full(d.head(args.start))
+        sub = d.head(args.start)
+        h.load_full(sub)
+        if sub.truth is not None and not args.dead_reckoned:
+            h.set_states(sub.truth)
+        h.batch()
         h.batch()
         print(f"[{h.impl}] bulk {args.start} poses + batch: {time.time() - t0:.2f} s", flush=True)
     if b:
