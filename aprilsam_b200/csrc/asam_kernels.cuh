@@ -1046,18 +1046,50 @@ __global__ void __launch_bounds__(256, 1) k_factor(FacArgs a)
             for (int i = tid; i <= cr; i += nt)
                 dmap[i] = (i < cr) ? 3 * crel[(cc + i) / 3] + (cc + i) % 3 : m;
             __syncthreads();
-            for (int j = warp; j < cr; j += nwarps) {
-                const double *ccol = CF + (size_t) (cc + j) * cld + cc;
-                double *fcol = F + (size_t) dmap[j] * ld;
-                for (int i0 = j + lane; i0 <= cr; i0 += 256) { // eight independent loads in flight per lane
-                    double v[8];
+            if (use_sm && cr <= 159) {
+                // the whole update matrix in few round trips: four columns per warp and pass, up to
+                // 160 rows each -> 20 independent loads in flight per lane (the critical path of a
+                // small solve is a chain of these extend-adds, each bound by L2 latency, not bytes)
+                for (int j0 = warp; j0 < cr; j0 += 4 * nwarps) {
+                    double v[4][5];
 #pragma unroll
-                    for (int u = 0; u < 8; u++)
-                        v[u] = (i0 + 32 * u <= cr) ? __ldcg(ccol + i0 + 32 * u) : 0.0;
+                    for (int q = 0; q < 4; q++) {
+                        const int j = j0 + q * nwarps;
+                        const double *ccol = CF + (size_t) (cc + min(j, cr - 1)) * cld + cc;
 #pragma unroll
-                    for (int u = 0; u < 8; u++)
-                        if (i0 + 32 * u <= cr)
-                            fcol[dmap[i0 + 32 * u]] += v[u];
+                        for (int u = 0; u < 5; u++) {
+                            const int i = j + lane + 32 * u;
+                            v[q][u] = (j < cr && i <= cr) ? __ldcg(ccol + i) : 0.0;
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const int j = j0 + q * nwarps;
+                        if (j < cr) {
+                            double *fcol = F + (size_t) dmap[j] * ld;
+#pragma unroll
+                            for (int u = 0; u < 5; u++) {
+                                const int i = j + lane + 32 * u;
+                                if (i <= cr)
+                                    fcol[dmap[i]] += v[q][u];
+                            }
+                        }
+                    }
+                }
+            } else {
+                for (int j = warp; j < cr; j += nwarps) {
+                    const double *ccol = CF + (size_t) (cc + j) * cld + cc;
+                    double *fcol = F + (size_t) dmap[j] * ld;
+                    for (int i0 = j + lane; i0 <= cr; i0 += 256) { // eight independent loads in flight per lane
+                        double v[8];
+#pragma unroll
+                        for (int u = 0; u < 8; u++)
+                            v[u] = (i0 + 32 * u <= cr) ? __ldcg(ccol + i0 + 32 * u) : 0.0;
+#pragma unroll
+                        for (int u = 0; u < 8; u++)
+                            if (i0 + 32 * u <= cr)
+                                fcol[dmap[i0 + 32 * u]] += v[u];
+                    }
                 }
             }
             __syncthreads();
@@ -1113,20 +1145,27 @@ __global__ void __launch_bounds__(256, 1) k_factor(FacArgs a)
         if (a.trace && tid == 0)
             tr4 = d_now();
 
-        // ---- 5. publish: y, L panel + update matrix ---------------------------------------
+        // ---- 5. publish: the update matrix first (that is all the parent waits for), then y and
+        // the L panel, which only the back-substitution and later incremental steps read ----------
+        if (use_sm) {
+            for (int j = c + warp; j < m; j += nwarps)
+                for (int i = j + lane; i <= m; i += 32)
+                    Fg[i + (size_t) j * ld] = F[i + (size_t) j * ld];
+        }
+        __syncthreads();
+        if (tid == 0 && d.parent >= 0) {
+            __threadfence();
+            atomicAdd(&a.arrive[d.parent], 1);
+        }
         for (int e = tid; e < c; e += nt)
             a.y[3 * (size_t) d.first + e] = F[m + (size_t) e * ld];
         if (use_sm) {
-            for (int j = warp; j < m; j += nwarps)
+            for (int j = warp; j < c; j += nwarps)
                 for (int i = j + lane; i <= m; i += 32)
                     Fg[i + (size_t) j * ld] = F[i + (size_t) j * ld];
         }
         __syncthreads();
         if (tid == 0) {
-            if (d.parent >= 0) {
-                __threadfence();
-                atomicAdd(&a.arrive[d.parent], 1);
-            }
             if (a.trace) {
                 unsigned smid;
                 asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
