@@ -21,12 +21,13 @@ LIB_DIR = os.path.join(PKG, "lib")
 OBJ_DIR = os.path.join(PKG, "lib", "obj")
 LIB = os.path.join(LIB_DIR, "libaprilsam_b200.so")
 HARNESS = os.path.join(ROOT, "harness", "_build", "harness_b200.so")
+REPLAY_CLI = os.path.join(ROOT, "examples", "_build", "asam_replay")
 
 NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 CC = os.environ.get("CC", "gcc")
 
 CUDA_SRCS = [os.path.join(PKG, "csrc", "asam_cuda.cu")]
-HOST_SRCS = [os.path.join(PKG, "host", f) for f in ("graph.c", "ordering.c", "plan.c", "solver.c", "debug.c")]
+HOST_SRCS = [os.path.join(PKG, "host", f) for f in ("graph.c", "ordering.c", "plan.c", "solver.c", "serial.c", "debug.c")]
 INCLUDES = ["-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "include", "aprilsam"),
             "-I" + os.path.join(PKG, "host")]
 
@@ -83,6 +84,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
         _run([CC, "-std=gnu99", "-O2", "-g", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include", "aprilsam"),
               "-o", HARNESS, hsrc, "-L" + LIB_DIR, "-laprilsam_b200", "-Wl,-rpath," + LIB_DIR,
               "-Wl,-rpath,$ORIGIN/../../aprilsam_b200/lib", "-lm"], log)
+    csrc = os.path.join(ROOT, "examples", "asam_replay.c")
+    os.makedirs(os.path.dirname(REPLAY_CLI), exist_ok=True)
+    if force or _stale(REPLAY_CLI, [csrc, LIB] + hdrs):
+        _run([CC, "-std=gnu99", "-O2", "-g", "-I" + os.path.join(ROOT, "include", "aprilsam"), "-o", REPLAY_CLI, csrc,
+              "-L" + LIB_DIR, "-laprilsam_b200", "-Wl,-rpath," + LIB_DIR, "-Wl,-rpath,$ORIGIN/../../aprilsam_b200/lib",
+              "-lm"], log)
     # the oracle: C restatement always; the real reference only where its sources exist
     _run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "all"], log)
     with open(os.path.join(LIB_DIR, "build.log"), "w") as f:

@@ -80,6 +80,13 @@ def _load(impl: str) -> C.CDLL:
     lib.h_param.argtypes = [C.c_void_p]
     lib.h_param.restype = C.c_void_p
     lib.h_load_full.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int, _ip, _ip, _dp, _dp]
+    lib.h_save.argtypes = [C.c_void_p, C.c_char_p]
+    lib.h_load.argtypes = [C.c_void_p, C.c_char_p]
+    lib.h_attr_put_string.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_char_p]
+    lib.h_attr_put_u64.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_uint64]
+    lib.h_attr_get.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p]
+    lib.h_attr_get.restype = C.c_void_p
+    lib.h_factor.argtypes = [C.c_void_p, C.c_int, _dp]
     _LIBS[impl] = lib
     return lib
 
@@ -172,6 +179,33 @@ class Harness:
 
     def load_full(self, d: PoseGraphData):
         self.lib.h_load_full(self.h, d.n_nodes, _d(d.init), d.n_edges, _i(d.ea), _i(d.eb), _d(d.ez), _d(d.eW))
+
+    # -- files and attributes (aprilsam.h:185, :288-299) --------------------------------------
+    GRAPH, NODE, FACTOR = 0, 1, 2
+
+    def save(self, path: str) -> bool:
+        return bool(self.lib.h_save(self.h, path.encode()))
+
+    def load(self, path: str) -> int:
+        """Replace the graph by the one stored in `path`; returns the node count (-1: failure)."""
+        return self.lib.h_load(self.h, path.encode())
+
+    def attr_put(self, which: int, idx: int, key: str, value) -> None:
+        if isinstance(value, str):
+            self.lib.h_attr_put_string(self.h, which, idx, key.encode(), value.encode())
+        else:
+            self.lib.h_attr_put_u64(self.h, which, idx, key.encode(), int(value))
+
+    def attr_get(self, which: int, idx: int, key: str, kind: str = "string"):
+        p = self.lib.h_attr_get(self.h, which, idx, key.encode())
+        if not p:
+            return None
+        return C.cast(p, C.c_char_p).value.decode() if kind == "string" else C.cast(p, C.POINTER(C.c_uint64))[0]
+
+    def factor(self, idx: int):
+        out = np.zeros(14, dtype=np.float64)
+        t = self.lib.h_factor(self.h, idx, _d(out))
+        return t, int(out[0]), int(out[1]), out[2:5].copy(), out[5:14].copy()
 
     # -- state access ------------------------------------------------------------------
     @property

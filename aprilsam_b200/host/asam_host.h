@@ -8,6 +8,7 @@
 
 #include "aprilsam.h"
 #include "asam_cuda.h"
+#include "common/stype.h"
 
 #define ASAM_API __attribute__((visibility("default")))
 
@@ -141,6 +142,10 @@ int plan_append(plan_t *pl, asam_dev_t *dev, int N, int n_factors, const int *ft
 
 /* ---- solver context (solver.c) --------------------------------------------------------- */
 void asam_graph_forget(april_graph_t *g);
+/* serial.c */
+extern const stype_t stype_april_graph, stype_april_graph_attr, stype_april_node_xyt, stype_april_factor_xyt,
+    stype_april_factor_xytpos;
+april_graph_attr_t *asam_attr_dup(const april_graph_attr_t *a);
 void asam_set_error(const char *fmt, ...);
 void asam_fatal(const char *fmt, ...);
 

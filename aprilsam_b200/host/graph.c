@@ -63,6 +63,7 @@ ASAM_API april_graph_t *april_graph_create(void)
     april_graph_t *g = calloc(1, sizeof(april_graph_t));
     g->nodes = zarray_create(sizeof(april_graph_node_t *));
     g->factors = zarray_create(sizeof(april_graph_factor_t *));
+    g->stype = &stype_april_graph; /* april_graph.c:334 */
     return g;
 }
 
@@ -85,6 +86,7 @@ ASAM_API void april_graph_destroy(april_graph_t *g)
     }
     zarray_destroy(g->nodes);
     zarray_destroy(g->factors);
+    april_graph_attr_destroy(g->attr);
     free(g);
 }
 
@@ -141,6 +143,7 @@ static void node_xyt_destroy(april_graph_node_t *n)
     free(n->truth);
     free(n->l_point);
     free(n->delta_X);
+    april_graph_attr_destroy(n->attr);
     free(n);
 }
 
@@ -150,6 +153,7 @@ static april_graph_node_t *node_xyt_copy(april_graph_node_t *n)
     memcpy(c->l_point, n->l_point, 3 * sizeof(double));
     memcpy(c->delta_X, n->delta_X, 3 * sizeof(double));
     c->UID = n->UID;
+    c->attr = asam_attr_dup(n->attr);
     return c;
 }
 
@@ -161,14 +165,15 @@ ASAM_API april_graph_node_t *april_graph_node_xyt_create(const double *state, co
     n->type = APRIL_GRAPH_NODE_XYT_TYPE;
     n->length = 3;
     n->state = doubles_dup(state, 3);
-    n->init = doubles_dup(init ? init : state, 3);
-    n->truth = doubles_dup(truth ? truth : state, 3);
+    n->init = doubles_dup(init, 3);   /* NULL stays NULL (april_graph_xyt.c:421-423) */
+    n->truth = doubles_dup(truth, 3);
     n->l_point = doubles_dup(state, 3);
     n->delta_X = doubles_dup(zero3, 3);
     n->update = node_xyt_update;
     n->relinearize = node_xyt_relinearize;
     n->copy = node_xyt_copy;
     n->destroy = node_xyt_destroy;
+    n->stype = &stype_april_node_xyt;
     return n;
 }
 
@@ -236,12 +241,16 @@ static void factor_common_destroy(april_graph_factor_t *f)
     free(f->u.common.z);
     free(f->u.common.ztruth);
     matd_destroy(f->u.common.W);
+    april_graph_attr_destroy(f->attr);
     free(f);
 }
 
 static april_graph_factor_t *xyt_copy(april_graph_factor_t *f)
 {
-    return april_graph_factor_xyt_create(f->nodes[0], f->nodes[1], f->u.common.z, f->u.common.ztruth, f->u.common.W);
+    april_graph_factor_t *c =
+        april_graph_factor_xyt_create(f->nodes[0], f->nodes[1], f->u.common.z, f->u.common.ztruth, f->u.common.W);
+    c->attr = asam_attr_dup(f->attr);
+    return c;
 }
 
 ASAM_API april_graph_factor_t *april_graph_factor_xyt_create(int a, int b, const double *z, const double *ztruth,
@@ -261,6 +270,7 @@ ASAM_API april_graph_factor_t *april_graph_factor_xyt_create(int a, int b, const
     f->u.common.z = doubles_dup(z, 3);
     f->u.common.ztruth = ztruth ? doubles_dup(ztruth, 3) : NULL;
     f->u.common.W = matd_copy(W);
+    f->stype = &stype_april_factor_xyt;
     return f;
 }
 
@@ -282,7 +292,9 @@ static april_graph_factor_eval_t *xytpos_eval(april_graph_factor_t *f, april_gra
 
 static april_graph_factor_t *xytpos_copy(april_graph_factor_t *f)
 {
-    return april_graph_factor_xytpos_create(f->nodes[0], f->u.common.z, f->u.common.ztruth, f->u.common.W);
+    april_graph_factor_t *c = april_graph_factor_xytpos_create(f->nodes[0], f->u.common.z, f->u.common.ztruth, f->u.common.W);
+    c->attr = asam_attr_dup(f->attr);
+    return c;
 }
 
 ASAM_API april_graph_factor_t *april_graph_factor_xytpos_create(int a, double *z, double *ztruth, matd_t *W)
@@ -300,5 +312,6 @@ ASAM_API april_graph_factor_t *april_graph_factor_xytpos_create(int a, double *z
     f->u.common.z = doubles_dup(z, 3);
     f->u.common.ztruth = ztruth ? doubles_dup(ztruth, 3) : NULL;
     f->u.common.W = matd_copy(W);
+    f->stype = &stype_april_factor_xytpos;
     return f;
 }

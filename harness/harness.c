@@ -290,5 +290,102 @@ H_EXPORT void h_load_full(hctx_t *h, int N, const double *init, int E, const int
     h->next_step = N;
 }
 
+/* ---- files + attributes (aprilsam.h:185, :288-299): examples/aprilsam_graph_save_*.c in miniature ---- */
+static void serial_init(void)
+{
+    static int done = 0;
+    if (!done) {
+        stype_register_basic_types();
+        april_graph_stype_init();
+        done = 1;
+    }
+}
+
+H_EXPORT int h_save(hctx_t *h, const char *path)
+{
+    serial_init();
+    return april_graph_save(h->g, path);
+}
+
+/* replaces the graph (the solver state starts over); returns the node count or -1 */
+H_EXPORT int h_load(hctx_t *h, const char *path)
+{
+    serial_init();
+    april_graph_t *g = april_graph_create_from_file(path);
+    if (!g)
+        return -1;
+    april_graph_cholesky_param_destory(h->p);
+    h->p = calloc(1, sizeof(april_graph_cholesky_param_t));
+    april_graph_cholesky_param_init(h->p);
+    april_graph_destroy(h->g);
+    h->g = g;
+    h->next_step = zarray_size(g->nodes);
+    return zarray_size(g->nodes);
+}
+
+/* which: 0 graph, 1 node idx, 2 factor idx; string-valued attribute (stype "string") */
+H_EXPORT void h_attr_put_string(hctx_t *h, int which, int idx, const char *key, const char *value)
+{
+    serial_init();
+    stype_t *st = stype_get("string");
+    if (which == 0) {
+        april_graph_attr_put(h->g, st, key, strdup(value));
+    } else if (which == 1) {
+        april_graph_node_t *n;
+        zarray_get(h->g->nodes, idx, &n);
+        april_graph_node_attr_put(n, st, key, strdup(value));
+    } else {
+        april_graph_factor_t *f;
+        zarray_get(h->g->factors, idx, &f);
+        april_graph_factor_attr_put(f, st, key, strdup(value));
+    }
+}
+
+H_EXPORT void h_attr_put_u64(hctx_t *h, int which, int idx, const char *key, uint64_t value)
+{
+    serial_init();
+    stype_t *st = stype_get("uint64");
+    uint64_t *v = malloc(sizeof(uint64_t));
+    *v = value;
+    if (which == 0) {
+        april_graph_attr_put(h->g, st, key, v);
+    } else if (which == 1) {
+        april_graph_node_t *n;
+        zarray_get(h->g->nodes, idx, &n);
+        april_graph_node_attr_put(n, st, key, v);
+    } else {
+        april_graph_factor_t *f;
+        zarray_get(h->g->factors, idx, &f);
+        april_graph_factor_attr_put(f, st, key, v);
+    }
+}
+
+/* returns the attribute's raw pointer (char* for "string", uint64_t* for "uint64") or NULL */
+H_EXPORT const void *h_attr_get(hctx_t *h, int which, int idx, const char *key)
+{
+    if (which == 0)
+        return april_graph_attr_get(h->g, key);
+    if (which == 1) {
+        april_graph_node_t *n;
+        zarray_get(h->g->nodes, idx, &n);
+        return april_graph_node_attr_get(n, key);
+    }
+    april_graph_factor_t *f;
+    zarray_get(h->g->factors, idx, &f);
+    return april_graph_factor_attr_get(f, key);
+}
+
+/* factor record for comparisons: out[0..1] node ids (-1 if unary), out[2..4] z, out[5..13] W; returns type */
+H_EXPORT int h_factor(hctx_t *h, int idx, double *out)
+{
+    april_graph_factor_t *f;
+    zarray_get(h->g->factors, idx, &f);
+    out[0] = f->nodes[0];
+    out[1] = f->nnodes > 1 ? f->nodes[1] : -1;
+    memcpy(out + 2, f->u.common.z, 3 * sizeof(double));
+    memcpy(out + 5, f->u.common.W->data, 9 * sizeof(double));
+    return f->type;
+}
+
 H_EXPORT void *h_graph(hctx_t *h) { return h->g; }
 H_EXPORT void *h_param(hctx_t *h) { return h->p; }

@@ -20,6 +20,7 @@
 
 #include "common/doubles.h"
 #include "common/matd.h"
+#include "common/stype.h"
 #include "common/zarray.h"
 
 #ifdef __cplusplus
@@ -28,7 +29,6 @@ extern "C" {
 
 /* Types the reference exposes through pointers only; opaque here. */
 typedef struct zhash zhash_t;
-typedef struct stype stype_t;
 typedef struct smatd smatd_t;
 
 /* reference: aprilsam/common/smatd.h:62-67.  In this library `u` is unused and the
@@ -43,9 +43,11 @@ void APRILSAM_VERSION(void); /* aprilsam.h:44 */
 /* ---- attributes (aprilsam.h:46-61): string -> (stype, value) table ---------------- */
 typedef struct april_graph_attr april_graph_attr_t;
 struct april_graph_attr {
-    zhash_t *hash;
+    zhash_t *hash; /* opaque: this library keeps a small insertion-ordered table behind it */
     const stype_t *stype;
 };
+april_graph_attr_t *april_graph_attr_create(void);          /* aprilsam.h:60 */
+void april_graph_attr_destroy(april_graph_attr_t *attr);    /* aprilsam.h:61; NULL is fine */
 
 /* ---- graph (aprilsam.h:64-72) ------------------------------------------------------ */
 typedef struct april_graph april_graph_t;
@@ -215,6 +217,21 @@ double april_graph_chi2(april_graph_t *graph);
 april_graph_node_t *april_graph_node_xyt_create(const double *state, const double *init, const double *truth);
 april_graph_factor_t *april_graph_factor_xyt_create(int a, int b, const double *z, const double *ztruth, const matd_t *W);
 april_graph_factor_t *april_graph_factor_xytpos_create(int a, double *z, double *ztruth, matd_t *W);
+
+/* ---- files and attributes (aprilsam.h:185, :288-299) --------------
+ * ".graph" files in the reference's stype framing (big-endian, self-describing); call
+ * april_graph_stype_init() (and stype_register_basic_types() for "string"/"uint64" attribute
+ * values) once before loading.  Values put into an attribute table are owned by it afterwards
+ * (destroyed through their stype); a value replaced by a second put stays the caller's. */
+april_graph_t *april_graph_create_from_file(const char *path); /* NULL on failure */
+int april_graph_save(april_graph_t *graph, const char *path); /* 1 on success, 0 on failure */
+void april_graph_stype_init(void);
+void april_graph_attr_put(april_graph_t *graph, const stype_t *type, const char *key, void *data);
+void *april_graph_attr_get(april_graph_t *graph, const char *key);
+void april_graph_factor_attr_put(april_graph_factor_t *factor, const stype_t *type, const char *key, void *data);
+void *april_graph_factor_attr_get(april_graph_factor_t *factor, const char *key);
+void april_graph_node_attr_put(april_graph_node_t *node, const stype_t *type, const char *key, void *data);
+void *april_graph_node_attr_get(april_graph_node_t *node, const char *key);
 
 /* Last error text of this library on the calling thread ("" if none).  Extension: the
  * reference reports nothing (void returns, asserts, NULL dereference on non-SPD). */

@@ -10,6 +10,8 @@
 
 static inline double *doubles_dup(const double *v, int len)
 {
+    if (!v) /* reference: common/doubles_floats_impl.h:66-75 */
+        return NULL;
     double *r = (double *) malloc(sizeof(double) * len);
     memcpy(r, v, sizeof(double) * len);
     return r;

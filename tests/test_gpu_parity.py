@@ -300,3 +300,30 @@ def test_factor_between_old_poses_is_exact(m3500):
     want = lp + x
     want[:, 2] = emul.mod2pi(want[:, 2])
     assert rel_state_err(st, want) < RTOL
+
+
+def test_replay_cli_text_and_graph_files(m3500, tmp_path):
+    """examples/asam_replay: a Manhattan text file and the ".graph" file the CLI
+    saves from it replay to the same final chi2 as the harness-driven replay of the same poses."""
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cli = os.path.join(root, "examples", "_build", "asam_replay")
+    assert os.path.exists(cli), "run __graft_entry__.build()"
+    sub = m3500.head(150)
+    txt, gfile = str(tmp_path / "m150.txt"), str(tmp_path / "m150.graph")
+    with open(txt, "w") as f:
+        for i, p in enumerate(sub.init):
+            f.write("VERTEX2 %d %r %r %r\n" % (i, float(p[0]), float(p[1]), float(p[2])))
+        for a, b, z, W in zip(sub.ea, sub.eb, sub.ez, sub.eW):
+            f.write("EDGE2 %d %d " % (a, b) + " ".join(repr(float(v)) for v in (*z, W[0], W[1], W[4], W[8], W[2], W[5])) + "\n")
+    with H.Harness("b200") as h:
+        h.replay_begin(sub)
+        chi2, _, _ = h.replay_to(sub.n_nodes)
+    want = chi2[-1]
+    for args in (["--datapath", txt, "--save", gfile, "--quiet"], ["--datapath", gfile, "--quiet"]):
+        out = subprocess.run([cli] + args, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr
+        got = float(re.search(r"final chi2 ([0-9.eE+-]+)", out.stdout).group(1))
+        assert abs(got - want) <= RTOL * max(1.0, want), (args, got, want)
