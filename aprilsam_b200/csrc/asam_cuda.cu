@@ -587,6 +587,21 @@ ASAM_EXPORT int asam_upload_points(asam_dev_t *d, int which, int first, int coun
     return upload(d, (double *) b.p + 3 * (size_t) first, p3, (size_t) count * 3 * sizeof(double));
 }
 
+ASAM_EXPORT int asam_copy_points(asam_dev_t *d, int from, int to, int first, int count)
+{
+    if (count <= 0 || from == to)
+        return 0;
+    CK(cudaSetDevice(d->device));
+    Buf &src = from == 0 ? d->lp : d->st, &dst = to == 0 ? d->lp : d->st;
+    const size_t off = (size_t) first * 3 * sizeof(double), bytes = (size_t) count * 3 * sizeof(double);
+    if (off + bytes > src.cap || off + bytes > dst.cap)
+        return set_err("asam_copy_points: capacity");
+    if (flush_uploads(d)) // the source may still be queued
+        return 1;
+    CK(cudaMemcpyAsync((char *) dst.p + off, (const char *) src.p + off, bytes, cudaMemcpyDeviceToDevice, d->stream));
+    return 0;
+}
+
 ASAM_EXPORT int asam_upload_node2q(asam_dev_t *d, int first, int count, const int32_t *node2q)
 {
     if (count <= 0)

@@ -1274,6 +1274,7 @@ int plan_append(plan_t *pl, asam_dev_t *dev, int N, int n_factors, const int *ft
     }
     pl->N = N;
     pl->n_factors = n_factors;
+    pl->struct_hash = 0; /* appended order: never to be reused by a batch solve (it re-orders) */
 
 done:
     for (int i = 0; i < nm; i++)

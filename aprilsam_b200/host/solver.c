@@ -79,6 +79,33 @@ ASAM_API void asam_dbg_profile(double *out, int reset)
             asam_fatal("%s failed: %s / %s", #call, asam_last_error(), g_error);           \
     } while (0)
 
+/* ---- param->show_timing (aprilsam.c:317-318, :553-555, :587-588): phase table in the reference's
+ * timeprofile_display format ("%2d %32s %15f ms %15f ms": this phase, cumulative), host phases plus
+ * the device time of the three kernels (CUDA events on the library's stream) ------------------- */
+typedef struct {
+    const char *name[12];
+    double t[12];
+    int n;
+} stamps_t;
+
+static inline void stamp(stamps_t *sp, const char *name)
+{
+    if (sp->n < 12) {
+        sp->name[sp->n] = name;
+        sp->t[sp->n++] = prof_now();
+    }
+}
+
+static void stamps_display(const stamps_t *sp, asam_dev_t *dev)
+{
+    for (int i = 0; i < sp->n; i++)
+        printf("%2d %32s %15f ms %15f ms\n", i, sp->name[i], i ? sp->t[i] - sp->t[i - 1] : 0.0, sp->t[i] - sp->t[0]);
+    float lin = 0, fac = 0, bs = 0;
+    if (dev && asam_last_kernel_ms(dev, &lin, &fac, &bs) == 0)
+        printf("   %32s %15f ms\n   %32s %15f ms\n   %32s %15f ms\n", "device: k_linearize", lin,
+               "device: k_factor(+leaf)", fac, "device: k_backsolve(+leaf)", bs);
+}
+
 /* ---- per-graph device context ---------------------------------------------------------------- */
 typedef struct gctx {
     april_graph_t *graph; /* NULL once the graph was destroyed */
@@ -431,6 +458,11 @@ ASAM_API void april_graph_cholesky(april_graph_t *graph, april_graph_cholesky_pa
     solver_t *s = solver_get(graph, param);
     gctx_t *c = s->gc;
     asam_dev_t *dev = c->dev;
+    stamps_t tp = { .n = 0 };
+    if (param->show_timing) {
+        asam_set_timing(dev, 1);
+        stamp(&tp, "begin");
+    }
     check_nodes(graph, 0, N);
     gctx_sync_factors(c, graph);
 
@@ -444,7 +476,12 @@ ASAM_API void april_graph_cholesky(april_graph_t *graph, april_graph_cholesky_pa
 
     PROF_LAP(11);
     /* ordering + symbolic analysis: cached while the factor structure is unchanged */
-    uint64_t h = structure_hash(N, F, c->ftype, c->fa, c->fb);
+    /* the API is append-only and factor node ids are immutable, so a cached plan with the same
+     * counts on the same graph has the same structure; the hash (O(F)) is only taken when the
+     * counts changed */
+    uint64_t h = (s->plan_valid && s->plan.N == N && s->plan.n_factors == F && s->plan.struct_hash != 0)
+                     ? s->plan.struct_hash
+                     : structure_hash(N, F, c->ftype, c->fa, c->fb);
     int plan_reused = 1;
     /* several GPUs (asam_comm_init + asam_comm_set_sharding): this rank factors its shards of the
      * elimination tree and the part above the cut; every rank calls april_graph_cholesky on its
@@ -464,9 +501,11 @@ ASAM_API void april_graph_cholesky(april_graph_t *graph, april_graph_cholesky_pa
     }
     plan_t *pl = &s->plan;
     PROF_LAP(12);
+    if (param->show_timing)
+        stamp(&tp, plan_reused ? "relinearize, plan (cached)" : "relinearize, ordering+symbolic");
 
     DEV_OK(asam_upload_points(dev, 0, 0, N, lp));
-    DEV_OK(asam_upload_points(dev, 1, 0, N, lp));
+    DEV_OK(asam_copy_points(dev, 0, 1, 0, N)); /* state mirror = linearisation points, copied in HBM */
     DEV_OK(asam_hessian_reset(dev, N, pl->n_slots, N, param->tikhanov > 0 ? param->tikhanov : 0.0));
     DEV_OK(asam_linearize(dev, 0, F, NULL));
     DEV_OK(asam_factor_full(dev));
@@ -478,6 +517,8 @@ ASAM_API void april_graph_cholesky(april_graph_t *graph, april_graph_cholesky_pa
     PROF_LAP(14);
     report_factor_status(s, fstatus, "april_graph_cholesky");
     PROF_LAP(15);
+    if (param->show_timing)
+        stamp(&tp, "H2D, kernels, D2H of the solution");
 
     /* persistent state the incremental path continues from (:260-288) */
     if (plan_reused && s->tree_fresh && param->tr && param->tr->nnodes == N) {
@@ -511,6 +552,10 @@ ASAM_API void april_graph_cholesky(april_graph_t *graph, april_graph_cholesky_pa
     for (int i = N - 1; i >= 0; i--)
         apply_update(node_at(graph, i), x + 3 * (size_t) pl->node2q[i]);
     PROF_LAP(16);
+    if (param->show_timing) {
+        stamp(&tp, "tree, state update");
+        stamps_display(&tp, dev);
+    }
 }
 
 /* ---- incremental step ---------------------------------------------------------------------------- */
@@ -625,6 +670,11 @@ ASAM_API void april_graph_cholesky_inc(april_graph_t *graph, april_graph_cholesk
                    pl->n_factors, F0);
     PROF_BEGIN();
     g_prof[8] += 1;
+    stamps_t tp = { .n = 0 };
+    if (param->show_timing) {
+        asam_set_timing(dev, 1);
+        stamp(&tp, "begin");
+    }
     s->tree_fresh = 0;
     check_nodes(graph, N0, N);
     gctx_sync_factors(c, graph);
@@ -707,6 +757,8 @@ ASAM_API void april_graph_cholesky_inc(april_graph_t *graph, april_graph_cholesk
     if (rc != 0)
         asam_fatal("april_graph_cholesky_inc: %s %s", g_error, asam_last_error());
     PROF_LAP(1);
+    if (param->show_timing)
+        stamp(&tp, "mark root paths, symbolic append");
     DEV_OK(asam_step_begin(dev)); /* record the step's kernels; one upload flush at asam_step_run */
     DEV_OK(asam_linearize(dev, F0, nf, pts));
     DEV_OK(asam_factor(dev, ntasks, tasks, nwait));
@@ -765,10 +817,16 @@ ASAM_API void april_graph_cholesky_inc(april_graph_t *graph, april_graph_cholesk
         PROF_LAP(4);
         report_factor_status(s, fstatus, "april_graph_cholesky_inc");
         PROF_LAP(5);
+        if (param->show_timing)
+            stamp(&tp, "H2D, kernels, D2H of the solution");
         apply_solution(s, tr, x, qbase);
         PROF_LAP(6);
         if (tr->naffected > 5)
             g_prof[17] += 1;
+        if (param->show_timing) {
+            stamp(&tp, "solve_node bookkeeping");
+            stamps_display(&tp, dev);
+        }
     }
     free(tasks);
     free(nwait);

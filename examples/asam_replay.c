@@ -1,7 +1,7 @@
 /* asam_replay.c -- command-line driver of the drop-in library.
  *
  *   asam_replay --datapath FILE [--batch_update_only] [--delta_xy 0.1] [--delta_theta 0.1]
- *               [--nthreshold 100] [--quiet] [--save OUT.graph]
+ *               [--nthreshold 100] [--quiet] [--show_timing] [--save OUT.graph]
  *
  * FILE is a Manhattan-style text file (VERTEX2 id x y theta / EDGE2 a b dx dy dth I11 I12 I22 I33
  * I13 I23) or a ".graph" file in the stype framing.  The graph is then replayed pose by pose with
@@ -78,13 +78,14 @@ bad:
 int main(int argc, char **argv)
 {
     const char *path = NULL, *save = NULL;
-    int batch_only = 0, quiet = 0, nthreshold = 100;
+    int batch_only = 0, quiet = 0, nthreshold = 100, show_timing = 0;
     double delta_xy = 0.1, delta_theta = 0.1;
     for (int i = 1; i < argc; i++) {
         if (!strcmp(argv[i], "--datapath") && i + 1 < argc) path = argv[++i];
         else if (!strcmp(argv[i], "--save") && i + 1 < argc) save = argv[++i];
         else if (!strcmp(argv[i], "--batch_update_only")) batch_only = 1;
         else if (!strcmp(argv[i], "--quiet")) quiet = 1;
+        else if (!strcmp(argv[i], "--show_timing")) show_timing = 1;
         else if (!strcmp(argv[i], "--delta_xy") && i + 1 < argc) delta_xy = atof(argv[++i]);
         else if (!strcmp(argv[i], "--delta_theta") && i + 1 < argc) delta_theta = atof(argv[++i]);
         else if (!strcmp(argv[i], "--nthreshold") && i + 1 < argc) nthreshold = atoi(argv[++i]);
@@ -139,6 +140,7 @@ int main(int argc, char **argv)
     param->delta_xy = delta_xy;
     param->delta_theta = delta_theta;
     param->nthreshold = nthreshold;
+    param->show_timing = show_timing; /* per-phase table after every solve (aprilsam.c:317) */
     double total = 0.0;
     for (int k = 0; k < N; k++) {
         april_graph_node_t *src;

@@ -59,6 +59,8 @@ int asam_upload_factors(asam_dev_t *d, int first, int count, const int32_t *type
                         const int32_t *nb, const double *z3, const double *W9);
 /* which: 0 = l_point, 1 = state */
 int asam_upload_points(asam_dev_t *d, int which, int first, int count, const double *p3);
+/* copy poses [first, first+count) between the two mirrors inside HBM (which: 0 = l_point, 1 = state) */
+int asam_copy_points(asam_dev_t *d, int from, int to, int first, int count);
 
 /* Symbolic plan pieces. */
 int asam_upload_node2q(asam_dev_t *d, int first, int count, const int32_t *node2q);
