@@ -59,6 +59,7 @@ int pairmap_get_or_add(pairmap_t *m, int lo, int hi, int next_slot, int *created
 /* Reference-equivalent elimination order; adj lists ascending, no self loops.
  * Returns malloc'd order[pos] = node. */
 int *asam_ref_ordering(int N, const int *adj_ptr, const int *adj);
+int *asam_ref_ordering_explicit(int N, const int *adj_ptr, const int *adj); /* cross-check (tests) */
 
 /* ---- symbolic plan (plan.c) ----------------------------------------------------------- */
 #define ASAM_TR_FLAG (1 << 30) /* a_rb flag: gather the slot transposed */

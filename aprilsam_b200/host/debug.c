@@ -112,5 +112,13 @@ ASAM_API int asam_dbg_ref_ordering(int N, const int *adj_ptr, const int *adj, in
     return 0;
 }
 
+ASAM_API int asam_dbg_ref_ordering_explicit(int N, const int *adj_ptr, const int *adj, int *out)
+{
+    int *o = asam_ref_ordering_explicit(N, adj_ptr, adj);
+    memcpy(out, o, sizeof(int) * (size_t) (N > 0 ? N : 0));
+    free(o);
+    return 0;
+}
+
 void asam_dbg_plan_profile(double *out, int reset);
 ASAM_API void asam_dbg_plan_profile_get(double *out, int reset) { asam_dbg_plan_profile(out, reset); }

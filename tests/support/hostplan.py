@@ -27,6 +27,7 @@ def lib():
         L.asam_dbg_plan_array.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]
         L.asam_dbg_plan_array.restype = _ip
         L.asam_dbg_ref_ordering.argtypes = [C.c_int, _ip, _ip, _ip]
+        L.asam_dbg_ref_ordering_explicit.argtypes = [C.c_int, _ip, _ip, _ip]
         L.aprilsam_b200_last_error.restype = C.c_char_p
         _lib = L
     return _lib
@@ -117,8 +118,8 @@ class HostPlan:
                     a_cnt=raw[:, 6], level=raw[:, 7], f_off=f_off)
 
 
-def ref_ordering(N, pairs_lo, pairs_hi):
-    """Run the library's ordering on an undirected edge list."""
+def ref_ordering(N, pairs_lo, pairs_hi, explicit=False):
+    """Run the library's ordering on an undirected edge list (explicit: the O(sum d^2) cross-check)."""
     import scipy.sparse as sp
     A = sp.coo_matrix((np.ones(len(pairs_lo)), (pairs_lo, pairs_hi)), shape=(N, N))
     A = ((A + A.T) > 0).astype(np.int8).tocsr()
@@ -128,5 +129,5 @@ def ref_ordering(N, pairs_lo, pairs_hi):
     ptr = A.indptr.astype(np.int32)
     idx = A.indices.astype(np.int32)
     out = np.zeros(N, dtype=np.int32)
-    lib().asam_dbg_ref_ordering(N, _i(ptr), _i(idx), _i(out))
+    (lib().asam_dbg_ref_ordering_explicit if explicit else lib().asam_dbg_ref_ordering)(N, _i(ptr), _i(idx), _i(out))
     return out

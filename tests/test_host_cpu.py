@@ -146,6 +146,28 @@ def test_synthetic_ordering_matches_reference():
     assert np.array_equal(p.array("order"), ref_order)
 
 
+def test_quotient_graph_ordering_equals_explicit_elimination():
+    """The production ordering keeps the elimination graph implicitly (elements + exact degrees on
+    demand); it must give the permutation of the explicit-clique implementation on any graph."""
+    from support.hostplan import ref_ordering
+    rng = np.random.default_rng(11)
+    for n, extra in [(1, 0), (2, 1), (7, 5), (40, 60), (300, 200), (300, 2000), (2500, 4000)]:
+        lo = list(range(n - 1))
+        hi = list(range(1, n))
+        for _ in range(extra):
+            a, b = rng.integers(0, n, 2)
+            if a != b:
+                lo.append(int(min(a, b)))
+                hi.append(int(max(a, b)))
+        lo, hi = np.array(lo, dtype=np.int64), np.array(hi, dtype=np.int64)
+        if n == 1:
+            continue
+        assert np.array_equal(ref_ordering(n, lo, hi), ref_ordering(n, lo, hi, explicit=True)), (n, extra)
+    for d in (datasets.manhattan_dense(4000, seed=9), datasets.manhattan_sparse(9000, seed=4)):
+        lo, hi = np.minimum(d.ea, d.eb), np.maximum(d.ea, d.eb)
+        assert np.array_equal(ref_ordering(d.n_nodes, lo, hi), ref_ordering(d.n_nodes, lo, hi, explicit=True))
+
+
 # ---------------------------------------------------------------------------------------------
 # plan + emulated kernels == reference solution
 # ---------------------------------------------------------------------------------------------
