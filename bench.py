@@ -331,13 +331,22 @@ def run_b200(args, d, label, world, rank, local, dist):
     nnz_l = 9 * (pinfo["nnz_l_blocks"] - pinfo["N"]) + 6 * pinfo["N"]
     nnz_a = 6 * pinfo["N"] + 9 * pinfo["n_slots"]
     alg_bytes = 8 * nnz_a + 16 * nnz_l
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f).get(args.workload, {}).get("bytes")
+    except Exception:
+        pass
     if is_batch and fac_ms:
         t_fac = float(np.mean(fac_ms)) * 1e-3
         achieved = alg_bytes / t_fac / 1e9
-        roof = {"kernel": "k_factor", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+        fp64_peak = 37.1e3  # GFLOP/s, measured on this pool (profiles/r2_fp64_pipe_ubench.txt); tcgen05 has no FP64 kind
+        roof = {"kernel": "k_factor (+k_factor_leaf on large graphs)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": t_fac * 1e3,
-                "fp64_gflops": pinfo["flops"] / t_fac / 1e9, "flops_per_launch": pinfo["flops"]}
+                "fp64_gflops": pinfo["flops"] / t_fac / 1e9, "flops_per_launch": pinfo["flops"],
+                "fp64_peak_gflops": fp64_peak, "fp64_frac": pinfo["flops"] / t_fac / 1e9 / fp64_peak,
+                "note": "latency-bound: the dependent chain of supernode levels / panel steps, not bytes or flops, sets the time"}
     else:
         roof = {"kernel": "k_factor", "bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None,
                 "traffic": None, "peak_source": peak_src}
