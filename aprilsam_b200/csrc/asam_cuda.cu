@@ -833,15 +833,20 @@ ASAM_EXPORT int asam_set_leaf_tasks(asam_dev_t *d, int n, const int32_t *tasks)
 {
     CK(cudaSetDevice(d->device));
     d->n_leaf = 0;
-    d->bt_nleaf = 0;
     if (n <= 0)
         return 0;
-    if (n > d->bt_count)
-        return set_err("asam_set_leaf_tasks: %d leaf supernodes but only %d in the back-solve list", n, d->bt_count);
     if (buf_reserve(d, d->leaf_tasks, (size_t) n * sizeof(int), false, false) ||
         upload(d, d->leaf_tasks.p, tasks, (size_t) n * sizeof(int)))
         return 1;
     d->n_leaf = n;
+    return 0;
+}
+
+// The LAST n entries of the back-solve list (asam_set_full_tasks) go through k_backsolve_leaf.
+ASAM_EXPORT int asam_set_bs_leaf_count(asam_dev_t *d, int n)
+{
+    if (n < 0 || n > d->bt_count)
+        return set_err("asam_set_bs_leaf_count: %d of %d", n, d->bt_count);
     d->bt_nleaf = n;
     return 0;
 }

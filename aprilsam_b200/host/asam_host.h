@@ -102,6 +102,8 @@ typedef struct {
     int *leaf_tasks; /* supernodes factored by k_factor_leaf before `tasks` (large graphs only) */
     int n_leaf;
     int n_btasks;    /* entries of btasks (= nsn on a single GPU) */
+    char *bs_leaf;   /* per supernode: back-solved by k_backsolve_leaf (last n_bs_leaf entries of btasks) */
+    int n_bs_leaf;
 
     /* multi-GPU sharding (world > 1): tasks / leaf_tasks / btasks then cover this rank's shards
      * (+ the top in btasks); see build_schedule() in plan.c */

@@ -39,6 +39,8 @@ void asam_dbg_plan_profile(double *out, int reset)
 
 #define RELAX_Z 2     /* relaxed amalgamation: missing block rows tolerated per merge */
 #define RELAX_FILL 24 /* ... and explicit zero blocks (3x3) added per merge */
+#define ASAM_BSLEAF_MAX 64       /* = ASAM_BSL_XS of k_backsolve_leaf: own columns / rows below */
+#define ASAM_BSLEAF_MIN_COUNT 4096 /* measured: no gain on M3500-sized trees (the kernel boundary eats it) */
 #define ASAM_LEAF_MAX_M 48       /* = ASAM_LEAF_M of k_factor_leaf */
 #define ASAM_LEAF_MIN_COUNT 4096 /* below this one k_factor launch does it all */
 #define MAX_SN_COLS 32 /* block columns per supernode: L11 (96x96) fits k_backsolve shared memory */
@@ -191,6 +193,7 @@ void plan_free(plan_t *pl)
     free(pl->nwait);
     free(pl->btasks);
     free(pl->leaf_tasks);
+    free(pl->bs_leaf);
     free(pl->top_tasks);
     free(pl->top_nwait);
     free(pl->shard_owner);
@@ -229,6 +232,10 @@ static void sn_arrays_reserve(plan_t *pl, int n)
     pl->snh = realloc(pl->snh, sizeof(sn_host_t) * cap);
     memset(pl->snh + pl->sn_cap, 0, sizeof(sn_host_t) * (cap - pl->sn_cap));
     memset(pl->desc + pl->sn_cap, 0, sizeof(asam_sn_desc_t) * (cap - pl->sn_cap));
+    if (pl->bs_leaf) { /* supernodes created later are never in the back-solve leaf set */
+        pl->bs_leaf = realloc(pl->bs_leaf, (size_t) cap + 1);
+        memset(pl->bs_leaf + pl->sn_cap, 0, (size_t) (cap - pl->sn_cap) + 1);
+    }
     pl->sn_cap = cap;
 }
 
@@ -478,6 +485,17 @@ static void build_schedule(plan_t *pl)
     }
     if (n_leaf_all < ASAM_LEAF_MIN_COUNT)
         memset(leaf, 0, (size_t) nsn);
+    /* the warp-per-supernode BACK-SOLVE takes any downward-closed set with <= 64 own columns and
+     * <= 64 rows below (a superset of the factor leaf set); it pays from a few dozen supernodes on:
+     * a warp per supernode has everything fetched before its parent's flag arrives */
+    free(pl->bs_leaf);
+    pl->bs_leaf = calloc((size_t) pl->sn_cap + 1, 1);
+    for (int s = 0; s < nsn; s++) {
+        int ok = 3 * pl->desc[s].cb <= ASAM_BSLEAF_MAX && 3 * (pl->desc[s].mb - pl->desc[s].cb) <= ASAM_BSLEAF_MAX;
+        for (int c = 0; ok && c < pl->snh[s].children.n; c++)
+            ok = pl->bs_leaf[pl->snh[s].children.p[c]];
+        pl->bs_leaf[s] = (char) ok;
+    }
 
     /* counting sort by level, ids ascending inside a level */
     int *byl = malloc(sizeof(int) * (size_t) (nsn + 1));
@@ -491,15 +509,21 @@ static void build_schedule(plan_t *pl)
     free(cnt);
 
     int64_t n_local = 0, n_top = 0;
-    int n_leaf = 0, n_main_sn = 0, n_top_sn = 0;
+    int n_leaf = 0, n_main_sn = 0, n_top_sn = 0, n_bsl = 0;
+    for (int s = 0; s < nsn; s++)
+        n_bsl += owner[s] == me && pl->bs_leaf[s];
+    if (n_bsl < ASAM_BSLEAF_MIN_COUNT) {
+        memset(pl->bs_leaf, 0, (size_t) nsn);
+        n_bsl = 0;
+    }
     for (int s = 0; s < nsn; s++) {
         if (owner[s] == me) {
             if (leaf[s])
                 n_leaf++;
-            else {
+            else
                 n_local += team_size(pl->desc[s].mb, pl->desc[s].cb);
+            if (!pl->bs_leaf[s])
                 n_main_sn++;
-            }
         } else if (owner[s] == -1) {
             n_top += team_size(pl->desc[s].mb, pl->desc[s].cb);
             n_top_sn++;
@@ -514,9 +538,10 @@ static void build_schedule(plan_t *pl)
     pl->n_top_sn = n_top_sn;
     pl->top_tasks = malloc(sizeof(int) * (size_t) (n_top + 1));
     pl->top_nwait = malloc(sizeof(int) * (size_t) (n_top + 1));
-    pl->n_btasks = n_top_sn + n_main_sn + n_leaf;
+    pl->n_bs_leaf = n_bsl;
+    pl->n_btasks = n_top_sn + n_main_sn + n_bsl;
     pl->btasks = malloc(sizeof(int) * (size_t) (pl->n_btasks + 1));
-    /* back-solve list, parents first: [top | own shards outside the leaf set | own leaf set] */
+    /* back-solve list, parents first: [top | own shards outside the back-solve leaf set | that set] */
     int t = 0, tl = 0, tt = 0;
     int bt = n_top_sn - 1, bm = n_top_sn + n_main_sn - 1, bl = pl->n_btasks - 1;
     for (int k = 0; k < nsn; k++) {
@@ -535,12 +560,14 @@ static void build_schedule(plan_t *pl)
         }
         if (owner[s] != me)
             continue;
-        if (leaf[s]) {
+        if (pl->bs_leaf[s])
             pl->btasks[bl--] = s;
+        else
+            pl->btasks[bm--] = s;
+        if (leaf[s]) {
             pl->leaf_tasks[tl++] = s;
             continue;
         }
-        pl->btasks[bm--] = s;
         /* nwait counts ALL children: those of the leaf set arrived in the earlier launch */
         int G = team_size(pl->desc[s].mb, pl->desc[s].cb);
         for (int w = 0; w < G; w++, t++) {
@@ -888,6 +915,7 @@ static int plan_build_impl(plan_t *pl, asam_dev_t *dev, int N, int n_factors, co
     rc |= asam_upload_fslot(dev, 0, n_factors, pl->fslot);
     rc |= asam_set_full_tasks(dev, pl->ntasks, pl->tasks, pl->nwait, pl->n_btasks, pl->btasks);
     rc |= asam_set_leaf_tasks(dev, pl->n_leaf, pl->leaf_tasks);
+    rc |= asam_set_bs_leaf_count(dev, pl->n_bs_leaf);
     if (pl->world > 1) {
         asam_shard_sched_t sh;
         memset(&sh, 0, sizeof(sh));
@@ -1008,7 +1036,7 @@ int plan_append(plan_t *pl, asam_dev_t *dev, int N, int n_factors, const int *ft
     for (int i = 0; i < nm; i++)
         mark_idx[msn[i]] = i;
 
-    int rc = 0;
+    int rc = 0, bs_leaf_broken = 0;
     ivec_t *gain = calloc((size_t) nm + 1, sizeof(ivec_t));
     ivec_t *pend = calloc((size_t) nnew + 1, sizeof(ivec_t)); /* children of each new supernode */
     ivec_t *nbelow = calloc((size_t) nnew + 1, sizeof(ivec_t));
@@ -1047,6 +1075,8 @@ int plan_append(plan_t *pl, asam_dev_t *dev, int N, int n_factors, const int *ft
         d->mb = h->rows.n;
         if (3 * d->mb > pl->max_m)
             pl->max_m = 3 * d->mb;
+        if (pl->n_bs_leaf > 0 && pl->bs_leaf[s] && 3 * (d->mb - d->cb) > ASAM_BSLEAF_MAX)
+            bs_leaf_broken = 1; /* outgrew the warp kernel: everything goes through k_backsolve from now on */
         if (d->mb != old_mb && front_doubles(d->mb) > d->reserved) {
             /* the front outgrew its allocation: move it, with head-room for the poses that
              * later steps will append (the old space is reclaimed at the next batch) */
@@ -1110,6 +1140,8 @@ int plan_append(plan_t *pl, asam_dev_t *dev, int N, int n_factors, const int *ft
             asam_sn_desc_t *d = &pl->desc[R];
             sn_host_t *h = &pl->snh[R];
             d->cb += 1;
+            if (pl->n_bs_leaf > 0 && pl->bs_leaf[R] && 3 * d->cb > ASAM_BSLEAF_MAX)
+                bs_leaf_broken = 1;
             for (int c = 0; c < pend[j].n; c++) {
                 int X = pend[j].p[c];
                 if (X == R)
@@ -1233,6 +1265,10 @@ int plan_append(plan_t *pl, asam_dev_t *dev, int N, int n_factors, const int *ft
                     pre[k] = nsn0 + ncreated - 1 - k;
                 rc |= asam_btasks_prepend(dev, ncreated, pre);
                 free(pre);
+            }
+            if (!rc && bs_leaf_broken) {
+                pl->n_bs_leaf = 0;
+                rc |= asam_set_bs_leaf_count(dev, 0);
             }
             if (!rc)
                 rc |= asam_upload_fslot(dev, F0, n_factors - F0, pl->fslot + F0);

@@ -94,11 +94,13 @@ int asam_set_full_tasks(asam_dev_t *d, int ntasks, const int32_t *tasks, const i
                         int nbtasks, const int32_t *btasks);
 /* Large graphs: supernodes (children first) whose fronts are at most 48 x 48 and whose whole
  * subtree is of that kind are factored by a warp-per-front kernel launched right before the list
- * above by asam_factor_full, and back-solved by a warp-per-supernode kernel right after the rest
- * by asam_backsolve_full: the LAST n entries of the btasks list given to asam_set_full_tasks must
- * be exactly these supernodes (parents first).  Call after asam_set_full_tasks; n = 0 disables
- * (the whole btasks list then goes through k_backsolve, which is what incremental steps use). */
+ * above by asam_factor_full.  Call after asam_set_full_tasks; n = 0 disables. */
 int asam_set_leaf_tasks(asam_dev_t *d, int n, const int32_t *tasks);
+/* Back-substitution: the LAST n entries of the btasks list given to asam_set_full_tasks (a
+ * downward-closed set of supernodes with <= 64 own columns and <= 64 rows below, parents first) are
+ * solved by a warp-per-supernode kernel right after k_backsolve has done the rest.  n = 0: the whole
+ * list goes through k_backsolve.  Call after asam_set_full_tasks. */
+int asam_set_bs_leaf_count(asam_dev_t *d, int n);
 int asam_factor_full(asam_dev_t *d);
 /* Supernodes created after asam_set_full_tasks (poses appended by incremental steps) are
  * ancestors of everything older: prepend them (parents first) to the full back-solve list. */
