@@ -33,7 +33,8 @@ INCLUDES = ["-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "inc
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v"]
-CC_FLAGS = ["-std=gnu11", "-O2", "-g", "-fPIC", "-fvisibility=hidden", "-Wall", "-Wextra", "-Wno-unused-parameter"]
+CC_FLAGS = ["-std=gnu11", "-O2", "-g", "-fPIC", "-fvisibility=hidden", "-fopenmp", "-Wall", "-Wextra",
+            "-Wno-unused-parameter"]
 
 
 def _run(cmd: list[str], log: list[str]) -> None:
@@ -78,7 +79,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             _run([CC] + CC_FLAGS + INCLUDES + ["-c", src, "-o", obj], log)
     if force or _stale(LIB, objs):
         _run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs +
-             ["-Xlinker", "-Bsymbolic", "-lm"], log)
+             ["-Xlinker", "-Bsymbolic", "-Xcompiler", "-fopenmp", "-lm"], log)
     hsrc = os.path.join(ROOT, "harness", "harness.c")
     if force or _stale(HARNESS, [hsrc, LIB] + hdrs):
         _run([CC, "-std=gnu99", "-O2", "-g", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include", "aprilsam"),

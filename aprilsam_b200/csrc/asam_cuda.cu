@@ -58,7 +58,7 @@ struct BatchItem {
 };
 #define ASAM_MAX_ITEMS 1024
 #define ASAM_TABLE_BYTES (ASAM_MAX_ITEMS * sizeof(BatchItem))
-#define ASAM_ITEM_CHUNK (64u << 10)
+#define ASAM_ITEM_CHUNK (8u << 10) // one k_scatter block per item: small chunks keep that kernel at a few microseconds
 
 struct asam_dev {
     int device = 0;

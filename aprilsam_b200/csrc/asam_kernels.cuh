@@ -685,21 +685,22 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
         trow[3] = d_now();
 
     // ---- panels, with one panel of look-ahead ---------------------------------------------------
-    // Panel k+1 is factored by a small CREW (the workers that own its 256-row chunks) while the
-    // other workers are still applying panel k to the rest of the trailing matrix: in iteration k
-    //   crew worker w:  update rows chunk w of the NEXT panel's columns with panel k
-    //                   -> [crew barrier] -> diagonal block (redundantly) + TRSM of chunk w
-    //   everybody:      tiles of the trailing update with panel k right of the next panel
+    // Panel k+1 is factored by a small CREW while the other workers are still applying panel k to
+    // the rest of the trailing matrix.  In iteration k
+    //   crew worker 0:   applies panel k to the 48x48 diagonal block of panel k+1, factors it (once,
+    //                    left-looking 3-column steps), writes L11 / 1/diag and raises a flag
+    //   crew worker w>0: applies panel k to its 256-row chunk of panel k+1's columns (as long as the
+    //                    factorisation of the block takes), waits for the flag, solves its rows
+    //   everybody else:  tiles of the trailing update with panel k right of panel k+1
     //   -> [team barrier]
-    // so the dependent chain per panel is one chunk update + the panel factorisation + one
-    // barrier instead of panel factorisation + barrier + a whole trailing update + barrier.
+    // so the dependent chain per panel is max(chunk update, block update + factorisation) + row solve
+    // + one barrier, instead of factorisation + barrier + a whole trailing update + barrier.
     double *D = sm;                              // ASAM_TPB x ASAM_TPB diagonal block
     double *rdv = D + ASAM_TPB * ASAM_TPB;       // ASAM_TPB reciprocal diagonal entries
     double *Li = rdv + ASAM_TPB;                 // ASAM_TROWS x pb   (row chunk / row tile)
     double *Lj = Li + ASAM_TROWS * ASAM_TPB;     // ASAM_TCOLS x pb   (column tile)
     double *dinv = a.dinv + 3 * (size_t) d.first;
-    int *crew_bar = a.tbar + 2 * (size_t) s + 1;
-    int crew_cum = 0;
+    int *crew_bar = a.tbar + 2 * (size_t) s + 1; // flag: index (1-based) of the last published panel
 
     // C[rb0.., cb0..] -= L[rb0.., k0..k0+pb) * L[cb0.., k0..k0+pb)'  (lower trapezoid only)
     auto tile = [&](int k0, int pb, int cb0, int ncol, int rb0, int nrow) {
@@ -811,6 +812,61 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
             dinv[k0 + e] = rdv[e];
     };
 
+    // worker 0 of the crew: the diagonal block of the panel at k0 (already updated by its own tile) is
+    // factored ONCE and published -- L11 into the front, 1/diag into dinv, then the flag
+    auto diag_publish = [&](int k0, int pb, int seq) {
+        __syncthreads();
+        for (int e = tid; e < ASAM_TPB * ASAM_TPB; e += nt) {
+            const int i = e % ASAM_TPB, j = e / ASAM_TPB;
+            D[e] = (i >= j && i < pb && j < pb) ? __ldcg(&F[(k0 + i) + (size_t) (k0 + j) * ld]) : 0.0;
+        }
+        __syncthreads();
+        diag_factor(D, pb, rdv, s, err);
+        writeback(k0, pb);
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            atomicExch(crew_bar, seq);
+        }
+    };
+    // the other crew workers: rows [rb0, rb0+256) of the panel are fetched while worker 0 factors the
+    // block, then solved against the published L11
+    auto rows_solve = [&](int k0, int pb, int rb0, int seq) {
+        __syncthreads();
+        const int i = rb0 + tid;
+        const bool row = i <= m;
+        if (row)
+            for (int j = 0; j < pb; j++)
+                Li[tid + j * ASAM_TROWS] = __ldcg(&F[i + (size_t) (k0 + j) * ld]);
+        if (tid == 0) {
+            long long spins = 0;
+            int ok = 1;
+            while (ld_volatile(crew_bar) < seq) {
+                __nanosleep(20);
+                if (++spins > a.spin_limit || ld_volatile(err) < 0) {
+                    atomicCAS(err, 0, -(1 + s));
+                    ok = 0;
+                    break;
+                }
+            }
+            __threadfence();
+            *s_flag = ok;
+        }
+        __syncthreads();
+        if (!*s_flag)
+            return false;
+        for (int e = tid; e < ASAM_TPB * ASAM_TPB; e += nt) {
+            const int ii = e % ASAM_TPB, j = e / ASAM_TPB;
+            D[e] = (ii >= j && ii < pb && j < pb) ? __ldcg(&F[(k0 + ii) + (size_t) (k0 + j) * ld]) : 0.0;
+        }
+        for (int e = tid; e < ASAM_TPB; e += nt)
+            rdv[e] = e < pb ? __ldcg(&dinv[k0 + e]) : 0.0;
+        __syncthreads();
+        if (row)
+            trsm_row(Li, D, rdv, pb, F + i + (size_t) k0 * ld, ld);
+        return true;
+    };
+
     // prologue: panel 0 by everybody (row chunks of 256 from the panel's first row, round-robin)
     {
         const int pb = min(ASAM_TPB, c);
@@ -829,48 +885,35 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
         if (w == 0)
             writeback(0, pb);
     }
+    int seq = 0;
     for (int k0 = 0; k0 < c; k0 += ASAM_TPB) {
         const int pb = min(ASAM_TPB, c - k0);
         const int kn0 = k0 + pb;                       // first trailing column = next panel
         const bool has_next = kn0 < c;
         const int pbn = has_next ? min(ASAM_TPB, c - kn0) : 0;
-        const int ncrew = has_next ? (m - kn0 + 1 + ASAM_TROWS - 1) / ASAM_TROWS : 0;
+        // crew of the next panel: worker 0 owns its diagonal block, workers 1.. the 256-row chunks below
+        const int ncrew = has_next ? 1 + (m - (kn0 + pbn) + 1 + ASAM_TROWS - 1) / ASAM_TROWS : 0;
+        ++seq;
         if (w < ncrew) {
             if (trow && tid == 0)
                 t_mark = d_now();
-            const int rb0 = kn0 + w * ASAM_TROWS;
-            tile(k0, pb, kn0, pbn, rb0, min(ASAM_TROWS, m - rb0 + 1));
-            // crew barrier: the next panel's columns have received panel k on all their rows
-            __syncthreads();
-            if (tid == 0) {
-                __threadfence();
-                atomicAdd(crew_bar, 1);
-                long long spins = 0;
-                int ok = 1;
-                while (ld_volatile(crew_bar) < crew_cum + ncrew) {
-                    __nanosleep(20);
-                    if (++spins > a.spin_limit || ld_volatile(err) < 0) {
-                        atomicCAS(err, 0, -(1 + s));
-                        ok = 0;
-                        break;
-                    }
-                }
-                __threadfence();
-                *s_flag = ok;
+            if (w == 0) {
+                tile(k0, pb, kn0, pbn, kn0, pbn);
+                diag_publish(kn0, pbn, seq);
+            } else {
+                const int rb0 = kn0 + pbn + (w - 1) * ASAM_TROWS;
+                tile(k0, pb, kn0, pbn, rb0, min(ASAM_TROWS, m - rb0 + 1));
+                if (!rows_solve(kn0, pbn, rb0, seq))
+                    return false;
             }
-            __syncthreads();
-            if (!*s_flag)
-                return false;
-            panel(kn0, pbn, rb0);
             if (trow && tid == 0)
                 t_panel += d_now() - t_mark;
         }
-        crew_cum += ncrew;
 
         // trailing update with panel k right of the next panel: tiles of TR rows x 64 columns over
         // the lower trapezoid (TR = 128 when 256-row tiles would leave workers idle).  The crew is
-        // on the critical path already (its chain is longer than two tiles): the tiles go to the
-        // other workers only, unless the team is all crew
+        // on the critical path already: the tiles go to the other workers only, unless the team is
+        // all crew
         const int j0 = kn0 + pbn;
         const int nfree = (G - ncrew >= 2) ? G - ncrew : G, wfree = (G - ncrew >= 2) ? w - ncrew : w;
         int n256 = 0;
@@ -886,11 +929,9 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
         }
         if (!team_barrier(tc, s_flag))
             return false;
-        if (w == 0 && has_next)
-            writeback(kn0, pbn);
     }
     if (w == 0 && tid == 0)
-        atomicExch(crew_bar, 0); // everybody is past its last crew barrier (team barrier above)
+        atomicExch(crew_bar, 0); // everybody is past its last wait on the crew flag (team barrier above)
 
     if (trow && tid == 0) {
         trow[4] = d_now();

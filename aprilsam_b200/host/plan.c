@@ -326,7 +326,7 @@ static int team_size(int mb, int cb)
     int64_t j0 = c < 48 ? c : 48, tiles = 0;
     for (int64_t cb0 = j0; cb0 < m; cb0 += 64)
         tiles += (m - cb0 + 1 + 255) / 256;
-    int64_t chunks = (m - j0 + 1 + 255) / 256; /* row chunks of the panel solve */
+    int64_t chunks = 1 + (m - j0 + 1 + 255) / 256; /* look-ahead crew: the diagonal block + the row chunks */
     int G = (int) (tiles + chunks); /* the look-ahead crew (one CTA per chunk) takes no tiles */
     if (G < 2)
         G = 2;

@@ -73,6 +73,11 @@ ASAM_API void asam_dbg_profile(double *out, int reset)
         memset(g_prof, 0, sizeof(g_prof));
 }
 
+/* host threads for the per-node loops of a batch solve on a large graph (never for small ones: the
+ * fork/join costs more than 3500 poses do) */
+#define ASAM_OMP_MIN_NODES 16384
+#define ASAM_OMP_THREADS 8
+
 #define DEV_OK(call)                                                                       \
     do {                                                                                   \
         if ((call) != 0)                                                                   \
@@ -467,7 +472,10 @@ ASAM_API void april_graph_cholesky(april_graph_t *graph, april_graph_cholesky_pa
     gctx_sync_factors(c, graph);
 
     /* relinearise every node at its current state (:131-135) and stage the poses */
+    /* (large graphs: the per-node loops of this function chase one pointer per pose into separately
+     * malloc'd arrays -- they are split over a few host threads, SURVEY.md section 7 "host marshalling") */
     double *lp = gctx_stage(c, 3 * N);
+#pragma omp parallel for schedule(static) if (N >= ASAM_OMP_MIN_NODES) num_threads(ASAM_OMP_THREADS)
     for (int i = 0; i < N; i++) {
         april_graph_node_t *n = node_at(graph, i);
         memcpy(n->l_point, n->state, 3 * sizeof(double));
@@ -524,6 +532,7 @@ ASAM_API void april_graph_cholesky(april_graph_t *graph, april_graph_cholesky_pa
     if (plan_reused && s->tree_fresh && param->tr && param->tr->nnodes == N) {
         /* same structure as the previous batch: same tree; only the per-solve labels reset */
         search_tree_t *tr = param->tr;
+#pragma omp parallel for schedule(static) if (N >= ASAM_OMP_MIN_NODES) num_threads(ASAM_OMP_THREADS)
         for (int i = 0; i < N; i++) {
             tr->nodes[i].label_changed = 0;
             tr->nodes[i].label_relinearized = 0;
@@ -549,7 +558,8 @@ ASAM_API void april_graph_cholesky(april_graph_t *graph, april_graph_cholesky_pa
     param->factor_num = F;
 
     /* state = l_point + x (:311-315) */
-    for (int i = N - 1; i >= 0; i--)
+#pragma omp parallel for schedule(static) if (N >= ASAM_OMP_MIN_NODES) num_threads(ASAM_OMP_THREADS)
+    for (int i = 0; i < N; i++)
         apply_update(node_at(graph, i), x + 3 * (size_t) pl->node2q[i]);
     PROF_LAP(16);
     if (param->show_timing) {

@@ -253,6 +253,7 @@ def test_edge_cases_full_W_duplicates_reversed_edges_several_priors():
     extra = [(3, 11), (11, 3), (3, 11), (20, 7), (25, 2), (14, 13), (29, 0), (28, 9)]  # duplicates and reversed pairs
     recs = {e: (rel(*e), full_W()) for e in set(edges + extra)}
     init = truth + 0.05 * rng.standard_normal(truth.shape)
+    W_prior2 = full_W()  # drawn once: both arms must see the same numbers
 
     def drive(h):
         out = []
@@ -260,7 +261,7 @@ def test_edge_cases_full_W_duplicates_reversed_edges_several_priors():
         for k in range(n0):
             h.add_node(init[k])
         h.add_xytpos(0, truth[0], np.diag([1e4, 1e4, 1e3]))
-        h.add_xytpos(17, truth[17] + 0.01, full_W())
+        h.add_xytpos(17, truth[17] + 0.01, W_prior2)
         for (a, b) in edges + extra:
             if max(a, b) < n0:
                 h.add_xyt(a, b, *recs[(a, b)])
