@@ -703,7 +703,9 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
     int *crew_bar = a.tbar + 2 * (size_t) s + 1; // flag: index (1-based) of the last published panel
 
     // C[rb0.., cb0..] -= L[rb0.., k0..k0+pb) * L[cb0.., k0..k0+pb)'  (lower trapezoid only)
-    auto tile = [&](int k0, int pb, int cb0, int ncol, int rb0, int nrow) {
+    // (Dout != nullptr: the tile is the diagonal block of the next panel; its values also go straight
+    // into the shared-memory block that diag_factor works on, saving the round trip through L2)
+    auto tile = [&](int k0, int pb, int cb0, int ncol, int rb0, int nrow, double *Dout) {
         __syncthreads();
         // two panel columns per warp and pass: 20 independent loads in flight per lane
         for (int p = warp; p < pb; p += 2 * nwarps) {
@@ -778,8 +780,12 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
                     for (int q = 0; q < 8; q++) {
                         const int ii = ib + lane + 32 * r, jj = tj + q;
                         const int i = rb0 + ii, j = cb0 + jj;
-                        if (ii < nrow && jj < ncol && i >= j)
-                            F[i + (size_t) j * ld] = cv[r][q] - acc[r][q];
+                        if (ii < nrow && jj < ncol && i >= j) {
+                            const double v = cv[r][q] - acc[r][q];
+                            F[i + (size_t) j * ld] = v;
+                            if (Dout)
+                                Dout[ii + jj * ASAM_TPB] = v;
+                        }
                     }
             }
         }
@@ -815,12 +821,7 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
     // worker 0 of the crew: the diagonal block of the panel at k0 (already updated by its own tile) is
     // factored ONCE and published -- L11 into the front, 1/diag into dinv, then the flag
     auto diag_publish = [&](int k0, int pb, int seq) {
-        __syncthreads();
-        for (int e = tid; e < ASAM_TPB * ASAM_TPB; e += nt) {
-            const int i = e % ASAM_TPB, j = e / ASAM_TPB;
-            D[e] = (i >= j && i < pb && j < pb) ? __ldcg(&F[(k0 + i) + (size_t) (k0 + j) * ld]) : 0.0;
-        }
-        __syncthreads();
+        __syncthreads(); // D was zeroed before, and filled by, the tile that updated this block
         diag_factor(D, pb, rdv, s, err);
         writeback(k0, pb);
         __syncthreads();
@@ -895,14 +896,23 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
         const int ncrew = has_next ? 1 + (m - (kn0 + pbn) + 1 + ASAM_TROWS - 1) / ASAM_TROWS : 0;
         ++seq;
         if (w < ncrew) {
+            // crew items: 0 = the diagonal block, i >= 1 = row chunk i-1; dealt round-robin (a team
+            // scaled down by the host may be smaller than the crew), the block first
             if (trow && tid == 0)
                 t_mark = d_now();
             if (w == 0) {
-                tile(k0, pb, kn0, pbn, kn0, pbn);
+                __syncthreads(); // worker 0 has written the previous panel's block back
+                for (int e = tid; e < ASAM_TPB * ASAM_TPB; e += nt)
+                    D[e] = 0.0;
+                tile(k0, pb, kn0, pbn, kn0, pbn, D);
                 diag_publish(kn0, pbn, seq);
-            } else {
-                const int rb0 = kn0 + pbn + (w - 1) * ASAM_TROWS;
-                tile(k0, pb, kn0, pbn, rb0, min(ASAM_TROWS, m - rb0 + 1));
+            }
+            for (int it = (w == 0 ? G : w); it < ncrew; it += G) {
+                const int rb0 = kn0 + pbn + (it - 1) * ASAM_TROWS;
+                tile(k0, pb, kn0, pbn, rb0, min(ASAM_TROWS, m - rb0 + 1), nullptr);
+            }
+            for (int it = (w == 0 ? G : w); it < ncrew; it += G) {
+                const int rb0 = kn0 + pbn + (it - 1) * ASAM_TROWS;
                 if (!rows_solve(kn0, pbn, rb0, seq))
                     return false;
             }
@@ -925,7 +935,7 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
             for (int cb0 = j0; cb0 < m; cb0 += ASAM_TCOLS)
                 for (int rb0 = cb0; rb0 <= m; rb0 += TR, ++u)
                     if (u % nfree == wfree)
-                        tile(k0, pb, cb0, min(ASAM_TCOLS, m - cb0), rb0, min(TR, m - rb0 + 1));
+                        tile(k0, pb, cb0, min(ASAM_TCOLS, m - cb0), rb0, min(TR, m - rb0 + 1), nullptr);
         }
         if (!team_barrier(tc, s_flag))
             return false;

@@ -39,6 +39,7 @@ void asam_dbg_plan_profile(double *out, int reset)
 
 #define RELAX_Z 2     /* relaxed amalgamation: missing block rows tolerated per merge */
 #define RELAX_FILL 24 /* ... and explicit zero blocks (3x3) added per merge */
+#define ASAM_TEAM_ROOM 140       /* CTAs that the team fronts of one tree level may claim together */
 #define ASAM_BSLEAF_MAX 64       /* = ASAM_BSL_XS of k_backsolve_leaf: own columns / rows below */
 #define ASAM_BSLEAF_MIN_COUNT 4096 /* measured: no gain on M3500-sized trees (the kernel boundary eats it) */
 #define ASAM_LEAF_MAX_M 48       /* = ASAM_LEAF_M of k_factor_leaf */
@@ -508,6 +509,28 @@ static void build_schedule(plan_t *pl)
         byl[cnt[pl->desc[s].level]++] = s;
     free(cnt);
 
+    /* team sizes.  A front's team is bound by latency, not throughput (team_size()), so where one tree
+     * level holds more team fronts than the 148 SMs can seat side by side, smaller teams finish the
+     * LEVEL sooner: CTA-time per front (G x duration) falls with G.  Scale the teams of such a level
+     * down to the room there is (never below 2). */
+    int *G_of = malloc(sizeof(int) * (size_t) (nsn + 1));
+    {
+        int64_t *want = calloc((size_t) pl->n_levels + 1, sizeof(int64_t));
+        for (int s = 0; s < nsn; s++) {
+            G_of[s] = (owner[s] == me || owner[s] == -1) && !leaf[s] ? team_size(pl->desc[s].mb, pl->desc[s].cb) : 1;
+            if (G_of[s] > 1)
+                want[pl->desc[s].level] += G_of[s];
+        }
+        for (int s = 0; s < nsn; s++) {
+            int64_t w = want[pl->desc[s].level];
+            if (G_of[s] > 1 && w > ASAM_TEAM_ROOM) {
+                int g = (int) ((int64_t) G_of[s] * ASAM_TEAM_ROOM / w);
+                G_of[s] = g < 2 ? 2 : g;
+            }
+        }
+        free(want);
+    }
+
     int64_t n_local = 0, n_top = 0;
     int n_leaf = 0, n_main_sn = 0, n_top_sn = 0, n_bsl = 0;
     for (int s = 0; s < nsn; s++)
@@ -521,11 +544,11 @@ static void build_schedule(plan_t *pl)
             if (leaf[s])
                 n_leaf++;
             else
-                n_local += team_size(pl->desc[s].mb, pl->desc[s].cb);
+                n_local += G_of[s];
             if (!pl->bs_leaf[s])
                 n_main_sn++;
         } else if (owner[s] == -1) {
-            n_top += team_size(pl->desc[s].mb, pl->desc[s].cb);
+            n_top += G_of[s];
             n_top_sn++;
         }
     }
@@ -551,7 +574,7 @@ static void build_schedule(plan_t *pl)
             int nw = 0; /* children above the cut: the others were exchanged before this launch */
             for (int c = 0; c < pl->snh[s].children.n; c++)
                 nw += owner[pl->snh[s].children.p[c]] == -1;
-            int G = team_size(pl->desc[s].mb, pl->desc[s].cb);
+            int G = G_of[s];
             for (int w = 0; w < G; w++, tt++) {
                 pl->top_tasks[tt] = s;
                 pl->top_nwait[tt] = pack_nwait(nw, w, G > 1 ? G : 0);
@@ -569,12 +592,13 @@ static void build_schedule(plan_t *pl)
             continue;
         }
         /* nwait counts ALL children: those of the leaf set arrived in the earlier launch */
-        int G = team_size(pl->desc[s].mb, pl->desc[s].cb);
+        int G = G_of[s];
         for (int w = 0; w < G; w++, t++) {
             pl->tasks[t] = s;
             pl->nwait[t] = pack_nwait(pl->desc[s].ch_cnt, w, G > 1 ? G : 0);
         }
     }
+    free(G_of);
     free(byl);
     free(leaf);
     free(owner);
