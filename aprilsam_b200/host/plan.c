@@ -39,7 +39,7 @@ void asam_dbg_plan_profile(double *out, int reset)
 
 #define RELAX_Z 2     /* relaxed amalgamation: missing block rows tolerated per merge */
 #define RELAX_FILL 24 /* ... and explicit zero blocks (3x3) added per merge */
-#define ASAM_TEAM_ROOM 140       /* CTAs that the team fronts of one tree level may claim together */
+#define ASAM_TEAM_ROOM 120       /* CTAs that the team fronts of one tree level may claim together */
 #define ASAM_BSLEAF_MAX 64       /* = ASAM_BSL_XS of k_backsolve_leaf: own columns / rows below */
 #define ASAM_BSLEAF_MIN_COUNT 4096 /* measured: no gain on M3500-sized trees (the kernel boundary eats it) */
 #define ASAM_LEAF_MAX_M 48       /* = ASAM_LEAF_M of k_factor_leaf */
@@ -521,10 +521,14 @@ static void build_schedule(plan_t *pl)
             if (G_of[s] > 1)
                 want[pl->desc[s].level] += G_of[s];
         }
+        int64_t room = ASAM_TEAM_ROOM;
+        const char *er = getenv("ASAM_TEAM_ROOM"); /* tuning knob (tools only) */
+        if (er && atoi(er) > 0)
+            room = atoi(er);
         for (int s = 0; s < nsn; s++) {
             int64_t w = want[pl->desc[s].level];
-            if (G_of[s] > 1 && w > ASAM_TEAM_ROOM) {
-                int g = (int) ((int64_t) G_of[s] * ASAM_TEAM_ROOM / w);
+            if (G_of[s] > 1 && w > room) {
+                int g = (int) ((int64_t) G_of[s] * room / w);
                 G_of[s] = g < 2 ? 2 : g;
             }
         }
