@@ -1469,7 +1469,7 @@ __device__ __forceinline__ double bs_dot(const double *lk, const double *xs, int
     return acc0;
 }
 
-__global__ void __launch_bounds__(128) k_backsolve(BsArgs a)
+__global__ void __launch_bounds__(256) k_backsolve(BsArgs a)
 {
     extern __shared__ __align__(16) double sm[]; // xf[m] | w[bw] | rd[bw] | staged L (panel or L11 of one block)
     __shared__ int s_task, s_abort;
