@@ -272,39 +272,31 @@ int *asam_ref_ordering_explicit(int N, const int *adj_ptr, const int *adj)
  * evaluated only when v is popped (the queue is lazy anyway), by marking.  A live element never
  * holds an eliminated pose (eliminating a member absorbs the element), nor does any A_v.
  * Work is O(sum |L|) per elimination / pop instead of O(d^2): 50 k-pose sparse graph 220 ms -> 20 ms. */
-typedef struct {
-    int *p;
-    int n, cap;
-} ilist_t;
-
-static inline void il_push(ilist_t *l, int x)
-{
-    if (l->n == l->cap) {
-        l->cap = l->cap ? 2 * l->cap : 8;
-        l->p = realloc(l->p, sizeof(int) * (size_t) l->cap);
-    }
-    l->p[l->n++] = x;
-}
-
+/* storage: A_v and E_v share the slot of deg0(v) ints that held v's original neighbour list (A_v
+ * from the front, E_v from the back: |A_v| + |E_v| <= deg0(v) always, because a pose enters an
+ * element only by losing a neighbour entry or an absorbed element); the member lists L_u come from a
+ * bump pool (sum |L_u| = number of block non-zeros of the factor).  No per-pose malloc. */
 int *asam_ref_ordering(int N, const int *adj_ptr, const int *adj)
 {
     int *order = calloc(N > 0 ? N : 1, sizeof(int));
     if (N <= 0)
         return order;
 
-    ilist_t *A = calloc((size_t) N, sizeof(ilist_t)); /* variable neighbours not covered by an element */
-    ilist_t *E = calloc((size_t) N, sizeof(ilist_t)); /* adjacent elements */
-    ilist_t *L = calloc((size_t) N, sizeof(ilist_t)); /* members of element u (valid while !dead[u]) */
-    char *dead = calloc((size_t) N, 1);
+    const int S2 = adj_ptr[N];
+    int *slot = malloc(sizeof(int) * (size_t) (S2 + 1));
+    memcpy(slot, adj, sizeof(int) * (size_t) S2);
+    int *an = malloc(sizeof(int) * (size_t) N);  /* |A_v| */
+    int *en = calloc((size_t) N, sizeof(int));   /* |E_v| */
     int *deg0 = malloc(sizeof(int) * (size_t) N);
-    for (int i = 0; i < N; i++) {
-        int d = adj_ptr[i + 1] - adj_ptr[i];
-        deg0[i] = d;
-        A[i].cap = d + 2;
-        A[i].p = malloc(sizeof(int) * (size_t) A[i].cap);
-        memcpy(A[i].p, adj + adj_ptr[i], sizeof(int) * (size_t) d);
-        A[i].n = d;
-    }
+    for (int i = 0; i < N; i++)
+        an[i] = deg0[i] = adj_ptr[i + 1] - adj_ptr[i];
+#define A_OF(v) (slot + adj_ptr[v])
+#define E_OF(v) (slot + adj_ptr[(v) + 1] - en[v]) /* en[v] entries ending at the slot's end */
+    int64_t lcap = 4 * (int64_t) S2 + 1024, ln = 0;
+    int *lpool = malloc(sizeof(int) * (size_t) lcap);
+    int64_t *loff = malloc(sizeof(int64_t) * (size_t) N); /* element u: lpool[loff[u] .. +llen[u]) */
+    int *llen = calloc((size_t) N, sizeof(int));
+    char *dead = calloc((size_t) N, 1);
 
     mdq_t q;
     memset(&q, 0, sizeof(q));
@@ -320,7 +312,7 @@ int *asam_ref_ordering(int N, const int *adj_ptr, const int *adj)
         enqueue_registered(&q, (unsigned) (deg0[last] + 2 * last), last);
         pinned[last] = 1;
         for (int i = 0; i < deg0[last]; i++) {
-            int c = A[last].p[i];
+            int c = A_OF(last)[i];
             for (int idx = c - 5; idx < c + 5; idx++) {
                 if (idx < 0 || idx > N - 1 || pinned[idx])
                     continue;
@@ -356,80 +348,92 @@ int *asam_ref_ordering(int N, const int *adj_ptr, const int *adj)
             int du = 0;
             token++;
             stamp[u] = token;
-            for (int i = 0; i < A[u].n; i++) {
-                int w = A[u].p[i];
+            const int *Au = A_OF(u);
+            for (int i = 0; i < an[u]; i++) {
+                int w = Au[i];
                 if (stamp[w] != token) {
                     stamp[w] = token;
                     du++;
                 }
             }
             {
-                int ne = 0;
-                for (int i = 0; i < E[u].n; i++) {
-                    int e = E[u].p[i];
+                /* E_u sits at the END of the slot: compact towards the end, keeping the order */
+                int *Eu = E_OF(u), ne = 0;
+                for (int i = en[u] - 1; i >= 0; i--) {
+                    int e = Eu[i];
                     if (dead[e])
                         continue;
-                    E[u].p[ne++] = e;
-                    for (int j = 0; j < L[e].n; j++) {
-                        int w = L[e].p[j];
+                    Eu[en[u] - 1 - ne] = e;
+                    ne++;
+                }
+                en[u] = ne;
+                Eu = E_OF(u);
+                for (int i = 0; i < ne; i++) {
+                    int e = Eu[i];
+                    const int *Le = lpool + loff[e];
+                    for (int j = 0; j < llen[e]; j++) {
+                        int w = Le[j];
                         if (stamp[w] != token) {
                             stamp[w] = token;
                             du++;
                         }
                     }
                 }
-                E[u].n = ne;
             }
             if ((float) du <= -v) {
                 order[k++] = u;
                 gone[u] = 1;
                 /* eliminate u: L_u = everything marked above (stamp == token) except u itself */
-                ilist_t *Lu = &L[u];
-                Lu->n = 0;
                 stamp[u] = -token; /* u itself is a member of every element in E_u: not of L_u */
-                if (Lu->cap < du) {
-                    Lu->cap = du;
-                    Lu->p = realloc(Lu->p, sizeof(int) * (size_t) (du > 0 ? du : 1));
+                if (ln + du > lcap) {
+                    while (ln + du > lcap)
+                        lcap *= 2;
+                    lpool = realloc(lpool, sizeof(int) * (size_t) lcap);
                 }
-                for (int i = 0; i < A[u].n; i++) {
-                    int w = A[u].p[i];
+                int *Lu = lpool + ln;
+                int nl = 0;
+                for (int i = 0; i < an[u]; i++) {
+                    int w = Au[i];
                     if (stamp[w] == token) { /* first visit collects, stamp flipped to avoid duplicates */
                         stamp[w] = -token;
-                        Lu->p[Lu->n++] = w;
+                        Lu[nl++] = w;
                     }
                 }
-                for (int i = 0; i < E[u].n; i++) {
-                    int e = E[u].p[i];
-                    for (int j = 0; j < L[e].n; j++) {
-                        int w = L[e].p[j];
+                const int *Eu = E_OF(u);
+                for (int i = 0; i < en[u]; i++) {
+                    int e = Eu[i];
+                    const int *Le = lpool + loff[e];
+                    for (int j = 0; j < llen[e]; j++) {
+                        int w = Le[j];
                         if (stamp[w] == token) {
                             stamp[w] = -token;
-                            Lu->p[Lu->n++] = w;
+                            Lu[nl++] = w;
                         }
                     }
                     dead[e] = 1; /* absorbed */
-                    free(L[e].p);
-                    L[e].p = NULL;
-                    L[e].n = L[e].cap = 0;
                 }
-                free(A[u].p);
-                A[u].p = NULL;
-                A[u].n = A[u].cap = 0;
-                free(E[u].p);
-                E[u].p = NULL;
-                E[u].n = E[u].cap = 0;
+                loff[u] = ln;
+                llen[u] = nl;
+                ln += nl;
+                an[u] = en[u] = 0;
                 /* members: drop neighbours now covered by the new element, swap absorbed elements for it */
-                for (int i = 0; i < Lu->n; i++) {
-                    int m = Lu->p[i], na = 0, ne = 0;
-                    for (int j = 0; j < A[m].n; j++)
-                        if (stamp[A[m].p[j]] != -token)
-                            A[m].p[na++] = A[m].p[j];
-                    A[m].n = na;
-                    for (int j = 0; j < E[m].n; j++)
-                        if (!dead[E[m].p[j]])
-                            E[m].p[ne++] = E[m].p[j];
-                    E[m].n = ne;
-                    il_push(&E[m], u);
+                for (int i = 0; i < nl; i++) {
+                    int m = Lu[i], na = 0;
+                    int *Am = A_OF(m);
+                    for (int j = 0; j < an[m]; j++)
+                        if (stamp[Am[j]] != -token)
+                            Am[na++] = Am[j];
+                    an[m] = na;
+                    int *Em = E_OF(m), ne = 0;
+                    for (int j = en[m] - 1; j >= 0; j--) {
+                        int e = Em[j];
+                        if (dead[e])
+                            continue;
+                        Em[en[m] - 1 - ne] = e;
+                        ne++;
+                    }
+                    en[m] = ne + 1;
+                    *E_OF(m) = u; /* one position further down: room is guaranteed (see above) */
                 }
             } else {
                 unsigned key = (unsigned) du;
@@ -450,23 +454,22 @@ int *asam_ref_ordering(int N, const int *adj_ptr, const int *adj)
             if (!gone[i])
                 order[k++] = i;
     }
-
-    for (int i = 0; i < N; i++) {
-        free(A[i].p);
-        free(E[i].p);
-        free(L[i].p);
-    }
+#undef A_OF
+#undef E_OF
     for (int i = 0; i < q.nb; i++)
         free(q.b[i].it);
     free(q.b);
     free(q.reg);
     free(q.hv);
     free(q.hb);
-    free(A);
-    free(E);
-    free(L);
-    free(dead);
+    free(slot);
+    free(an);
+    free(en);
     free(deg0);
+    free(lpool);
+    free(loff);
+    free(llen);
+    free(dead);
     free(gone);
     free(stamp);
     return order;
