@@ -21,8 +21,13 @@ JSON line (rank 0):
   roofline     dominant kernel k_factor: algorithmic bytes 8*nnz(A_upper)+16*nnz(L) per launch
                 / measured launch time, against MEASURED_PEAKS.json hbm_gbs
   cpu_baseline the reference's own CPU implementation (oracle/_ref) on this box, 1 thread
-Multi-GPU: M3500 and every incremental workload do not shard ("replicas
-only"): each rank solves its own replica, value = total solves of all ranks / max rank time.
+Multi-GPU (one process per GPU, torchrun): M3500 and every incremental workload do not shard
+("replicas only"): each rank solves its own replica, value = total solves of
+all ranks / max rank time, scaling "weak".  The 100 k batch workload (manhattan_batch) shards ONE
+solve over the GPUs: elimination-tree shards per rank, NCCL broadcast of the shard roots' update
+matrices and of the solution segments, the top of the tree replicated; every
+rank calls april_graph_cholesky on its copy of the graph, value = solves / max rank time, scaling
+"strong".  --shard on|off overrides.
 """
 from __future__ import annotations
 
