@@ -27,7 +27,7 @@ NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nv
 CC = os.environ.get("CC", "gcc")
 
 CUDA_SRCS = [os.path.join(PKG, "csrc", "asam_cuda.cu")]
-HOST_SRCS = [os.path.join(PKG, "host", f) for f in ("graph.c", "ordering.c", "plan.c", "solver.c", "serial.c", "debug.c")]
+HOST_SRCS = [os.path.join(PKG, "host", f) for f in ("graph.c", "ordering.c", "plan.c", "solver.c", "serial.c", "cliopt.c", "debug.c")]
 INCLUDES = ["-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "include", "aprilsam"),
             "-I" + os.path.join(PKG, "host")]
 
@@ -91,6 +91,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
         _run([CC, "-std=gnu99", "-O2", "-g", "-I" + os.path.join(ROOT, "include", "aprilsam"), "-o", REPLAY_CLI, csrc,
               "-L" + LIB_DIR, "-laprilsam_b200", "-Wl,-rpath," + LIB_DIR, "-Wl,-rpath,$ORIGIN/../../aprilsam_b200/lib",
               "-lm"], log)
+    # the reference's own example programs, UNCHANGED, linked against this library (drop-in proof, run by
+    # the GPU tests); only where the reference sources exist -- binaries only, git-ignored like oracle/_ref
+    ref_ex = "/root/reference/examples"
+    if os.path.isdir(ref_ex):
+        for name in ("aprilsam_tutorial", "aprilsam_demo", "aprilsam_graph_save_simple", "aprilsam_graph_save_with_attributes"):
+            src, out = os.path.join(ref_ex, name + ".c"), os.path.join(os.path.dirname(REPLAY_CLI), "ref_" + name)
+            if os.path.exists(src) and (force or _stale(out, [src, LIB] + hdrs)):
+                _run([CC, "-std=gnu99", "-O2", "-w", "-I" + os.path.join(ROOT, "include"), "-o", out, src, "-L" + LIB_DIR,
+                      "-laprilsam_b200", "-Wl,-rpath," + LIB_DIR, "-Wl,-rpath,$ORIGIN/../../aprilsam_b200/lib", "-lm"], log)
     # the oracle: C restatement always; the real reference only where its sources exist
     _run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "all"], log)
     with open(os.path.join(LIB_DIR, "build.log"), "w") as f:

@@ -588,9 +588,13 @@ ASAM_API int april_graph_save(april_graph_t *g, const char *path)
     return rc == 0;
 }
 
-/* NULL on failure; april_graph_stype_init() must have been called (april_graph.c:400-426) */
+/* NULL on failure (april_graph.c:400-426) */
 ASAM_API april_graph_t *april_graph_create_from_file(const char *path)
 {
+    /* the built-in graph / node / factor types are registered on first use: the reference's
+     * aprilsam_graph_save_simple.c forgets april_graph_stype_init() and dies in the reference's own
+     * decoder (stype.c:163); here it loads */
+    april_graph_stype_init();
     uint32_t len = 0, pos = 0;
     uint8_t *buf = read_whole(path, &len);
     if (!buf)

@@ -15,6 +15,7 @@
 #ifndef APRILSAM_B200_APRILSAM_H
 #define APRILSAM_B200_APRILSAM_H
 
+#include <stdbool.h> /* the reference's headers pull it in; its examples rely on that */
 #include <stdint.h>
 #include <stdlib.h>
 
@@ -39,6 +40,7 @@ typedef struct {
 } smatd_chol_t;
 
 void APRILSAM_VERSION(void); /* aprilsam.h:44 */
+int64_t utime_now(void);     /* common/time_util.h:45: microseconds since the epoch (the examples time with it) */
 
 /* ---- attributes (aprilsam.h:46-61): string -> (stype, value) table ---------------- */
 typedef struct april_graph_attr april_graph_attr_t;

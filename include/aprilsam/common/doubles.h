@@ -47,6 +47,12 @@ static inline void doubles_xyt_inv_mul(const double a[3], const double b[3], dou
 }
 
 /* wrap to [-pi, pi)  (reference: aprilsam/common/math_util.h:107-122) */
+/* degrees <-> radians (common/math_util.h:50-51; the tutorial uses them) */
+#ifndef to_radians
+#define to_radians(x) ((x) * (3.14159265358979323846 / 180.0))
+#define to_degrees(x) ((x) * (180.0 / 3.14159265358979323846))
+#endif
+
 static inline double mod2pi(double v)
 {
     const double twopi = 6.283185307179586476925287;

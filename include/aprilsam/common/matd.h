@@ -25,6 +25,7 @@ matd_t *matd_create_data(int rows, int cols, const double *data); /* row-major c
 matd_t *matd_identity(int dim);
 matd_t *matd_copy(const matd_t *m);
 void matd_destroy(matd_t *m);
+void matd_print(const matd_t *m, const char *fmt); /* common/matd.h:158 */
 
 #ifdef __cplusplus
 }

@@ -405,3 +405,45 @@ def test_replay_cli_text_and_graph_files(m3500, tmp_path):
         assert out.returncode == 0, out.stderr
         got = float(re.search(r"final chi2 ([0-9.eE+-]+)", out.stdout).group(1))
         assert abs(got - want) <= RTOL * max(1.0, want), (args, got, want)
+
+
+def test_reference_example_programs_unchanged_on_this_library(m3500, tmp_path):
+    """The reference's own aprilsam_tutorial.c / aprilsam_demo.c, compiled WITHOUT a source change against
+    include/ + libaprilsam_b200 (aprilsam_b200/build.py, binaries only): the tutorial prints what it prints
+    with the reference library (tests/golden/tutorial_stdout_*.txt, generated with oracle/_ref), the demo
+    replays a Manhattan text file to the chi2 of the harness-driven replay."""
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tut = os.path.join(root, "examples", "_build", "ref_aprilsam_tutorial")
+    demo = os.path.join(root, "examples", "_build", "ref_aprilsam_demo")
+    if not (os.path.exists(tut) and os.path.exists(demo)):
+        pytest.skip("reference examples were not built (no /root/reference at build time)")
+
+    def norm(text):
+        return [l.rstrip().replace("-0.00", "0.00") for l in text.splitlines()
+                if l.strip() and "running time" not in l and "APRILSAM" not in l and set(l.strip()) - set("=|")]
+
+    for args, gold in (([], "tutorial_stdout_inc.txt"), (["--batch_update_only"], "tutorial_stdout_batch.txt")):
+        out = subprocess.run([tut] + args, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-1000:]
+        want = norm(open(os.path.join(root, "tests", "golden", gold)).read())
+        got = norm(out.stdout)
+        assert got == want, "\n".join(f"{a!r} | {b!r}" for a, b in zip(got, want) if a != b)[:2000]
+
+    sub = m3500.head(200)
+    txt = str(tmp_path / "m200.txt")
+    with open(txt, "w") as f:
+        for i, p in enumerate(sub.init):
+            f.write("VERTEX2 %d %r %r %r\n" % (i, float(p[0]), float(p[1]), float(p[2])))
+        for a, b, z, W in zip(sub.ea, sub.eb, sub.ez, sub.eW):
+            f.write("EDGE2 %d %d " % (a, b) + " ".join(repr(float(v)) for v in (*z, W[0], W[1], W[4], W[8], W[2], W[5])) + "\n")
+    with H.Harness("b200") as h:
+        h.replay_begin(sub)
+        chi2, _, _ = h.replay_to(sub.n_nodes)
+    out = subprocess.run([demo, "--datapath", txt], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-1000:]
+    vals = [float(v) for v in re.findall(r"[Cc]hi[^0-9-]*([0-9.eE+-]+)", out.stdout)]
+    assert vals, out.stdout[-500:]
+    assert abs(vals[-1] - chi2[-1]) <= 1e-5 * max(1.0, chi2[-1]), (vals[-1], chi2[-1])

@@ -510,3 +510,27 @@ def test_graph_file_interchange_with_reference(m3500, tmp_path):
         # single-attribute objects are encoded identically; only the cookie counter and the order of
         # multi-attribute tables (hash order in the reference) may differ between the two files
         assert abs(os.path.getsize(ours) - os.path.getsize(theirs)) == 0
+
+
+def test_reference_examples_link_unchanged(built, tmp_path):
+    """the reference's four example programs compile and link against this library
+    without a source change (only where /root/reference is present); the two that do not solve anything
+    run here on the CPU, save + load included (the upstream simple example dies in the reference's own
+    decoder because it forgets april_graph_stype_init(); this library registers the built-in types itself)."""
+    exdir = "/root/reference/examples"
+    if not os.path.isdir(exdir):
+        pytest.skip("reference sources not present")
+    libdir = os.path.join(ROOT, "aprilsam_b200", "lib")
+    names = ["aprilsam_graph_save_simple", "aprilsam_graph_save_with_attributes", "aprilsam_tutorial", "aprilsam_demo"]
+    for n in names:
+        r = subprocess.run(["gcc", "-std=gnu99", "-I" + os.path.join(ROOT, "include"), "-o", str(tmp_path / n),
+                            os.path.join(exdir, n + ".c"), "-L" + libdir, "-laprilsam_b200", "-Wl,-rpath," + libdir, "-lm"],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, (n, r.stderr[-2000:])
+    for n in names[:2]:
+        r = subprocess.run([str(tmp_path / n), "--path", str(tmp_path / (n + ".graph"))], capture_output=True, text=True, timeout=60)
+        assert r.returncode == 0, (n, r.stdout[-500:], r.stderr[-500:])
+        out = r.stdout
+        a, b = out.split("Load graph")
+        assert [l for l in a.splitlines() if l.startswith("node_")] == [l for l in b.splitlines() if l.startswith("node_")]
+    assert "Graph name: AprilSAM-Graph" in out and out.count("factor type: geopin") == 2
