@@ -294,18 +294,13 @@ static void emit_segment(plan_t *pl, int s, ivec_t *buf, int64_t base)
     d->a_cnt = h->a_slot.n;
     int need = buf->n + 2 * h->rows.n + h->children.n + 3 * h->a_slot.n;
     ivec_reserve(buf, need);
-    memcpy(buf->p + buf->n, h->rows.p, sizeof(int) * h->rows.n);
-    buf->n += h->rows.n;
-    memcpy(buf->p + buf->n, h->rel.p, sizeof(int) * h->rows.n);
-    buf->n += h->rows.n;
-    memcpy(buf->p + buf->n, h->children.p, sizeof(int) * h->children.n);
-    buf->n += h->children.n;
-    memcpy(buf->p + buf->n, h->a_slot.p, sizeof(int) * h->a_slot.n);
-    buf->n += h->a_slot.n;
-    memcpy(buf->p + buf->n, h->a_rb.p, sizeof(int) * h->a_slot.n);
-    buf->n += h->a_slot.n;
-    memcpy(buf->p + buf->n, h->a_cb.p, sizeof(int) * h->a_slot.n);
-    buf->n += h->a_slot.n;
+    const ivec_t *parts[6] = { &h->rows, &h->rel, &h->children, &h->a_slot, &h->a_rb, &h->a_cb };
+    const int lens[6] = { h->rows.n, h->rows.n, h->children.n, h->a_slot.n, h->a_slot.n, h->a_slot.n };
+    for (int i = 0; i < 6; i++) {
+        if (lens[i] > 0) /* (an empty list may have no storage at all) */
+            memcpy(buf->p + buf->n, parts[i]->p, sizeof(int) * (size_t) lens[i]);
+        buf->n += lens[i];
+    }
 }
 
 /* CTAs that share one front in k_factor: fronts that fit in shared memory (200 KB) take one.

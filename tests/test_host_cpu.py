@@ -534,3 +534,22 @@ def test_reference_examples_link_unchanged(built, tmp_path):
         a, b = out.split("Load graph")
         assert [l for l in a.splitlines() if l.startswith("node_")] == [l for l in b.splitlines() if l.startswith("node_")]
     assert "Graph name: AprilSAM-Graph" in out and out.count("factor type: geopin") == 2
+
+
+def test_host_plan_under_sanitizers(tmp_path):
+    """plan.c + ordering.c under AddressSanitizer / UBSan / LeakSanitizer: batch plan (leaf set, merged chains, team sizes),
+    the schedules of 3 and 8 ranks, and 40 incremental appends on top of a batch plan."""
+    csan = os.path.join(ROOT, "tests", "support", "csan")
+    exe = str(tmp_path / "plan_san")
+    inc = ["-I" + os.path.join(ROOT, p) for p in ("include", "include/aprilsam", "aprilsam_b200/host")]
+    r = subprocess.run(["gcc", "-g", "-O1", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-std=gnu11"] + inc +
+                       ["-o", exe, os.path.join(csan, "plan_driver.c"), os.path.join(csan, "device_stubs.c"),
+                        os.path.join(ROOT, "aprilsam_b200", "host", "plan.c"), os.path.join(ROOT, "aprilsam_b200", "host", "ordering.c"), "-lm"],
+                       capture_output=True, text=True)
+    if r.returncode != 0 and "sanitize" in r.stderr:
+        pytest.skip("no sanitizer runtime in this toolchain")
+    assert r.returncode == 0, r.stderr[-2000:]
+    for args in (["3000", "1"], ["20000", "1"], ["20000", "3"], ["30000", "8"]):
+        r = subprocess.run([exe] + args, capture_output=True, text=True, timeout=600, env=dict(os.environ, ASAN_OPTIONS="detect_leaks=1"))
+        assert r.returncode == 0 and "ERROR" not in r.stderr and "runtime error" not in r.stderr, (args, r.stderr[-1500:])
+        assert "rank 0/" in r.stdout
