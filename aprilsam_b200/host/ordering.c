@@ -24,9 +24,10 @@
 
 #include "asam_host.h"
 
+/* FIFO bucket: a singly linked list of items drawn from one pool shared by all buckets (no per-bucket
+ * allocation: a replay re-orders the graph at every batch escalation, thousands of buckets each time) */
 typedef struct {
-    int *it;
-    int head, n, cap;
+    int head, tail, n; /* indices into the item pool, -1 = none */
 } bucket_t;
 
 typedef struct {
@@ -37,6 +38,8 @@ typedef struct {
     float *hv; /* heap values */
     int *hb;   /* heap payload: bucket index */
     int hn, hcap;
+    int *inode, *inext; /* item pool */
+    int ni, icap;
 } mdq_t;
 
 static void heap_push(mdq_t *q, int bucket, float v)
@@ -93,19 +96,40 @@ static int bucket_new(mdq_t *q)
         q->b = realloc(q->b, sizeof(bucket_t) * q->capb);
     }
     bucket_t *b = &q->b[q->nb];
-    memset(b, 0, sizeof(*b));
+    b->head = b->tail = -1;
+    b->n = 0;
     return q->nb++;
 }
 
 static void bucket_push(mdq_t *q, int bi, int node)
 {
-    bucket_t *b = &q->b[bi];
-    if (b->head + b->n == b->cap) {
-        b->cap = b->cap ? 2 * b->cap : 4;
-        b->it = realloc(b->it, sizeof(int) * b->cap);
+    if (q->ni == q->icap) {
+        q->icap = q->icap ? 2 * q->icap : 1024;
+        q->inode = realloc(q->inode, sizeof(int) * (size_t) q->icap);
+        q->inext = realloc(q->inext, sizeof(int) * (size_t) q->icap);
     }
-    b->it[b->head + b->n] = node;
+    const int it = q->ni++;
+    q->inode[it] = node;
+    q->inext[it] = -1;
+    bucket_t *b = &q->b[bi];
+    if (b->tail >= 0)
+        q->inext[b->tail] = it;
+    else
+        b->head = it;
+    b->tail = it;
     b->n++;
+}
+
+/* pop the oldest item of a non-empty bucket */
+static inline int bucket_pop(mdq_t *q, int bi)
+{
+    bucket_t *b = &q->b[bi];
+    const int it = b->head;
+    b->head = q->inext[it];
+    if (b->head < 0)
+        b->tail = -1;
+    b->n--;
+    return q->inode[it];
 }
 
 /* enqueue into the registered bucket of `key`, creating + registering it on first use */
@@ -191,10 +215,7 @@ int *asam_ref_ordering_explicit(int N, const int *adj_ptr, const int *adj)
     float v;
     while (heap_pop(&q, &bi, &v)) {
         while (q.b[bi].n > 0) {
-            bucket_t *b = &q.b[bi];
-            int u = b->it[b->head];
-            b->head++;
-            b->n--;
+            int u = bucket_pop(&q, bi);
             if (gone[u])
                 continue;
             if ((float) deg[u] <= -v) {
@@ -249,8 +270,8 @@ int *asam_ref_ordering_explicit(int N, const int *adj_ptr, const int *adj)
 
     for (int i = 0; i < N; i++)
         free(nbr[i]);
-    for (int i = 0; i < q.nb; i++)
-        free(q.b[i].it);
+    free(q.inode);
+    free(q.inext);
     free(q.b);
     free(q.reg);
     free(q.hv);
@@ -338,10 +359,7 @@ int *asam_ref_ordering(int N, const int *adj_ptr, const int *adj)
     float v;
     while (heap_pop(&q, &bi, &v)) {
         while (q.b[bi].n > 0) {
-            bucket_t *b = &q.b[bi];
-            int u = b->it[b->head];
-            b->head++;
-            b->n--;
+            int u = bucket_pop(&q, bi);
             if (gone[u])
                 continue;
             /* exact degree of u now; its element list is compacted on the way */
@@ -456,8 +474,8 @@ int *asam_ref_ordering(int N, const int *adj_ptr, const int *adj)
     }
 #undef A_OF
 #undef E_OF
-    for (int i = 0; i < q.nb; i++)
-        free(q.b[i].it);
+    free(q.inode);
+    free(q.inext);
     free(q.b);
     free(q.reg);
     free(q.hv);
