@@ -42,3 +42,31 @@ def test_two_rank_gloo_aggregation():
     for rank, slowest, rate in res:
         assert slowest == 2.0
         assert rate == 10.0
+
+
+def test_reference_arm_json_contract():
+    """`bench.py --impl reference` (the unmodified reference on host cores) prints ONE JSON line with the keys of
+    the bench contract; the b200 arm refuses to run without a CUDA device (no CPU fallback)."""
+    import json
+    import subprocess
+    sys.path.insert(0, ROOT)
+    from aprilsam_b200 import harness as H
+    if not H.available("reference"):
+        pytest.skip("reference oracle not built")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-1000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
+        assert k in j, k
+    assert j["impl"] == "reference" and j["dtype"] == "f64" and j["unit"] == "solves/s" and j["steps"] == 2
+    assert j["cpu_baseline"]["kind"] == "reference" and j["cpu_baseline"]["cores"] == 1
+    assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0
+    assert 5 < j["value"] < 500 and abs(j["value"] - j["e2e"]["value"]) < 1e-9
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "2"], capture_output=True, text=True, timeout=300)
+        assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
