@@ -53,6 +53,9 @@ def lib() -> C.CDLL:
     L.asam_comm_destroy.restype = None
     L.asam_comm_info.argtypes = [_ip, _ip, _ip]
     L.asam_comm_set_sharding.argtypes = [C.c_int]
+    L.asam_measure_fp64_peak.argtypes = [C.c_void_p, _dp]
+    L.asam_dbg_profile.argtypes = [_dp, C.c_int]
+    L.asam_dbg_profile.restype = None
     _lib = L
     return L
 

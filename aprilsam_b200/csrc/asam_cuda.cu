@@ -282,6 +282,10 @@ static int download(asam_dev *d, void *dst, const void *src, size_t bytes)
 
 #include "asam_kernels.cuh"
 
+// wall-clock bound of every inter-CTA wait (see SpinClock): 20 s -- far above any real solve, far below
+// the limits of the job schedulers around us
+#define ASAM_SPIN_LIMIT_NS 20000000000LL
+
 struct Pending {
     int kind; // 0 linearize, 1 factor, 2 backsolve
     int grid;
@@ -754,7 +758,7 @@ static int launch_factor(asam_dev *d, int ntasks, const int *tasks_dev, const in
     a.ntasks = ntasks;
     a.ctrl = (int *) d->ctrl.p;
     a.smem_doubles = d->fac_smem / (int) sizeof(double);
-    a.spin_limit = 4000000LL; // a few seconds; a dependency bug must not hang the GPU
+    a.spin_limit = ASAM_SPIN_LIMIT_NS;
     a.trace = nullptr;
     if (d->trace_on) {
         if (buf_reserve(d, d->trace_fac, (size_t) ntasks * 8 * sizeof(unsigned long long), false, false))
@@ -792,7 +796,7 @@ static int launch_backsolve(asam_dev *d, int ntasks, const int *btasks_dev, int 
     a.ctrl = (int *) d->ctrl.p;
     a.epoch = d->epoch;
     a.smem_doubles = d->bs_smem / (int) sizeof(double);
-    a.spin_limit = 4000000LL;
+    a.spin_limit = ASAM_SPIN_LIMIT_NS;
     a.trace = nullptr;
     if (d->trace_on) {
         if (buf_reserve(d, d->trace_bs, (size_t) ntasks * 8 * sizeof(unsigned long long), false, false))
@@ -1304,6 +1308,54 @@ ASAM_EXPORT int asam_l2_flush(asam_dev_t *d)
         return 1;
     d->flush_val ^= 0x5a;
     CK(cudaMemsetAsync(d->flush.p, d->flush_val, bytes, d->stream));
+    return 0;
+}
+
+// FP64 peak of this device, measured: a register-resident DFMA loop (8 independent chains per thread,
+// 512 threads per SM) timed with CUDA events on the library's stream.  MEASURED_PEAKS.json carries HBM
+// and bf16 figures only; the factorisation's second roofline is the FP64 pipe.
+__global__ void k_fp64_peak(double *out, int iters)
+{
+    double a[8], b = 1.000001, c = 0.5;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        a[i] = threadIdx.x + i;
+    for (int it = 0; it < iters; it++)
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            a[i] = fma(a[i], b, c);
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        s += a[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+ASAM_EXPORT int asam_measure_fp64_peak(asam_dev_t *d, double *tflops_out)
+{
+    CK(cudaSetDevice(d->device));
+    *tflops_out = 0.0;
+    const int threads = 512, iters = 20000;
+    if (buf_reserve(d, d->partial, (size_t) d->n_sm * threads * sizeof(double), false, false) || flush_uploads(d))
+        return 1;
+    if (!d->tev[0]) {
+        CK(cudaEventCreate(&d->tev[0]));
+        CK(cudaEventCreate(&d->tev[1]));
+    }
+    double best = 0.0;
+    for (int rep = 0; rep < 4; rep++) { // first repetition = warm-up
+        CK(cudaEventRecord(d->tev[0], d->stream));
+        k_fp64_peak<<<d->n_sm, threads, 0, d->stream>>>((double *) d->partial.p, iters);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(d->tev[1], d->stream));
+        CK(cudaEventSynchronize(d->tev[1]));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, d->tev[0], d->tev[1]));
+        const double tf = 2.0 * 8 * iters * (double) threads * d->n_sm / (ms * 1e-3) * 1e-12;
+        if (rep > 0 && tf > best)
+            best = tf;
+    }
+    *tflops_out = best;
     return 0;
 }
 

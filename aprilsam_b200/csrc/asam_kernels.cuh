@@ -109,6 +109,26 @@ __device__ __forceinline__ unsigned long long d_now()
     return t;
 }
 
+// Bounded spin: every wait on a counter/flag written by another CTA gives up after `limit_ns` of WALL
+// time (globaltimer, sampled every 1024 polls), flags the error word and lets the launch drain -- a
+// dependency bug must not hang the GPU, and a legitimately long factorisation (the root waits for the
+// whole tree) must not be cut short by a poll count.
+struct SpinClock {
+    long long n = 0;
+    unsigned long long t0 = 0;
+};
+__device__ __forceinline__ bool spin_over(SpinClock &c, long long limit_ns)
+{
+    if ((++c.n & 1023) != 0)
+        return false;
+    const unsigned long long now = d_now();
+    if (c.t0 == 0) {
+        c.t0 = now;
+        return false;
+    }
+    return (long long) (now - c.t0) > limit_ns;
+}
+
 // k_linearize aggregates the per-node contributions inside the warp before touching HBM: lanes
 // whose destination node matches (__match_any_sync) are summed with shuffles and only the lowest
 // such lane issues the atomics.  Factors are listed by (max node id, min node id), so the closures
@@ -441,11 +461,11 @@ __device__ __forceinline__ bool team_barrier(TeamCtx &tc, int *s_flag)
         __threadfence();
         atomicAdd(tc.tbar_s, 1);
         const int target = (++tc.phase) * tc.G;
-        long long spins = 0;
+        SpinClock spins;
         int ok = 1;
         while (ld_volatile(tc.tbar_s) < target) {
             __nanosleep(20);
-            if (++spins > tc.spin_limit || ld_volatile(tc.err) < 0) {
+            if (spin_over(spins, tc.spin_limit) || ld_volatile(tc.err) < 0) {
                 atomicCAS(tc.err, 0, -(1 + tc.sn));
                 ok = 0;
                 break;
@@ -626,11 +646,11 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
     // every worker waits for the children re-factored in this launch (the counter is zeroed by
     // worker 0 after the first team barrier, when nobody looks at it any more)
     if (nw > 0 && tid == 0) {
-        long long spins = 0;
+        SpinClock spins;
         int ok = 1;
         while (ld_volatile(&a.arrive[s]) < nw) {
             __nanosleep(20);
-            if (++spins > a.spin_limit || ld_volatile(err) < 0) {
+            if (spin_over(spins, a.spin_limit) || ld_volatile(err) < 0) {
                 atomicCAS(err, 0, -(1 + s));
                 ok = 0;
                 break;
@@ -840,11 +860,11 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
             for (int j = 0; j < pb; j++)
                 Li[tid + j * ASAM_TROWS] = __ldcg(&F[i + (size_t) (k0 + j) * ld]);
         if (tid == 0) {
-            long long spins = 0;
+            SpinClock spins;
             int ok = 1;
             while (ld_volatile(crew_bar) < seq) {
                 __nanosleep(20);
-                if (++spins > a.spin_limit || ld_volatile(err) < 0) {
+                if (spin_over(spins, a.spin_limit) || ld_volatile(err) < 0) {
                     atomicCAS(err, 0, -(1 + s));
                     ok = 0;
                     break;
@@ -1069,10 +1089,10 @@ __global__ void __launch_bounds__(256, 1) k_factor(FacArgs a)
 
         // ---- 2. wait for the children that are being re-factored in this launch ---------
         if (nw > 0 && tid == 0) {
-            long long spins = 0;
+            SpinClock spins;
             while (ld_volatile(&a.arrive[s]) < nw) {
                 __nanosleep(32);
-                if (++spins > a.spin_limit || ld_volatile(err) < 0) {
+                if (spin_over(spins, a.spin_limit) || ld_volatile(err) < 0) {
                     atomicCAS(err, 0, -(1 + s));
                     s_abort = 1;
                     break;
@@ -1313,10 +1333,10 @@ __global__ void __launch_bounds__(32 * ASAM_LEAF_WARPS, 1) k_factor_leaf(LeafArg
         int abort_ = 0;
         if (d.ch_cnt > 0) {
             if (lane == 0) {
-                long long spins = 0;
+                SpinClock spins;
                 while (ld_volatile(&a.arrive[s]) < d.ch_cnt) {
                     __nanosleep(20);
-                    if (++spins > a.spin_limit || ld_volatile(err) < 0) {
+                    if (spin_over(spins, a.spin_limit) || ld_volatile(err) < 0) {
                         atomicCAS(err, 0, -(1 + s));
                         abort_ = 1;
                         break;
@@ -1536,10 +1556,10 @@ __global__ void __launch_bounds__(256) k_backsolve(BsArgs a)
                 if (a.trace && tid == 0)
                     tr1 = d_now();
                 if (d.parent >= 0 && tid == 0) {
-                    long long spins = 0;
+                    SpinClock spins;
                     while (ld_volatile(&a.xdone[d.parent]) != a.epoch) {
                         __nanosleep(20);
-                        if (++spins > a.spin_limit || ld_volatile(err) < 0) {
+                        if (spin_over(spins, a.spin_limit) || ld_volatile(err) < 0) {
                             atomicCAS(err, 0, -(1 + s));
                             s_abort = 1;
                             break;
@@ -1671,10 +1691,10 @@ __global__ void __launch_bounds__(32 * ASAM_BSL_WARPS) k_backsolve_leaf(BsArgs a
         int abort_ = 0;
         if (d.parent >= 0) {
             if (lane == 0) {
-                long long spins = 0;
+                SpinClock spins;
                 while (ld_volatile(&a.xdone[d.parent]) != a.epoch) {
                     __nanosleep(20);
-                    if (++spins > a.spin_limit || ld_volatile(err) < 0) {
+                    if (spin_over(spins, a.spin_limit) || ld_volatile(err) < 0) {
                         atomicCAS(err, 0, -(1 + s));
                         abort_ = 1;
                         break;

@@ -87,6 +87,12 @@ def _load(impl: str) -> C.CDLL:
     lib.h_attr_get.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p]
     lib.h_attr_get.restype = C.c_void_p
     lib.h_factor.argtypes = [C.c_void_p, C.c_int, _dp]
+    lib.h_set_factor.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
+    lib.h_replace_xyt.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, _dp]
+    lib.h_invalidate_plan.argtypes = [C.c_void_p]
+    lib.h_set_policy_ratio.argtypes = [C.c_void_p, C.c_double]
+    lib.h_set_show_timing.argtypes = [C.c_void_p, C.c_int]
+    lib.h_inc_solver.argtypes = [C.c_void_p]
     _LIBS[impl] = lib
     return lib
 
@@ -207,6 +213,28 @@ class Harness:
         t = self.lib.h_factor(self.h, idx, _d(out))
         return t, int(out[0]), int(out[1]), out[2:5].copy(), out[5:14].copy()
 
+    def set_factor(self, idx: int, z, W) -> None:
+        """Overwrite z / W of factor idx in place (the caller-side edit the reference honours on the next batch call)."""
+        z = np.ascontiguousarray(z, dtype=np.float64)
+        W = np.ascontiguousarray(W, dtype=np.float64).reshape(9)
+        self.lib.h_set_factor(self.h, idx, _d(z), _d(W))
+
+    def replace_xyt(self, idx: int, a: int, b: int, z, W) -> None:
+        z = np.ascontiguousarray(z, dtype=np.float64)
+        W = np.ascontiguousarray(W, dtype=np.float64).reshape(9)
+        self.lib.h_replace_xyt(self.h, idx, a, b, _d(z), _d(W))
+
+    def invalidate_plan(self) -> None:
+        """aprilsam_b200 extension: the next batch call orders + analyses again (no-op for the reference)."""
+        self.lib.h_invalidate_plan(self.h)
+
+    def set_policy_ratio(self, ratio: float) -> None:
+        """aprilsam_b200 extension: deterministic escalation policy (no-op for the reference)."""
+        self.lib.h_set_policy_ratio(self.h, ratio)
+
+    def set_show_timing(self, on: bool) -> None:
+        self.lib.h_set_show_timing(self.h, int(on))
+
     # -- state access ------------------------------------------------------------------
     @property
     def n_nodes(self) -> int:
@@ -251,6 +279,10 @@ class Harness:
 
     def chi2(self) -> float:
         return self.lib.h_chi2(self.h)
+
+    def inc_solver(self) -> None:
+        """april_graph_cholesky_inc_solver(graph, param, NULL)."""
+        self.lib.h_inc_solver(self.h)
 
     def info(self) -> dict:
         a = np.zeros(8, dtype=np.int32)

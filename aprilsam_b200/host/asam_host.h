@@ -108,6 +108,7 @@ typedef struct {
     /* multi-GPU sharding (world > 1): tasks / leaf_tasks / btasks then cover this rank's shards
      * (+ the top in btasks); see build_schedule() in plan.c */
     int world, rank;
+    int max_team;   /* largest CTA team k_factor can seat (resident CTAs of the device; 0 = default) */
     int *top_tasks, *top_nwait;
     int n_top, n_top_sn;
     int n_shards;
@@ -142,6 +143,12 @@ int plan_build_with_order(plan_t *pl, asam_dev_t *dev, int N, int n_factors, con
  * Returns 0 ok, 1 error, 2 = not an append-only update (caller falls back). */
 int plan_append(plan_t *pl, asam_dev_t *dev, int N, int n_factors, const int *ftype, const int *fa, const int *fb,
                 const int *marked_old, int n_marked, int **tasks_out, int **nwait_out, int *ntasks_out);
+
+/* Modelled cost (columns x rows^2 + a latency term per front, the measure build_schedule balances
+ * shards with) of re-factoring the distinct supernodes in tasks[0..ntasks) and of factoring every
+ * supernode of the plan; feeds the escalation policy hook (aprilsam.h). */
+void plan_work(const plan_t *pl, const int *tasks, int ntasks, double *step_work, int *step_fronts, double *batch_work,
+               int *batch_fronts);
 
 /* ---- solver context (solver.c) --------------------------------------------------------- */
 void asam_graph_forget(april_graph_t *g);

@@ -314,7 +314,7 @@ static int front_fits_smem(int mb)
     return (m + 1) * m + (m + 2) / 2 + 2 <= 25600;
 }
 
-static int team_size(int mb, int cb)
+static int team_size(int mb, int cb, int cap)
 {
     int64_t m = 3 * (int64_t) mb, c = 3 * (int64_t) cb;
     if (front_fits_smem(mb))
@@ -324,14 +324,29 @@ static int team_size(int mb, int cb)
         tiles += (m - cb0 + 1 + 255) / 256;
     int64_t chunks = 1 + (m - j0 + 1 + 255) / 256; /* look-ahead crew: the diagonal block + the row chunks */
     int G = (int) (tiles + chunks); /* the look-ahead crew (one CTA per chunk) takes no tiles */
+    /* every worker of a team must be resident at the same time (spin barriers in a persistent,
+     * non-cooperative launch): never more workers than the device seats CTAs of k_factor */
+    if (cap < 2)
+        cap = 2;
+    if (cap > 120)
+        cap = 120;
     if (G < 2)
         G = 2;
-    if (G > 120)
-        G = 120;
+    if (G > cap)
+        G = cap;
     return G;
 }
 
-static inline int pack_nwait(int nw, int w, int G) { return (nw & 0xffff) | (w << 16) | (G << 24); }
+/* nwait word of a task: bits 0-15 children to wait for, 16-23 worker index, 24-30 team size */
+static inline int pack_nwait(int nw, int w, int G)
+{
+    if (nw < 0 || nw > 0xffff || w < 0 || w > 0xff || G < 0 || G > 0x7f)
+        asam_fatal("plan: task word overflow (%d children in one launch, worker %d of %d): hub supernodes with more "
+                   "than 65535 re-factored children are not supported", nw, w, G);
+    return (nw & 0xffff) | (w << 16) | (G << 24);
+}
+
+static int plan_team_cap(const plan_t *pl) { return pl->max_team > 0 ? pl->max_team : 120; }
 
 static int64_t front_doubles(int mb)
 {
@@ -354,6 +369,26 @@ static double sn_work(const asam_sn_desc_t *d)
 {
     double m = 3.0 * d->mb, c = 3.0 * d->cb;
     return c * m * m + 3.0e4; /* flops + a per-front latency floor */
+}
+
+void plan_work(const plan_t *pl, const int *tasks, int ntasks, double *step_work, int *step_fronts, double *batch_work,
+               int *batch_fronts)
+{
+    double sw = 0.0, bw = 0.0;
+    int sf = 0, last = -1;
+    for (int t = 0; t < ntasks; t++) { /* the workers of a team are consecutive entries of one supernode */
+        if (tasks[t] == last)
+            continue;
+        last = tasks[t];
+        sw += sn_work(&pl->desc[last]);
+        sf++;
+    }
+    for (int s = 0; s < pl->nsn; s++)
+        bw += sn_work(&pl->desc[s]);
+    *step_work = sw;
+    *step_fronts = sf;
+    *batch_work = bw;
+    *batch_fronts = pl->nsn;
 }
 
 static void build_schedule(plan_t *pl)
@@ -512,11 +547,11 @@ static void build_schedule(plan_t *pl)
     {
         int64_t *want = calloc((size_t) pl->n_levels + 1, sizeof(int64_t));
         for (int s = 0; s < nsn; s++) {
-            G_of[s] = (owner[s] == me || owner[s] == -1) && !leaf[s] ? team_size(pl->desc[s].mb, pl->desc[s].cb) : 1;
+            G_of[s] = (owner[s] == me || owner[s] == -1) && !leaf[s] ? team_size(pl->desc[s].mb, pl->desc[s].cb, plan_team_cap(pl)) : 1;
             if (G_of[s] > 1)
                 want[pl->desc[s].level] += G_of[s];
         }
-        int64_t room = ASAM_TEAM_ROOM;
+        int64_t room = ASAM_TEAM_ROOM < plan_team_cap(pl) ? ASAM_TEAM_ROOM : plan_team_cap(pl);
         const char *er = getenv("ASAM_TEAM_ROOM"); /* tuning knob (tools only) */
         if (er && atoi(er) > 0)
             room = atoi(er);
@@ -608,11 +643,17 @@ static int plan_build_impl(plan_t *pl, asam_dev_t *dev, int N, int n_factors, co
                            const int *fb, const int *order_keep, int N_keep)
 {
     uint64_t keep_hash = pl->struct_hash;
-    int keep_world = pl->world, keep_rank = pl->rank;
+    int keep_world = pl->world, keep_rank = pl->rank, keep_team = pl->max_team;
     plan_free(pl);
     pl->struct_hash = keep_hash;
     pl->world = keep_world;
     pl->rank = keep_rank;
+    pl->max_team = keep_team;
+    if (dev) { /* teams are sized for the CTAs this device actually seats (MIG slice, smaller part, ...) */
+        int n_sm = 0, fac_grid = 0, fac_smem = 0, bs_grid = 0;
+        if (asam_device_info(dev, &n_sm, &fac_grid, &fac_smem, &bs_grid) == 0 && fac_grid > 0)
+            pl->max_team = fac_grid < 120 ? fac_grid : 120;
+    }
     if (N <= 0)
         return 0;
     node_arrays_reserve(pl, N);
@@ -1253,7 +1294,7 @@ int plan_append(plan_t *pl, asam_dev_t *dev, int N, int n_factors, const int *ft
             for (int c = 0; c < pl->snh[s].children.n; c++)
                 if (mark_idx[pl->snh[s].children.p[c]] >= 0)
                     w++;
-            nwait[t] = w;
+            nwait[t] = pack_nwait(w, 0, 0);
             emit_segment(pl, s, &seg, pl->ipool_n);
         }
         if (!rc) {
@@ -1309,12 +1350,12 @@ int plan_append(plan_t *pl, asam_dev_t *dev, int N, int n_factors, const int *ft
             /* expand big fronts into teams of consecutive entries */
             int total = 0;
             for (int t = 0; t < nt; t++)
-                total += team_size(pl->desc[tasks[t]].mb, pl->desc[tasks[t]].cb);
+                total += team_size(pl->desc[tasks[t]].mb, pl->desc[tasks[t]].cb, plan_team_cap(pl));
             if (total != nt) {
                 int *t2 = malloc(sizeof(int) * (size_t) total), *w2 = malloc(sizeof(int) * (size_t) total);
                 int k = 0;
                 for (int t = 0; t < nt; t++) {
-                    int G = team_size(pl->desc[tasks[t]].mb, pl->desc[tasks[t]].cb);
+                    int G = team_size(pl->desc[tasks[t]].mb, pl->desc[tasks[t]].cb, plan_team_cap(pl));
                     for (int w = 0; w < G; w++, k++) {
                         t2[k] = tasks[t];
                         w2[k] = pack_nwait(nwait[t], w, G > 1 ? G : 0);

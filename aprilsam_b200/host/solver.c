@@ -17,7 +17,9 @@
  *   - a factor added between two already-solved poses is handled exactly (full symbolic
  *     rebuild, no relinearisation) where the reference corrupts its tree (aprilsam.c:925-941).
  */
+#include <limits.h>
 #include <math.h>
+#include <pthread.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -118,38 +120,54 @@ typedef struct gctx {
     int refs;
     int nf_dev; /* factors mirrored in HBM */
     int *ftype, *fa, *fb;
+    double *zw; /* host mirror of what HBM holds: 12 doubles per factor (z[3], W[9]) */
     int fcap;
     double *stage; /* host staging for poses */
     int stage_cap;
     struct gctx *next;
 } gctx_t;
 
+/* The registry is the only state shared between graphs: two threads may solve two different graphs
+ * concurrently (as with the reference, whose solver state lives in graph + param), so lookups,
+ * inserts and removals are serialised.  One graph is still one caller thread at a time. */
 static gctx_t *g_ctx_list = NULL;
+static pthread_mutex_t g_ctx_lock = PTHREAD_MUTEX_INITIALIZER;
 
 static gctx_t *gctx_get(april_graph_t *g)
 {
+    pthread_mutex_lock(&g_ctx_lock);
     for (gctx_t *c = g_ctx_list; c; c = c->next)
-        if (c->graph == g)
+        if (c->graph == g) {
+            pthread_mutex_unlock(&g_ctx_lock);
             return c;
+        }
+    pthread_mutex_unlock(&g_ctx_lock);
     gctx_t *c = calloc(1, sizeof(*c));
     c->graph = g;
     if (asam_dev_create(&c->dev) != 0)
         asam_fatal("no usable CUDA device (%s); aprilsam_b200 has no CPU path", asam_last_error());
     c->refs = 1; /* the registry */
+    pthread_mutex_lock(&g_ctx_lock);
     c->next = g_ctx_list;
     g_ctx_list = c;
+    pthread_mutex_unlock(&g_ctx_lock);
     return c;
 }
 
 static void gctx_unref(gctx_t *c)
 {
-    if (--c->refs > 0)
+    pthread_mutex_lock(&g_ctx_lock);
+    if (--c->refs > 0) {
+        pthread_mutex_unlock(&g_ctx_lock);
         return;
+    }
     for (gctx_t **pp = &g_ctx_list; *pp; pp = &(*pp)->next)
         if (*pp == c) {
             *pp = c->next;
             break;
         }
+    pthread_mutex_unlock(&g_ctx_lock);
+    free(c->zw);
     asam_dev_destroy(c->dev);
     free(c->ftype);
     free(c->fa);
@@ -160,12 +178,17 @@ static void gctx_unref(gctx_t *c)
 
 void asam_graph_forget(april_graph_t *g)
 {
+    pthread_mutex_lock(&g_ctx_lock);
+    gctx_t *hit = NULL;
     for (gctx_t *c = g_ctx_list; c; c = c->next)
         if (c->graph == g) {
             c->graph = NULL;
-            gctx_unref(c);
-            return;
+            hit = c;
+            break;
         }
+    pthread_mutex_unlock(&g_ctx_lock);
+    if (hit)
+        gctx_unref(hit);
 }
 
 static double *gctx_stage(gctx_t *c, int doubles)
@@ -200,6 +223,7 @@ static void gctx_sync_factors(gctx_t *c, april_graph_t *g)
         c->ftype = realloc(c->ftype, sizeof(int) * (size_t) c->fcap);
         c->fa = realloc(c->fa, sizeof(int) * (size_t) c->fcap);
         c->fb = realloc(c->fb, sizeof(int) * (size_t) c->fcap);
+        c->zw = realloc(c->zw, sizeof(double) * 12 * (size_t) c->fcap);
     }
     int first = c->nf_dev, cnt = F - first;
     double *zw = malloc(sizeof(double) * 12 * (size_t) cnt);
@@ -223,6 +247,8 @@ static void gctx_sync_factors(gctx_t *c, april_graph_t *g)
             asam_fatal("factor %d: W must be 3x3 and z non-NULL", i);
         memcpy(z + 3 * (size_t) k, f->u.common.z, 3 * sizeof(double));
         memcpy(W + 9 * (size_t) k, Wm->data, 9 * sizeof(double));
+        memcpy(c->zw + 12 * (size_t) i, f->u.common.z, 3 * sizeof(double));
+        memcpy(c->zw + 12 * (size_t) i + 3, Wm->data, 9 * sizeof(double));
         for (int j = 0; j < f->nnodes; j++)
             if (f->nodes[j] < 0 || f->nodes[j] >= N)
                 asam_fatal("factor %d references node %d outside the graph (%d nodes)", i, f->nodes[j], N);
@@ -233,6 +259,56 @@ static void gctx_sync_factors(gctx_t *c, april_graph_t *g)
     c->nf_dev = F;
 }
 
+/* The reference reads every factor on every batch call (aprilsam.c:154-195), so a caller may edit
+ * z / W in place between calls (re-weighting, robust kernels) or swap a factor for another one.
+ * The HBM mirror is checked against the host structs on every batch call: factors [0, upto) whose
+ * measurement or information matrix changed are re-uploaded; a change of type or node ids is
+ * reported through the return value (the symbolic plan has to be rebuilt).  The check costs one
+ * 96-byte compare per factor and is run WHILE the kernels of the call are in flight (see
+ * april_graph_cholesky): in the common case -- nothing changed -- it is free.
+ * Returns 0 = unchanged, 1 = values re-uploaded, 2 = structure changed (mirror updated). */
+static int gctx_verify_factors(gctx_t *c, april_graph_t *g, int upto)
+{
+    int changed = 0, structural = 0;
+    int lo = upto, hi = -1;
+#pragma omp parallel for schedule(static) reduction(| : changed, structural) reduction(min : lo) reduction(max : hi) \
+    if (upto >= 4 * ASAM_OMP_MIN_NODES) num_threads(ASAM_OMP_THREADS)
+    for (int i = 0; i < upto; i++) {
+        const april_graph_factor_t *f = factor_at(g, i);
+        const matd_t *Wm = f->u.common.W;
+        int na = f->nnodes > 0 ? f->nodes[0] : -1, nb = f->nnodes > 1 ? f->nodes[1] : -1;
+        if (f->type != c->ftype[i] || na != c->fa[i] || nb != c->fb[i] || !Wm || !f->u.common.z) {
+            structural = 1;
+            continue;
+        }
+        double *m = c->zw + 12 * (size_t) i;
+        if (memcmp(m, f->u.common.z, 3 * sizeof(double)) != 0 || memcmp(m + 3, Wm->data, 9 * sizeof(double)) != 0) {
+            memcpy(m, f->u.common.z, 3 * sizeof(double));
+            memcpy(m + 3, Wm->data, 9 * sizeof(double));
+            changed = 1;
+            if (i < lo)
+                lo = i;
+            if (i > hi)
+                hi = i;
+        }
+    }
+    if (structural)
+        return 2;
+    if (!changed)
+        return 0;
+    /* re-upload the dirty range [lo, hi] (edits are usually a contiguous run or everything) */
+    int cnt = hi - lo + 1;
+    double *zw = malloc(sizeof(double) * 12 * (size_t) cnt);
+    double *z = zw, *W = zw + 3 * (size_t) cnt;
+    for (int k = 0; k < cnt; k++) {
+        memcpy(z + 3 * (size_t) k, c->zw + 12 * (size_t) (lo + k), 3 * sizeof(double));
+        memcpy(W + 9 * (size_t) k, c->zw + 12 * (size_t) (lo + k) + 3, 9 * sizeof(double));
+    }
+    DEV_OK(asam_upload_factors(c->dev, lo, cnt, c->ftype + lo, c->fa + lo, c->fb + lo, z, W));
+    free(zw);
+    return 1;
+}
+
 /* ---- chi2 (april_graph.c:79-98) -------------------------------------------------------------- */
 ASAM_API double april_graph_chi2(april_graph_t *g)
 {
@@ -240,6 +316,8 @@ ASAM_API double april_graph_chi2(april_graph_t *g)
     if (F == 0)
         return 0.0;
     gctx_t *c = gctx_get(g);
+    if (gctx_verify_factors(c, g, c->nf_dev < F ? c->nf_dev : F) == 2)
+        c->nf_dev = 0; /* a factor was replaced: mirror everything again */
     gctx_sync_factors(c, g);
     double *st = gctx_stage(c, 3 * N);
     for (int i = 0; i < N; i++)
@@ -265,7 +343,18 @@ typedef struct solver {
     int tree_fresh; /* param->tr is exactly the tree of `plan` as built by the last batch */
     int *scratch;
     int scratch_cap;
+    aprilsam_b200_escalation_fn policy; /* deterministic escalation hook (aprilsam.h) */
+    void *policy_user;
 } solver_t;
+
+/* policies set before the first batch solve wait here for their solver (param -> fn) */
+typedef struct pending_policy {
+    april_graph_cholesky_param_t *param;
+    aprilsam_b200_escalation_fn fn;
+    void *user;
+    struct pending_policy *next;
+} pending_policy_t;
+static pending_policy_t *g_pending_policy = NULL;
 
 static solver_t *solver_of(april_graph_cholesky_param_t *param)
 {
@@ -301,10 +390,74 @@ static solver_t *solver_get(april_graph_t *g, april_graph_cholesky_param_t *para
         s->magic = SOLVER_MAGIC;
         s->hdr.is_spd = 1;
         s->gc = gctx_get(g);
+        pthread_mutex_lock(&g_ctx_lock);
         s->gc->refs++;
+        for (pending_policy_t **pp = &g_pending_policy; *pp; pp = &(*pp)->next)
+            if ((*pp)->param == param) {
+                pending_policy_t *hit = *pp;
+                s->policy = hit->fn;
+                s->policy_user = hit->user;
+                *pp = hit->next;
+                free(hit);
+                break;
+            }
+        pthread_mutex_unlock(&g_ctx_lock);
         param->chol = &s->hdr;
     }
     return s;
+}
+
+ASAM_API void aprilsam_b200_set_escalation_policy(april_graph_cholesky_param_t *param, aprilsam_b200_escalation_fn fn,
+                                                  void *user)
+{
+    if (!param)
+        return;
+    if (param->chol) {
+        solver_t *s = solver_of(param);
+        s->policy = fn;
+        s->policy_user = user;
+        return;
+    }
+    pthread_mutex_lock(&g_ctx_lock);
+    pending_policy_t *e = NULL;
+    for (pending_policy_t **pp = &g_pending_policy; *pp; pp = &(*pp)->next)
+        if ((*pp)->param == param) {
+            e = *pp;
+            if (!fn) { /* removal */
+                *pp = e->next;
+                free(e);
+                pthread_mutex_unlock(&g_ctx_lock);
+                return;
+            }
+            break;
+        }
+    if (fn) {
+        if (!e) {
+            e = calloc(1, sizeof(*e));
+            e->param = param;
+            e->next = g_pending_policy;
+            g_pending_policy = e;
+        }
+        e->fn = fn;
+        e->user = user;
+    }
+    pthread_mutex_unlock(&g_ctx_lock);
+}
+
+ASAM_API int aprilsam_b200_policy_work_ratio(const aprilsam_b200_step_cost_t *cost, void *user)
+{
+    double ratio = user ? *(const double *) user : 1.0 / 3.0;
+    return cost->step_work > ratio * cost->batch_work;
+}
+
+ASAM_API void aprilsam_b200_invalidate_plan(april_graph_cholesky_param_t *param)
+{
+    solver_t *s = param && param->chol ? solver_of(param) : NULL;
+    if (s) {
+        s->plan_valid = 0;
+        s->plan.struct_hash = 0;
+        s->tree_fresh = 0;
+    }
 }
 
 static double *solver_x(solver_t *s, int N)
@@ -348,6 +501,7 @@ ASAM_API void april_graph_cholesky_param_destory(april_graph_cholesky_param_t *p
 {
     if (!param)
         return;
+    aprilsam_b200_set_escalation_policy(param->chol ? NULL : param, NULL, NULL); /* forget a policy that never met a solver */
     solver_destroy(solver_of(param));
     if (param->tr)
         search_tree_destroy(param->tr);
@@ -469,6 +623,9 @@ ASAM_API void april_graph_cholesky(april_graph_t *graph, april_graph_cholesky_pa
         stamp(&tp, "begin");
     }
     check_nodes(graph, 0, N);
+    int restarted = 0;
+restart:;
+    const int F_mirrored = c->nf_dev < F ? c->nf_dev : F; /* already in HBM: checked while the kernels run */
     gctx_sync_factors(c, graph);
 
     /* relinearise every node at its current state (:131-135) and stage the poses */
@@ -519,6 +676,27 @@ ASAM_API void april_graph_cholesky(april_graph_t *graph, april_graph_cholesky_pa
     DEV_OK(asam_factor_full(dev));
     DEV_OK(asam_backsolve_full(dev));
     PROF_LAP(13);
+    /* the kernels are in flight: compare the factors HBM holds with the caller's structs (the reference
+     * re-reads every factor on every call).  Nothing changed (the usual case): no cost.  Otherwise the
+     * changed measurements are uploaded and the pipeline runs again; a replaced factor (other nodes or
+     * type) also rebuilds the plan. */
+    if (F_mirrored > 0 && !restarted) {
+        int v = gctx_verify_factors(c, graph, F_mirrored);
+        if (v) {
+            int st_ = 0;
+            DEV_OK(asam_factor_status(dev, &st_)); /* drain the stale run (its pivots may have failed) */
+            restarted = 1;
+            if (v == 2) {
+                c->nf_dev = 0;
+                s->plan_valid = 0;
+                goto restart;
+            }
+            DEV_OK(asam_hessian_reset(dev, N, pl->n_slots, N, param->tikhanov > 0 ? param->tikhanov : 0.0));
+            DEV_OK(asam_linearize(dev, 0, F, NULL));
+            DEV_OK(asam_factor_full(dev));
+            DEV_OK(asam_backsolve_full(dev));
+        }
+    }
     double *x = solver_x(s, N);
     int fstatus = 0;
     DEV_OK(asam_download_x_status(dev, 0, N, x, &fstatus));
@@ -766,6 +944,16 @@ ASAM_API void april_graph_cholesky_inc(april_graph_t *graph, april_graph_cholesk
     }
     if (rc != 0)
         asam_fatal("april_graph_cholesky_inc: %s %s", g_error, asam_last_error());
+    int policy_escalate = 0;
+    if (s->policy) {
+        aprilsam_b200_step_cost_t cost;
+        memset(&cost, 0, sizeof(cost));
+        plan_work(pl, tasks, ntasks, &cost.step_work, &cost.step_fronts, &cost.batch_work, &cost.batch_fronts);
+        cost.naffected = tr->naffected;
+        cost.nnodes = N;
+        cost.start_over = tr->start_over;
+        policy_escalate = s->policy(&cost, s->policy_user) != 0;
+    }
     PROF_LAP(1);
     if (param->show_timing)
         stamp(&tp, "mark root paths, symbolic append");
@@ -840,6 +1028,9 @@ ASAM_API void april_graph_cholesky_inc(april_graph_t *graph, april_graph_cholesk
     }
     free(tasks);
     free(nwait);
+
+    if (policy_escalate) /* the deterministic stand-in for the wall-clock rule (:556-559): same effect */
+        param->tr->start_over = INT_MAX;
 
 escalate:
     /* too many poses moved since the last batch: relinearise everything (:566-575) */

@@ -2,7 +2,8 @@
 """bench.py -- Gauss-Newton solves/sec of the april_graph_cholesky{,_inc} path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
-                    [--workload m3500_batch|manhattan_batch|m3500_replay|manhattan_replay] [--poses P]
+                    [--workload all|manhattan_batch|m3500_batch|m3500_replay|manhattan_replay]
+                    [--poses P] [--replay-from S] [--shard auto|on|off]
 
 One "step" is one pass of the hot path over one batch of synthetic/fixture input:
   *_batch   one april_graph_cholesky() call on the full graph (relinearise -> assemble ->
@@ -10,24 +11,32 @@ One "step" is one pass of the hot path over one batch of synthetic/fixture input
             initial estimate before every call so each call does identical work;
   *_replay  one april_graph_cholesky_inc() call of the demo-protocol pose-by-pose replay
             (includes any batch escalation it triggers).
-Default workload: BASELINE.json configs[1] = "M3500 batch Cholesky on 1xB200".
+
+The metric (BASELINE.json) names four workloads.  The default run (--workload all) measures all of
+them in ONE JSON line: the headline keys describe `manhattan_batch` (100 k poses / 400 k factors, the
+largest single-GPU configuration; K timed steps exactly), and `workloads` carries one record each for
+`m3500_batch`, `m3500_replay` and `manhattan_replay` (window from pose --replay-from), every one with
+its own value / e2e / roofline / cpu_baseline, timed for >= 1 s.  --workload X measures X alone.
 
 JSON line (rank 0):
   value        solves/s with every input already resident in HBM: the GPU pipeline
                (reset + k_linearize + k_factor + k_backsolve) timed per step with CUDA events on
                the library's stream, L2 flushed between steps (outside the timed events)
   e2e.value    solves/s through the public C API (april_graph_cholesky on HOST structs): host
-               pose gather, H2D, kernels, D2H of the solution, host state update all inside
-  roofline     dominant kernel k_factor: algorithmic bytes 8*nnz(A_upper)+16*nnz(L) per launch
-                / measured launch time, against MEASURED_PEAKS.json hbm_gbs
+               pose gather, H2D, kernels, D2H of the solution, host state update all inside;
+               e2e_uncached = the same with ordering + symbolic analysis redone on every call (what the
+               reference does), through aprilsam_b200_invalidate_plan()
+  roofline     dominant kernel k_factor; roofline_kernels = k_linearize, k_factor, k_backsolve, each with
+               algorithmic bytes per launch, the live CUDA-event time of the kernel
+               inside the e2e calls, and the fraction of MEASURED_PEAKS.json hbm_gbs (k_factor also against
+               the FP64 peak measured live by asam_measure_fp64_peak)
   cpu_baseline the reference's own CPU implementation (oracle/_ref) on this box, 1 thread
-Multi-GPU (one process per GPU, torchrun): M3500 and every incremental workload do not shard
-("replicas only"): each rank solves its own replica, value = total solves of
-all ranks / max rank time, scaling "weak".  The 100 k batch workload (manhattan_batch) shards ONE
-solve over the GPUs: elimination-tree shards per rank, NCCL broadcast of the shard roots' update
-matrices and of the solution segments, the top of the tree replicated; every
-rank calls april_graph_cholesky on its copy of the graph, value = solves / max rank time, scaling
-"strong".  --shard on|off overrides.
+Multi-GPU (one process per GPU, torchrun).  manhattan_batch shards ONE solve over the GPUs
+(elimination-tree shards per rank, NCCL broadcast of the shard roots' update matrices and of the solution
+segments, the top of the tree replicated -- DESIGN.md section 6): every rank calls april_graph_cholesky
+on its copy of the graph, value = solves / max rank time, scaling "strong", and the line carries
+`parity.sharded_vs_single_gpu_max_rel`.  M3500 and every incremental workload do not shard (SURVEY.md
+section 8e "replicas only"): each rank runs its own replica, value = total solves / max rank time.
 """
 from __future__ import annotations
 
@@ -48,6 +57,8 @@ from aprilsam_b200 import capi, datasets  # noqa: E402
 from aprilsam_b200 import harness as H  # noqa: E402
 
 METRIC = "Gauss-Newton solves/sec (batch + incremental) on M3500 & 100k-pose graph"
+ALL = ["manhattan_batch", "m3500_batch", "m3500_replay", "manhattan_replay"]
+MIN_TIMED_S = 1.0  # sub-workloads: timed region at least this long
 
 
 def load_workload(name: str, poses: int):
@@ -65,6 +76,10 @@ def load_workload(name: str, poses: int):
     return d, label
 
 
+def data_kind(name: str) -> str:
+    return "synthetic" if "manhattan" in name else "fixture M3500 (public dataset) + synthetic prior"
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -74,7 +89,7 @@ def peaks():
 
 
 class ClockSampler:
-    def __init__(self, device: int, period_ms: int = 500):
+    def __init__(self, device: int, period_ms: int = 200):
         self.p = None
         self.device = device
         self.period_ms = period_ms
@@ -163,20 +178,22 @@ def aggregate_rate(dist, local, world: int, steps_this_rank: int, seconds_this_r
 
 
 # ----------------------------------------------------------------------------------------------
-# reference arm / cpu baseline
+# the reference on host cores (reference arm / cpu_baseline legs)
 # ----------------------------------------------------------------------------------------------
-def time_reference_batch(d, calls: int, warm: int = 1):
-    h = H.Harness("reference")
+def time_reference_batch(d, calls: int, warm: int = 1, impl: str = "reference", keep_states: bool = False):
+    h = H.Harness(impl)
     h.load_full(d)
     init = d.init.copy()
-    ms = []
+    ms, first = [], None
     for i in range(warm + calls):
         h.set_states(init)
         t = h.batch()
+        if i == 0 and keep_states:
+            first = h.states()
         if i >= warm:
             ms.append(t)
     h.close()
-    return np.array(ms)
+    return (np.array(ms), first) if keep_states else np.array(ms)
 
 
 BULK_START = 2000  # replay windows that start later are reached by one batch solve, not by replay
@@ -201,226 +218,408 @@ def replay_seek(h, d, s_begin: int):
         h.batch()
 
 
-def time_reference_replay(d, s_begin: int, steps: int):
-    h = H.Harness("reference")
+def time_reference_replay(d, s_begin: int, steps: int, impl: str = "reference"):
+    h = H.Harness(impl)
     replay_seek(h, d, s_begin)
-    _, ms, _ = h.replay_to(s_begin + steps, want_chi2=False)
+    _, ms, info = h.replay_to(s_begin + steps, want_chi2=False)
     h.close()
-    return ms
+    return ms, info
 
 
-def run_reference(args, d, label, world, rank):
+BUCKETS = ("naffected_le5", "naffected_6_50", "naffected_gt50", "batch_escalation")
+
+
+def step_buckets(info) -> np.ndarray:
+    """Bucket index per replay step: by naffected (search_tree_t.naffected after the step); a step that
+    escalated to a batch solve leaves a fresh tree behind (naffected == 0, aprilsam.c:613-657) and is
+    counted apart."""
+    na = info[:, 0].astype(np.int64)
+    b = np.where(na <= 5, 0, np.where(na <= 50, 1, 2))
+    b[na == 0] = 3
+    return b
+
+
+def bucket_latency(ms, info) -> dict:
+    b = step_buckets(info)
+    out = {}
+    for i, name in enumerate(BUCKETS):
+        sel = ms[b == i]
+        out[name] = {"steps": int(sel.size), "median_us": float(np.median(sel) * 1e3) if sel.size else None,
+                     "mean_us": float(np.mean(sel) * 1e3) if sel.size else None}
+    return out
+
+
+def replay_start(args, d, name: str) -> int:
+    if name == "m3500_replay":
+        return 1
+    return max(1, min(args.replay_from, d.n_nodes - 1))
+
+
+def reference_record(args, name: str, d, label: str, steps: int, warmup: int, wallclock: bool = False) -> dict:
+    """One workload on the unmodified reference (oracle/_ref), 1 thread."""
+    if name.endswith("_batch"):
+        ms = time_reference_batch(d, steps, warmup)
+        sample = f"{steps} april_graph_cholesky calls on the full graph after {warmup} untimed"
+        rec_extra = {}
+    else:
+        s0 = replay_start(args, d, name)
+        ms, info = time_reference_replay(d, s0, steps)
+        sample = f"demo replay steps [{s0}, {s0 + len(ms)})" + ("" if s0 <= BULK_START else f"; first {s0} poses loaded at once at ground truth + two batch solves")
+        rec_extra = {"latency_by_bucket": bucket_latency(ms, info)}
+        if wallclock and H.available("reference_wallclock"):
+            wms, _ = time_reference_replay(d, s0, steps, impl="reference_wallclock")
+            rec_extra["cpu_baseline_wallclock"] = {
+                "value": len(wms) / (float(wms.sum()) / 1e3), "unit": "solves/s", "cores": 1, "kind": "reference",
+                "sample": sample + "; the reference AS SHIPPED (wall-clock escalation heuristic aprilsam.c:556-559 active: "
+                                   "non-deterministic, not a parity reference)"}
+    total_s = float(ms.sum()) / 1e3
+    val = len(ms) / total_s
+    rec = {"workload": name, "graph": label, "value": val, "unit": "solves/s", "steps": int(len(ms)), "warmup": warmup,
+           "ms_per_step": float(ms.mean()), "data": data_kind(name),
+           "cpu_baseline": {"value": val, "unit": "solves/s", "cores": 1, "kind": "reference", "sample": sample},
+           "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    rec.update(rec_extra)
+    return rec
+
+
+def run_reference(args, names, world, rank):
     if rank != 0:
         return
     if not H.available("reference"):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (needs /root/reference at build time)"}))
         return
-    if args.workload.endswith("_batch"):
-        ms = time_reference_batch(d, args.steps, args.warmup)
-        sample = f"{args.steps} april_graph_cholesky calls on the full graph after {args.warmup} warm-up"
-    else:
-        s0 = replay_start(args, d)
-        ms = time_reference_replay(d, s0, args.steps)
-        sample = f"demo replay steps [{s0}, {s0 + len(ms)})"
-    total_s = float(ms.sum()) / 1e3
-    val = len(ms) / total_s
-    line = {"metric": METRIC, "value": val, "unit": "solves/s", "impl": "reference", "n_gpus": args.gpus,
-            "steps": int(len(ms)), "warmup": args.warmup, "ms_per_step": float(ms.mean()), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic" if "manhattan" in args.workload else "fixture M3500 (public dataset) + synthetic prior",
-            "config": {"workload": args.workload, "graph": label},
-            "cpu_baseline": {"value": val, "unit": "solves/s", "cores": 1, "kind": "reference", "sample": sample},
-            "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+    recs = {}
+    for i, name in enumerate(names):
+        d, label = load_workload(name, args.poses)
+        if i == 0:
+            steps, warm = args.steps, args.warmup
+        elif name == "m3500_batch":
+            steps, warm = 100, 2
+        elif name == "m3500_replay":
+            steps, warm = d.n_nodes - 1, 0
+        else:
+            steps, warm = 60, 0
+        recs[name] = reference_record(args, name, d, label, steps, warm, wallclock=(i > 0 or len(names) == 1))
+    head = recs[names[0]]
+    line = {"metric": METRIC, "value": head["value"], "unit": "solves/s", "impl": "reference", "n_gpus": args.gpus,
+            "steps": head["steps"], "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong" if names[0] == "manhattan_batch" and args.shard != "off" else "weak", "vs_baseline": None,
+            "dtype": "f64", "data": head["data"], "config": {"workload": names[0], "graph": head["graph"]},
+            "cpu_baseline": head["cpu_baseline"], "e2e": head["e2e"], "gpu_launches": 0}
+    for k in ("latency_by_bucket", "cpu_baseline_wallclock"):
+        if k in head:
+            line[k] = head[k]
+    if len(names) > 1:
+        line["workloads"] = {n: recs[n] for n in names[1:]}
     print(json.dumps(line))
-
-
-def replay_start(args, d) -> int:
-    return max(1, min(args.replay_from, d.n_nodes - 1))
 
 
 # ----------------------------------------------------------------------------------------------
 # b200 arm
 # ----------------------------------------------------------------------------------------------
-def run_b200(args, d, label, world, rank, local, dist):
-    L = capi.lib()
-    if L.asam_device_count() <= 0:
-        raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU fallback")
-    hbm_peak, peak_src = peaks()
-    is_batch = args.workload.endswith("_batch")
-    sampler = ClockSampler(local, period_ms=int(os.environ.get("ASAM_CLOCK_PERIOD_MS", "500")))
+class Ctx:
+    """What every workload of one run shares."""
 
-    sharded = world > 1 and is_batch and (args.shard == "on" or (args.shard == "auto" and args.workload == "manhattan_batch"))
-    if sharded:
-        capi.comm_init_torch(dist, local)
-        capi.check(L.asam_comm_set_sharding(1), "asam_comm_set_sharding")
-    h = H.Harness("b200")
+    def __init__(self, args, world, rank, local, dist):
+        self.args, self.world, self.rank, self.local, self.dist = args, world, rank, local, dist
+        self.L = capi.lib()
+        self.hbm_peak, self.peak_src = peaks()
+        self.fp64_peak_tf = None
+        self.traffic = {}
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                self.traffic = json.load(f)
+        except Exception:
+            pass
+
+
+def roofline_entries(ctx: Ctx, name: str, pinfo: dict, kern_ms) -> list:
+    """algorithmic bytes per launch / live CUDA-event time of the kernel."""
+    N, S, F = pinfo["N"], pinfo["n_slots"], pinfo["n_factors"]
+    nnz_l = 9 * (pinfo["nnz_l_blocks"] - N) + 6 * N
+    nnz_a = 6 * N + 9 * S
+    idx = pinfo["nnz_l_blocks"]  # one 32-bit row index per 3x3 block row of L (supernodal: fewer)
+    alg = {"k_linearize": 368 * F,
+           "k_factor": 8 * nnz_a + 16 * nnz_l,
+           "k_backsolve": 8 * nnz_l + 4 * idx + 24 * 3 * N}
+    tr = ctx.traffic.get(name, {})
+    out = []
+    for i, k in enumerate(("k_linearize", "k_factor", "k_backsolve")):
+        t = float(np.median(kern_ms[:, i])) * 1e-3 if len(kern_ms) else 0.0
+        if t <= 0:
+            continue
+        ach = alg[k] / t / 1e9
+        e = {"kernel": k + (" (+leaf kernel on large graphs)" if k != "k_linearize" else ""), "bound": "hbm", "achieved": ach,
+             "peak": ctx.hbm_peak, "unit": "GB/s", "frac": ach / ctx.hbm_peak, "peak_source": ctx.peak_src,
+             "algorithmic_bytes_per_launch": int(alg[k]), "avg_launch_ms": t * 1e3,
+             "traffic": tr.get(k, {}).get("bytes") if isinstance(tr.get(k), dict) else (tr.get("bytes") if k == "k_factor" else None),
+             "traffic_source": tr.get("source")}
+        if k == "k_factor":
+            e.update({"flops_per_launch": pinfo["flops"], "fp64_tflops": pinfo["flops"] / t / 1e12,
+                      "fp64_peak_tflops": ctx.fp64_peak_tf,
+                      "fp64_peak_source": "measured live (asam_measure_fp64_peak: DFMA loop, 512 thr/SM); tcgen05 has no FP64 kind",
+                      "fp64_frac": (pinfo["flops"] / t / 1e12 / ctx.fp64_peak_tf) if ctx.fp64_peak_tf else None,
+                      "note": "latency-bound: the dependent chain of supernode levels / panel steps sets the time (DESIGN.md section 4)"})
+        out.append(e)
+    return out
+
+
+def bench_batch(ctx: Ctx, name: str, d, label: str, K: int, W: int, sharded: bool, with_cpu: bool) -> dict:
+    L, dist, local, world, rank = ctx.L, ctx.dist, ctx.local, ctx.world, ctx.rank
     init = d.init.copy()
-    if is_batch:
-        h.load_full(d)
-        t0 = time.perf_counter()
-        h.batch()  # cold call: ordering + symbolic analysis + plan upload
-        cold_ms = (time.perf_counter() - t0) * 1e3
-    else:
-        s0 = replay_start(args, d)
-        replay_seek(h, d, s0)
-        cold_ms = None
+    h = H.Harness("b200")
+    h.load_full(d)
+    t0 = time.perf_counter()
+    h.batch()  # cold call: ordering + symbolic analysis + plan upload (+ CUDA context on the first workload)
+    cold_ms = (time.perf_counter() - t0) * 1e3
+    first_states = h.states()
     dev = L.asam_dbg_dev_of_graph(h.graph_ptr())
     pinfo = capi.plan_info(L.asam_dbg_plan_of_param(h.param_ptr()))
     L.asam_set_timing(dev, 1)
+    if ctx.fp64_peak_tf is None:
+        tf = C.c_double()
+        capi.check(L.asam_measure_fp64_peak(dev, C.byref(tf)), "asam_measure_fp64_peak")
+        ctx.fp64_peak_tf = tf.value
+    jobs = 1 if sharded else world
 
     # ---- e2e: through the public API, host structs in, host structs out ----------------------
-    K, W = args.steps, args.warmup
     e2e_ms, kern = [], []
     launches0 = h2d0 = d2h0 = 0
-    if rank == 0:
-        sampler.start()
-    if is_batch:
-        for i in range(W + K):
-            h.set_states(init)
-            if i == W:
-                barrier_max(dist, local, 0.0)
-                launches0, h2d0, d2h0 = capi.counters(dev)
-            e2e_t = h.batch()
-            if i >= W:
-                e2e_ms.append(e2e_t)
-                kern.append(capi.kernel_ms(dev))
-    else:
-        h.replay_to(s0 + W, want_chi2=False)
-        barrier_max(dist, local, 0.0)
-        launches0, h2d0, d2h0 = capi.counters(dev)
-        _, ms, info = h.replay_to(s0 + W + K, want_chi2=False)
-        e2e_ms = list(ms)
+    for i in range(W + K):
+        h.set_states(init)
+        if i == W:
+            barrier_max(dist, local, 0.0)
+            launches0, h2d0, d2h0 = capi.counters(dev)
+        t = h.batch()
+        if i >= W:
+            e2e_ms.append(t)
+            kern.append(capi.kernel_ms(dev))
     launches1, h2d1, d2h1 = capi.counters(dev)
-    nsteps = len(e2e_ms)
-    # replicas: every rank solved its own copy; sharded: all ranks worked on the SAME solves
-    jobs = 1 if sharded else world
-    e2e_val = aggregate_rate(dist, local, jobs, nsteps, float(np.sum(e2e_ms)) / 1e3)
+    e2e_val = aggregate_rate(dist, local, jobs, len(e2e_ms), float(np.sum(e2e_ms)) / 1e3)
+    kern = np.array(kern)
+
+    # ---- e2e with the plan rebuilt on every call (ordering + symbolic, like the reference) ---------
+    n_unc = max(3, min(K, int(1.0 / max(cold_ms * 1e-3, 1e-3)) + 3)) if not sharded else 3
+    unc_ms = []
+    prof0 = (C.c_double * 24)()
+    L.asam_dbg_profile(prof0, 1)
+    for i in range(n_unc + 1):
+        h.set_states(init)
+        h.invalidate_plan()
+        t = h.batch()
+        if i >= 1:
+            unc_ms.append(t)
+        else:
+            L.asam_dbg_profile(prof0, 1)
+    prof = (C.c_double * 24)()
+    L.asam_dbg_profile(prof, 1)
+    plan_ms = prof[12] / max(n_unc, 1)
+    unc_val = aggregate_rate(dist, local, jobs, len(unc_ms), float(np.sum(unc_ms)) / 1e3)
 
     # ---- device-resident: same pipeline, inputs already in HBM, CUDA events per step ----------
+    h.set_states(init)
+    h.batch()
+    N, S, F = pinfo["N"], pinfo["n_slots"], pinfo["n_factors"]
+    ms = C.c_float()
     dev_ms = []
-    fac_ms = []
-    if is_batch:
-        h.set_states(init)
-        h.batch()
-        N, S, F = pinfo["N"], pinfo["n_slots"], pinfo["n_factors"]
-        ms = C.c_float()
-        launches_a = capi.counters(dev)[0]
-        for i in range(W + K):
-            if i == W:
-                launches_a = capi.counters(dev)[0]
-            capi.check(L.asam_l2_flush(dev), "l2_flush")
-            capi.check(L.asam_timer_start(dev), "timer")
-            capi.check(L.asam_hessian_reset(dev, N, S, N, 1e-4), "reset")
-            capi.check(L.asam_linearize(dev, 0, F, None), "linearize")
-            capi.check(L.asam_factor_full(dev), "factor")
-            capi.check(L.asam_backsolve_full(dev), "backsolve")
-            capi.check(L.asam_timer_stop(dev, C.byref(ms)), "timer")
-            if i >= W:
-                dev_ms.append(ms.value)
-                fac_ms.append(capi.kernel_ms(dev)[1])
-        launches_dev = capi.counters(dev)[0] - launches_a
-        st = C.c_int()
-        L.asam_factor_status(dev, C.byref(st))
-        if st.value != 0:
-            raise SystemExit(f"bench.py: factorisation status {st.value}")
-        value = aggregate_rate(dist, local, jobs, len(dev_ms), float(np.sum(dev_ms)) / 1e3)
-        ms_per_step = float(np.mean(dev_ms))
-        gpu_launches = launches_dev
-    else:
-        value = e2e_val
-        ms_per_step = float(np.mean(e2e_ms))
-        gpu_launches = launches1 - launches0
-    clocks = sampler.stop() if rank == 0 else {}
-
-    # ---- roofline of the dominant kernel (k_factor) -------------------------------------------
-    nnz_l = 9 * (pinfo["nnz_l_blocks"] - pinfo["N"]) + 6 * pinfo["N"]
-    nnz_a = 6 * pinfo["N"] + 9 * pinfo["n_slots"]
-    alg_bytes = 8 * nnz_a + 16 * nnz_l
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            traffic = json.load(f).get(args.workload, {}).get("bytes")
-    except Exception:
-        pass
-    if is_batch and fac_ms:
-        t_fac = float(np.mean(fac_ms)) * 1e-3
-        achieved = alg_bytes / t_fac / 1e9
-        fp64_peak = 37.1e3  # GFLOP/s, measured on this pool (profiles/r2_fp64_pipe_ubench.txt); tcgen05 has no FP64 kind
-        roof = {"kernel": "k_factor (+k_factor_leaf on large graphs)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
-                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": t_fac * 1e3,
-                "fp64_gflops": pinfo["flops"] / t_fac / 1e9, "flops_per_launch": pinfo["flops"],
-                "fp64_peak_gflops": fp64_peak, "fp64_frac": pinfo["flops"] / t_fac / 1e9 / fp64_peak,
-                "note": "latency-bound: the dependent chain of supernode levels / panel steps, not bytes or flops, sets the time"}
-    else:
-        roof = {"kernel": "k_factor", "bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None,
-                "traffic": None, "peak_source": peak_src}
-
-    # ---- cpu baseline (rank 0, N=1): the reference on this box's host cores -------------------
-    cpu = None
-    if rank == 0 and world == 1 and H.available("reference") and not args.no_cpu_baseline:
-        if is_batch:
-            probe = time_reference_batch(d, 1, 0)
-            calls = int(max(1, min(300, 10e3 / max(probe[0], 1e-3))))
-            ms = time_reference_batch(d, calls, 0)
-            cpu = {"value": calls / (float(ms.sum()) / 1e3), "unit": "solves/s", "cores": 1, "kind": "reference",
-                   "sample": f"{calls} april_graph_cholesky calls of the same graph (oracle/_ref, 1 thread: the reference has no threads)"}
-        else:
-            ms = time_reference_replay(d, s0, W + (K if d.n_nodes <= 5000 else min(K, 1000)))[W:]
-            cpu = {"value": len(ms) / (float(ms.sum()) / 1e3), "unit": "solves/s", "cores": 1, "kind": "reference",
-                   "sample": f"replay steps [{s0 + W}, {s0 + W + len(ms)}) (oracle/_ref, deterministic clock)"
-                             + ("" if s0 <= BULK_START else f"; first {s0} poses loaded at once at ground truth + two batch solves")}
+    launches_a = capi.counters(dev)[0]
+    for i in range(W + K):
+        if i == W:
+            launches_a = capi.counters(dev)[0]
+        capi.check(L.asam_l2_flush(dev), "l2_flush")
+        capi.check(L.asam_timer_start(dev), "timer")
+        capi.check(L.asam_hessian_reset(dev, N, S, N, 1e-4), "reset")
+        capi.check(L.asam_linearize(dev, 0, F, None), "linearize")
+        capi.check(L.asam_factor_full(dev), "factor")
+        capi.check(L.asam_backsolve_full(dev), "backsolve")
+        capi.check(L.asam_timer_stop(dev, C.byref(ms)), "timer")
+        if i >= W:
+            dev_ms.append(ms.value)
+    launches_dev = capi.counters(dev)[0] - launches_a
+    st = C.c_int()
+    L.asam_factor_status(dev, C.byref(st))
+    if st.value != 0:
+        raise SystemExit(f"bench.py: factorisation status {st.value}")
+    value = aggregate_rate(dist, local, jobs, len(dev_ms), float(np.sum(dev_ms)) / 1e3)
     h.close()
 
+    rec = {"workload": name, "graph": label, "value": value, "unit": "solves/s", "steps": K, "warmup": W,
+           "ms_per_step": float(np.mean(dev_ms)), "data": data_kind(name),
+           "e2e": {"value": e2e_val, "unit": "solves/s", "ms_per_step": float(np.mean(e2e_ms)),
+                   "h2d_bytes_per_step": (h2d1 - h2d0) // max(len(e2e_ms), 1),
+                   "d2h_bytes_per_step": (d2h1 - d2h0) // max(len(e2e_ms), 1)},
+           "e2e_uncached": {"value": unc_val, "unit": "solves/s", "ms_per_step": float(np.mean(unc_ms)), "calls": len(unc_ms),
+                            "plan_build_ms_per_call": plan_ms,
+                            "note": "ordering + symbolic analysis + plan upload redone on every call (aprilsam_b200_invalidate_plan), "
+                                    "as the reference does; like-for-like with cpu_baseline"},
+           "gpu_launches": int(launches_dev),
+           "kernel_ms": {"k_linearize": float(np.median(kern[:, 0])), "k_factor": float(np.median(kern[:, 1])),
+                         "k_backsolve": float(np.median(kern[:, 2]))},
+           "roofline_kernels": roofline_entries(ctx, name, pinfo, kern),
+           "plan": {k: pinfo[k] for k in ("N", "nsn", "n_slots", "n_levels", "max_m", "nnz_l_blocks")},
+           "cold_first_call_ms": cold_ms,
+           "cache": "L2 flushed (384 MiB overwrite) between timed device-resident steps"}
+    # ---- cpu baseline + parity against it (rank 0, N = 1) ----------------------------------------
+    if with_cpu and rank == 0 and world == 1 and H.available("reference"):
+        probe, ref_first = time_reference_batch(d, 1, 0, keep_states=True)
+        calls = int(max(2, min(300, 12e3 / max(probe[0], 1e-3))))
+        ms_ref = time_reference_batch(d, calls, 0)
+        rec["cpu_baseline"] = {"value": calls / (float(ms_ref.sum()) / 1e3), "unit": "solves/s", "cores": 1, "kind": "reference",
+                               "sample": f"{calls} april_graph_cholesky calls of the same graph (oracle/_ref, 1 thread: the reference has no threads)"}
+        scale = max(1.0, float(np.abs(ref_first).max()))
+        rec["parity"] = {"vs_reference_first_iteration_max_rel": float(np.abs(first_states - ref_first).max() / scale),
+                         "tolerance": 1e-6}
+    rec["_first_states"] = first_states
+    return rec
+
+
+def bench_replay(ctx: Ctx, name: str, d, label: str, K: int, W: int, with_cpu: bool) -> dict:
+    L, dist, local, world, rank = ctx.L, ctx.dist, ctx.local, ctx.world, ctx.rank
+    s0 = replay_start(ctx.args, d, name)
+    K = min(K, d.n_nodes - s0 - W)
+    h = H.Harness("b200")
+    replay_seek(h, d, s0)
+    dev = L.asam_dbg_dev_of_graph(h.graph_ptr())
+    h.replay_to(s0 + W, want_chi2=False)
+    barrier_max(dist, local, 0.0)
+    launches0, h2d0, d2h0 = capi.counters(dev)
+    _, ms, info = h.replay_to(s0 + W + K, want_chi2=False)
+    launches1, h2d1, d2h1 = capi.counters(dev)
+    chi2_end = h.chi2()
+    end_states = h.states()
+    h.close()
+    val = aggregate_rate(dist, local, world, len(ms), float(np.sum(ms)) / 1e3)
+    n = max(len(ms), 1)
+    rec = {"workload": name, "graph": label, "value": val, "unit": "solves/s", "steps": int(len(ms)), "warmup": W,
+           "ms_per_step": float(np.mean(ms)), "data": data_kind(name),
+           "window": f"replay steps [{s0 + W}, {s0 + W + len(ms)})" + ("" if s0 <= BULK_START else f"; first {s0} poses loaded at once at ground truth + two batch solves"),
+           "e2e": {"value": val, "unit": "solves/s", "ms_per_step": float(np.mean(ms)), "h2d_bytes_per_step": (h2d1 - h2d0) // n,
+                   "d2h_bytes_per_step": (d2h1 - d2h0) // n},
+           "gpu_launches": int(launches1 - launches0),
+           "latency_by_bucket": bucket_latency(ms, info),
+           "roofline_kernels": None,
+           "roofline_note": "incremental steps re-factor a handful of fronts (median naffected <= 5): launch + dependency latency, "
+                            "not bytes; the per-bucket latencies above are the measure"}
+    if with_cpu and rank == 0 and world == 1 and H.available("reference"):
+        nref = len(ms) if d.n_nodes <= 5000 else min(len(ms), 100)
+        rms, rinfo = time_reference_replay(d, s0, W + nref)
+        rms, rinfo = rms[W:], rinfo[W:]
+        rec["cpu_baseline"] = {"value": len(rms) / (float(rms.sum()) / 1e3), "unit": "solves/s", "cores": 1, "kind": "reference",
+                               "sample": f"replay steps [{s0 + W}, {s0 + W + len(rms)}) (oracle/_ref, deterministic clock)",
+                               "latency_by_bucket": bucket_latency(rms, rinfo)}
+        same = min(len(rms), len(ms))
+        rec["parity"] = {"naffected_equal_steps": int(np.sum(info[:same, 0] == rinfo[:same, 0])), "steps_compared": int(same)}
+        if H.available("reference_wallclock"):
+            wms, _ = time_reference_replay(d, s0, W + nref, impl="reference_wallclock")
+            wms = wms[W:]
+            rec["cpu_baseline_wallclock"] = {"value": len(wms) / (float(wms.sum()) / 1e3), "unit": "solves/s", "cores": 1,
+                                             "kind": "reference",
+                                             "sample": "same steps, the reference AS SHIPPED (wall-clock escalation heuristic "
+                                                       "aprilsam.c:556-559 active; non-deterministic, speed reference only)"}
+    rec["_chi2_end"] = chi2_end
+    rec["_end_states"] = end_states
+    return rec
+
+
+def run_b200(args, names, world, rank, local, dist):
+    L = capi.lib()
+    if L.asam_device_count() <= 0:
+        raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU fallback")
+    ctx = Ctx(args, world, rank, local, dist)
+    sampler = ClockSampler(local, period_ms=int(os.environ.get("ASAM_CLOCK_PERIOD_MS", "200")))
+    recs = {}
+    sharded_head = False
+    if rank == 0:
+        sampler.start()
+    for i, name in enumerate(names):
+        d, label = load_workload(name, args.poses)
+        is_batch = name.endswith("_batch")
+        sharded = world > 1 and is_batch and (args.shard == "on" or (args.shard == "auto" and name == "manhattan_batch"))
+        if sharded:
+            capi.comm_init_torch(dist, local)
+            capi.check(L.asam_comm_set_sharding(1), "asam_comm_set_sharding")
+        if i == 0:
+            K, W = args.steps, args.warmup
+            sharded_head = sharded
+        elif name == "m3500_batch":
+            K, W = max(args.steps, 1500), max(args.warmup, 5)
+        elif name == "m3500_replay":
+            K, W = d.n_nodes, 0
+        else:
+            K, W = 1000, args.warmup
+        if is_batch:
+            rec = bench_batch(ctx, name, d, label, K, W, sharded, with_cpu=not args.no_cpu_baseline)
+        else:
+            rec = bench_replay(ctx, name, d, label, K, W, with_cpu=not args.no_cpu_baseline)
+        if sharded:
+            # in-line parity of the sharded solve: the same graph, one GN iteration, on this rank's GPU alone
+            capi.check(L.asam_comm_set_sharding(0), "asam_comm_set_sharding")
+            if rank == 0:
+                with H.Harness("b200") as h1:
+                    h1.load_full(d)
+                    h1.batch()
+                    single = h1.states()
+                scale = max(1.0, float(np.abs(single).max()))
+                rec.setdefault("parity", {})["sharded_vs_single_gpu_max_rel"] = float(np.abs(rec["_first_states"] - single).max() / scale)
+                rec["parity"]["tolerance"] = 1e-6
+            barrier_max(dist, local, 0.0)
+        recs[name] = rec
+    clocks = sampler.stop() if rank == 0 else {}
     if rank != 0:
         return
-    per_step = max(nsteps, 1)
-    line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
-            "dtype": "f64",
-            "data": "synthetic" if "manhattan" in args.workload else "fixture M3500 (public dataset) + synthetic prior",
-            "config": {"workload": args.workload, "graph": label,
-                       "parallelism": (f"elimination-tree shards x{world}, top of the tree replicated, NCCL broadcast of shard "
-                                       f"root fronts and solution segments") if sharded else f"replicas x{world}",
-                       "cache": "L2 flushed (384 MiB overwrite) between timed steps" if is_batch else "working set grows each step",
-                       "plan": {k: pinfo[k] for k in ("N", "nsn", "n_slots", "n_levels", "max_m", "nnz_l_blocks")},
-                       "cold_first_call_ms": cold_ms},
-            "e2e": {"value": e2e_val, "unit": "solves/s", "ms_per_step": float(np.mean(e2e_ms)),
-                    "h2d_bytes_per_step": (h2d1 - h2d0) // per_step, "d2h_bytes_per_step": (d2h1 - d2h0) // per_step},
-            "gpu_launches": int(gpu_launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks}
-    if kern:
-        k = np.array(kern)
-        line["kernel_ms"] = {"k_linearize": float(np.median(k[:, 0])), "k_factor": float(np.median(k[:, 1])),
-                             "k_backsolve": float(np.median(k[:, 2]))}
+    for r in recs.values():
+        for k in [k for k in r if k.startswith("_")]:
+            del r[k]
+    head = recs[names[0]]
+    is_batch = names[0].endswith("_batch")
+    par = (f"elimination-tree shards x{world}, top of the tree replicated, NCCL broadcast of shard root fronts and solution "
+           f"segments") if sharded_head else f"replicas x{world}"
+    line = {"metric": METRIC, "value": head["value"], "unit": "solves/s", "n_gpus": world, "steps": head["steps"],
+            "warmup": head["warmup"], "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong" if sharded_head else "weak", "vs_baseline": None, "dtype": "f64", "data": head["data"],
+            "config": {"workload": names[0], "graph": head["graph"], "parallelism": par,
+                       "cache": head.get("cache", "working set grows each step"), "plan": head.get("plan"),
+                       "cold_first_call_ms": head.get("cold_first_call_ms"),
+                       "sub_workloads": names[1:]},
+            "e2e": head["e2e"], "gpu_launches": head["gpu_launches"],
+            "roofline": (next((e for e in head["roofline_kernels"] if e["kernel"].startswith("k_factor")), None)
+                         if head.get("roofline_kernels") else
+                         {"kernel": "k_factor", "bound": "hbm", "achieved": None, "peak": ctx.hbm_peak, "unit": "GB/s", "frac": None,
+                          "traffic": None, "peak_source": ctx.peak_src, "note": head.get("roofline_note")}),
+            "cpu_baseline": head.get("cpu_baseline"), "clocks": clocks}
+    for k in ("e2e_uncached", "kernel_ms", "roofline_kernels", "parity", "latency_by_bucket", "cpu_baseline_wallclock", "window"):
+        if head.get(k) is not None:
+            line[k] = head[k]
+    if len(names) > 1:
+        line["workloads"] = {n: recs[n] for n in names[1:]}
     print(json.dumps(line))
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="m3500_batch",
-                    choices=["m3500_batch", "manhattan_batch", "m3500_replay", "manhattan_replay"])
+    ap.add_argument("--workload", default="all", choices=["all"] + ALL)
     ap.add_argument("--poses", type=int, default=100000)
-    ap.add_argument("--replay-from", type=int, default=1, help="replay workloads: first timed step")
+    ap.add_argument("--replay-from", type=int, default=50000, help="manhattan_replay: first timed step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--shard", choices=["auto", "on", "off"], default="auto",
                     help="--gpus N > 1: shard the elimination tree of ONE solve over the GPUs (NCCL) instead of "
                          "running N replicas; auto = on for manhattan_batch (SURVEY.md section 8e)")
     args = ap.parse_args()
-    if args.warmup < 3 and args.impl == "b200" and args.workload.endswith("_batch"):
-        args.warmup = 3
-    d, label = load_workload(args.workload, args.poses)
+    names = ALL if args.workload == "all" else [args.workload]
     if args.impl == "reference":
         world = int(os.environ.get("WORLD_SIZE", "1"))
         rank = int(os.environ.get("RANK", "0"))
-        run_reference(args, d, label, world, rank)
+        run_reference(args, names, world, rank)
         return
+    if args.warmup < 3:
+        args.warmup = 3
     world, rank, local, dist = dist_setup(args.gpus)
     try:
-        run_b200(args, d, label, world, rank, local, dist)
+        run_b200(args, names, world, rank, local, dist)
     finally:
         if dist is not None:
             dist.destroy_process_group()

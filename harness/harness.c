@@ -387,5 +387,61 @@ H_EXPORT int h_factor(hctx_t *h, int idx, double *out)
     return f->type;
 }
 
+/* overwrite measurement and information matrix of factor idx IN PLACE (what a robust-kernel or
+ * re-weighting loop around the reference does between batch calls) */
+H_EXPORT void h_set_factor(hctx_t *h, int idx, const double *z, const double *W9)
+{
+    april_graph_factor_t *f;
+    zarray_get(h->g->factors, idx, &f);
+    memcpy(f->u.common.z, z, 3 * sizeof(double));
+    memcpy(f->u.common.W->data, W9, 9 * sizeof(double));
+}
+
+/* replace factor idx by a new xyt factor between a and b (same count, other structure) */
+H_EXPORT void h_replace_xyt(hctx_t *h, int idx, int a, int b, const double *z, const double *W9)
+{
+    april_graph_factor_t *old;
+    zarray_get(h->g->factors, idx, &old);
+    matd_t *W = matd_create_data(3, 3, W9);
+    april_graph_factor_t *f = april_graph_factor_xyt_create(a, b, z, NULL, W);
+    matd_destroy(W);
+    zarray_set(h->g->factors, idx, &f, NULL);
+    old->destroy(old);
+}
+
+/* aprilsam_b200 extensions (no-ops in the reference build) */
+H_EXPORT void h_invalidate_plan(hctx_t *h)
+{
+#ifndef HARNESS_REFERENCE
+    aprilsam_b200_invalidate_plan(h->p);
+#else
+    (void) h;
+#endif
+}
+
+/* ratio > 0: deterministic escalation policy step_work > ratio * batch_work; <= 0: none */
+H_EXPORT void h_set_policy_ratio(hctx_t *h, double ratio)
+{
+#ifndef HARNESS_REFERENCE
+    static double ratios[64];
+    static int next = 0;
+    if (ratio > 0) {
+        double *r = &ratios[next++ % 64];
+        *r = ratio;
+        aprilsam_b200_set_escalation_policy(h->p, aprilsam_b200_policy_work_ratio, r);
+    } else {
+        aprilsam_b200_set_escalation_policy(h->p, NULL, NULL);
+    }
+#else
+    (void) h;
+    (void) ratio;
+#endif
+}
+
+/* april_graph_cholesky_inc_solver (aprilsam.h:276): the reference never reads idxs (aprilsam.c:578-597) */
+H_EXPORT void h_inc_solver(hctx_t *h) { april_graph_cholesky_inc_solver(h->g, h->p, NULL); }
+
+H_EXPORT void h_set_show_timing(hctx_t *h, int on) { h->p->show_timing = on; }
+
 H_EXPORT void *h_graph(hctx_t *h) { return h->g; }
 H_EXPORT void *h_param(hctx_t *h) { return h->p; }

@@ -239,6 +239,37 @@ void *april_graph_node_attr_get(april_graph_node_t *node, const char *key);
  * reference reports nothing (void returns, asserts, NULL dereference on non-SPD). */
 const char *aprilsam_b200_last_error(void);
 
+/* Drop the cached ordering + symbolic analysis of `param`: the next april_graph_cholesky() orders
+ * and analyses the graph again, as the reference does on every call (aprilsam.c:104-128, :216-258).
+ * Extension; never needed for correctness (the cache is keyed on the factor structure and factor
+ * values are re-checked on every batch call) -- it exists so that the uncached cost can be measured. */
+void aprilsam_b200_invalidate_plan(april_graph_cholesky_param_t *param);
+
+/* Relinearisation / re-ordering policy of april_graph_cholesky_inc().  The reference escalates an
+ * incremental step to a full batch solve when `start_over > nthreshold` (kept) and, as shipped, also
+ * when the step took longer than a third of the last batch solve by the WALL CLOCK
+ * (aprilsam.c:556-559 "HACK", :569-572) -- results then depend on machine load.  This hook is the
+ * deterministic replacement: after the symbolic update of every incremental step the policy sees the
+ * modelled cost of that step next to the modelled cost of a batch solve of the whole graph (both from
+ * the supernodal plan: sum over the fronts to (re-)factor of columns x rows^2 plus a per-front
+ * latency term) and returns non-zero to escalate.  No policy (the default) = the reference with a
+ * constant clock, which is what the parity tests pin. */
+typedef struct {
+    double step_work;   /* fronts re-factored by this step                                      */
+    double batch_work;  /* every front of the current plan                                       */
+    int step_fronts, batch_fronts;
+    int naffected;      /* poses on the marked root paths (search_tree_t.naffected)              */
+    int nnodes;         /* poses in the graph                                                    */
+    int start_over;     /* poses relinearised since the last batch (compared with nthreshold)    */
+} aprilsam_b200_step_cost_t;
+typedef int (*aprilsam_b200_escalation_fn)(const aprilsam_b200_step_cost_t *cost, void *user);
+/* fn == NULL removes the policy.  May be called before the first april_graph_cholesky(). */
+void aprilsam_b200_set_escalation_policy(april_graph_cholesky_param_t *param, aprilsam_b200_escalation_fn fn,
+                                         void *user);
+/* Built-in policy, the reference's ratio made deterministic: escalate when
+ * step_work > ratio * batch_work; `user` points to the ratio (double), NULL = 1/3. */
+int aprilsam_b200_policy_work_ratio(const aprilsam_b200_step_cost_t *cost, void *user);
+
 /* ---- ABI checks against the reference layout ------------------ */
 #if defined(__x86_64__) && !defined(__cplusplus)
 #include <stddef.h>

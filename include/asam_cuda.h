@@ -180,6 +180,8 @@ int asam_timer_start(asam_dev_t *d);
 int asam_timer_stop(asam_dev_t *d, float *ms);
 int asam_l2_flush(asam_dev_t *d);
 int asam_device_info(asam_dev_t *d, int *n_sm, int *fac_grid, int *fac_smem, int *bs_grid);
+/* measured FP64 (DFMA) peak of the device in TFLOP/s: the factorisation's compute roofline (bench.py) */
+int asam_measure_fp64_peak(asam_dev_t *d, double *tflops_out);
 int asam_last_kernel_ms(asam_dev_t *d, float *lin_ms, float *fac_ms, float *bs_ms);
 
 #ifdef __cplusplus

@@ -53,8 +53,8 @@ def test_reference_arm_json_contract():
     from aprilsam_b200 import harness as H
     if not H.available("reference"):
         pytest.skip("reference oracle not built")
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
-                       capture_output=True, text=True, timeout=300)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "m3500_batch",
+                        "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-1000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -68,5 +68,35 @@ def test_reference_arm_json_contract():
     assert 5 < j["value"] < 500 and abs(j["value"] - j["e2e"]["value"]) < 1e-9
     import torch
     if not torch.cuda.is_available():
-        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "2"], capture_output=True, text=True, timeout=300)
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "2", "--workload", "m3500_batch"],
+                           capture_output=True, text=True, timeout=300)
         assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
+
+
+def test_reference_arm_default_line_covers_all_four_workloads():
+    """The default line (--workload all) headlines the batch solve of the synthetic Manhattan world and carries one
+    record each for m3500_batch, m3500_replay (with the as-shipped wall-clock variant beside it) and manhattan_replay,
+    every record with value / e2e / cpu_baseline; replay records with per-naffected-bucket latencies.  Small world here."""
+    import json
+    import subprocess
+    sys.path.insert(0, ROOT)
+    from aprilsam_b200 import harness as H
+    if not H.available("reference"):
+        pytest.skip("reference oracle not built")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--poses", "3000",
+                        "--replay-from", "1500", "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-1000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["config"]["workload"] == "manhattan_batch" and j["steps"] == 2 and j["impl"] == "reference"
+    assert set(j["workloads"]) == {"m3500_batch", "m3500_replay", "manhattan_replay"}
+    for name, rec in j["workloads"].items():
+        for k in ("value", "unit", "steps", "ms_per_step", "e2e", "cpu_baseline"):
+            assert k in rec, (name, k)
+        assert rec["value"] > 0
+    rp = j["workloads"]["m3500_replay"]
+    assert rp["steps"] == 3499 and set(rp["latency_by_bucket"]) == {"naffected_le5", "naffected_6_50", "naffected_gt50", "batch_escalation"}
+    assert rp["latency_by_bucket"]["batch_escalation"]["steps"] == 49  # SURVEY.md section 8c: 49 batch escalations
+    assert rp["latency_by_bucket"]["naffected_le5"]["steps"] > 2000
+    assert rp["cpu_baseline_wallclock"]["value"] > 0
