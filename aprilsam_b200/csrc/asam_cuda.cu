@@ -114,6 +114,10 @@ struct asam_dev {
     int defer = 0;
     struct Pending *pend = nullptr;
     int npend = 0;
+    int step_seq = 0;  // sequence number of the last k_step launch (completion flag in pin_down)
+    int solo_pb = 48;  // ASAM_SOLO_PB: staged panel width of single-CTA fronts that live in HBM
+    int small_ok = 1;  // ASAM_SMALL_STEP=0 disables the fused small-step kernel (A/B measurements)
+    int64_t n_small = 0;
 
     // launch config
     int fac_threads = 256, fac_grid = 0, fac_smem = 0;
@@ -130,9 +134,12 @@ struct asam_dev {
     int trace_on = 0;
     Buf trace_fac, trace_bs;
     int trace_nfac = 0, trace_nbs = 0;
+    Buf ptrace; // panel-step stamps of one team front (asam_set_panel_trace)
+    int ptrace_sn = -1, ptrace_panels = 0;
 };
 
 static int flush_uploads(asam_dev *d);
+static int clear_status(asam_dev *d);
 
 static int buf_reserve(asam_dev *d, Buf &b, size_t bytes, bool keep, bool zero_new)
 {
@@ -414,6 +421,70 @@ ASAM_EXPORT int asam_step_run(asam_dev_t *d)
     return 0;
 }
 
+// A small incremental step in ONE launch (k_step): the uploads queued since asam_step_begin stay in
+// the pinned staging buffer and are fetched by the kernel itself; the recorded linearize / factor /
+// back-solve run inside that kernel; x of the back-solved supernodes (list order, 3*cb doubles each)
+// and the status word come back through pinned memory, the host spins on a sequence flag.
+// Preconditions (checked): exactly linearize + factor + backsolve recorded, no leaf kernels, every
+// factor task a single-CTA front.  Returns 2 if the step does not qualify (nothing launched; call
+// asam_step_run instead).
+ASAM_EXPORT int asam_step_small_supported(asam_dev_t *d) { return d->small_ok && !d->timing && !d->trace_on && !d->sharded; }
+
+ASAM_EXPORT int asam_step_run_small(asam_dev_t *d, double *x_out, int x_doubles, int *status_out)
+{
+    CK(cudaSetDevice(d->device));
+    if (!d->defer || d->npend != 3 || d->pend[0].kind != 0 || d->pend[1].kind != 1 || d->pend[2].kind != 2 ||
+        d->pend[2].nleaf != 0 || (size_t) x_doubles * sizeof(double) + 64 > d->pin_down_cap || d->n_items <= 0)
+        return 2;
+    if (d->up_busy) { // an earlier flush may still be reading the staging buffer
+        CK(cudaEventSynchronize(d->up_ev));
+        d->up_busy = 0;
+    }
+    d->defer = 0;
+    StepArgs a;
+    memcpy(d->pin, d->items, (size_t) d->n_items * sizeof(BatchItem));
+    a.host_in = (const uint4 *) d->pin;
+    a.stage = (uint4 *) d->dstage;
+    a.table_bytes = (unsigned int) (d->n_items * sizeof(BatchItem));
+    a.payload_off = (unsigned int) ASAM_TABLE_BYTES;
+    a.payload_bytes = (unsigned int) d->pin_off;
+    a.n_items = d->n_items;
+    a.lin = d->pend[0].lin;
+    a.fac = d->pend[1].fac;
+    a.bs = d->pend[2].bs;
+    a.bs.smem_doubles = d->fac_smem / (int) sizeof(double); // the CTA's whole dynamic shared memory
+    a.x_out = (double *) (d->pin_down + 64);
+    a.done = (volatile int *) d->pin_down;
+    a.seq = ++d->step_seq;
+    k_step<<<1, 256, d->fac_smem, d->stream>>>(a);
+    CK(cudaGetLastError());
+    d->n_launch++;
+    d->n_small++;
+    d->n_items = 0;
+    d->pin_off = 0;
+    d->npend = 0;
+    d->n_d2h += (int64_t) x_doubles * 8 + 8;
+    volatile int *done = (volatile int *) d->pin_down;
+    for (long long spins = 0; done[0] != a.seq; ++spins) {
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+        if ((spins & 0xffff) == 0xffff) { // a faulted launch never raises the flag
+            cudaError_t q = cudaStreamQuery(d->stream);
+            if (q != cudaSuccess && q != cudaErrorNotReady)
+                return set_err("k_step failed: %s", cudaGetErrorString(q));
+            if (q == cudaSuccess && done[0] != a.seq)
+                return set_err("k_step finished without raising its flag");
+        }
+    }
+    __sync_synchronize();
+    *status_out = done[1];
+    memcpy(x_out, d->pin_down + 64, (size_t) x_doubles * sizeof(double));
+    if (*status_out != 0)
+        return clear_status(d);
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // C-ABI
 // ------------------------------------------------------------------------------------------
@@ -496,6 +567,12 @@ ASAM_EXPORT int asam_dev_create(asam_dev_t **out)
     if (occ < 1)
         return set_err("k_backsolve does not fit on an SM");
     d->bs_grid = occ * d->n_sm;
+    CK(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, d->fac_smem));
+    if (getenv("ASAM_SOLO_PB") && atoi(getenv("ASAM_SOLO_PB")) >= 12)
+        d->solo_pb = atoi(getenv("ASAM_SOLO_PB")) / 12 * 12;
+    if (getenv("ASAM_SMALL_STEP"))
+        d->small_ok = atoi(getenv("ASAM_SMALL_STEP")) != 0;
+    memset(d->pin_down, 0, 64);
     *out = d;
     return 0;
 }
@@ -509,7 +586,7 @@ ASAM_EXPORT void asam_dev_destroy(asam_dev_t *d)
     Buf *all[] = { &d->f_type, &d->f_a, &d->f_b, &d->f_z, &d->f_W, &d->f_slot, &d->lp, &d->st, &d->node2q, &d->q2node,
                    &d->Adiag, &d->Aoff, &d->Bq, &d->y, &d->x, &d->dinv, &d->sn, &d->ipool, &d->arena, &d->arrive,
                    &d->xdone, &d->tbar, &d->tasks_full, &d->nwait_full, &d->btasks_full, &d->tasks_tmp, &d->nwait_tmp,
-                   &d->btasks_tmp, &d->leaf_tasks, &d->top_tasks, &d->top_nwait, &d->ctrl, &d->partial, &d->patch_ids, &d->patch_desc, &d->pts, &d->flush, &d->trace_fac, &d->trace_bs };
+                   &d->btasks_tmp, &d->leaf_tasks, &d->top_tasks, &d->top_nwait, &d->ctrl, &d->partial, &d->patch_ids, &d->patch_desc, &d->pts, &d->flush, &d->trace_fac, &d->trace_bs, &d->ptrace };
     for (int i = 0; i < 2; i++)
         if (d->tev[i])
             cudaEventDestroy(d->tev[i]);
@@ -759,6 +836,7 @@ static int launch_factor(asam_dev *d, int ntasks, const int *tasks_dev, const in
     a.ctrl = (int *) d->ctrl.p;
     a.smem_doubles = d->fac_smem / (int) sizeof(double);
     a.spin_limit = ASAM_SPIN_LIMIT_NS;
+    a.solo_pb = d->solo_pb;
     a.trace = nullptr;
     if (d->trace_on) {
         if (buf_reserve(d, d->trace_fac, (size_t) ntasks * 8 * sizeof(unsigned long long), false, false))
@@ -766,6 +844,9 @@ static int launch_factor(asam_dev *d, int ntasks, const int *tasks_dev, const in
         a.trace = (unsigned long long *) d->trace_fac.p;
         d->trace_nfac = ntasks;
     }
+    a.ptrace = d->ptrace_sn >= 0 ? (unsigned long long *) d->ptrace.p : nullptr;
+    a.ptrace_sn = d->ptrace_sn;
+    a.ptrace_panels = d->ptrace_panels;
     int grid = d->fac_grid < ntasks ? d->fac_grid : ntasks;
     if (d->defer) {
         if (with_leaves && d->n_leaf > 0)
@@ -1267,6 +1348,8 @@ ASAM_EXPORT int asam_download_x_status(asam_dev_t *d, int q_first, int q_count, 
     return 0;
 }
 
+ASAM_EXPORT int64_t asam_small_steps(asam_dev_t *d) { return d->n_small; }
+
 ASAM_EXPORT int asam_counters(asam_dev_t *d, int64_t *out3)
 {
     out3[0] = d->n_launch;
@@ -1388,6 +1471,34 @@ ASAM_EXPORT int asam_download_trace(asam_dev_t *d, int which, unsigned long long
     if (n <= 0 || !b.p)
         return 0;
     CK(cudaMemcpyAsync(out, b.p, (size_t) n * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d->stream));
+    CK(cudaStreamSynchronize(d->stream));
+    return 0;
+}
+
+// Panel-step stamps of team front `sn` (-1: off): 8 x uint64 per (panel, worker < 8); see team_front.
+ASAM_EXPORT int asam_set_panel_trace(asam_dev_t *d, int sn, int max_panels)
+{
+    CK(cudaSetDevice(d->device));
+    d->ptrace_sn = -1;
+    if (sn < 0 || max_panels <= 0)
+        return 0;
+    const size_t bytes = (size_t) max_panels * 64 * sizeof(unsigned long long);
+    if (buf_reserve(d, d->ptrace, bytes, false, false) || flush_uploads(d))
+        return 1;
+    CK(cudaMemsetAsync(d->ptrace.p, 0, bytes, d->stream));
+    d->ptrace_sn = sn;
+    d->ptrace_panels = max_panels;
+    return 0;
+}
+
+ASAM_EXPORT int asam_download_panel_trace(asam_dev_t *d, unsigned long long *out, int max_panels)
+{
+    CK(cudaSetDevice(d->device));
+    if (!d->ptrace.p || max_panels > d->ptrace_panels)
+        return set_err("asam_download_panel_trace: no trace");
+    if (flush_uploads(d))
+        return 1;
+    CK(cudaMemcpyAsync(out, d->ptrace.p, (size_t) max_panels * 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, d->stream));
     CK(cudaStreamSynchronize(d->stream));
     return 0;
 }

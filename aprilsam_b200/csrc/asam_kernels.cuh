@@ -147,9 +147,9 @@ struct LinArgs {
     int f_first, f_count;
 };
 
-__global__ void __launch_bounds__(128) k_linearize(LinArgs a)
+// one factor per lane; every lane of a warp must call this together (warp-wide match / shuffles)
+__device__ __forceinline__ void linearize_body(const LinArgs &a, const int t)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = t < a.f_count;
     const int f = a.f_first + (live ? t : 0);
     const int type = live ? a.f_type[f] : 0;
@@ -271,6 +271,11 @@ __global__ void __launch_bounds__(128) k_linearize(LinArgs a)
     }
 }
 
+__global__ void __launch_bounds__(128) k_linearize(LinArgs a)
+{
+    linearize_body(a, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
 __global__ void k_hessian_reset(double *Adiag, double *Aoff, double *Bq, int n_nodes, int n_slots, int n_lambda,
                                 double lambda)
 {
@@ -306,6 +311,9 @@ struct FacArgs {
     int smem_doubles;
     long long spin_limit;
     unsigned long long *trace; // optional: 8 words per task
+    int solo_pb; // widest staged panel of a front that one CTA handles out of HBM (multiple of ASAM_PB)
+    unsigned long long *ptrace; // optional: panel-step stamps of supernode ptrace_sn, [panel][worker < 8][8]
+    int ptrace_sn, ptrace_panels;
 };
 
 // Trailing update  C[i,j] -= sum_{p<pb} P[i,p] * P[j,p]  for j in [j0, m), i in [j, m]
@@ -316,14 +324,15 @@ struct FacArgs {
 // pipe, the limiter (2R + TN wavefronts feed R*TN warp-wide DFMAs per panel column).
 // Out-of-range rows/columns are clamped for the loads and masked at the store.
 template <int R, int TN>
-__device__ __forceinline__ void trailing_update(double *C, int ld, const double *P, int ldp, int pb, int j0, int m)
+__device__ __forceinline__ void trailing_update(double *C, int ld, const double *P, int ldp, int pb, int j0, int jend, int m)
 {
+    // columns [j0, jend) (jend <= m), rows [j, m]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    for (int tj = j0 + TN * warp; tj < m; tj += TN * nwarps) {
+    for (int tj = j0 + TN * warp; tj < jend; tj += TN * nwarps) {
         int jc[TN];
 #pragma unroll
         for (int q = 0; q < TN; q++)
-            jc[q] = min(tj + q, m - 1);
+            jc[q] = min(tj + q, jend - 1);
         for (int ib = tj; ib <= m; ib += 32 * R) {
             double acc[R][TN];
             int irow[R], ic[R];
@@ -356,7 +365,7 @@ __device__ __forceinline__ void trailing_update(double *C, int ld, const double 
 #pragma unroll
                 for (int q = 0; q < TN; q++) {
                     const int i = irow[r], j = tj + q;
-                    if (i <= m && j < m && i >= j)
+                    if (i <= m && j < jend && i >= j)
                         C[i + (size_t) j * ld] -= acc[r][q];
                 }
         }
@@ -907,7 +916,17 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
             writeback(0, pb);
     }
     int seq = 0;
+    const bool pt_on = a.ptrace && s == a.ptrace_sn && w < 8 && tid == 0;
     for (int k0 = 0; k0 < c; k0 += ASAM_TPB) {
+        // panel trace (diagnostics): [0] iteration start, [1] own crew tiles done, [2] block factored and
+        // published (w 0) / flag seen and rows solved (w > 0), [3] own trailing tiles done, [4] past the barrier
+        unsigned long long *pt = (pt_on && k0 / ASAM_TPB < a.ptrace_panels) ? a.ptrace + ((size_t) (k0 / ASAM_TPB) * 8 + w) * 8 : nullptr;
+        if (pt) {
+            pt[0] = d_now();
+            pt[1] = pt[2] = pt[3] = pt[0];
+            pt[5] = (unsigned long long) m;
+            pt[6] = (unsigned long long) G;
+        }
         const int pb = min(ASAM_TPB, c - k0);
         const int kn0 = k0 + pb;                       // first trailing column = next panel
         const bool has_next = kn0 < c;
@@ -925,17 +944,25 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
                 for (int e = tid; e < ASAM_TPB * ASAM_TPB; e += nt)
                     D[e] = 0.0;
                 tile(k0, pb, kn0, pbn, kn0, pbn, D);
+                if (pt)
+                    pt[1] = d_now();
                 diag_publish(kn0, pbn, seq);
+                if (pt)
+                    pt[2] = d_now();
             }
             for (int it = (w == 0 ? G : w); it < ncrew; it += G) {
                 const int rb0 = kn0 + pbn + (it - 1) * ASAM_TROWS;
                 tile(k0, pb, kn0, pbn, rb0, min(ASAM_TROWS, m - rb0 + 1), nullptr);
             }
+            if (pt && w > 0)
+                pt[1] = d_now();
             for (int it = (w == 0 ? G : w); it < ncrew; it += G) {
                 const int rb0 = kn0 + pbn + (it - 1) * ASAM_TROWS;
                 if (!rows_solve(kn0, pbn, rb0, seq))
                     return false;
             }
+            if (pt && w > 0)
+                pt[2] = d_now();
             if (trow && tid == 0)
                 t_panel += d_now() - t_mark;
         }
@@ -957,8 +984,14 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
                     if (u % nfree == wfree)
                         tile(k0, pb, cb0, min(ASAM_TCOLS, m - cb0), rb0, min(TR, m - rb0 + 1), nullptr);
         }
+        if (pt)
+            pt[3] = d_now();
         if (!team_barrier(tc, s_flag))
             return false;
+        if (pt) {
+            pt[4] = d_now();
+            pt[7] = (unsigned long long) ncrew;
+        }
     }
     if (w == 0 && tid == 0)
         atomicExch(crew_bar, 0); // everybody is past its last wait on the crew flag (team barrier above)
@@ -996,6 +1029,241 @@ __device__ __forceinline__ void ticket_release(int *ticket, int *done)
     }
 }
 
+// One front handled by ONE CTA (the front in shared memory when it fits, else in HBM with staged
+// panels): zero + gather the Hessian entries, wait for the children of this launch, extend-add the
+// children's update matrices, eliminate the supernode's columns, publish.  t = index in the task
+// list (trace slot).  Returns false on abort.
+__device__ bool cta_front(const FacArgs &a, const int t, const int s, const int nw, const asam_sn_desc_t &d, double *sm,
+                          asam_sn_desc_t *s_cd, int *s_abort, unsigned long long tr0)
+{
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    int *err = a.ctrl + 1;
+    unsigned long long tr1 = 0, tr2 = 0, tr3 = 0, tr4 = 0, accA = 0, accB = 0;
+    const int m = 3 * d.mb, c = 3 * d.cb, ld = m + 1;
+    const int *seg = a.ipool + d.seg;
+    const int *children = seg + 2 * d.mb;
+    const int *a_slot = children + d.ch_cnt;
+    const int *a_rb = a_slot + d.a_cnt;
+    const int *a_cb = a_rb + d.a_cnt;
+    double *Fg = a.arena + d.f_off;
+    // shared-memory budget: front + destination map (ld ints) when the front fits
+    const long long fsz = (long long) ld * m;
+    const bool use_sm = fsz + (ld + 1) / 2 + 2 <= (long long) a.smem_doubles;
+    double *F = use_sm ? sm : Fg;
+    int *dmap = (int *) (sm + (use_sm ? fsz : 0)); // ld ints
+    double *Pbuf = sm + (ld + 1) / 2 + 1;           // big mode only: staged panel
+    double *dinv = a.dinv + 3 * (size_t) d.first;   // 1/L_kk of this supernode's columns
+
+    // ---- 1. zero the lower trapezoid (+ rhs row), gather the original entries ---------
+    if (use_sm) {
+        for (int i = tid; i < (int) fsz; i += nt)
+            F[i] = 0.0;
+    } else {
+        for (int j = warp; j < m; j += nwarps)
+            for (int i = j + lane; i <= m; i += 32)
+                F[i + (size_t) j * ld] = 0.0;
+    }
+    for (int e = tid; e < d.ch_cnt && e < ASAM_MAX_CACHED_CHILDREN; e += nt)
+        s_cd[e] = a.sn[children[e]];
+    __syncthreads();
+    for (int e = tid; e < d.cb * 9; e += nt) {
+        int k = e / 9, p = (e % 9) / 3, q = e % 3; // F[row 3k+p, col 3k+q], p >= q
+        if (p >= q)
+            F[(3 * k + p) + (size_t) (3 * k + q) * ld] =
+                a.Adiag[9 * (size_t) a.q2node[d.first + k] + q * 3 + p];
+    }
+    for (int e = tid; e < c; e += nt) // rhs row
+        F[m + (size_t) e * ld] = a.Bq[3 * (size_t) a.q2node[d.first + e / 3] + e % 3];
+    for (int e = tid; e < d.a_cnt * 9; e += nt) {
+        int i = e / 9, p = (e % 9) / 3, q = e % 3; // late-node component p (row), early q (col)
+        const int rbf = a_rb[i];
+        const int rb = rbf & ~ASAM_TR_FLAG;
+        // slot is S[lo id][hi id]; flag set when the early (column) node is the higher id
+        const int si = (rbf & ASAM_TR_FLAG) ? (p * 3 + q) : (q * 3 + p);
+        F[(3 * rb + p) + (size_t) (3 * a_cb[i] + q) * ld] = a.Aoff[9 * (size_t) a_slot[i] + si];
+    }
+    if (a.trace && tid == 0)
+        tr1 = d_now();
+
+    // ---- 2. wait for the children that are being re-factored in this launch ---------
+    if (nw > 0 && tid == 0) {
+        SpinClock spins;
+        while (ld_volatile(&a.arrive[s]) < nw) {
+            __nanosleep(32);
+            if (spin_over(spins, a.spin_limit) || ld_volatile(err) < 0) {
+                atomicCAS(err, 0, -(1 + s));
+                *s_abort = 1;
+                break;
+            }
+        }
+        a.arrive[s] = 0;
+        __threadfence();
+    }
+    __syncthreads();
+    if (*s_abort)
+        return false;
+    if (a.trace && tid == 0)
+        tr2 = d_now();
+
+    // ---- 3. extend-add the children's update matrices (fixed order: deterministic) ----
+    for (int ci = 0; ci < d.ch_cnt; ++ci) {
+        const asam_sn_desc_t cd = ci < ASAM_MAX_CACHED_CHILDREN ? s_cd[ci] : a.sn[children[ci]];
+        const int cm = 3 * cd.mb, cc = 3 * cd.cb, cr = cm - cc, cld = cm + 1;
+        const double *CF = a.arena + cd.f_off;
+        const int *crel = a.ipool + cd.seg + cd.mb; // rel[]
+        // destination row of child row cc+i (i in [0,cr]); the child's rhs row -> ours
+        for (int i = tid; i <= cr; i += nt)
+            dmap[i] = (i < cr) ? 3 * crel[(cc + i) / 3] + (cc + i) % 3 : m;
+        __syncthreads();
+        if (use_sm && cr <= 159) {
+            // the whole update matrix in few round trips: four columns per warp and pass, up to
+            // 160 rows each -> 20 independent loads in flight per lane (the critical path of a
+            // small solve is a chain of these extend-adds, each bound by L2 latency, not bytes)
+            for (int j0 = warp; j0 < cr; j0 += 4 * nwarps) {
+                double v[4][5];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int j = j0 + q * nwarps;
+                    const double *ccol = CF + (size_t) (cc + min(j, cr - 1)) * cld + cc;
+#pragma unroll
+                    for (int u = 0; u < 5; u++) {
+                        const int i = j + lane + 32 * u;
+                        v[q][u] = (j < cr && i <= cr) ? __ldcg(ccol + i) : 0.0;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int j = j0 + q * nwarps;
+                    if (j < cr) {
+                        double *fcol = F + (size_t) dmap[j] * ld;
+#pragma unroll
+                        for (int u = 0; u < 5; u++) {
+                            const int i = j + lane + 32 * u;
+                            if (i <= cr)
+                                fcol[dmap[i]] += v[q][u];
+                        }
+                    }
+                }
+            }
+        } else {
+            for (int j = warp; j < cr; j += nwarps) {
+                const double *ccol = CF + (size_t) (cc + j) * cld + cc;
+                double *fcol = F + (size_t) dmap[j] * ld;
+                for (int i0 = j + lane; i0 <= cr; i0 += 256) { // eight independent loads in flight per lane
+                    double v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++)
+                        v[u] = (i0 + 32 * u <= cr) ? __ldcg(ccol + i0 + 32 * u) : 0.0;
+#pragma unroll
+                    for (int u = 0; u < 8; u++)
+                        if (i0 + 32 * u <= cr)
+                            fcol[dmap[i0 + 32 * u]] += v[u];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (a.trace && tid == 0)
+        tr3 = d_now();
+
+    // ---- 4. eliminate this supernode's columns, panel by panel ------------------------
+    if (use_sm) {
+        for (int k0 = 0; k0 < c; k0 += ASAM_PB) {
+            const int pb = min(ASAM_PB, c - k0);
+            double *P = F + (size_t) k0 * ld; // panel columns live inside the front
+            unsigned long long ta = 0, tb = 0;
+            if (a.trace && tid == 0)
+                ta = d_now();
+            panel_factor(P, ld, k0, pb, m, s, err, dinv);
+            if (a.trace && tid == 0) {
+                tb = d_now();
+                accA += tb - ta;
+            }
+            const int n = m - (k0 + pb);
+            if (n > 48)
+                trailing_update<2, 8>(F, ld, P, ld, pb, k0 + pb, m, m);
+            else
+                trailing_update<1, 4>(F, ld, P, ld, pb, k0 + pb, m, m);
+            __syncthreads();
+        }
+    } else {
+        // big front handled by this CTA alone: the front stays in HBM/L2, one WIDE panel (up to
+        // a.solo_pb columns, rows k0..m) at a time is staged in shared memory, factored there in
+        // 12-column sub-panels (closed-form 3x3 steps + register-tiled update of the rest of the
+        // panel), written back, and applied to the trailing matrix in one pass.  Mid-size fronts
+        // (m of a few hundred) are latency-bound on a team -- two barriers and several L2 round trips
+        // per 48 columns for a few microseconds of arithmetic -- so while the tree is wide they go
+        // through here, one SM each (host: team_size()).
+        const int avail = a.smem_doubles - ((ld + 1) / 2 + 2);
+        int PB = avail / ld;
+        PB = PB > a.solo_pb ? a.solo_pb : PB;
+        PB = PB >= ASAM_PB ? PB - (PB % ASAM_PB) : PB - (PB % 3);
+        if (PB < 3) { // front too tall for even a 3-column panel (cannot happen below m ~ 8000)
+            if (tid == 0)
+                atomicCAS(err, 0, -(1 + s));
+            return false;
+        }
+        for (int k0 = 0; k0 < c; k0 += PB) {
+            const int pbw = min(PB, c - k0);
+            for (int p = warp; p < pbw; p += nwarps)
+                for (int i = k0 + lane; i <= m; i += 32)
+                    Pbuf[i + (size_t) p * ld] = F[i + (size_t) (k0 + p) * ld];
+            __syncthreads();
+            double *Cp = Pbuf - (size_t) k0 * ld; // the panel addressed by FRONT column index
+            for (int k1 = 0; k1 < pbw; k1 += ASAM_PB) {
+                const int pb = min(ASAM_PB, pbw - k1);
+                panel_factor(Pbuf + (size_t) k1 * ld, ld, k0 + k1, pb, m, s, err, dinv);
+                if (k1 + pb < pbw) {
+                    trailing_update<2, 8>(Cp, ld, Pbuf + (size_t) k1 * ld, ld, pb, k0 + k1 + pb, k0 + pbw, m);
+                    __syncthreads();
+                }
+            }
+            for (int p = warp; p < pbw; p += nwarps)
+                for (int i = k0 + lane; i <= m; i += 32)
+                    F[i + (size_t) (k0 + p) * ld] = Pbuf[i + (size_t) p * ld];
+            trailing_update<4, 8>(F, ld, Pbuf, ld, pbw, k0 + pbw, m, m);
+            __syncthreads();
+        }
+    }
+    if (a.trace && tid == 0)
+        tr4 = d_now();
+
+    // ---- 5. publish: the update matrix first (that is all the parent waits for), then y and
+    // the L panel, which only the back-substitution and later incremental steps read ----------
+    if (use_sm) {
+        for (int j = c + warp; j < m; j += nwarps)
+            for (int i = j + lane; i <= m; i += 32)
+                Fg[i + (size_t) j * ld] = F[i + (size_t) j * ld];
+    }
+    __syncthreads();
+    if (tid == 0 && d.parent >= 0) {
+        __threadfence();
+        atomicAdd(&a.arrive[d.parent], 1);
+    }
+    for (int e = tid; e < c; e += nt)
+        a.y[3 * (size_t) d.first + e] = F[m + (size_t) e * ld];
+    if (use_sm) {
+        for (int j = warp; j < c; j += nwarps)
+            for (int i = j + lane; i <= m; i += 32)
+                Fg[i + (size_t) j * ld] = F[i + (size_t) j * ld];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (a.trace) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            unsigned long long *tr = a.trace + 8 * (size_t) t;
+            tr[0] = tr0; tr[1] = tr1; tr[2] = tr2; tr[3] = tr3; tr[4] = tr4; tr[5] = d_now();
+            (void) smid;
+            tr[6] = (unsigned long long) s | (accB << 32); // low: supernode, high: ns in panel TRSM
+            tr[7] = (unsigned long long) (unsigned) m | (accA << 32); // low: m, high: ns in diag blocks
+        }
+    }
+    __syncthreads();
+    return true;
+}
+
 __global__ void __launch_bounds__(256, 1) k_factor(FacArgs a)
 {
     extern __shared__ __align__(16) double sm[];
@@ -1013,7 +1281,7 @@ __global__ void __launch_bounds__(256, 1) k_factor(FacArgs a)
         const int t = s_task;
         if (t >= a.ntasks)
             break;
-        unsigned long long tr0 = 0, tr1 = 0, tr2 = 0, tr3 = 0, tr4 = 0, accA = 0, accB = 0;
+        unsigned long long tr0 = 0;
         if (a.trace && tid == 0)
             tr0 = d_now();
         const int s = a.tasks[t];
@@ -1041,213 +1309,8 @@ __global__ void __launch_bounds__(256, 1) k_factor(FacArgs a)
             __syncthreads();
             continue;
         }
-        const int m = 3 * d.mb, c = 3 * d.cb, ld = m + 1;
-        const int *seg = a.ipool + d.seg;
-        const int *children = seg + 2 * d.mb;
-        const int *a_slot = children + d.ch_cnt;
-        const int *a_rb = a_slot + d.a_cnt;
-        const int *a_cb = a_rb + d.a_cnt;
-        double *Fg = a.arena + d.f_off;
-        // shared-memory budget: front + destination map (ld ints) when the front fits
-        const long long fsz = (long long) ld * m;
-        const bool use_sm = fsz + (ld + 1) / 2 + 2 <= (long long) a.smem_doubles;
-        double *F = use_sm ? sm : Fg;
-        int *dmap = (int *) (sm + (use_sm ? fsz : 0)); // ld ints
-        double *Pbuf = sm + (ld + 1) / 2 + 1;           // big mode only: staged panel
-        double *dinv = a.dinv + 3 * (size_t) d.first;   // 1/L_kk of this supernode's columns
-
-        // ---- 1. zero the lower trapezoid (+ rhs row), gather the original entries ---------
-        if (use_sm) {
-            for (int i = tid; i < (int) fsz; i += nt)
-                F[i] = 0.0;
-        } else {
-            for (int j = warp; j < m; j += nwarps)
-                for (int i = j + lane; i <= m; i += 32)
-                    F[i + (size_t) j * ld] = 0.0;
-        }
-        for (int e = tid; e < d.ch_cnt && e < ASAM_MAX_CACHED_CHILDREN; e += nt)
-            s_cd[e] = a.sn[children[e]];
-        __syncthreads();
-        for (int e = tid; e < d.cb * 9; e += nt) {
-            int k = e / 9, p = (e % 9) / 3, q = e % 3; // F[row 3k+p, col 3k+q], p >= q
-            if (p >= q)
-                F[(3 * k + p) + (size_t) (3 * k + q) * ld] =
-                    a.Adiag[9 * (size_t) a.q2node[d.first + k] + q * 3 + p];
-        }
-        for (int e = tid; e < c; e += nt) // rhs row
-            F[m + (size_t) e * ld] = a.Bq[3 * (size_t) a.q2node[d.first + e / 3] + e % 3];
-        for (int e = tid; e < d.a_cnt * 9; e += nt) {
-            int i = e / 9, p = (e % 9) / 3, q = e % 3; // late-node component p (row), early q (col)
-            const int rbf = a_rb[i];
-            const int rb = rbf & ~ASAM_TR_FLAG;
-            // slot is S[lo id][hi id]; flag set when the early (column) node is the higher id
-            const int si = (rbf & ASAM_TR_FLAG) ? (p * 3 + q) : (q * 3 + p);
-            F[(3 * rb + p) + (size_t) (3 * a_cb[i] + q) * ld] = a.Aoff[9 * (size_t) a_slot[i] + si];
-        }
-        if (a.trace && tid == 0)
-            tr1 = d_now();
-
-        // ---- 2. wait for the children that are being re-factored in this launch ---------
-        if (nw > 0 && tid == 0) {
-            SpinClock spins;
-            while (ld_volatile(&a.arrive[s]) < nw) {
-                __nanosleep(32);
-                if (spin_over(spins, a.spin_limit) || ld_volatile(err) < 0) {
-                    atomicCAS(err, 0, -(1 + s));
-                    s_abort = 1;
-                    break;
-                }
-            }
-            a.arrive[s] = 0;
-            __threadfence();
-        }
-        __syncthreads();
-        if (s_abort)
+        if (!cta_front(a, t, s, nw, d, sm, s_cd, &s_abort, tr0))
             break;
-        if (a.trace && tid == 0)
-            tr2 = d_now();
-
-        // ---- 3. extend-add the children's update matrices (fixed order: deterministic) ----
-        for (int ci = 0; ci < d.ch_cnt; ++ci) {
-            const asam_sn_desc_t cd = ci < ASAM_MAX_CACHED_CHILDREN ? s_cd[ci] : a.sn[children[ci]];
-            const int cm = 3 * cd.mb, cc = 3 * cd.cb, cr = cm - cc, cld = cm + 1;
-            const double *CF = a.arena + cd.f_off;
-            const int *crel = a.ipool + cd.seg + cd.mb; // rel[]
-            // destination row of child row cc+i (i in [0,cr]); the child's rhs row -> ours
-            for (int i = tid; i <= cr; i += nt)
-                dmap[i] = (i < cr) ? 3 * crel[(cc + i) / 3] + (cc + i) % 3 : m;
-            __syncthreads();
-            if (use_sm && cr <= 159) {
-                // the whole update matrix in few round trips: four columns per warp and pass, up to
-                // 160 rows each -> 20 independent loads in flight per lane (the critical path of a
-                // small solve is a chain of these extend-adds, each bound by L2 latency, not bytes)
-                for (int j0 = warp; j0 < cr; j0 += 4 * nwarps) {
-                    double v[4][5];
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const int j = j0 + q * nwarps;
-                        const double *ccol = CF + (size_t) (cc + min(j, cr - 1)) * cld + cc;
-#pragma unroll
-                        for (int u = 0; u < 5; u++) {
-                            const int i = j + lane + 32 * u;
-                            v[q][u] = (j < cr && i <= cr) ? __ldcg(ccol + i) : 0.0;
-                        }
-                    }
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const int j = j0 + q * nwarps;
-                        if (j < cr) {
-                            double *fcol = F + (size_t) dmap[j] * ld;
-#pragma unroll
-                            for (int u = 0; u < 5; u++) {
-                                const int i = j + lane + 32 * u;
-                                if (i <= cr)
-                                    fcol[dmap[i]] += v[q][u];
-                            }
-                        }
-                    }
-                }
-            } else {
-                for (int j = warp; j < cr; j += nwarps) {
-                    const double *ccol = CF + (size_t) (cc + j) * cld + cc;
-                    double *fcol = F + (size_t) dmap[j] * ld;
-                    for (int i0 = j + lane; i0 <= cr; i0 += 256) { // eight independent loads in flight per lane
-                        double v[8];
-#pragma unroll
-                        for (int u = 0; u < 8; u++)
-                            v[u] = (i0 + 32 * u <= cr) ? __ldcg(ccol + i0 + 32 * u) : 0.0;
-#pragma unroll
-                        for (int u = 0; u < 8; u++)
-                            if (i0 + 32 * u <= cr)
-                                fcol[dmap[i0 + 32 * u]] += v[u];
-                    }
-                }
-            }
-            __syncthreads();
-        }
-        if (a.trace && tid == 0)
-            tr3 = d_now();
-
-        // ---- 4. eliminate this supernode's columns, panel by panel ------------------------
-        if (use_sm) {
-            for (int k0 = 0; k0 < c; k0 += ASAM_PB) {
-                const int pb = min(ASAM_PB, c - k0);
-                double *P = F + (size_t) k0 * ld; // panel columns live inside the front
-                unsigned long long ta = 0, tb = 0;
-                if (a.trace && tid == 0)
-                    ta = d_now();
-                panel_factor(P, ld, k0, pb, m, s, err, dinv);
-                if (a.trace && tid == 0) {
-                    tb = d_now();
-                    accA += tb - ta;
-                }
-                const int n = m - (k0 + pb);
-                if (n > 48)
-                    trailing_update<2, 8>(F, ld, P, ld, pb, k0 + pb, m);
-                else
-                    trailing_update<1, 4>(F, ld, P, ld, pb, k0 + pb, m);
-                __syncthreads();
-            }
-        } else {
-            // big front: stage each panel (rows k0..m, pb columns) in shared memory
-            const int avail = a.smem_doubles - ((ld + 1) / 2 + 2);
-            int PB = avail / ld;
-            PB = PB > ASAM_PB ? ASAM_PB : PB;
-            PB = PB - (PB % 3);
-            if (PB < 3) { // front too tall for even a 4-column panel (cannot happen below m ~ 6000)
-                if (tid == 0)
-                    atomicCAS(err, 0, -(1 + s));
-                break;
-            }
-            for (int k0 = 0; k0 < c; k0 += PB) {
-                const int pb = min(PB, c - k0);
-                for (int p = warp; p < pb; p += nwarps)
-                    for (int i = k0 + lane; i <= m; i += 32)
-                        Pbuf[i + (size_t) p * ld] = F[i + (size_t) (k0 + p) * ld];
-                __syncthreads();
-                panel_factor(Pbuf, ld, k0, pb, m, s, err, dinv);
-                for (int p = warp; p < pb; p += nwarps)
-                    for (int i = k0 + lane; i <= m; i += 32)
-                        F[i + (size_t) (k0 + p) * ld] = Pbuf[i + (size_t) p * ld];
-                trailing_update<4, 8>(F, ld, Pbuf, ld, pb, k0 + pb, m);
-                __syncthreads();
-            }
-        }
-        if (a.trace && tid == 0)
-            tr4 = d_now();
-
-        // ---- 5. publish: the update matrix first (that is all the parent waits for), then y and
-        // the L panel, which only the back-substitution and later incremental steps read ----------
-        if (use_sm) {
-            for (int j = c + warp; j < m; j += nwarps)
-                for (int i = j + lane; i <= m; i += 32)
-                    Fg[i + (size_t) j * ld] = F[i + (size_t) j * ld];
-        }
-        __syncthreads();
-        if (tid == 0 && d.parent >= 0) {
-            __threadfence();
-            atomicAdd(&a.arrive[d.parent], 1);
-        }
-        for (int e = tid; e < c; e += nt)
-            a.y[3 * (size_t) d.first + e] = F[m + (size_t) e * ld];
-        if (use_sm) {
-            for (int j = warp; j < c; j += nwarps)
-                for (int i = j + lane; i <= m; i += 32)
-                    Fg[i + (size_t) j * ld] = F[i + (size_t) j * ld];
-        }
-        __syncthreads();
-        if (tid == 0) {
-            if (a.trace) {
-                unsigned smid;
-                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-                unsigned long long *tr = a.trace + 8 * (size_t) t;
-                tr[0] = tr0; tr[1] = tr1; tr[2] = tr2; tr[3] = tr3; tr[4] = tr4; tr[5] = d_now();
-                (void) smid;
-                tr[6] = (unsigned long long) s | (accB << 32); // low: supernode, high: ns in panel TRSM
-                tr[7] = (unsigned long long) (unsigned) m | (accA << 32); // low: m, high: ns in diag blocks
-            }
-        }
-        __syncthreads();
     }
     ticket_release(&a.ctrl[0], &a.ctrl[3]);
 }
@@ -1489,6 +1552,142 @@ __device__ __forceinline__ double bs_dot(const double *lk, const double *xs, int
     return acc0;
 }
 
+// One supernode of the back-substitution handled by ONE CTA (see the comment above).  t = index in the
+// task list (trace slot).  Returns false on abort.
+__device__ bool cta_backsolve(const BsArgs &a, const int t, const int s, double *sm, int *s_abort)
+{
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    int *err = a.ctrl + 1;
+    unsigned long long tr0 = 0, tr1 = 0, tr2 = 0;
+    if (a.trace && tid == 0)
+        tr0 = d_now();
+    const asam_sn_desc_t d = a.sn[s];
+    const int m = 3 * d.mb, c = 3 * d.cb, r = m - c, ld = m + 1;
+    const int *rows = a.ipool + d.seg;
+    const double *Lg = a.arena + d.f_off;
+    const int bwmax = min(c, ASAM_BSW);
+    if (m + 2 * bwmax + 2 > a.smem_doubles) { // host sizes shared memory for the largest front
+        if (tid == 0)
+            atomicCAS(err, 0, -(1 + s));
+        return false;
+    }
+    double *xf = sm;          // x over the front's rows: [0,c) own columns, [c,m) ancestors
+    double *w = sm + m;       // bwmax
+    double *rd = w + bwmax;   // bwmax
+    double *Ls = rd + bwmax;
+    const long long room = (long long) a.smem_doubles - (m + 2 * bwmax);
+    const int nblk = (c + ASAM_BSW - 1) / ASAM_BSW;
+
+    for (int blk = nblk - 1; blk >= 0; --blk) {
+        const int b0 = blk * ASAM_BSW, bw = min(ASAM_BSW, c - b0), be = b0 + bw, hb = m - b0;
+        // staging mode: 2 = whole panel of the block (rows b0..m-1, ld lm), 1 = its diagonal
+        // block only (ld lc), 0 = none.  Staged leading dimensions are ODD: the triangular
+        // solve reads row k across columns, an even stride would pile the lanes onto a few banks
+        const int lm = hb | 1, lc = bw | 1;
+        const int mode = ((long long) lm * bw <= room) ? 2 : (((long long) lc * bw <= room) ? 1 : 0);
+        const int ll = mode == 2 ? lm : (mode == 1 ? lc : ld);
+        if (blk != nblk - 1)
+            __syncthreads(); // the previous block is done with w / rd / Ls
+        if (mode == 2) {
+            for (int k = warp; k < bw; k += nwarps)
+                for (int i = k + lane; i < hb; i += 32)
+                    Ls[i + (size_t) k * lm] = Lg[(b0 + i) + (size_t) (b0 + k) * ld];
+        } else if (mode == 1) {
+            for (int k = warp; k < bw; k += nwarps)
+                for (int i = k + lane; i < bw; i += 32)
+                    Ls[i + (size_t) k * lc] = Lg[(b0 + i) + (size_t) (b0 + k) * ld];
+        }
+        for (int k = tid; k < bw; k += nt) {
+            w[k] = a.y[3 * (size_t) d.first + b0 + k];
+            rd[k] = a.dinv[3 * (size_t) d.first + b0 + k];
+        }
+        const double *L11 = mode ? Ls : (Lg + b0 + (size_t) b0 * ld); // (row, col) at L11[row + col*ll]
+
+        if (blk == nblk - 1) {
+            if (a.trace && tid == 0)
+                tr1 = d_now();
+            if (d.parent >= 0 && tid == 0) {
+                SpinClock spins;
+                while (ld_volatile(&a.xdone[d.parent]) != a.epoch) {
+                    __nanosleep(20);
+                    if (spin_over(spins, a.spin_limit) || ld_volatile(err) < 0) {
+                        atomicCAS(err, 0, -(1 + s));
+                        *s_abort = 1;
+                        break;
+                    }
+                }
+                __threadfence();
+            }
+            __syncthreads();
+            if (*s_abort)
+                break;
+            if (a.trace && tid == 0)
+                tr2 = d_now();
+            for (int i = tid; i < r; i += nt)
+                xf[c + i] = __ldcg(&a.x[3 * (size_t) rows[d.cb + i / 3] + i % 3]);
+        }
+        __syncthreads();
+        // w_k -= sum_{i >= be} L[i, b0+k] * xf[i]   (one warp per column)
+        const int nr = m - be;
+        if (nr > 0) {
+            for (int k = warp; k < bw; k += nwarps) {
+                const double *lk = (mode == 2) ? (Ls + (size_t) k * lm + bw) : (Lg + (size_t) (b0 + k) * ld + be);
+                const double acc = nr > 512 ? bs_dot<16>(lk, xf + be, nr, lane) : bs_dot<8>(lk, xf + be, nr, lane);
+                if (lane == 0)
+                    w[k] -= acc;
+            }
+            __syncthreads();
+        }
+        // L11' x = w, right-looking: x_k = w_k / L_kk, then w_j -= L[k, j] * x_k for j < k.
+        // One warp, w in registers (lane l holds entries l, l+32, l+64), x_k travels by shuffle:
+        // no shared-memory round trip on the dependent chain.
+        if (warp == 0) {
+            double wr[3];
+#pragma unroll
+            for (int t3 = 0; t3 < 3; t3++)
+                wr[t3] = (lane + 32 * t3 < bw) ? w[lane + 32 * t3] : 0.0;
+#pragma unroll 2
+            for (int k = bw - 1; k >= 0; --k) {
+                const int ks = k >> 5;
+                const double mine = ks == 0 ? wr[0] : (ks == 1 ? wr[1] : wr[2]);
+                const double xk = __shfl_sync(0xffffffffu, mine, k & 31) * rd[k];
+#pragma unroll
+                for (int t3 = 0; t3 < 3; t3++) {
+                    const int j = lane + 32 * t3;
+                    if (j < k)
+                        wr[t3] -= L11[k + (size_t) j * ll] * xk;
+                    else if (j == k)
+                        wr[t3] = xk;
+                }
+            }
+#pragma unroll
+            for (int t3 = 0; t3 < 3; t3++) {
+                const int k = lane + 32 * t3;
+                if (k < bw) {
+                    a.x[3 * (size_t) d.first + b0 + k] = wr[t3];
+                    xf[b0 + k] = wr[t3];
+                }
+            }
+            __syncwarp();
+        }
+    }
+    if (*s_abort)
+        return false;
+    if (warp == 0 && lane == 0) {
+        __threadfence();
+        atomicExch(&a.xdone[s], a.epoch);
+        if (a.trace) {
+            unsigned long long *tr = a.trace + 8 * (size_t) t;
+            tr[0] = tr0; tr[1] = tr1; tr[2] = tr2; tr[3] = d_now();
+            tr[6] = (unsigned long long) s;
+            tr[7] = (unsigned) m;
+        }
+    }
+    __syncthreads();
+    return true;
+}
+
 __global__ void __launch_bounds__(256) k_backsolve(BsArgs a)
 {
     extern __shared__ __align__(16) double sm[]; // xf[m] | w[bw] | rd[bw] | staged L (panel or L11 of one block)
@@ -1506,133 +1705,8 @@ __global__ void __launch_bounds__(256) k_backsolve(BsArgs a)
         const int t = s_task;
         if (t >= a.ntasks)
             break;
-        unsigned long long tr0 = 0, tr1 = 0, tr2 = 0;
-        if (a.trace && tid == 0)
-            tr0 = d_now();
-        const int s = a.btasks[t];
-        const asam_sn_desc_t d = a.sn[s];
-        const int m = 3 * d.mb, c = 3 * d.cb, r = m - c, ld = m + 1;
-        const int *rows = a.ipool + d.seg;
-        const double *Lg = a.arena + d.f_off;
-        const int bwmax = min(c, ASAM_BSW);
-        if (m + 2 * bwmax + 2 > a.smem_doubles) { // host sizes shared memory for the largest front
-            if (tid == 0)
-                atomicCAS(err, 0, -(1 + s));
+        if (!cta_backsolve(a, t, a.btasks[t], sm, &s_abort))
             break;
-        }
-        double *xf = sm;          // x over the front's rows: [0,c) own columns, [c,m) ancestors
-        double *w = sm + m;       // bwmax
-        double *rd = w + bwmax;   // bwmax
-        double *Ls = rd + bwmax;
-        const long long room = (long long) a.smem_doubles - (m + 2 * bwmax);
-        const int nblk = (c + ASAM_BSW - 1) / ASAM_BSW;
-
-        for (int blk = nblk - 1; blk >= 0; --blk) {
-            const int b0 = blk * ASAM_BSW, bw = min(ASAM_BSW, c - b0), be = b0 + bw, hb = m - b0;
-            // staging mode: 2 = whole panel of the block (rows b0..m-1, ld lm), 1 = its diagonal
-            // block only (ld lc), 0 = none.  Staged leading dimensions are ODD: the triangular
-            // solve reads row k across columns, an even stride would pile the lanes onto a few banks
-            const int lm = hb | 1, lc = bw | 1;
-            const int mode = ((long long) lm * bw <= room) ? 2 : (((long long) lc * bw <= room) ? 1 : 0);
-            const int ll = mode == 2 ? lm : (mode == 1 ? lc : ld);
-            if (blk != nblk - 1)
-                __syncthreads(); // the previous block is done with w / rd / Ls
-            if (mode == 2) {
-                for (int k = warp; k < bw; k += nwarps)
-                    for (int i = k + lane; i < hb; i += 32)
-                        Ls[i + (size_t) k * lm] = Lg[(b0 + i) + (size_t) (b0 + k) * ld];
-            } else if (mode == 1) {
-                for (int k = warp; k < bw; k += nwarps)
-                    for (int i = k + lane; i < bw; i += 32)
-                        Ls[i + (size_t) k * lc] = Lg[(b0 + i) + (size_t) (b0 + k) * ld];
-            }
-            for (int k = tid; k < bw; k += nt) {
-                w[k] = a.y[3 * (size_t) d.first + b0 + k];
-                rd[k] = a.dinv[3 * (size_t) d.first + b0 + k];
-            }
-            const double *L11 = mode ? Ls : (Lg + b0 + (size_t) b0 * ld); // (row, col) at L11[row + col*ll]
-
-            if (blk == nblk - 1) {
-                if (a.trace && tid == 0)
-                    tr1 = d_now();
-                if (d.parent >= 0 && tid == 0) {
-                    SpinClock spins;
-                    while (ld_volatile(&a.xdone[d.parent]) != a.epoch) {
-                        __nanosleep(20);
-                        if (spin_over(spins, a.spin_limit) || ld_volatile(err) < 0) {
-                            atomicCAS(err, 0, -(1 + s));
-                            s_abort = 1;
-                            break;
-                        }
-                    }
-                    __threadfence();
-                }
-                __syncthreads();
-                if (s_abort)
-                    break;
-                if (a.trace && tid == 0)
-                    tr2 = d_now();
-                for (int i = tid; i < r; i += nt)
-                    xf[c + i] = __ldcg(&a.x[3 * (size_t) rows[d.cb + i / 3] + i % 3]);
-            }
-            __syncthreads();
-            // w_k -= sum_{i >= be} L[i, b0+k] * xf[i]   (one warp per column)
-            const int nr = m - be;
-            if (nr > 0) {
-                for (int k = warp; k < bw; k += nwarps) {
-                    const double *lk = (mode == 2) ? (Ls + (size_t) k * lm + bw) : (Lg + (size_t) (b0 + k) * ld + be);
-                    const double acc = nr > 512 ? bs_dot<16>(lk, xf + be, nr, lane) : bs_dot<8>(lk, xf + be, nr, lane);
-                    if (lane == 0)
-                        w[k] -= acc;
-                }
-                __syncthreads();
-            }
-            // L11' x = w, right-looking: x_k = w_k / L_kk, then w_j -= L[k, j] * x_k for j < k.
-            // One warp, w in registers (lane l holds entries l, l+32, l+64), x_k travels by shuffle:
-            // no shared-memory round trip on the dependent chain.
-            if (warp == 0) {
-                double wr[3];
-#pragma unroll
-                for (int t3 = 0; t3 < 3; t3++)
-                    wr[t3] = (lane + 32 * t3 < bw) ? w[lane + 32 * t3] : 0.0;
-#pragma unroll 2
-                for (int k = bw - 1; k >= 0; --k) {
-                    const int ks = k >> 5;
-                    const double mine = ks == 0 ? wr[0] : (ks == 1 ? wr[1] : wr[2]);
-                    const double xk = __shfl_sync(0xffffffffu, mine, k & 31) * rd[k];
-#pragma unroll
-                    for (int t3 = 0; t3 < 3; t3++) {
-                        const int j = lane + 32 * t3;
-                        if (j < k)
-                            wr[t3] -= L11[k + (size_t) j * ll] * xk;
-                        else if (j == k)
-                            wr[t3] = xk;
-                    }
-                }
-#pragma unroll
-                for (int t3 = 0; t3 < 3; t3++) {
-                    const int k = lane + 32 * t3;
-                    if (k < bw) {
-                        a.x[3 * (size_t) d.first + b0 + k] = wr[t3];
-                        xf[b0 + k] = wr[t3];
-                    }
-                }
-                __syncwarp();
-            }
-        }
-        if (s_abort)
-            break;
-        if (warp == 0 && lane == 0) {
-            __threadfence();
-            atomicExch(&a.xdone[s], a.epoch);
-            if (a.trace) {
-                unsigned long long *tr = a.trace + 8 * (size_t) t;
-                tr[0] = tr0; tr[1] = tr1; tr[2] = tr2; tr[3] = d_now();
-                tr[6] = (unsigned long long) s;
-                tr[7] = (unsigned) m;
-            }
-        }
-        __syncthreads();
     }
     ticket_release(&a.ctrl[2], &a.ctrl[4]);
 }
@@ -1755,6 +1829,139 @@ __global__ void __launch_bounds__(32 * ASAM_BSL_WARPS) k_backsolve_leaf(BsArgs a
         __syncwarp();
     }
     ticket_release(&a.ctrl[5], &a.ctrl[6]);
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel 4: a SMALL incremental step in one launch.
+//
+// The reference spends 18-60 us on an incremental step that touches a handful of poses
+// (aprilsam.c:377-576; SURVEY.md section 7 "a GPU step must be a single small launch").  The general
+// path costs five stream operations (H2D copy, scatter, k_linearize, k_factor, k_backsolve) plus two
+// D2H copies and a stream synchronisation -- a dependent chain of launch latencies several times
+// longer than the arithmetic.  Here ONE CTA does the whole step:
+//   1. fetches the step's uploads (item table + payload queued by the host in PINNED memory) over
+//      PCIe in one wave of 16-byte loads and scatters them to their places in HBM,
+//   2. linearises the new factors,
+//   3. re-factors the marked supernodes in list order (children first; all of them single-CTA fronts),
+//   4. back-substitutes the visited supernodes in list order (parents first),
+//   5. writes the solution of those supernodes and the status word straight into pinned host memory
+//      and raises a sequence flag there -- the host spins on that flag instead of synchronising the
+//      stream.
+// The per-front / per-supernode code is the same device function the persistent kernels run
+// (cta_front, cta_backsolve): the counters they wait on are already satisfied when they look.
+// ------------------------------------------------------------------------------------------
+struct StepArgs {
+    const uint4 *host_in; // pinned host memory: [item table | payload]
+    uint4 *stage;         // device mirror of it
+    unsigned int table_bytes, payload_off, payload_bytes; // table = n_items * sizeof(BatchItem)
+    int n_items;
+    LinArgs lin;
+    FacArgs fac;
+    BsArgs bs;
+    double *x_out;      // pinned host memory: x of the back-solved supernodes, in list order
+    volatile int *done; // pinned host memory: [0] sequence number of the last finished step, [1] status
+    int seq;
+};
+
+__global__ void __launch_bounds__(256, 1) k_step(StepArgs a)
+{
+    extern __shared__ __align__(16) double sm[];
+    __shared__ int s_abort;
+    __shared__ asam_sn_desc_t s_cd[ASAM_MAX_CACHED_CHILDREN];
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+
+    // ---- 1. uploads: host -> staging (all loads of a thread in flight before the first store) ----
+    {
+        const unsigned nt16 = (a.table_bytes + 15) >> 4, np16 = (a.payload_bytes + 15) >> 4, p0 = a.payload_off >> 4;
+        const unsigned n16 = nt16 + np16;
+        for (unsigned i0 = tid; i0 < n16; i0 += 4 * nt) {
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const unsigned i = i0 + u * nt;
+                if (i < n16)
+                    v[u] = a.host_in[i < nt16 ? i : p0 + (i - nt16)];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const unsigned i = i0 + u * nt;
+                if (i < n16)
+                    a.stage[i < nt16 ? i : p0 + (i - nt16)] = v[u];
+            }
+        }
+    }
+    __syncthreads();
+    {
+        const BatchItem *items = (const BatchItem *) a.stage;
+        const char *payload = (const char *) a.stage + a.payload_off;
+        for (int it = warp; it < a.n_items; it += nwarps) {
+            const BatchItem bi = items[it];
+            unsigned int *dst = (unsigned int *) bi.dst;
+            const unsigned int words = bi.bytes >> 2;
+            if (bi.fill) {
+                for (unsigned int i = lane; i < words; i += 32)
+                    dst[i] = bi.val;
+            } else {
+                const unsigned int *src = (const unsigned int *) (payload + bi.off);
+                for (unsigned int i = lane; i < words; i += 32)
+                    dst[i] = __ldcg(src + i);
+            }
+        }
+    }
+    __threadfence();
+    __syncthreads();
+
+    // ---- 2. new factors -----------------------------------------------------------------------
+    for (int t0 = 0; t0 < a.lin.f_count; t0 += nt)
+        linearize_body(a.lin, t0 + tid);
+    __threadfence();
+    __syncthreads();
+
+    // ---- 3. marked supernodes, children first ---------------------------------------------------
+    bool ok = true;
+    for (int t = 0; t < a.fac.ntasks && ok; ++t) {
+        if (tid == 0)
+            s_abort = 0;
+        __syncthreads();
+        const int s = a.fac.tasks[t];
+        const int nwp = a.fac.nwait[t];
+        const asam_sn_desc_t d = a.fac.sn[s];
+        if (((nwp >> 24) & 0x7f) > 1) { // a team front: the host must not send it here
+            if (tid == 0)
+                atomicCAS(a.fac.ctrl + 1, 0, -(1 + s));
+            ok = false;
+            break;
+        }
+        ok = cta_front(a.fac, t, s, nwp & 0xffff, d, sm, s_cd, &s_abort, 0ULL);
+    }
+
+    // ---- 4. visited supernodes, parents first ---------------------------------------------------
+    for (int t = 0; t < a.bs.ntasks && ok; ++t) {
+        if (tid == 0)
+            s_abort = 0;
+        __syncthreads();
+        ok = cta_backsolve(a.bs, t, a.bs.btasks[t], sm, &s_abort);
+    }
+    __syncthreads();
+
+    // ---- 5. results to the host ---------------------------------------------------------------
+    if (ok) {
+        int off = 0;
+        for (int t = 0; t < a.bs.ntasks; ++t) {
+            const int s = a.bs.btasks[t];
+            const int first = a.bs.sn[s].first, c = 3 * a.bs.sn[s].cb;
+            for (int k = tid; k < c; k += nt)
+                a.x_out[off + k] = __ldcg(&a.bs.x[3 * (size_t) first + k]);
+            off += c;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+        a.done[1] = ld_volatile(a.fac.ctrl + 1);
+        __threadfence_system();
+        a.done[0] = a.seq;
+    }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -122,3 +122,6 @@ ASAM_API int asam_dbg_ref_ordering_explicit(int N, const int *adj_ptr, const int
 
 void asam_dbg_plan_profile(double *out, int reset);
 ASAM_API void asam_dbg_plan_profile_get(double *out, int reset) { asam_dbg_plan_profile(out, reset); }
+
+void asam_dbg_build_profile(double *out, int reset);
+ASAM_API void asam_dbg_build_profile_get(double *out, int reset) { asam_dbg_build_profile(out, reset); }

@@ -24,6 +24,7 @@
 
 /* diagnostics: time spent in the phases of plan_append (ms), read by tools/gpu_diag.py */
 static double g_plan_prof[8];
+static double g_build_prof[8]; /* phases of plan_build (ms): see BUILD_LAP */
 static double pp_now(void)
 {
     struct timespec ts;
@@ -36,6 +37,12 @@ void asam_dbg_plan_profile(double *out, int reset)
     if (reset)
         memset(g_plan_prof, 0, sizeof(g_plan_prof));
 }
+void asam_dbg_build_profile(double *out, int reset)
+{
+    memcpy(out, g_build_prof, sizeof(g_build_prof));
+    if (reset)
+        memset(g_build_prof, 0, sizeof(g_build_prof));
+}
 
 #define RELAX_Z 2     /* relaxed amalgamation: missing block rows tolerated per merge */
 #define RELAX_FILL 24 /* ... and explicit zero blocks (3x3) added per merge */
@@ -44,6 +51,7 @@ void asam_dbg_plan_profile(double *out, int reset)
 #define ASAM_BSLEAF_MIN_COUNT 4096 /* measured: no gain on M3500-sized trees (the kernel boundary eats it) */
 #define ASAM_LEAF_MAX_M 48       /* = ASAM_LEAF_M of k_factor_leaf */
 #define ASAM_LEAF_MIN_COUNT 4096 /* below this one k_factor launch does it all */
+#define ASAM_SOLO_MAX_M_DEFAULT 0 /* see solo_max_m() */
 #define MAX_SN_COLS 32 /* block columns per supernode: L11 (96x96) fits k_backsolve shared memory */
 
 /* ---- pair map ---------------------------------------------------------------------------- */
@@ -314,10 +322,25 @@ static int front_fits_smem(int mb)
     return (m + 1) * m + (m + 2) / 2 + 2 <= 25600;
 }
 
+/* Fronts up to this order that do not fit in shared memory are still handled by ONE CTA (out of
+ * HBM/L2, wide staged panels: cta_front's second mode): a team pays two barriers and several L2 round
+ * trips per 48 columns, which for a few hundred rows is all latency -- measured 96 us x 2.2 CTAs per
+ * front of order 160-300 in the 100 k world, where 740 such fronts queue for the SMs.  ASAM_SOLO_MAX_M
+ * overrides (tuning). */
+static int solo_max_m(void)
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("ASAM_SOLO_MAX_M");
+        v = e ? atoi(e) : ASAM_SOLO_MAX_M_DEFAULT;
+    }
+    return v;
+}
+
 static int team_size(int mb, int cb, int cap)
 {
     int64_t m = 3 * (int64_t) mb, c = 3 * (int64_t) cb;
-    if (front_fits_smem(mb))
+    if (front_fits_smem(mb) || m <= solo_max_m())
         return 1;
     int64_t j0 = c < 48 ? c : 48, tiles = 0;
     for (int64_t cb0 = j0; cb0 < m; cb0 += 64)
@@ -661,6 +684,13 @@ static int plan_build_impl(plan_t *pl, asam_dev_t *dev, int N, int n_factors, co
     pl->N = N;
     pl->n_factors = n_factors;
 
+    double bt_ = pp_now(), bt2_;
+#define BUILD_LAP(i)                 \
+    do {                             \
+        bt2_ = pp_now();             \
+        g_build_prof[i] += bt2_ - bt_; \
+        bt_ = bt2_;                  \
+    } while (0)
     /* 1. unique node pairs -> Hessian slots */
     pairmap_init(&pl->pairs, n_factors);
     ivec_t plo = { 0 }, phi = { 0 };
@@ -711,6 +741,7 @@ static int plan_build_impl(plan_t *pl, asam_dev_t *dev, int N, int n_factors, co
         sort_ints(adj + adj_ptr[i], adj_ptr[i + 1] - adj_ptr[i]);
     free(fill);
 
+    BUILD_LAP(0); /* slots + adjacency */
     /* 3. elimination order */
     if (order_keep) {
         for (int p = 0; p < N_keep; p++)
@@ -725,6 +756,7 @@ static int plan_build_impl(plan_t *pl, asam_dev_t *dev, int N, int n_factors, co
     for (int p = 0; p < N; p++)
         pl->pos[pl->order[p]] = p;
 
+    BUILD_LAP(1); /* ordering */
     /* 4. block symbolic factorisation in reference positions */
     int *parent = pl->parent_pos;
     int *head = malloc(sizeof(int) * (size_t) N), *tail = malloc(sizeof(int) * (size_t) N);
@@ -771,6 +803,7 @@ static int plan_build_impl(plan_t *pl, asam_dev_t *dev, int N, int n_factors, co
     free(adj);
     free(adj_ptr);
 
+    BUILD_LAP(2); /* block symbolic */
     /* 5. post-order -> numeric positions q.  Children are visited in ascending structure
      * size so that the child with the largest front is numbered right before its parent and can
      * share a supernode with it (step 6). */
@@ -877,6 +910,7 @@ static int plan_build_impl(plan_t *pl, asam_dev_t *dev, int N, int n_factors, co
         pl->sn_of_q[q] = pl->nsn - 1;
     }
 
+    BUILD_LAP(3); /* post-order + supernodes */
     /* 7. row lists, parents, children, levels */
     pl->max_m = 0;
     for (int s = 0; s < pl->nsn; s++) {
@@ -921,6 +955,7 @@ static int plan_build_impl(plan_t *pl, asam_dev_t *dev, int N, int n_factors, co
     free(qpos);
     free(pofq);
 
+    BUILD_LAP(4); /* row lists, rel */
     /* 8. Hessian gather lists */
     for (int sl = 0; sl < S; sl++) {
         int lo = plo.p[sl], hi = phi.p[sl];
@@ -940,6 +975,7 @@ static int plan_build_impl(plan_t *pl, asam_dev_t *dev, int N, int n_factors, co
     ivec_free(&plo);
     ivec_free(&phi);
 
+    BUILD_LAP(5); /* gather lists */
     /* 9. layout + schedule */
     ivec_t seg = { 0 };
     pl->arena_n = 0;
@@ -953,6 +989,7 @@ static int plan_build_impl(plan_t *pl, asam_dev_t *dev, int N, int n_factors, co
 
     build_schedule(pl);
 
+    BUILD_LAP(6); /* segments + schedule */
     /* host mirror of the device int pool (debug / tests) */
     ivec_free(&pl->ipool_host);
     ivec_reserve(&pl->ipool_host, seg.n);
@@ -999,6 +1036,7 @@ static int plan_build_impl(plan_t *pl, asam_dev_t *dev, int N, int n_factors, co
     }
     free(ids);
     ivec_free(&seg);
+    BUILD_LAP(7); /* upload */
     return rc;
 }
 

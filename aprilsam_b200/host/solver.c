@@ -77,6 +77,11 @@ ASAM_API void asam_dbg_profile(double *out, int reset)
 
 /* host threads for the per-node loops of a batch solve on a large graph (never for small ones: the
  * fork/join costs more than 3500 poses do) */
+/* the fused small-step kernel (k_step) takes steps with at most this many fronts to re-factor /
+ * supernodes to back-solve; anything larger has parallelism the persistent kernels exploit */
+#define ASAM_SMALL_MAX_TASKS 32
+#define ASAM_SMALL_MAX_BS 64
+
 #define ASAM_OMP_MIN_NODES 16384
 #define ASAM_OMP_THREADS 8
 
@@ -704,7 +709,7 @@ restart:;
     report_factor_status(s, fstatus, "april_graph_cholesky");
     PROF_LAP(15);
     if (param->show_timing)
-        stamp(&tp, "H2D, kernels, D2H of the solution");
+        stamp(&tp, "H2D, kernels, D2H of solution");
 
     /* persistent state the incremental path continues from (:260-288) */
     if (plan_reused && s->tree_fresh && param->tr && param->tr->nnodes == N) {
@@ -956,7 +961,7 @@ ASAM_API void april_graph_cholesky_inc(april_graph_t *graph, april_graph_cholesk
     }
     PROF_LAP(1);
     if (param->show_timing)
-        stamp(&tp, "mark root paths, symbolic append");
+        stamp(&tp, "mark paths, symbolic append");
     DEV_OK(asam_step_begin(dev)); /* record the step's kernels; one upload flush at asam_step_run */
     DEV_OK(asam_linearize(dev, F0, nf, pts));
     DEV_OK(asam_factor(dev, ntasks, tasks, nwait));
@@ -1006,9 +1011,35 @@ ASAM_API void april_graph_cholesky_inc(april_graph_t *graph, april_graph_cholesk
                 bt[j + 1] = v;
             }
             DEV_OK(asam_backsolve(dev, nbt, bt));
-            DEV_OK(asam_step_run(dev));
-            qbase = qmin;
-            DEV_OK(asam_download_x_status(dev, qbase, N - qbase, x, &fstatus));
+            /* a handful of single-CTA fronts: the whole step in ONE launch, results through pinned memory */
+            int small = nbt <= ASAM_SMALL_MAX_BS && ntasks <= ASAM_SMALL_MAX_TASKS && asam_step_small_supported(dev);
+            for (int t = 0; small && t < ntasks; t++)
+                small = ((nwait[t] >> 24) & 0x7f) <= 1;
+            if (small) {
+                int xd = 0;
+                for (int i = 0; i < nbt; i++)
+                    xd += 3 * pl->desc[bt[i]].cb;
+                double *xc = gctx_stage(c, 6 * nf + xd) + 6 * (size_t) nf; /* behind the evaluation points */
+                int rs = asam_step_run_small(dev, xc, xd, &fstatus);
+                if (rs == 0) {
+                    for (int i = 0, off = 0; i < nbt; i++) {
+                        const asam_sn_desc_t *sd = &pl->desc[bt[i]];
+                        memcpy(x + 3 * (size_t) sd->first, xc + off, sizeof(double) * 3 * (size_t) sd->cb);
+                        off += 3 * sd->cb;
+                    }
+                    qbase = 0;
+                    g_prof[18] += 1;
+                } else if (rs == 2) {
+                    small = 0;
+                } else {
+                    asam_fatal("april_graph_cholesky_inc: %s", asam_last_error());
+                }
+            }
+            if (!small) {
+                DEV_OK(asam_step_run(dev));
+                qbase = qmin;
+                DEV_OK(asam_download_x_status(dev, qbase, N - qbase, x, &fstatus));
+            }
             free(stamp);
             free(bt);
         }
@@ -1016,7 +1047,7 @@ ASAM_API void april_graph_cholesky_inc(april_graph_t *graph, april_graph_cholesk
         report_factor_status(s, fstatus, "april_graph_cholesky_inc");
         PROF_LAP(5);
         if (param->show_timing)
-            stamp(&tp, "H2D, kernels, D2H of the solution");
+            stamp(&tp, "H2D, kernels, D2H of solution");
         apply_solution(s, tr, x, qbase);
         PROF_LAP(6);
         if (tr->naffected > 5)

@@ -147,6 +147,15 @@ int asam_backsolve_full(asam_dev_t *d);
 int asam_step_begin(asam_dev_t *d);
 int asam_step_run(asam_dev_t *d);
 
+/* A small incremental step in one launch (k_step: the queued uploads, linearize, factor and
+ * back-solve recorded since asam_step_begin, all in one CTA; results through pinned memory, no
+ * stream synchronisation).  x_out receives, in the order of the recorded back-solve list, the
+ * 3*cb solution entries of every supernode in it (x_doubles in total).  Returns 0 ok, 2 = the
+ * recorded step does not qualify (nothing was launched: call asam_step_run), 1 = error. */
+int asam_step_small_supported(asam_dev_t *d);
+int asam_step_run_small(asam_dev_t *d, double *x_out, int x_doubles, int *status_out);
+int64_t asam_small_steps(asam_dev_t *d);
+
 /* Solution read-back: x in elimination order, positions [q_first, q_first+q_count). */
 int asam_download_x(asam_dev_t *d, int q_first, int q_count, double *x3);
 int asam_download_y(asam_dev_t *d, int q_first, int q_count, double *y3);
@@ -174,6 +183,11 @@ int asam_set_timing(asam_dev_t *d, int enabled);
  * 8 x uint64 per task in task-list order (diagnostics only). */
 int asam_set_trace(asam_dev_t *d, int enabled);
 int asam_download_trace(asam_dev_t *d, int which, unsigned long long *out, int max_tasks);
+/* Panel-step stamps of ONE team front of k_factor (sn < 0: off): per 48-column panel and worker < 8,
+ * 8 x uint64 = iteration start, crew tiles done, block published / rows solved, trailing tiles done,
+ * past the team barrier, m, team size, crew size (diagnostics: tools/panel_trace.py). */
+int asam_set_panel_trace(asam_dev_t *d, int sn, int max_panels);
+int asam_download_panel_trace(asam_dev_t *d, unsigned long long *out, int max_panels);
 /* Device stopwatch on the library's stream around any sequence of calls; an L2 flush
  * (384 MiB overwrite) for cold-cache timing; launch geometry of the persistent kernels. */
 int asam_timer_start(asam_dev_t *d);

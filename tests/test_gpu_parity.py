@@ -553,27 +553,36 @@ def test_inc_solver_entry_point_matches_reference(m3500):
 
 
 def test_escalation_policy_hook_is_deterministic(m3500):
-    """aprilsam_b200_set_escalation_policy: with a ratio of 0+ every incremental step escalates to a batch solve, so
-    the replay equals the batch-only protocol; with a huge ratio nothing changes against the default."""
+    """aprilsam_b200_set_escalation_policy: a policy that always fires turns every incremental step into
+    "incremental update, then batch solve" (fresh tree after every step), identically on every run; a policy that
+    never fires changes nothing against the default; the built-in 1/3 work-ratio rule escalates on some steps only."""
     n = 120
-    with H.Harness("b200") as pol, H.Harness("b200") as bat, H.Harness("b200") as dflt, H.Harness("b200") as big:
+    with H.Harness("b200") as pol, H.Harness("b200") as pol2, H.Harness("b200") as dflt, H.Harness("b200") as big:
         pol.set_policy_ratio(1e-12)
+        pol2.set_policy_ratio(1e-12)
         big.set_policy_ratio(1e12)
-        for h in (pol, bat, dflt, big):
+        for h in (pol, pol2, dflt, big):
             h.replay_begin(m3500)
-        _, _, ip = pol.replay_to(n)
-        bat.replay_to(n, batch_only=True)
+        cp, _, ip = pol.replay_to(n)
+        cp2, _, ip2 = pol2.replay_to(n)
         _, _, idf = dflt.replay_to(n)
         _, _, ib = big.replay_to(n)
         assert (ip[1:, 0] == 0).all(), "every incremental step ended in a batch solve (fresh tree, naffected 0)"
-        assert rel_state_err(pol.states(), bat.states()) < 1e-8
+        assert (idf[1:, 0] > 0).all(), "no escalation in the first 120 default steps"
+        assert np.array_equal(ip, ip2) and rel_state_err(pol.states(), pol2.states()) < 1e-12
+        assert np.allclose(cp, cp2, rtol=1e-12, atol=0)
         assert np.array_equal(idf, ib) and rel_state_err(dflt.states(), big.states()) == 0.0
-    # the built-in 1/3 rule fires on some steps of a real replay and never before the threshold rule would matter
-    with H.Harness("b200") as third:
+        # an escalated replay is a better-converged estimate of the same problem: close to the default one
+        assert rel_state_err(pol.states(), dflt.states()) < 1e-2
+    with H.Harness("b200") as third, H.Harness("b200") as dflt:
         third.set_policy_ratio(1.0 / 3.0)
-        third.replay_begin(m3500)
+        for h in (third, dflt):
+            h.replay_begin(m3500)
         c, _, it = third.replay_to(400)
+        _, _, idf = dflt.replay_to(400)
         assert np.isfinite(c).all()
+        n_pol, n_dflt = int((it[1:, 0] == 0).sum()), int((idf[1:, 0] == 0).sum())
+        assert n_dflt <= n_pol < 399, (n_pol, n_dflt)
 
 
 def test_show_timing_prints_the_reference_table_format(m3500, tmp_path, capfd):
