@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 
 #include "asam_cuda.h"
 
@@ -115,9 +116,11 @@ struct asam_dev {
     struct Pending *pend = nullptr;
     int npend = 0;
     int step_seq = 0;  // sequence number of the last k_step launch (completion flag in pin_down)
+    int tile_mode = 2; // ASAM_TILE_MODE: 0 DFMA tiles, 1 mma.sync f64, 2 mma.sync f64 + bulk async copies (team path)
     int solo_pb = 48;  // ASAM_SOLO_PB: staged panel width of single-CTA fronts that live in HBM
     int small_ok = 1;  // ASAM_SMALL_STEP=0 disables the fused small-step kernel (A/B measurements)
     int64_t n_small = 0;
+    double small_us[8] = {0, 0, 0, 0, 0, 0, 0, 0}; // accumulated phases of k_step (device stamps) + host launch / wait
 
     // launch config
     int fac_threads = 256, fac_grid = 0, fac_smem = 0;
@@ -456,8 +459,11 @@ ASAM_EXPORT int asam_step_run_small(asam_dev_t *d, double *x_out, int x_doubles,
     a.x_out = (double *) (d->pin_down + 64);
     a.done = (volatile int *) d->pin_down;
     a.seq = ++d->step_seq;
+    struct timespec ts0, ts1, ts2;
+    clock_gettime(CLOCK_MONOTONIC, &ts0);
     k_step<<<1, 256, d->fac_smem, d->stream>>>(a);
     CK(cudaGetLastError());
+    clock_gettime(CLOCK_MONOTONIC, &ts1);
     d->n_launch++;
     d->n_small++;
     d->n_items = 0;
@@ -478,6 +484,14 @@ ASAM_EXPORT int asam_step_run_small(asam_dev_t *d, double *x_out, int x_doubles,
         }
     }
     __sync_synchronize();
+    clock_gettime(CLOCK_MONOTONIC, &ts2);
+    {
+        const volatile unsigned long long *st = (const volatile unsigned long long *) (d->pin_down + 8);
+        for (int i = 0; i < 5; i++)
+            d->small_us[i] += (double) (long long) (st[i + 1] - st[i]) * 1e-3;
+        d->small_us[5] += (ts1.tv_sec - ts0.tv_sec) * 1e6 + (ts1.tv_nsec - ts0.tv_nsec) * 1e-3; // launch call
+        d->small_us[6] += (ts2.tv_sec - ts1.tv_sec) * 1e6 + (ts2.tv_nsec - ts1.tv_nsec) * 1e-3; // flag wait
+    }
     *status_out = done[1];
     memcpy(x_out, d->pin_down + 64, (size_t) x_doubles * sizeof(double));
     if (*status_out != 0)
@@ -570,6 +584,8 @@ ASAM_EXPORT int asam_dev_create(asam_dev_t **out)
     CK(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, d->fac_smem));
     if (getenv("ASAM_SOLO_PB") && atoi(getenv("ASAM_SOLO_PB")) >= 12)
         d->solo_pb = atoi(getenv("ASAM_SOLO_PB")) / 12 * 12;
+    if (getenv("ASAM_TILE_MODE"))
+        d->tile_mode = atoi(getenv("ASAM_TILE_MODE"));
     if (getenv("ASAM_SMALL_STEP"))
         d->small_ok = atoi(getenv("ASAM_SMALL_STEP")) != 0;
     memset(d->pin_down, 0, 64);
@@ -837,6 +853,7 @@ static int launch_factor(asam_dev *d, int ntasks, const int *tasks_dev, const in
     a.smem_doubles = d->fac_smem / (int) sizeof(double);
     a.spin_limit = ASAM_SPIN_LIMIT_NS;
     a.solo_pb = d->solo_pb;
+    a.tile_mode = d->tile_mode;
     a.trace = nullptr;
     if (d->trace_on) {
         if (buf_reserve(d, d->trace_fac, (size_t) ntasks * 8 * sizeof(unsigned long long), false, false))
@@ -1349,6 +1366,16 @@ ASAM_EXPORT int asam_download_x_status(asam_dev_t *d, int q_first, int q_count, 
 }
 
 ASAM_EXPORT int64_t asam_small_steps(asam_dev_t *d) { return d->n_small; }
+
+// Accumulated microseconds of the fused small steps so far: [0] upload fetch + scatter, [1] linearize,
+// [2] factor, [3] back-solve, [4] result write-back (device globaltimer), [5] host launch call, [6] host
+// wait on the completion flag; reset = 1 zeroes the accumulators (diagnostics: tools/step_profile.py).
+ASAM_EXPORT void asam_small_step_profile(asam_dev_t *d, double *out7, int reset)
+{
+    memcpy(out7, d->small_us, 7 * sizeof(double));
+    if (reset)
+        memset(d->small_us, 0, sizeof(d->small_us));
+}
 
 ASAM_EXPORT int asam_counters(asam_dev_t *d, int64_t *out3)
 {

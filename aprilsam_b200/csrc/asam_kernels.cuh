@@ -13,8 +13,9 @@
 //   k_chi2_*      deterministic reduction of the factor energies at `state`.
 //                 reference: april_graph.c:79-98, april_graph_xyt.c:126-188
 //
-// Front layout (arena[f_off ...], (m+1)*m doubles): column-major, leading dimension
-// ld = m+1, m = 3*mb.  Rows 0..m-1 are the supernode's block rows, ROW m is the right-hand
+// Front layout (arena[f_off ...], ld*m doubles): column-major, leading dimension
+// ld = ASAM_LD(m) = m+1 rounded up to EVEN (every column starts 16-byte aligned: bulk async copies),
+// m = 3*mb.  Rows 0..m-1 are the supernode's block rows, ROW m is the right-hand
 // side.  After elimination of the first c = 3*cb columns: columns [0,c) hold L (L11 on top of
 // L21) and, in row m, y1 = L11^-1 b1; the trailing (m-c) x (m-c) lower triangle holds the
 // update matrix (Schur complement) and row m, columns [c,m), the updated rhs b2 - L21 y1 --
@@ -311,6 +312,7 @@ struct FacArgs {
     int smem_doubles;
     long long spin_limit;
     unsigned long long *trace; // optional: 8 words per task
+    int tile_mode; // trailing-update tiles of the team path: 0 DFMA, 1 mma.sync f64, 2 mma.sync f64 + bulk async copies
     int solo_pb; // widest staged panel of a front that one CTA handles out of HBM (multiple of ASAM_PB)
     unsigned long long *ptrace; // optional: panel-step stamps of supernode ptrace_sn, [panel][worker < 8][8]
     int ptrace_sn, ptrace_panels;
@@ -454,6 +456,182 @@ __device__ __forceinline__ void panel_factor(double *P, int ldp, int k0, int pb,
 #define ASAM_TPB 48   // panel width of the team path
 #define ASAM_TROWS 256
 #define ASAM_TCOLS 64
+
+#define ASAM_CROWS 128 // rows of one look-ahead crew item (row chunk of the next panel)
+// Staged operands of the tensor-pipe tile: column p of the row operand at Li[p * ASAM_LDI], of the
+// column operand at Lj[p * ASAM_LDJ].  Both leading dimensions are = 4 (mod 16) doubles, which makes the
+// m8n8k4 fragment loads (8 consecutive rows x 4 consecutive panel columns per warp) bank-conflict free,
+// and even, so every staged column starts 16-byte aligned (bulk asynchronous copies).
+#define ASAM_LDI (ASAM_TROWS + 4)
+#define ASAM_LDJ (ASAM_TCOLS + 4)
+#define ASAM_TEAM_SMEM_DOUBLES (ASAM_TPB * ASAM_TPB + ASAM_TPB + ASAM_LDI * ASAM_TPB + ASAM_LDJ * ASAM_TPB)
+
+// ---- mbarrier / bulk asynchronous copy (TMA engine, 1-D) --------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned ok;
+    long long tries = 0;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+        if (!ok && ++tries > (1LL << 24)) // a copy that never completes must not hang the GPU: fail the launch loudly
+            __trap();
+    } while (!ok);
+}
+
+// global -> shared, `bytes` (multiple of 16) from a 16-byte aligned source to a 16-byte aligned
+// destination; completion is counted on `bar` (complete_tx)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, const double a, const double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// C[rb0.., cb0..] -= L[rb0.., k0..k0+pb) * L[cb0.., k0..k0+pb)'  (lower trapezoid of the front only) on the
+// FP64 tensor pipe: mma.sync.m8n8k4.f64.  The operands are staged in shared memory (Li: nrow x pb, Lj: ncol x pb,
+// columns pb..pb4 zero) either by the threads (bulk == 0) or by the TMA engine: one bulk asynchronous copy
+// per panel column, completion on an mbarrier (bulk == 1; sources are rounded down to an even front row, the
+// fragment loads skip the extra leading row: shi / shj).  Warp w owns the 8*MT-row strip w of the tile and all
+// of its (at most 8) 8-column blocks: MT*8 accumulator fragments; per 4 panel columns MT + 8 shared-memory
+// fragment loads feed MT*8 tensor instructions of 256 multiply-adds each (the DFMA formulation needed 12 loads
+// per 1024 multiply-adds).  The C values are fetched before the products and written after them.
+// Dout != nullptr: the tile is the diagonal block of the next panel; its values also go straight into the
+// shared-memory block that diag_factor works on.
+template <int MT>
+__device__ __noinline__ void tile_mma(double *F, const int ld, const int m, const int k0, const int pb, const int cb0,
+                                         const int ncol, const int rb0, const int nrow, double *Dout, double *Li, double *Lj,
+                                         unsigned long long *bar, unsigned &parity, const int bulk)
+{
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    const int pb4 = (pb + 3) & ~3;
+    const int shi = bulk ? (rb0 & 1) : 0, shj = bulk ? (cb0 & 1) : 0;
+    __syncthreads(); // everybody is done with the previous contents of Li / Lj
+    if (bulk) {
+        const unsigned bi = (unsigned) ((shi + nrow + 1) & ~1) * 8u, bj = (unsigned) ((shj + ncol + 1) & ~1) * 8u;
+        if (warp == 0) {
+            asm volatile("fence.proxy.async;" ::: "memory"); // generic-proxy accesses (ours to shared memory, the other
+                                                             // workers' to the front) before the async-proxy copies
+            if (lane == 0)
+                mbar_expect_tx(bar, (unsigned) pb * (bi + bj));
+            __syncwarp();
+            for (int p = lane; p < pb; p += 32) {
+                const double *col = F + (size_t) (k0 + p) * ld;
+                bulk_g2s(Li + (size_t) p * ASAM_LDI, col + (rb0 - shi), bi, bar);
+                bulk_g2s(Lj + (size_t) p * ASAM_LDJ, col + (cb0 - shj), bj, bar);
+            }
+        }
+        for (int e = tid; e < (pb4 - pb) * ASAM_LDI; e += nt) // zero padding of the k dimension (last panel only)
+            Li[(size_t) pb * ASAM_LDI + e] = 0.0;
+        for (int e = tid; e < (pb4 - pb) * ASAM_LDJ; e += nt)
+            Lj[(size_t) pb * ASAM_LDJ + e] = 0.0;
+    } else {
+        // two panel columns per warp and pass: 20 independent loads in flight per lane
+        for (int p = warp; p < pb4; p += 2 * nwarps) {
+            double vj[2][2], vi[2][8];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int pp = p + h * nwarps;
+                const double *src = F + (size_t) (k0 + min(pp, pb - 1)) * ld;
+#pragma unroll
+                for (int u = 0; u < 2; u++)
+                    vj[h][u] = (pp < pb && lane + 32 * u < ncol) ? __ldcg(src + cb0 + lane + 32 * u) : 0.0;
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                    vi[h][u] = (pp < pb && lane + 32 * u < nrow) ? __ldcg(src + rb0 + lane + 32 * u) : 0.0;
+            }
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int pp = p + h * nwarps;
+                if (pp < pb4) {
+#pragma unroll
+                    for (int u = 0; u < 2; u++)
+                        Lj[lane + 32 * u + pp * ASAM_LDJ] = vj[h][u];
+#pragma unroll
+                    for (int u = 0; u < 8; u++)
+                        Li[lane + 32 * u + pp * ASAM_LDI] = vi[h][u];
+                }
+            }
+        }
+    }
+    // this warp's strip and its accumulators, initialised with the C values
+    const int g = lane >> 2, t = lane & 3;
+    const int r0 = warp * 8 * MT;
+    const int nnt = (ncol + 7) >> 3;
+    // 8-column blocks that reach the strip's last row (lower trapezoid): nothing to do above the diagonal
+    const int rowmax = rb0 + min(r0 + 8 * MT, nrow) - 1;
+    const int nneed = (r0 < nrow && rowmax >= cb0) ? min(nnt, ((rowmax - cb0) >> 3) + 1) : 0;
+    double acc[MT][8][2];
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int ii = r0 + 8 * mt + g, jj = 8 * q + 2 * t + e;
+                const bool ok = q < nneed && ii < nrow && jj < ncol && rb0 + ii >= cb0 + jj;
+                acc[mt][q][e] = ok ? __ldcg(&F[(rb0 + ii) + (size_t) (cb0 + jj) * ld]) : 0.0;
+            }
+    if (bulk) {
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+    }
+    __syncthreads(); // staged operands (and the zero padding) visible to every warp
+    if (nneed > 0) {
+        const double *ai = Li + shi + r0 + g + (size_t) t * ASAM_LDI;
+        const double *bj_ = Lj + shj + g + (size_t) t * ASAM_LDJ;
+#pragma unroll 2
+        for (int kk = 0; kk < pb4; kk += 4) {
+            double av[MT];
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++)
+                av[mt] = -ai[8 * mt + (size_t) kk * ASAM_LDI];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                if (q < nneed) {
+                    const double bv = bj_[8 * q + (size_t) kk * ASAM_LDJ];
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++)
+                        dmma_8x8x4(acc[mt][q][0], acc[mt][q][1], av[mt], bv);
+                }
+            }
+        }
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int ii = r0 + 8 * mt + g, jj = 8 * q + 2 * t + e;
+                    if (q < nneed && ii < nrow && jj < ncol && rb0 + ii >= cb0 + jj) {
+                        F[(rb0 + ii) + (size_t) (cb0 + jj) * ld] = acc[mt][q][e];
+                        if (Dout)
+                            Dout[ii + jj * ASAM_TPB] = acc[mt][q][e];
+                    }
+                }
+    }
+}
 
 struct TeamCtx {
     int *tbar_s;
@@ -603,13 +781,13 @@ __device__ __forceinline__ void trsm_row(double *Li, const double *D, const doub
 
 // returns false on abort
 __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int nw, int w, int G, double *sm,
-                           int *s_flag, unsigned long long *trow)
+                           int *s_flag, unsigned long long *trow, unsigned long long *mbar, unsigned &mb_parity)
 {
     // trow (worker 0, thread 0 only): [1] children ready, [2] assembled, [3] extend-added,
     // [4] eliminated; [7] high word: ns spent in the panel (diag + TRSM) phases
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
-    const int m = 3 * d.mb, c = 3 * d.cb, ld = m + 1;
+    const int m = 3 * d.mb, c = 3 * d.cb, ld = ASAM_LD(m);
     const int *seg = a.ipool + d.seg;
     const int *children = seg + 2 * d.mb;
     const int *a_slot = children + d.ch_cnt;
@@ -680,7 +858,7 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
     int *dmap = (int *) sm; // ld ints
     for (int ci = 0; ci < d.ch_cnt; ++ci) {
         const asam_sn_desc_t cd = a.sn[children[ci]];
-        const int cm = 3 * cd.mb, cc = 3 * cd.cb, cr = cm - cc, cld = cm + 1;
+        const int cm = 3 * cd.mb, cc = 3 * cd.cb, cr = cm - cc, cld = ASAM_LD(cm);
         const double *CF = a.arena + cd.f_off;
         const int *crel = a.ipool + cd.seg + cd.mb;
         __syncthreads();
@@ -726,8 +904,8 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
     // + one barrier, instead of factorisation + barrier + a whole trailing update + barrier.
     double *D = sm;                              // ASAM_TPB x ASAM_TPB diagonal block
     double *rdv = D + ASAM_TPB * ASAM_TPB;       // ASAM_TPB reciprocal diagonal entries
-    double *Li = rdv + ASAM_TPB;                 // ASAM_TROWS x pb   (row chunk / row tile)
-    double *Lj = Li + ASAM_TROWS * ASAM_TPB;     // ASAM_TCOLS x pb   (column tile)
+    double *Li = rdv + ASAM_TPB;                 // ASAM_LDI x pb   (row chunk / row tile)
+    double *Lj = Li + ASAM_LDI * ASAM_TPB;       // ASAM_LDJ x pb   (column tile)
     double *dinv = a.dinv + 3 * (size_t) d.first;
     int *crew_bar = a.tbar + 2 * (size_t) s + 1; // flag: index (1-based) of the last published panel
 
@@ -735,6 +913,17 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
     // (Dout != nullptr: the tile is the diagonal block of the next panel; its values also go straight
     // into the shared-memory block that diag_factor works on, saving the round trip through L2)
     auto tile = [&](int k0, int pb, int cb0, int ncol, int rb0, int nrow, double *Dout) {
+        if (a.tile_mode != 0) { // FP64 tensor pipe (1: operands staged by the threads, 2: by bulk asynchronous copies)
+            const int bulk = a.tile_mode == 2;
+            if (nrow <= 64)
+                tile_mma<1>(F, ld, m, k0, pb, cb0, ncol, rb0, nrow, Dout, Li, Lj, mbar, mb_parity, bulk);
+            else if (nrow <= 128)
+                tile_mma<2>(F, ld, m, k0, pb, cb0, ncol, rb0, nrow, Dout, Li, Lj, mbar, mb_parity, bulk);
+            else
+                tile_mma<4>(F, ld, m, k0, pb, cb0, ncol, rb0, nrow, Dout, Li, Lj, mbar, mb_parity, bulk);
+            return;
+        }
+        // DFMA formulation (ASAM_TILE_MODE=0, kept for A/B measurements)
         __syncthreads();
         // two panel columns per warp and pass: 20 independent loads in flight per lane
         for (int p = warp; p < pb; p += 2 * nwarps) {
@@ -859,12 +1048,12 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
             atomicExch(crew_bar, seq);
         }
     };
-    // the other crew workers: rows [rb0, rb0+256) of the panel are fetched while worker 0 factors the
+    // the other crew workers: rows [rb0, rb0+ASAM_CROWS) of the panel are fetched while worker 0 factors the
     // block, then solved against the published L11
     auto rows_solve = [&](int k0, int pb, int rb0, int seq) {
         __syncthreads();
         const int i = rb0 + tid;
-        const bool row = i <= m;
+        const bool row = tid < ASAM_CROWS && i <= m;
         if (row)
             for (int j = 0; j < pb; j++)
                 Li[tid + j * ASAM_TROWS] = __ldcg(&F[i + (size_t) (k0 + j) * ld]);
@@ -932,7 +1121,7 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
         const bool has_next = kn0 < c;
         const int pbn = has_next ? min(ASAM_TPB, c - kn0) : 0;
         // crew of the next panel: worker 0 owns its diagonal block, workers 1.. the 256-row chunks below
-        const int ncrew = has_next ? 1 + (m - (kn0 + pbn) + 1 + ASAM_TROWS - 1) / ASAM_TROWS : 0;
+        const int ncrew = has_next ? 1 + (m - (kn0 + pbn) + 1 + ASAM_CROWS - 1) / ASAM_CROWS : 0;
         ++seq;
         if (w < ncrew) {
             // crew items: 0 = the diagonal block, i >= 1 = row chunk i-1; dealt round-robin (a team
@@ -951,13 +1140,13 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
                     pt[2] = d_now();
             }
             for (int it = (w == 0 ? G : w); it < ncrew; it += G) {
-                const int rb0 = kn0 + pbn + (it - 1) * ASAM_TROWS;
-                tile(k0, pb, kn0, pbn, rb0, min(ASAM_TROWS, m - rb0 + 1), nullptr);
+                const int rb0 = kn0 + pbn + (it - 1) * ASAM_CROWS;
+                tile(k0, pb, kn0, pbn, rb0, min(ASAM_CROWS, m - rb0 + 1), nullptr);
             }
             if (pt && w > 0)
                 pt[1] = d_now();
             for (int it = (w == 0 ? G : w); it < ncrew; it += G) {
-                const int rb0 = kn0 + pbn + (it - 1) * ASAM_TROWS;
+                const int rb0 = kn0 + pbn + (it - 1) * ASAM_CROWS;
                 if (!rows_solve(kn0, pbn, rb0, seq))
                     return false;
             }
@@ -1040,7 +1229,7 @@ __device__ bool cta_front(const FacArgs &a, const int t, const int s, const int 
     const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
     int *err = a.ctrl + 1;
     unsigned long long tr1 = 0, tr2 = 0, tr3 = 0, tr4 = 0, accA = 0, accB = 0;
-    const int m = 3 * d.mb, c = 3 * d.cb, ld = m + 1;
+    const int m = 3 * d.mb, c = 3 * d.cb, ld = ASAM_LD(m);
     const int *seg = a.ipool + d.seg;
     const int *children = seg + 2 * d.mb;
     const int *a_slot = children + d.ch_cnt;
@@ -1109,7 +1298,7 @@ __device__ bool cta_front(const FacArgs &a, const int t, const int s, const int 
     // ---- 3. extend-add the children's update matrices (fixed order: deterministic) ----
     for (int ci = 0; ci < d.ch_cnt; ++ci) {
         const asam_sn_desc_t cd = ci < ASAM_MAX_CACHED_CHILDREN ? s_cd[ci] : a.sn[children[ci]];
-        const int cm = 3 * cd.mb, cc = 3 * cd.cb, cr = cm - cc, cld = cm + 1;
+        const int cm = 3 * cd.mb, cc = 3 * cd.cb, cr = cm - cc, cld = ASAM_LD(cm);
         const double *CF = a.arena + cd.f_off;
         const int *crel = a.ipool + cd.seg + cd.mb; // rel[]
         // destination row of child row cc+i (i in [0,cr]); the child's rhs row -> ours
@@ -1269,9 +1458,12 @@ __global__ void __launch_bounds__(256, 1) k_factor(FacArgs a)
     extern __shared__ __align__(16) double sm[];
     __shared__ int s_task, s_abort;
     __shared__ asam_sn_desc_t s_cd[ASAM_MAX_CACHED_CHILDREN];
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
-    int *err = a.ctrl + 1;
+    __shared__ __align__(8) unsigned long long s_mbar; // completion of the bulk copies of one tile (team path)
+    const int tid = threadIdx.x;
+    unsigned mb_parity = 0;
+    if (tid == 0)
+        mbar_init(&s_mbar, 1);
+    __syncthreads();
     for (;;) {
         if (tid == 0) {
             s_task = atomicAdd(&a.ctrl[0], 1);
@@ -1293,7 +1485,7 @@ __global__ void __launch_bounds__(256, 1) k_factor(FacArgs a)
             if (trow && tid == 0) {
                 trow[0] = tr0; trow[1] = tr0;
             }
-            if (!team_front(a, d, s, nw, tw, tG, sm, &s_abort, trow))
+            if (!team_front(a, d, s, nw, tw, tG, sm, &s_abort, trow, &s_mbar, mb_parity))
                 break;
             if (a.trace && tid == 0) {
                 unsigned long long *tr = a.trace + 8 * (size_t) t;
@@ -1326,7 +1518,7 @@ __global__ void __launch_bounds__(256, 1) k_factor(FacArgs a)
 // ------------------------------------------------------------------------------------------
 #define ASAM_LEAF_M 48
 #define ASAM_LEAF_WARPS 8
-#define ASAM_LEAF_STRIDE ((ASAM_LEAF_M + 1) * ASAM_LEAF_M + ASAM_LEAF_M / 2 + 2) // doubles per warp (even)
+#define ASAM_LEAF_STRIDE (ASAM_LD(ASAM_LEAF_M) * ASAM_LEAF_M + ASAM_LEAF_M / 2 + 2) // doubles per warp (even)
 
 struct LeafArgs {
     const asam_sn_desc_t *sn;
@@ -1348,7 +1540,7 @@ __global__ void __launch_bounds__(32 * ASAM_LEAF_WARPS, 1) k_factor_leaf(LeafArg
     extern __shared__ __align__(16) double sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *F = sm + (size_t) warp * ASAM_LEAF_STRIDE;
-    int *dmap = (int *) (F + (ASAM_LEAF_M + 1) * ASAM_LEAF_M);
+    int *dmap = (int *) (F + ASAM_LD(ASAM_LEAF_M) * ASAM_LEAF_M);
     int *err = a.ctrl + 1;
     for (;;) {
         int t = 0;
@@ -1359,7 +1551,7 @@ __global__ void __launch_bounds__(32 * ASAM_LEAF_WARPS, 1) k_factor_leaf(LeafArg
             break;
         const int s = a.tasks[t];
         const asam_sn_desc_t d = a.sn[s];
-        const int m = 3 * d.mb, c = 3 * d.cb, ld = m + 1;
+        const int m = 3 * d.mb, c = 3 * d.cb, ld = ASAM_LD(m);
         if (m > ASAM_LEAF_M) { // host error
             if (lane == 0)
                 atomicCAS(err, 0, -(1 + s));
@@ -1417,7 +1609,7 @@ __global__ void __launch_bounds__(32 * ASAM_LEAF_WARPS, 1) k_factor_leaf(LeafArg
         // ---- 3. extend-add --------------------------------------------------------------------
         for (int ci = 0; ci < d.ch_cnt; ++ci) {
             const asam_sn_desc_t cd = a.sn[children[ci]];
-            const int cm = 3 * cd.mb, cc = 3 * cd.cb, cr = cm - cc, cld = cm + 1;
+            const int cm = 3 * cd.mb, cc = 3 * cd.cb, cr = cm - cc, cld = ASAM_LD(cm);
             const double *CF = a.arena + cd.f_off + (size_t) cc * cld + cc; // (0,0) of the update matrix
             const int *crel = a.ipool + cd.seg + cd.mb;
             for (int i = lane; i <= cr; i += 32)
@@ -1563,7 +1755,7 @@ __device__ bool cta_backsolve(const BsArgs &a, const int t, const int s, double 
     if (a.trace && tid == 0)
         tr0 = d_now();
     const asam_sn_desc_t d = a.sn[s];
-    const int m = 3 * d.mb, c = 3 * d.cb, r = m - c, ld = m + 1;
+    const int m = 3 * d.mb, c = 3 * d.cb, r = m - c, ld = ASAM_LD(m);
     const int *rows = a.ipool + d.seg;
     const double *Lg = a.arena + d.f_off;
     const int bwmax = min(c, ASAM_BSW);
@@ -1738,7 +1930,7 @@ __global__ void __launch_bounds__(32 * ASAM_BSL_WARPS) k_backsolve_leaf(BsArgs a
             break;
         const int s = a.btasks[t];
         const asam_sn_desc_t d = a.sn[s];
-        const int m = 3 * d.mb, c = 3 * d.cb, r = m - c, ld = m + 1;
+        const int m = 3 * d.mb, c = 3 * d.cb, r = m - c, ld = ASAM_LD(m);
         if (r > ASAM_BSL_XS || c > 64) { // host error: not a leaf-set supernode
             if (lane == 0)
                 atomicCAS(err, 0, -(1 + s));
@@ -1859,7 +2051,9 @@ struct StepArgs {
     FacArgs fac;
     BsArgs bs;
     double *x_out;      // pinned host memory: x of the back-solved supernodes, in list order
-    volatile int *done; // pinned host memory: [0] sequence number of the last finished step, [1] status
+    volatile int *done; // pinned host memory: [0] sequence number of the last finished step, [1] status,
+                        // [2..15] as unsigned long long[7]: globaltimer at kernel start / uploads in place /
+                        // linearised / factored / back-solved / results written (diagnostics)
     int seq;
 };
 
@@ -1869,6 +2063,9 @@ __global__ void __launch_bounds__(256, 1) k_step(StepArgs a)
     __shared__ int s_abort;
     __shared__ asam_sn_desc_t s_cd[ASAM_MAX_CACHED_CHILDREN];
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    volatile unsigned long long *stamps = (volatile unsigned long long *) (a.done + 2);
+    if (tid == 0)
+        stamps[0] = d_now();
 
     // ---- 1. uploads: host -> staging (all loads of a thread in flight before the first store) ----
     {
@@ -1910,12 +2107,17 @@ __global__ void __launch_bounds__(256, 1) k_step(StepArgs a)
     }
     __threadfence();
     __syncthreads();
+    if (tid == 0)
+        stamps[1] = d_now();
 
     // ---- 2. new factors -----------------------------------------------------------------------
     for (int t0 = 0; t0 < a.lin.f_count; t0 += nt)
         linearize_body(a.lin, t0 + tid);
     __threadfence();
     __syncthreads();
+
+    if (tid == 0)
+        stamps[2] = d_now();
 
     // ---- 3. marked supernodes, children first ---------------------------------------------------
     bool ok = true;
@@ -1935,6 +2137,9 @@ __global__ void __launch_bounds__(256, 1) k_step(StepArgs a)
         ok = cta_front(a.fac, t, s, nwp & 0xffff, d, sm, s_cd, &s_abort, 0ULL);
     }
 
+    if (tid == 0)
+        stamps[3] = d_now();
+
     // ---- 4. visited supernodes, parents first ---------------------------------------------------
     for (int t = 0; t < a.bs.ntasks && ok; ++t) {
         if (tid == 0)
@@ -1943,6 +2148,9 @@ __global__ void __launch_bounds__(256, 1) k_step(StepArgs a)
         ok = cta_backsolve(a.bs, t, a.bs.btasks[t], sm, &s_abort);
     }
     __syncthreads();
+
+    if (tid == 0)
+        stamps[4] = d_now();
 
     // ---- 5. results to the host ---------------------------------------------------------------
     if (ok) {
@@ -1958,6 +2166,7 @@ __global__ void __launch_bounds__(256, 1) k_step(StepArgs a)
     __threadfence_system();
     __syncthreads();
     if (tid == 0) {
+        stamps[5] = d_now();
         a.done[1] = ld_volatile(a.fac.ctrl + 1);
         __threadfence_system();
         a.done[0] = a.seq;

@@ -319,7 +319,7 @@ static void emit_segment(plan_t *pl, int s, ivec_t *buf, int64_t base)
 static int front_fits_smem(int mb)
 {
     int64_t m = 3 * (int64_t) mb;
-    return (m + 1) * m + (m + 2) / 2 + 2 <= 25600;
+    return (int64_t) ASAM_LD(m) * m + (ASAM_LD(m) + 1) / 2 + 2 <= 25600;
 }
 
 /* Fronts up to this order that do not fit in shared memory are still handled by ONE CTA (out of
@@ -345,7 +345,7 @@ static int team_size(int mb, int cb, int cap)
     int64_t j0 = c < 48 ? c : 48, tiles = 0;
     for (int64_t cb0 = j0; cb0 < m; cb0 += 64)
         tiles += (m - cb0 + 1 + 255) / 256;
-    int64_t chunks = 1 + (m - j0 + 1 + 255) / 256; /* look-ahead crew: the diagonal block + the row chunks */
+    int64_t chunks = 1 + (m - j0 + 1 + 127) / 128; /* look-ahead crew: the diagonal block + the 128-row chunks (ASAM_CROWS) */
     int G = (int) (tiles + chunks); /* the look-ahead crew (one CTA per chunk) takes no tiles */
     /* every worker of a team must be resident at the same time (spin barriers in a persistent,
      * non-cooperative launch): never more workers than the device seats CTAs of k_factor */
@@ -374,7 +374,7 @@ static int plan_team_cap(const plan_t *pl) { return pl->max_team > 0 ? pl->max_t
 static int64_t front_doubles(int mb)
 {
     int64_t m = 3 * (int64_t) mb;
-    return m * m + m;
+    return (int64_t) ASAM_LD(m) * m;
 }
 
 /* ---- schedule: task lists of one batch solve ------------------------------------------------
@@ -508,7 +508,7 @@ static void build_schedule(plan_t *pl)
             load[best] += sub[s];
             owner[s] = best;
             const asam_sn_desc_t *d = &pl->desc[s];
-            int64_t m = 3 * (int64_t) d->mb, c = 3 * (int64_t) d->cb, ld = m + 1;
+            int64_t m = 3 * (int64_t) d->mb, c = 3 * (int64_t) d->cb, ld = ASAM_LD(m);
             pl->shard_owner[i] = best;
             pl->shard_off[i] = d->f_off + c * ld;   /* trailing columns: update matrix + rhs row */
             pl->shard_cnt[i] = (m - c) * ld;

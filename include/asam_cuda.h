@@ -27,6 +27,11 @@
 extern "C" {
 #endif
 
+/* Leading dimension of a front of order m (rows 0..m-1 + the rhs row m), in doubles: m+1 rounded up to
+ * even so that every column of the column-major front starts on a 16-byte boundary (the operands of the
+ * trailing update travel to shared memory as bulk asynchronous copies, which need that). */
+#define ASAM_LD(m) (((m) + 2) & ~1)
+
 typedef struct asam_dev asam_dev_t;
 
 /* Supernode descriptor as stored in HBM (48 bytes). `seg` is the offset into the int pool
@@ -155,6 +160,7 @@ int asam_step_run(asam_dev_t *d);
 int asam_step_small_supported(asam_dev_t *d);
 int asam_step_run_small(asam_dev_t *d, double *x_out, int x_doubles, int *status_out);
 int64_t asam_small_steps(asam_dev_t *d);
+void asam_small_step_profile(asam_dev_t *d, double *out7, int reset);
 
 /* Solution read-back: x in elimination order, positions [q_first, q_first+q_count). */
 int asam_download_x(asam_dev_t *d, int q_first, int q_count, double *x3);

@@ -572,8 +572,9 @@ def test_escalation_policy_hook_is_deterministic(m3500):
         assert np.array_equal(ip, ip2) and rel_state_err(pol.states(), pol2.states()) < 1e-12
         assert np.allclose(cp, cp2, rtol=1e-12, atol=0)
         assert np.array_equal(idf, ib) and rel_state_err(dflt.states(), big.states()) == 0.0
-        # an escalated replay is a better-converged estimate of the same problem: close to the default one
-        assert rel_state_err(pol.states(), dflt.states()) < 1e-2
+        # an escalated replay is the better-converged estimate of the same problem (the default one leaves the
+        # poses that back-substitution pruned stale until the next batch)
+        assert pol.chi2() <= dflt.chi2() * (1 + 1e-9)
     with H.Harness("b200") as third, H.Harness("b200") as dflt:
         third.set_policy_ratio(1.0 / 3.0)
         for h in (third, dflt):

@@ -232,7 +232,7 @@ def test_large_plan_leaf_set_and_merged_chains():
     wide = D["cb"] > 32
     assert wide.any(), "fundamental chains of team-sized fronts are merged past the 32-pose cap"
     m = 3 * D["mb"][wide]
-    assert ((m + 1) * m > 25600).all(), "only fronts of the team path may be wider than the cap"
+    assert ((((m + 2) // 2) * 2) * m > 25600).all(), "only fronts of the team path may be wider than the cap"
     st = emulate_batch(d)
     # exact Gauss-Newton step from the same Hessian
     Hs = emul.Hessian(n, p.info()["n_slots"])
@@ -284,7 +284,8 @@ def test_sharded_schedule_emulated(world):
     for s_ in range(nsn):
         m_, c_ = 3 * int(desc["mb"][s_]), 3 * int(desc["cb"][s_])
         for i in range(len(own)):
-            if int(desc["f_off"][s_]) + c_ * (m_ + 1) == off[i] and (m_ - c_) * (m_ + 1) == cnt[i]:
+            ld_ = (m_ + 2) & ~1  # ASAM_LD: leading dimension rounded up to even
+            if int(desc["f_off"][s_]) + c_ * ld_ == off[i] and (m_ - c_) * ld_ == cnt[i]:
                 root_of[s_] = i
     assert len(root_of) == len(own), "every exchanged range is the trailing part of one root front"
 

@@ -144,9 +144,10 @@ def check_batch(L, d, n, have_ref):
             seg = slice(3 * first, 3 * (first + cb))
             if np.abs(y[seg] - fr.y[seg]).max() > 1e-8 * max(1, np.abs(fr.y).max()):
                 m = 3 * int(desc["mb"][s])
-                Fd = np.zeros(m * m + m)
-                L.asam_debug_read_front(dev, int(desc["f_off"][s]), m * m + m, Fd.ctypes.data_as(_dp))
-                Fd_m = Fd.reshape(m, m + 1).T[:m, :]  # column-major, ld = m+1 -> [row, col]
+                ld = (m + 2) & ~1  # ASAM_LD
+                Fd = np.zeros(ld * m)
+                L.asam_debug_read_front(dev, int(desc["f_off"][s]), ld * m, Fd.ctypes.data_as(_dp))
+                Fd_m = Fd.reshape(m, ld).T[:m, :]  # column-major, ld = ASAM_LD(m) -> [row, col]
                 Fe = fr.F[int(desc["f_off"][s])]
                 log(f"    first bad supernode {s}: first={first} cb={cb} mb={desc['mb'][s]} level={desc['level'][s]} "
                     f"ch={desc['ch_cnt'][s]} a_cnt={desc['a_cnt'][s]}")

@@ -18,7 +18,7 @@ def factor_arrays(d):
 def stats(p, label, dt):
     D = p.descs(); info = p.info()
     m = 3 * D["mb"].astype(np.int64); c = 3 * D["cb"].astype(np.int64); par = D["parent"]
-    fits = (m + 1) * m + (m + 2) // 2 + 2 <= 25600
+    fits = ((m + 2) // 2 * 2) * m + ((m + 2) // 2 * 2 + 1) // 2 + 2 <= 25600
     # per-front latency model (us): team fronts 30/panel of 48 cols, smem fronts 4 + 1.2/panel of 12 cols
     lat = np.where(fits, 4.0 + 1.2 * np.ceil(c / 12.0) + 0.02 * m, 10.0 + 30.0 * np.ceil(c / 48.0))
     nsn = len(m); path = np.zeros(nsn); pan = np.zeros(nsn)
@@ -45,7 +45,7 @@ stats(p, "ref-MD", dt)
 def chain(p, label):
     D = p.descs()
     m = 3 * D["mb"].astype(np.int64); c = 3 * D["cb"].astype(np.int64); par = D["parent"]
-    fits = (m + 1) * m + (m + 2) // 2 + 2 <= 25600
+    fits = ((m + 2) // 2 * 2) * m + ((m + 2) // 2 * 2 + 1) // 2 + 2 <= 25600
     lat = np.where(fits, 4.0 + 1.2 * np.ceil(c / 12.0) + 0.02 * m, 10.0 + 30.0 * np.ceil(c / 48.0))
     nsn = len(m); path = lat.copy(); via = -np.ones(nsn, int)
     for s in range(nsn):

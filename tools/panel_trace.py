@@ -38,7 +38,7 @@ def main():
     fa = np.concatenate([[0], d.ea]).astype(np.int32); fb = np.concatenate([[-1], d.eb]).astype(np.int32)
     D = HostPlan().build(d.n_nodes, ftype, fa, fb).descs()
     m, c = 3 * D["mb"].astype(np.int64), 3 * D["cb"].astype(np.int64)
-    team = (m + 1) * m + (m + 2) // 2 + 2 > 25600
+    team = ((m + 2) // 2 * 2) * m + ((m + 2) // 2 * 2 + 1) // 2 + 2 > 25600
     order = np.argsort(-(c * team))[:args.fronts]
     with H.Harness("b200") as h:
         h.load_full(d)

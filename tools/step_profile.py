@@ -39,7 +39,14 @@ def main():
         dev = L.asam_dbg_dev_of_graph(h.graph_ptr())
         L.asam_small_steps.argtypes = [C.c_void_p]
         L.asam_small_steps.restype = C.c_int64
-        print("fused small steps:", L.asam_small_steps(dev), "of", len(rows))
+        ns = L.asam_small_steps(dev)
+        print("fused small steps:", ns, "of", len(rows))
+        L.asam_small_step_profile.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
+        sp = (C.c_double * 7)()
+        L.asam_small_step_profile(dev, sp, 0)
+        if ns:
+            nm = ["fetch uploads + scatter", "linearize", "factor", "back-solve", "write results", "host: launch call", "host: wait on flag"]
+            print("k_step phases, mean us per fused step: " + ", ".join(f"{n} {sp[i] / ns:.2f}" for i, n in enumerate(nm)))
     r = np.array(rows)
     for name, sel in (("naffected <= 5, fused", (r[:, 1] <= 5) & (r[:, 1] > 0) & (r[:, 9] > 0)),
                       ("naffected <= 5, general path", (r[:, 1] <= 5) & (r[:, 1] > 0) & (r[:, 9] == 0)),
