@@ -90,7 +90,8 @@ struct asam_dev {
     long long *sh_off = nullptr, *sh_cnt = nullptr;
     int bsl_grid = 0, bsl_smem = 0;
     int bt_start = 0, bt_count = 0, bt_cap = 0; // btasks_full holds [bt_start, bt_start+bt_count)
-    Buf tasks_tmp, nwait_tmp, btasks_tmp;
+    Buf tasks_tmp, nwait_tmp, btasks_tmp, keep_tmp;
+    int keep_off = 0; // ASAM_KEEP=0: always re-factor whole fronts (A/B measurements)
     // misc
     Buf ctrl;     // int[8]: [0] ticket, [1] err, [2] ticket backsolve
     Buf partial;  // chi2 partial sums
@@ -584,6 +585,8 @@ ASAM_EXPORT int asam_dev_create(asam_dev_t **out)
     CK(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, d->fac_smem));
     if (getenv("ASAM_SOLO_PB") && atoi(getenv("ASAM_SOLO_PB")) >= 12)
         d->solo_pb = atoi(getenv("ASAM_SOLO_PB")) / 12 * 12;
+    if (getenv("ASAM_KEEP"))
+        d->keep_off = atoi(getenv("ASAM_KEEP")) == 0;
     if (getenv("ASAM_TILE_MODE"))
         d->tile_mode = atoi(getenv("ASAM_TILE_MODE"));
     if (getenv("ASAM_SMALL_STEP"))
@@ -602,7 +605,7 @@ ASAM_EXPORT void asam_dev_destroy(asam_dev_t *d)
     Buf *all[] = { &d->f_type, &d->f_a, &d->f_b, &d->f_z, &d->f_W, &d->f_slot, &d->lp, &d->st, &d->node2q, &d->q2node,
                    &d->Adiag, &d->Aoff, &d->Bq, &d->y, &d->x, &d->dinv, &d->sn, &d->ipool, &d->arena, &d->arrive,
                    &d->xdone, &d->tbar, &d->tasks_full, &d->nwait_full, &d->btasks_full, &d->tasks_tmp, &d->nwait_tmp,
-                   &d->btasks_tmp, &d->leaf_tasks, &d->top_tasks, &d->top_nwait, &d->ctrl, &d->partial, &d->patch_ids, &d->patch_desc, &d->pts, &d->flush, &d->trace_fac, &d->trace_bs, &d->ptrace };
+                   &d->btasks_tmp, &d->keep_tmp, &d->leaf_tasks, &d->top_tasks, &d->top_nwait, &d->ctrl, &d->partial, &d->patch_ids, &d->patch_desc, &d->pts, &d->flush, &d->trace_fac, &d->trace_bs, &d->ptrace };
     for (int i = 0; i < 2; i++)
         if (d->tev[i])
             cudaEventDestroy(d->tev[i]);
@@ -828,7 +831,8 @@ ASAM_EXPORT int asam_linearize(asam_dev_t *d, int f_first, int f_count, const do
     return run_linearize(d, a);
 }
 
-static int launch_factor(asam_dev *d, int ntasks, const int *tasks_dev, const int *nwait_dev, int with_leaves = 0)
+static int launch_factor(asam_dev *d, int ntasks, const int *tasks_dev, const int *nwait_dev, int with_leaves = 0,
+                         const int *keep_dev = nullptr)
 {
     if (ntasks <= 0 && !(with_leaves && d->n_leaf > 0))
         return 0;
@@ -848,6 +852,7 @@ static int launch_factor(asam_dev *d, int ntasks, const int *tasks_dev, const in
     a.tbar = (int *) d->tbar.p;
     a.tasks = tasks_dev;
     a.nwait = nwait_dev;
+    a.keep = keep_dev;
     a.ntasks = ntasks;
     a.ctrl = (int *) d->ctrl.p;
     a.smem_doubles = d->fac_smem / (int) sizeof(double);
@@ -875,7 +880,7 @@ static int launch_factor(asam_dev *d, int ntasks, const int *tasks_dev, const in
     return run_factor(d, a, grid, with_leaves);
 }
 
-static int launch_backsolve(asam_dev *d, int ntasks, const int *btasks_dev, int nleaf = 0)
+static int launch_backsolve(asam_dev *d, int ntasks, const int *btasks_dev, int nleaf = 0, const int *bfirst_dev = nullptr)
 {
     if (ntasks <= 0)
         return 0;
@@ -890,6 +895,7 @@ static int launch_backsolve(asam_dev *d, int ntasks, const int *btasks_dev, int 
     a.x = (double *) d->x.p;
     a.xdone = (int *) d->xdone.p;
     a.btasks = btasks_dev;
+    a.bfirst = bfirst_dev;
     a.ntasks = ntasks;
     a.ctrl = (int *) d->ctrl.p;
     a.epoch = d->epoch;
@@ -1215,17 +1221,24 @@ ASAM_EXPORT int asam_factor_full(asam_dev_t *d)
     return rc;
 }
 
-ASAM_EXPORT int asam_factor(asam_dev_t *d, int ntasks, const int32_t *tasks, const int32_t *nwait)
+ASAM_EXPORT int asam_factor(asam_dev_t *d, int ntasks, const int32_t *tasks, const int32_t *nwait, const int32_t *keep)
 {
     if (ntasks <= 0)
         return 0;
     CK(cudaSetDevice(d->device));
     size_t b = (size_t) ntasks * sizeof(int);
-    if (buf_reserve(d, d->tasks_tmp, b, false, false) || buf_reserve(d, d->nwait_tmp, b, false, false))
+    if (buf_reserve(d, d->tasks_tmp, b, false, false) || buf_reserve(d, d->nwait_tmp, b, false, false) ||
+        buf_reserve(d, d->keep_tmp, b, false, false))
         return 1;
     if (upload(d, d->tasks_tmp.p, tasks, b) || upload(d, d->nwait_tmp.p, nwait, b))
         return 1;
-    return launch_factor(d, ntasks, (const int *) d->tasks_tmp.p, (const int *) d->nwait_tmp.p);
+    int any = 0;
+    for (int t = 0; keep && t < ntasks; t++)
+        any |= keep[t];
+    if (any && !d->keep_off && upload(d, d->keep_tmp.p, keep, b))
+        return 1;
+    return launch_factor(d, ntasks, (const int *) d->tasks_tmp.p, (const int *) d->nwait_tmp.p, 0,
+                         any && !d->keep_off ? (const int *) d->keep_tmp.p : nullptr);
 }
 
 ASAM_EXPORT int asam_backsolve_full(asam_dev_t *d)
@@ -1240,17 +1253,20 @@ ASAM_EXPORT int asam_backsolve_full(asam_dev_t *d)
     return rc;
 }
 
-ASAM_EXPORT int asam_backsolve(asam_dev_t *d, int ntasks, const int32_t *btasks)
+ASAM_EXPORT int asam_backsolve(asam_dev_t *d, int ntasks, const int32_t *btasks, const int32_t *bfirst)
 {
     if (ntasks <= 0)
         return 0;
     CK(cudaSetDevice(d->device));
     size_t b = (size_t) ntasks * sizeof(int);
-    if (buf_reserve(d, d->btasks_tmp, b, false, false))
+    if (buf_reserve(d, d->btasks_tmp, 2 * b, false, false))
         return 1;
     if (upload(d, d->btasks_tmp.p, btasks, b))
         return 1;
-    return launch_backsolve(d, ntasks, (const int *) d->btasks_tmp.p);
+    const bool part = bfirst && !d->keep_off;
+    if (part && upload(d, (int *) d->btasks_tmp.p + ntasks, bfirst, b))
+        return 1;
+    return launch_backsolve(d, ntasks, (const int *) d->btasks_tmp.p, 0, part ? (const int *) d->btasks_tmp.p + ntasks : nullptr);
 }
 
 ASAM_EXPORT int asam_download_x(asam_dev_t *d, int q_first, int q_count, double *x3)

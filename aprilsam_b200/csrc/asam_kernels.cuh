@@ -307,6 +307,7 @@ struct FacArgs {
     int *arrive;
     int *tbar; // team barrier counters, zeroed before the launch
     const int *tasks, *nwait; // nwait: bits 0-15 children in this launch, 16-23 worker, 24-30 team size
+    const int *keep; // optional, per task: (poses kept << 16) | block rows of the retained front; see cta_front
     int ntasks;
     int *ctrl; // [0] ticket, [1] err
     int smem_doubles;
@@ -871,15 +872,25 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
                 continue;
             const double *ccol = CF + (size_t) (cc + j) * cld + cc;
             double *fcol = F + (size_t) dj * ld;
+            // the column is this worker's own and dmap is injective: the destination values are fetched
+            // together with the child's (16 independent loads in flight per lane, one L2 round trip per
+            // 256 rows) instead of one read-modify-write after the other
             for (int i0 = j + lane; i0 <= cr; i0 += 256) {
-                double v[8];
+                double v[8], dv[8];
+                int di[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const bool ok = i0 + 32 * u <= cr;
+                    v[u] = ok ? __ldcg(ccol + i0 + 32 * u) : 0.0;
+                    di[u] = ok ? dmap[i0 + 32 * u] : -1;
+                }
 #pragma unroll
                 for (int u = 0; u < 8; u++)
-                    v[u] = (i0 + 32 * u <= cr) ? __ldcg(ccol + i0 + 32 * u) : 0.0;
+                    dv[u] = di[u] >= 0 ? __ldcg(fcol + di[u]) : 0.0;
 #pragma unroll
                 for (int u = 0; u < 8; u++)
-                    if (i0 + 32 * u <= cr)
-                        fcol[dmap[i0 + 32 * u]] += v[u];
+                    if (di[u] >= 0)
+                        fcol[di[u]] = dv[u] + v[u];
             }
         }
     }
@@ -1222,8 +1233,12 @@ __device__ __forceinline__ void ticket_release(int *ticket, int *done)
 // panels): zero + gather the Hessian entries, wait for the children of this launch, extend-add the
 // children's update matrices, eliminate the supernode's columns, publish.  t = index in the task
 // list (trace slot).  Returns false on abort.
+// Partial re-factorisation (incremental steps, keepw != 0): the first `keep` columns of the front are
+// unchanged by the step (host: plan_append), their L and y are still in the arena (front of order 3*old_mb at
+// the same offset).  The front is assembled as usual, those columns are overwritten with the retained L, applied
+// to the rest in ONE parallel pass, and only the columns from `keep` on go through the sequential elimination.
 __device__ bool cta_front(const FacArgs &a, const int t, const int s, const int nw, const asam_sn_desc_t &d, double *sm,
-                          asam_sn_desc_t *s_cd, int *s_abort, unsigned long long tr0)
+                          asam_sn_desc_t *s_cd, int *s_abort, unsigned long long tr0, const int keepw = 0)
 {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
@@ -1339,15 +1354,22 @@ __device__ bool cta_front(const FacArgs &a, const int t, const int s, const int 
             for (int j = warp; j < cr; j += nwarps) {
                 const double *ccol = CF + (size_t) (cc + j) * cld + cc;
                 double *fcol = F + (size_t) dmap[j] * ld;
-                for (int i0 = j + lane; i0 <= cr; i0 += 256) { // eight independent loads in flight per lane
-                    double v[8];
+                for (int i0 = j + lane; i0 <= cr; i0 += 256) { // sixteen independent loads in flight per lane
+                    double v[8], dv[8];
+                    int di[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const bool ok = i0 + 32 * u <= cr;
+                        v[u] = ok ? __ldcg(ccol + i0 + 32 * u) : 0.0;
+                        di[u] = ok ? dmap[i0 + 32 * u] : -1;
+                    }
 #pragma unroll
                     for (int u = 0; u < 8; u++)
-                        v[u] = (i0 + 32 * u <= cr) ? __ldcg(ccol + i0 + 32 * u) : 0.0;
+                        dv[u] = di[u] >= 0 ? fcol[di[u]] : 0.0;
 #pragma unroll
                     for (int u = 0; u < 8; u++)
-                        if (i0 + 32 * u <= cr)
-                            fcol[dmap[i0 + 32 * u]] += v[u];
+                        if (di[u] >= 0)
+                            fcol[di[u]] = dv[u] + v[u];
                 }
             }
         }
@@ -1357,8 +1379,28 @@ __device__ bool cta_front(const FacArgs &a, const int t, const int s, const int 
         tr3 = d_now();
 
     // ---- 4. eliminate this supernode's columns, panel by panel ------------------------
+    int kstart = 0;
+    if (use_sm && keepw != 0) {
+        const int keep = 3 * (keepw >> 16), m_old = 3 * (keepw & 0xffff), ld_old = ASAM_LD(m_old);
+        if (keep > 0 && keep < c && m_old <= m && keep <= m_old) {
+            // retained L (rows j..m_old-1) and y (old rhs row) of the kept columns; the rows of the poses
+            // appended since are structurally zero in them
+            for (int j = warp; j < keep; j += nwarps) {
+                const double *oc = Fg + (size_t) j * ld_old;
+                double *nc = F + (size_t) j * ld;
+                for (int i = j + lane; i < m; i += 32)
+                    nc[i] = i < m_old ? oc[i] : 0.0;
+                if (lane == 0)
+                    nc[m] = oc[m_old];
+            }
+            __syncthreads();
+            trailing_update<2, 8>(F, ld, F, ld, keep, keep, m, m);
+            __syncthreads();
+            kstart = keep;
+        }
+    }
     if (use_sm) {
-        for (int k0 = 0; k0 < c; k0 += ASAM_PB) {
+        for (int k0 = kstart; k0 < c; k0 += ASAM_PB) {
             const int pb = min(ASAM_PB, c - k0);
             double *P = F + (size_t) k0 * ld; // panel columns live inside the front
             unsigned long long ta = 0, tb = 0;
@@ -1501,7 +1543,7 @@ __global__ void __launch_bounds__(256, 1) k_factor(FacArgs a)
             __syncthreads();
             continue;
         }
-        if (!cta_front(a, t, s, nw, d, sm, s_cd, &s_abort, tr0))
+        if (!cta_front(a, t, s, nw, d, sm, s_cd, &s_abort, tr0, a.keep ? a.keep[t] : 0))
             break;
     }
     ticket_release(&a.ctrl[0], &a.ctrl[3]);
@@ -1703,6 +1745,7 @@ struct BsArgs {
     double *x;
     int *xdone;
     const int *btasks;
+    const int *bfirst; // optional, per task: first wanted pose of the supernode (see cta_backsolve, jcol)
     int ntasks;
     int *ctrl; // [2] ticket, [1] err
     int epoch;
@@ -1746,7 +1789,10 @@ __device__ __forceinline__ double bs_dot(const double *lk, const double *xs, int
 
 // One supernode of the back-substitution handled by ONE CTA (see the comment above).  t = index in the
 // task list (trace slot).  Returns false on abort.
-__device__ bool cta_backsolve(const BsArgs &a, const int t, const int s, double *sm, int *s_abort)
+// jcol > 0 (incremental steps with the reference's pruned traversal, aprilsam.c:752-772): only x of the
+// columns [jcol, c) is wanted -- back-substitution inside a supernode runs from its last column down, so it
+// simply stops there (the columns before depend on these, not the other way round).
+__device__ bool cta_backsolve(const BsArgs &a, const int t, const int s, double *sm, int *s_abort, const int jcol = 0)
 {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
@@ -1776,17 +1822,20 @@ __device__ bool cta_backsolve(const BsArgs &a, const int t, const int s, double 
         // staging mode: 2 = whole panel of the block (rows b0..m-1, ld lm), 1 = its diagonal
         // block only (ld lc), 0 = none.  Staged leading dimensions are ODD: the triangular
         // solve reads row k across columns, an even stride would pile the lanes onto a few banks
+        if (be <= jcol)
+            break; // nothing wanted in this block or the ones before it
+        const int kmin = max(0, jcol - b0); // first wanted column of this block
         const int lm = hb | 1, lc = bw | 1;
         const int mode = ((long long) lm * bw <= room) ? 2 : (((long long) lc * bw <= room) ? 1 : 0);
         const int ll = mode == 2 ? lm : (mode == 1 ? lc : ld);
         if (blk != nblk - 1)
             __syncthreads(); // the previous block is done with w / rd / Ls
         if (mode == 2) {
-            for (int k = warp; k < bw; k += nwarps)
+            for (int k = kmin + warp; k < bw; k += nwarps)
                 for (int i = k + lane; i < hb; i += 32)
                     Ls[i + (size_t) k * lm] = Lg[(b0 + i) + (size_t) (b0 + k) * ld];
         } else if (mode == 1) {
-            for (int k = warp; k < bw; k += nwarps)
+            for (int k = kmin + warp; k < bw; k += nwarps)
                 for (int i = k + lane; i < bw; i += 32)
                     Ls[i + (size_t) k * lc] = Lg[(b0 + i) + (size_t) (b0 + k) * ld];
         }
@@ -1823,7 +1872,7 @@ __device__ bool cta_backsolve(const BsArgs &a, const int t, const int s, double 
         // w_k -= sum_{i >= be} L[i, b0+k] * xf[i]   (one warp per column)
         const int nr = m - be;
         if (nr > 0) {
-            for (int k = warp; k < bw; k += nwarps) {
+            for (int k = kmin + warp; k < bw; k += nwarps) {
                 const double *lk = (mode == 2) ? (Ls + (size_t) k * lm + bw) : (Lg + (size_t) (b0 + k) * ld + be);
                 const double acc = nr > 512 ? bs_dot<16>(lk, xf + be, nr, lane) : bs_dot<8>(lk, xf + be, nr, lane);
                 if (lane == 0)
@@ -1840,14 +1889,14 @@ __device__ bool cta_backsolve(const BsArgs &a, const int t, const int s, double 
             for (int t3 = 0; t3 < 3; t3++)
                 wr[t3] = (lane + 32 * t3 < bw) ? w[lane + 32 * t3] : 0.0;
 #pragma unroll 2
-            for (int k = bw - 1; k >= 0; --k) {
+            for (int k = bw - 1; k >= kmin; --k) {
                 const int ks = k >> 5;
                 const double mine = ks == 0 ? wr[0] : (ks == 1 ? wr[1] : wr[2]);
                 const double xk = __shfl_sync(0xffffffffu, mine, k & 31) * rd[k];
 #pragma unroll
                 for (int t3 = 0; t3 < 3; t3++) {
                     const int j = lane + 32 * t3;
-                    if (j < k)
+                    if (j < k && j >= kmin)
                         wr[t3] -= L11[k + (size_t) j * ll] * xk;
                     else if (j == k)
                         wr[t3] = xk;
@@ -1856,7 +1905,7 @@ __device__ bool cta_backsolve(const BsArgs &a, const int t, const int s, double 
 #pragma unroll
             for (int t3 = 0; t3 < 3; t3++) {
                 const int k = lane + 32 * t3;
-                if (k < bw) {
+                if (k < bw && k >= kmin) {
                     a.x[3 * (size_t) d.first + b0 + k] = wr[t3];
                     xf[b0 + k] = wr[t3];
                 }
@@ -1897,7 +1946,7 @@ __global__ void __launch_bounds__(256) k_backsolve(BsArgs a)
         const int t = s_task;
         if (t >= a.ntasks)
             break;
-        if (!cta_backsolve(a, t, a.btasks[t], sm, &s_abort))
+        if (!cta_backsolve(a, t, a.btasks[t], sm, &s_abort, a.bfirst ? 3 * a.bfirst[t] : 0))
             break;
     }
     ticket_release(&a.ctrl[2], &a.ctrl[4]);
@@ -2134,7 +2183,7 @@ __global__ void __launch_bounds__(256, 1) k_step(StepArgs a)
             ok = false;
             break;
         }
-        ok = cta_front(a.fac, t, s, nwp & 0xffff, d, sm, s_cd, &s_abort, 0ULL);
+        ok = cta_front(a.fac, t, s, nwp & 0xffff, d, sm, s_cd, &s_abort, 0ULL, a.fac.keep ? a.fac.keep[t] : 0);
     }
 
     if (tid == 0)
@@ -2145,7 +2194,7 @@ __global__ void __launch_bounds__(256, 1) k_step(StepArgs a)
         if (tid == 0)
             s_abort = 0;
         __syncthreads();
-        ok = cta_backsolve(a.bs, t, a.bs.btasks[t], sm, &s_abort);
+        ok = cta_backsolve(a.bs, t, a.bs.btasks[t], sm, &s_abort, a.bs.bfirst ? 3 * a.bs.bfirst[t] : 0);
     }
     __syncthreads();
 

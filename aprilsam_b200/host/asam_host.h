@@ -90,6 +90,8 @@ typedef struct {
     asam_sn_desc_t *desc;
     sn_host_t *snh;
     int *sn_of_q;
+    int *mark_idx; /* plan_append scratch: supernode -> index among the marked ones, -1 between steps */
+    int mark_cap;
 
     ivec_t ipool_host; /* host copy of the device int pool */
     int64_t ipool_n;  /* ints used in the device pool   */
@@ -139,10 +141,11 @@ int plan_build_with_order(plan_t *pl, asam_dev_t *dev, int N, int n_factors, con
 /* Incremental append: nodes [pl->N, N) and factors [pl->n_factors, n_factors) are new and
  * every new binary factor touches at least one new node.  marked_old = graph-node ids of
  * old nodes on the root paths (any order).  On return tasks_out/nwait_out (malloc'd, length
- * *ntasks_out) list the supernodes to re-factor, children first.
+ * *ntasks_out) list the supernodes to re-factor, children first; keep_out (may be NULL) gets, per
+ * task, (poses kept << 16) | block rows before the step, 0 = re-factor the whole front.
  * Returns 0 ok, 1 error, 2 = not an append-only update (caller falls back). */
 int plan_append(plan_t *pl, asam_dev_t *dev, int N, int n_factors, const int *ftype, const int *fa, const int *fb,
-                const int *marked_old, int n_marked, int **tasks_out, int **nwait_out, int *ntasks_out);
+                const int *marked_old, int n_marked, int **tasks_out, int **nwait_out, int **keep_out, int *ntasks_out);
 
 /* Modelled cost (columns x rows^2 + a latency term per front, the measure build_schedule balances
  * shards with) of re-factoring the distinct supernodes in tasks[0..ntasks) and of factoring every

@@ -42,18 +42,21 @@ ASAM_API int asam_dbg_plan_build_with_order(void *p, int N, int F, const int *ft
 
 /* returns ntasks (>= 0) or -rc */
 ASAM_API int asam_dbg_plan_append(void *p, int N, int F, const int *ftype, const int *fa, const int *fb,
-                                  const int *marked, int n_marked, int *tasks_out, int *nwait_out, int cap)
+                                  const int *marked, int n_marked, int *tasks_out, int *nwait_out, int *keep_out, int cap)
 {
-    int *tasks = NULL, *nwait = NULL, nt = 0;
-    int rc = plan_append((plan_t *) p, NULL, N, F, ftype, fa, fb, marked, n_marked, &tasks, &nwait, &nt);
+    int *tasks = NULL, *nwait = NULL, *keep = NULL, nt = 0;
+    int rc = plan_append((plan_t *) p, NULL, N, F, ftype, fa, fb, marked, n_marked, &tasks, &nwait, &keep, &nt);
     if (rc)
         return -rc;
     if (nt > cap)
         nt = cap;
     memcpy(tasks_out, tasks, sizeof(int) * (size_t) nt);
     memcpy(nwait_out, nwait, sizeof(int) * (size_t) nt);
+    if (keep_out)
+        memcpy(keep_out, keep, sizeof(int) * (size_t) nt);
     free(tasks);
     free(nwait);
+    free(keep);
     return nt;
 }
 

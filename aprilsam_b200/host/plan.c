@@ -203,6 +203,7 @@ void plan_free(plan_t *pl)
     free(pl->btasks);
     free(pl->leaf_tasks);
     free(pl->bs_leaf);
+    free(pl->mark_idx);
     free(pl->top_tasks);
     free(pl->top_nwait);
     free(pl->shard_owner);
@@ -1057,11 +1058,13 @@ int plan_build_with_order(plan_t *pl, asam_dev_t *dev, int N, int n_factors, con
 
 /* ---- incremental append ------------------------------------------------------------------- */
 int plan_append(plan_t *pl, asam_dev_t *dev, int N, int n_factors, const int *ftype, const int *fa, const int *fb,
-                const int *marked_old, int n_marked, int **tasks_out, int **nwait_out, int *ntasks_out)
+                const int *marked_old, int n_marked, int **tasks_out, int **nwait_out, int **keep_out, int *ntasks_out)
 {
     const int N0 = pl->N, F0 = pl->n_factors, nsn0 = pl->nsn;
     double pp_t0 = pp_now();
     *tasks_out = *nwait_out = NULL;
+    if (keep_out)
+        *keep_out = NULL;
     *ntasks_out = 0;
     for (int f = F0; f < n_factors; f++) {
         if (ftype[f] == APRIL_GRAPH_FACTOR_XYT_TYPE) {
@@ -1132,11 +1135,35 @@ int plan_append(plan_t *pl, asam_dev_t *dev, int N, int n_factors, const int *ft
         if (marked_old[i] < N0)
             msn[nm++] = pl->sn_of_q[pl->node2q[marked_old[i]]];
     nm = sort_unique(msn, nm);
-    int *mark_idx = malloc(sizeof(int) * (size_t) (nsn0 + nnew + 1)); /* sn -> index in msn or -1 */
-    for (int s = 0; s < nsn0 + nnew; s++)
-        mark_idx[s] = -1;
+    /* sn -> index in msn or -1: kept across steps, all -1 between them (an O(nsn) fill per step is what made the
+     * reference's incremental steps grow with the graph) */
+    if (pl->sn_cap > pl->mark_cap) {
+        pl->mark_idx = realloc(pl->mark_idx, sizeof(int) * (size_t) pl->sn_cap);
+        for (int s = pl->mark_cap; s < pl->sn_cap; s++)
+            pl->mark_idx[s] = -1;
+        pl->mark_cap = pl->sn_cap;
+    }
+    int *mark_idx = pl->mark_idx;
     for (int i = 0; i < nm; i++)
         mark_idx[msn[i]] = i;
+
+    /* Partial re-factorisation: the columns of a marked supernode BEFORE its first marked pose are
+     * unchanged by this step (their Hessian entries, their children and -- because a new pose reaches an
+     * old column only through a marked one -- their rows), so the kernel keeps them (L and y) and
+     * re-eliminates from the first marked column on.  keepb[i] = poses kept of marked supernode i,
+     * oldmb[i] = its block rows before this step (the retained front still has that layout). */
+    int *keepb = malloc(sizeof(int) * (size_t) (nm + 1)), *oldmb = malloc(sizeof(int) * (size_t) (nm + 1));
+    for (int i = 0; i < nm; i++) {
+        keepb[i] = pl->desc[msn[i]].cb;
+        oldmb[i] = pl->snh[msn[i]].rows.n;
+    }
+    for (int i = 0; i < n_marked; i++)
+        if (marked_old[i] < N0) {
+            int q = pl->node2q[marked_old[i]], sidx = mark_idx[pl->sn_of_q[q]];
+            int k = q - pl->desc[msn[sidx]].first;
+            if (k < keepb[sidx])
+                keepb[sidx] = k;
+        }
 
     int rc = 0, bs_leaf_broken = 0;
     ivec_t *gain = calloc((size_t) nm + 1, sizeof(ivec_t));
@@ -1186,6 +1213,7 @@ int plan_append(plan_t *pl, asam_dev_t *dev, int N, int n_factors, const int *ft
             d->reserved = front_doubles(d->mb + slack);
             d->f_off = pl->arena_n;
             pl->arena_n += d->reserved;
+            keepb[i] = 0; /* the retained columns stay behind at the old place */
         }
         if (d->parent < 0 && gain[i].n > 0) { /* old root: hangs under the first new pose */
             ivec_push(&pend[gain[i].p[0] - N0], s); /* supernode id of that pose: set below */
@@ -1312,8 +1340,12 @@ int plan_append(plan_t *pl, asam_dev_t *dev, int N, int n_factors, const int *ft
     {
         int nt = nm + ncreated;
         int *tasks = malloc(sizeof(int) * (size_t) (nt + 1)), *nwait = malloc(sizeof(int) * (size_t) (nt + 1));
-        for (int i = 0; i < nm; i++)
+        int *keep = calloc((size_t) nt + 1, sizeof(int));
+        for (int i = 0; i < nm; i++) {
             tasks[i] = msn[i];
+            if (keepb[i] > 0 && keepb[i] < 0x7fff && oldmb[i] < 0xffff)
+                keep[i] = (keepb[i] << 16) | oldmb[i];
+        }
         for (int k = 0; k < ncreated; k++) { /* created supernodes have ids nsn0 .. nsn0+ncreated-1 */
             tasks[nm + k] = nsn0 + k;
             mark_idx[nsn0 + k] = nm + k;
@@ -1384,6 +1416,7 @@ int plan_append(plan_t *pl, asam_dev_t *dev, int N, int n_factors, const int *ft
         if (rc) {
             free(tasks);
             free(nwait);
+            free(keep);
         } else {
             /* expand big fronts into teams of consecutive entries */
             int total = 0;
@@ -1391,22 +1424,30 @@ int plan_append(plan_t *pl, asam_dev_t *dev, int N, int n_factors, const int *ft
                 total += team_size(pl->desc[tasks[t]].mb, pl->desc[tasks[t]].cb, plan_team_cap(pl));
             if (total != nt) {
                 int *t2 = malloc(sizeof(int) * (size_t) total), *w2 = malloc(sizeof(int) * (size_t) total);
+                int *k2 = calloc((size_t) total, sizeof(int)); /* teams re-factor whole fronts */
                 int k = 0;
                 for (int t = 0; t < nt; t++) {
                     int G = team_size(pl->desc[tasks[t]].mb, pl->desc[tasks[t]].cb, plan_team_cap(pl));
                     for (int w = 0; w < G; w++, k++) {
                         t2[k] = tasks[t];
                         w2[k] = pack_nwait(nwait[t], w, G > 1 ? G : 0);
+                        k2[k] = G > 1 ? 0 : keep[t];
                     }
                 }
                 free(tasks);
                 free(nwait);
+                free(keep);
                 tasks = t2;
                 nwait = w2;
+                keep = k2;
                 nt = total;
             }
             *tasks_out = tasks;
             *nwait_out = nwait;
+            if (keep_out)
+                *keep_out = keep;
+            else
+                free(keep);
             *ntasks_out = nt;
         }
     }
@@ -1421,11 +1462,16 @@ done:
         ivec_free(&pend[j]);
         ivec_free(&nbelow[j]);
     }
+    for (int i = 0; i < nm; i++)
+        mark_idx[msn[i]] = -1;
+    for (int sx = nsn0; sx < nsn0 + nnew && sx < pl->mark_cap; sx++)
+        mark_idx[sx] = -1;
     free(gain);
     free(pend);
     free(nbelow);
     free(msn);
-    free(mark_idx);
+    free(keepb);
+    free(oldmb);
     ivec_free(&nlo);
     ivec_free(&nhi);
     return rc;

@@ -348,6 +348,8 @@ typedef struct solver {
     int tree_fresh; /* param->tr is exactly the tree of `plan` as built by the last batch */
     int *scratch;
     int scratch_cap;
+    int *sn_stamp, *sn_jf, *sn_bt; /* per-supernode scratch of the pruned back-substitution (no O(nsn) work per step) */
+    int stamp_cap, stamp_epoch;
     aprilsam_b200_escalation_fn policy; /* deterministic escalation hook (aprilsam.h) */
     void *policy_user;
 } solver_t;
@@ -378,6 +380,9 @@ static void solver_destroy(solver_t *s)
         gctx_unref(s->gc);
     free(s->x);
     free(s->scratch);
+    free(s->sn_stamp);
+    free(s->sn_jf);
+    free(s->sn_bt);
     s->magic = 0;
     free(s);
 }
@@ -940,9 +945,9 @@ ASAM_API void april_graph_cholesky_inc(april_graph_t *graph, april_graph_cholesk
     }
 
     /* symbolic append + numeric re-factorisation of the marked supernodes */
-    int *tasks = NULL, *nwait = NULL, ntasks = 0;
+    int *tasks = NULL, *nwait = NULL, *keep = NULL, ntasks = 0;
     PROF_LAP(0);
-    int rc = plan_append(pl, dev, N, F, c->ftype, c->fa, c->fb, marked, n_marked, &tasks, &nwait, &ntasks);
+    int rc = plan_append(pl, dev, N, F, c->ftype, c->fa, c->fb, marked, n_marked, &tasks, &nwait, &keep, &ntasks);
     if (rc == 2) {
         inc_general_fallback(graph, param, s, N, F, F0);
         goto escalate;
@@ -964,7 +969,7 @@ ASAM_API void april_graph_cholesky_inc(april_graph_t *graph, april_graph_cholesk
         stamp(&tp, "mark paths, symbolic append");
     DEV_OK(asam_step_begin(dev)); /* record the step's kernels; one upload flush at asam_step_run */
     DEV_OK(asam_linearize(dev, F0, nf, pts));
-    DEV_OK(asam_factor(dev, ntasks, tasks, nwait));
+    DEV_OK(asam_factor(dev, ntasks, tasks, nwait, keep));
     param->factor_num = F;
     PROF_LAP(2);
 
@@ -983,22 +988,37 @@ ASAM_API void april_graph_cholesky_inc(april_graph_t *graph, april_graph_cholesk
             DEV_OK(asam_step_run(dev));
             DEV_OK(asam_download_x_status(dev, 0, N, x, &fstatus));
         } else {
-            /* visited = marked nodes + their children; close under ancestors */
-            int *stamp = calloc((size_t) pl->nsn, sizeof(int));
-            int *bt = malloc(sizeof(int) * (size_t) pl->nsn);
+            /* visited = marked nodes + their children; close under ancestors.  Per supernode the first
+             * wanted pose: the back-substitution of a supernode stops there (cta_backsolve, jcol) */
+            if (pl->sn_cap > s->stamp_cap) {
+                s->sn_stamp = realloc(s->sn_stamp, sizeof(int) * (size_t) pl->sn_cap);
+                s->sn_jf = realloc(s->sn_jf, sizeof(int) * (size_t) pl->sn_cap);
+                s->sn_bt = realloc(s->sn_bt, sizeof(int) * 2 * (size_t) pl->sn_cap);
+                memset(s->sn_stamp + s->stamp_cap, 0, sizeof(int) * (size_t) (pl->sn_cap - s->stamp_cap));
+                s->stamp_cap = pl->sn_cap;
+            }
+            if (++s->stamp_epoch == INT_MAX) {
+                memset(s->sn_stamp, 0, sizeof(int) * (size_t) s->stamp_cap);
+                s->stamp_epoch = 1;
+            }
+            int *stamp = s->sn_stamp, *jf = s->sn_jf, *bt = s->sn_bt;
+            const int ep = s->stamp_epoch;
             int nbt = 0, qmin = N;
             for (int i = 0; i < n_marked; i++) {
                 search_tree_node_t *node = &tr->nodes[marked[i]];
                 for (int ci = -1; ci < node->nchildren; ci++) {
                     int v = ci < 0 ? marked[i] : node->children[ci];
-                    int sn = pl->sn_of_q[pl->node2q[v]];
-                    while (sn >= 0 && !stamp[sn]) {
-                        stamp[sn] = 1;
+                    int q = pl->node2q[v], sn0 = pl->sn_of_q[q], sn = sn0;
+                    while (sn >= 0 && stamp[sn] != ep) {
+                        stamp[sn] = ep;
+                        jf[sn] = pl->desc[sn].cb;
                         bt[nbt++] = sn;
                         if (pl->desc[sn].first < qmin)
                             qmin = pl->desc[sn].first;
                         sn = pl->desc[sn].parent;
                     }
+                    if (q - pl->desc[sn0].first < jf[sn0])
+                        jf[sn0] = q - pl->desc[sn0].first;
                 }
             }
             /* parents before children: descending supernode id */
@@ -1010,7 +1030,10 @@ ASAM_API void april_graph_cholesky_inc(april_graph_t *graph, april_graph_cholesk
                 }
                 bt[j + 1] = v;
             }
-            DEV_OK(asam_backsolve(dev, nbt, bt));
+            int *bfirst = bt + pl->sn_cap;
+            for (int i = 0; i < nbt; i++)
+                bfirst[i] = jf[bt[i]] < pl->desc[bt[i]].cb ? jf[bt[i]] : 0;
+            DEV_OK(asam_backsolve(dev, nbt, bt, bfirst));
             /* a handful of single-CTA fronts: the whole step in ONE launch, results through pinned memory */
             int small = nbt <= ASAM_SMALL_MAX_BS && ntasks <= ASAM_SMALL_MAX_TASKS && asam_step_small_supported(dev);
             for (int t = 0; small && t < ntasks; t++)
@@ -1040,8 +1063,6 @@ ASAM_API void april_graph_cholesky_inc(april_graph_t *graph, april_graph_cholesk
                 qbase = qmin;
                 DEV_OK(asam_download_x_status(dev, qbase, N - qbase, x, &fstatus));
             }
-            free(stamp);
-            free(bt);
         }
         PROF_LAP(4);
         report_factor_status(s, fstatus, "april_graph_cholesky_inc");
@@ -1059,6 +1080,7 @@ ASAM_API void april_graph_cholesky_inc(april_graph_t *graph, april_graph_cholesk
     }
     free(tasks);
     free(nwait);
+    free(keep);
 
     if (policy_escalate) /* the deterministic stand-in for the wall-clock rule (:556-559): same effect */
         param->tr->start_over = INT_MAX;

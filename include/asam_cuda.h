@@ -93,7 +93,7 @@ int asam_linearize(asam_dev_t *d, int f_first, int f_count, const double *pts6);
  * consecutive; 0 or 1 = single CTA).  Replaces cs_schol/cs_chol + forward solve
  * (csparse.c:462-513, smatd.c:1051-1073) and, with a subset, the un-eliminate /
  * re-eliminate of the incremental path (aprilsam.c:791-906). */
-int asam_factor(asam_dev_t *d, int ntasks, const int32_t *tasks, const int32_t *nwait);
+int asam_factor(asam_dev_t *d, int ntasks, const int32_t *tasks, const int32_t *nwait, const int32_t *keep);
 /* Same, re-using the task list of the previous asam_factor_full upload. */
 int asam_set_full_tasks(asam_dev_t *d, int ntasks, const int32_t *tasks, const int32_t *nwait,
                         int nbtasks, const int32_t *btasks);
@@ -143,7 +143,7 @@ int asam_set_shard_schedule(asam_dev_t *d, const asam_shard_sched_t *sched /* NU
 
 /* Kernel 3: back-substitution over the given supernodes (parents before children; the
  * list must be closed under ancestors).  (smatd.c:1075-1097, aprilsam.c:721-779) */
-int asam_backsolve(asam_dev_t *d, int ntasks, const int32_t *btasks);
+int asam_backsolve(asam_dev_t *d, int ntasks, const int32_t *btasks, const int32_t *bfirst);
 int asam_backsolve_full(asam_dev_t *d);
 
 /* Between asam_step_begin and asam_step_run, asam_linearize / asam_factor* / asam_backsolve* only

@@ -49,7 +49,7 @@ int main(int argc, char **argv)
                     }
                 }
                 int *tasks = NULL, *nwait = NULL, nt = 0;
-                int rc = plan_append(&pl, NULL, k + 1, F2, ft, fa, fb, marked, nm, &tasks, &nwait, &nt);
+                int rc = plan_append(&pl, NULL, k + 1, F2, ft, fa, fb, marked, nm, &tasks, &nwait, NULL, &nt);
                 if (rc) { fprintf(stderr, "append rc %d at %d\n", rc, k); return 1; }
                 free(tasks); free(nwait); free(marked); free(seen);
                 Ncur = k + 1;

@@ -123,7 +123,7 @@ def seg_views(desc, ipool, s):
     return rows, rel, children, a_slot, a_rb, a_cb
 
 
-def factor(fr: Fronts, H: Hessian, desc, ipool, q2node, tasks, nwait=None, check_order=True, prior=(),
+def factor(fr: Fronts, H: Hessian, desc, ipool, q2node, tasks, nwait=None, check_order=True, prior=(), keep=None,
            count_prior=True):
     """k_factor: assemble + eliminate the listed supernodes (children first).  `prior` = supernodes
     factored by an earlier launch of the same solve; count_prior: their arrivals are part of nwait
@@ -189,6 +189,19 @@ def factor(fr: Fronts, H: Hessian, desc, ipool, q2node, tasks, nwait=None, check
             F[k + 1:, k + 1:] -= np.tril(np.outer(lk, lk))
             rhs[k + 1:] -= lk * rhs[k]
         off = int(desc["f_off"][s])
+        if keep is not None and int(keep[ti]) != 0:
+            # partial re-factorisation (cta_front, keepw): the host claims that the first kb poses' columns of the
+            # retained front are unchanged by this step -- check it against the full elimination just done
+            kb, omb = int(keep[ti]) >> 16, int(keep[ti]) & 0xffff
+            kc, mo = 3 * kb, 3 * omb
+            assert off in fr.F, "kept columns need the retained front at the same offset"
+            Fo, ro = fr.F[off], fr.rhs[off]
+            assert Fo.shape[0] == mo and 0 < kc < c and mo <= m
+            scale = max(1.0, np.abs(Fo).max())
+            assert np.abs(np.tril(F[:mo, :kc]) - np.tril(Fo[:, :kc])).max() < 1e-9 * scale, f"supernode {s}: kept L changed"
+            assert np.abs(F[mo:, :kc]).max(initial=0.0) == 0.0, f"supernode {s}: appended rows are not zero in kept columns"
+            assert np.abs(rhs[:kc] - ro[:kc]).max() < 1e-9 * max(1.0, np.abs(ro).max()), f"supernode {s}: kept y changed"
+            fr.kept_cols = getattr(fr, "kept_cols", 0) + kc
         fr.F[off] = F
         fr.rhs[off] = rhs
         fr.y[3 * first:3 * first + c] = rhs[:c]

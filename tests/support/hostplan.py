@@ -22,7 +22,7 @@ def lib():
         L.asam_dbg_plan_build.argtypes = [C.c_void_p, C.c_int, C.c_int, _ip, _ip, _ip]
         L.asam_dbg_plan_build_sharded.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, _ip]
         L.asam_dbg_plan_build_with_order.argtypes = [C.c_void_p, C.c_int, C.c_int, _ip, _ip, _ip, _ip, C.c_int]
-        L.asam_dbg_plan_append.argtypes = [C.c_void_p, C.c_int, C.c_int, _ip, _ip, _ip, _ip, C.c_int, _ip, _ip, C.c_int]
+        L.asam_dbg_plan_append.argtypes = [C.c_void_p, C.c_int, C.c_int, _ip, _ip, _ip, _ip, C.c_int, _ip, _ip, _ip, C.c_int]
         L.asam_dbg_plan_info.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double)]
         L.asam_dbg_plan_array.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]
         L.asam_dbg_plan_array.restype = _ip
@@ -83,12 +83,14 @@ class HostPlan:
         cap = N + 16
         tasks = np.zeros(cap, dtype=np.int32)
         nwait = np.zeros(cap, dtype=np.int32)
+        keep = np.zeros(cap, dtype=np.int32)
         nt = self.L.asam_dbg_plan_append(self.p, N, len(self.ftype), _i(self.ftype), _i(self.fa), _i(self.fb),
-                                         _i(marked), len(marked), _i(tasks), _i(nwait), cap)
+                                         _i(marked), len(marked), _i(tasks), _i(nwait), _i(keep), cap)
         if nt == -2:
             return None
         if nt < 0:
             raise RuntimeError(self.L.aprilsam_b200_last_error().decode())
+        self.last_keep = keep[:nt].copy()
         return tasks[:nt].copy(), nwait[:nt].copy()
 
     def info(self):

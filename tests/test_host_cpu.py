@@ -357,7 +357,7 @@ def test_emulated_incremental_append(m3500, n0, n1, step):
         node2q = p.array("node2q")
         Hs.linearize(range(F0, len(ftype)), ftype, fa, fb, fz, fW, lp, lp, node2q, p.array("fslot"))
         desc, ipool = p.descs(), p.array("ipool")
-        emul.factor(fr, Hs, desc, ipool, p.array("q2node"), tasks, nwait)
+        emul.factor(fr, Hs, desc, ipool, p.array("q2node"), tasks, nwait, keep=p.last_keep)  # checks the kept columns
         F0, N0 = len(ftype), n
     emul.backsolve(fr, desc, ipool, np.arange(info["nsn"] - 1, -1, -1))
     fslot = p.array("fslot")
@@ -369,6 +369,7 @@ def test_emulated_incremental_append(m3500, n0, n1, step):
     xs = spl.spsolve(A.tocsc(), Hs.B.reshape(-1))
     x_node = np.concatenate([fr.x[3 * node2q[i]:3 * node2q[i] + 3] for i in range(N0)])
     assert np.abs(x_node - xs).max() < 1e-8 * max(1.0, np.abs(xs).max())
+    assert getattr(fr, "kept_cols", 0) > 0, "some step kept the leading columns of a marked supernode"
 
 
 def test_append_rejects_edge_between_old_poses(m3500):

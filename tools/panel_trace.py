@@ -26,12 +26,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--poses", type=int, default=100000)
     ap.add_argument("--fronts", type=int, default=3)
+    ap.add_argument("--m3500", action="store_true", help="the M3500 fixture instead of the synthetic world")
     ap.add_argument("--dump-trace", default="", help="npz file: per-task stamps of one k_factor / k_backsolve launch + the plan")
     args = ap.parse_args()
     L = capi.lib()
     L.asam_set_panel_trace.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.asam_download_panel_trace.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_int]
-    d = datasets.manhattan_dense(args.poses, seed=1)
+    d = (H.PoseGraphData.load(os.path.join(ROOT, "tests", "golden", "m3500.npz")) if args.m3500
+         else datasets.manhattan_dense(args.poses, seed=1))
     # the plan (host only) to pick the fronts: widest supernodes of the team path
     E = d.n_edges
     ftype = np.ones(E + 1, np.int32); ftype[0] = 2
@@ -46,6 +48,8 @@ def main():
         dev = L.asam_dbg_dev_of_graph(h.graph_ptr())
         L.asam_set_timing(dev, 1)
         for s in order:
+            if not team[s]:
+                continue
             npan = int((c[s] + 47) // 48)
             capi.check(L.asam_set_panel_trace(dev, int(s), npan), "asam_set_panel_trace")
             h.set_states(d.init)
