@@ -634,6 +634,100 @@ __device__ __noinline__ void tile_mma(double *F, const int ld, const int m, cons
     }
 }
 
+// Row-major PANEL WORKSPACE of a team front (tile mode 3).  Behind the front (arena[f_off + ld*m ...]) sit two
+// buffers of (m+2) rows x ASAM_LDW doubles; buffer k&1 holds the factored panel k by ROWS: row r of the front
+// at W[r * ASAM_LDW .. + pb), zero up to the next multiple of 4.  A tile's operands -- a chunk of rows of the
+// panel -- are then ONE contiguous block each: two bulk asynchronous copies per tile instead of one per panel
+// column (measured: 96 small copies cost ~5 us, as much as staging by hand).  ASAM_LDW = 4 (mod 16) keeps the
+// m8n8k4 fragment loads conflict free, and a row is 416 bytes: every row 16-byte aligned.
+#define ASAM_LDW 52
+#define ASAM_WS_DOUBLES(m) (2 * (size_t) ((m) + 2) * ASAM_LDW)
+
+// C[rb0.., cb0..] -= L[rb0.., panel] * L[cb0.., panel]' with the panel taken from its row-major workspace Wk.
+// out_mode 0: C is read from and written back to the front (trailing update); 1: C is read from the front and
+// written to Out[ii + jj * ASAM_TPB] (the next panel's diagonal block, for diag_factor); 2: C is read from the
+// front and written to Out[ii + jj * ASAM_TROWS] (rows of the next panel, solved in place by trsm_row; Out may
+// alias Li).  Same warp layout as tile_mma.
+template <int MT>
+__device__ __noinline__ void tile_rm(double *F, const int ld, const double *Wk, const int pb4, const int cb0, const int ncol,
+                                     const int rb0, const int nrow, const int out_mode, double *Out, double *Li, double *Lj,
+                                     unsigned long long *bar, unsigned &parity)
+{
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const bool same = rb0 == cb0 && nrow >= ncol; // diagonal block: one operand
+    __syncthreads(); // everybody is done with the previous contents of Li / Lj
+    if (warp == 0) {
+        asm volatile("fence.proxy.async;" ::: "memory");
+        if (lane == 0) {
+            const unsigned bi = (unsigned) nrow * ASAM_LDW * 8u, bj = same ? 0u : (unsigned) ncol * ASAM_LDW * 8u;
+            mbar_expect_tx(bar, bi + bj);
+            bulk_g2s(Li, Wk + (size_t) rb0 * ASAM_LDW, bi, bar);
+            if (!same)
+                bulk_g2s(Lj, Wk + (size_t) cb0 * ASAM_LDW, bj, bar);
+        }
+    }
+    const double *Ljs = same ? Li : Lj;
+    const int g = lane >> 2, t = lane & 3;
+    const int r0 = warp * 8 * MT;
+    const int nnt = (ncol + 7) >> 3;
+    const int rowmax = rb0 + min(r0 + 8 * MT, nrow) - 1;
+    const int nneed = (r0 < nrow && rowmax >= cb0) ? min(nnt, ((rowmax - cb0) >> 3) + 1) : 0;
+    double acc[MT][8][2];
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int ii = r0 + 8 * mt + g, jj = 8 * q + 2 * t + e;
+                const bool ok = q < nneed && ii < nrow && jj < ncol && rb0 + ii >= cb0 + jj;
+                acc[mt][q][e] = ok ? __ldcg(&F[(rb0 + ii) + (size_t) (cb0 + jj) * ld]) : 0.0;
+            }
+    mbar_wait(bar, parity);
+    parity ^= 1u;
+    if (nneed > 0) {
+        const double *ai = Li + (size_t) (r0 + g) * ASAM_LDW + t;
+        const double *bj_ = Ljs + (size_t) g * ASAM_LDW + t;
+#pragma unroll 2
+        for (int kk = 0; kk < pb4; kk += 4) {
+            double av[MT];
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++)
+                av[mt] = -ai[(size_t) (8 * mt) * ASAM_LDW + kk];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                if (q < nneed) {
+                    const double bv = bj_[(size_t) (8 * q) * ASAM_LDW + kk];
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++)
+                        dmma_8x8x4(acc[mt][q][0], acc[mt][q][1], av[mt], bv);
+                }
+            }
+        }
+    }
+    if (out_mode == 2)
+        __syncthreads(); // Out may alias Li: every warp is done with its operand
+    if (nneed > 0) {
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int ii = r0 + 8 * mt + g, jj = 8 * q + 2 * t + e;
+                    if (q < nneed && ii < nrow && jj < ncol && rb0 + ii >= cb0 + jj) {
+                        if (out_mode == 0)
+                            F[(rb0 + ii) + (size_t) (cb0 + jj) * ld] = acc[mt][q][e];
+                        else if (out_mode == 1)
+                            Out[ii + jj * ASAM_TPB] = acc[mt][q][e];
+                        else
+                            Out[ii + jj * ASAM_TROWS] = acc[mt][q][e];
+                    }
+                }
+    }
+}
+
 struct TeamCtx {
     int *tbar_s;
     int G, w, phase;
@@ -738,11 +832,30 @@ __device__ __forceinline__ void diag_factor(double *D, int pb, double *rdv, int 
     __syncthreads();
 }
 
+// Same result, right-looking and blocked: 12-column sub-panels of closed-form 3x3 steps (panel_factor: every
+// thread of the CTA takes part in the row solves and the in-panel rank-3 updates) followed by a register-tiled
+// update of the rest of the block -- no dot products of growing length on the dependent chain.
+__device__ __forceinline__ void diag_factor_rl(double *D, int pb, double *rdv, int sn_id, int *err)
+{
+    constexpr int LDD = ASAM_TPB;
+    for (int k1 = 0; k1 < pb; k1 += ASAM_PB) {
+        const int pbb = min(ASAM_PB, pb - k1);
+        panel_factor(D + (size_t) k1 * LDD, LDD, k1, pbb, pb - 1, sn_id, err, rdv);
+        if (k1 + pbb < pb) {
+            trailing_update<1, 4>(D, LDD, D + (size_t) k1 * LDD, LDD, pbb, k1 + pbb, pb, pb - 1);
+            __syncthreads();
+        }
+    }
+}
+
 // One row of the panel per thread: x = row * L11^-T.  The row lives in Li (column p at
 // Li[tid + p*ASAM_TROWS]); it is processed 12 columns at a time in registers -- first the
 // contributions of the columns already solved (L entries fetched two at a time, broadcast), then
 // the 12x12 triangle fully unrolled.  Results go back to Li and to the front in HBM.
-__device__ __forceinline__ void trsm_row(double *Li, const double *D, const double *rdv, int pb, double *Frow, int ld)
+// Wrow != nullptr: the solved row also goes to the row-major panel workspace (Wrow[0..pb), zero up to the next
+// multiple of 4), where the next iteration's tiles fetch it as part of one contiguous block.
+__device__ __forceinline__ void trsm_row(double *Li, const double *D, const double *rdv, int pb, double *Frow, int ld,
+                                         double *Wrow = nullptr)
 {
     const int tid = threadIdx.x;
     constexpr int LDD = ASAM_TPB;
@@ -776,8 +889,13 @@ __device__ __forceinline__ void trsm_row(double *Li, const double *D, const doub
             if (q < nb) {
                 Li[tid + (b0 + q) * ASAM_TROWS] = r[q];
                 Frow[(size_t) (b0 + q) * ld] = r[q];
+                if (Wrow)
+                    Wrow[b0 + q] = r[q];
             }
     }
+    if (Wrow)
+        for (int q = pb; q < ((pb + 3) & ~3); q++)
+            Wrow[q] = 0.0;
 }
 
 // returns false on abort
@@ -917,6 +1035,11 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
     double *rdv = D + ASAM_TPB * ASAM_TPB;       // ASAM_TPB reciprocal diagonal entries
     double *Li = rdv + ASAM_TPB;                 // ASAM_LDI x pb   (row chunk / row tile)
     double *Lj = Li + ASAM_LDI * ASAM_TPB;       // ASAM_LDJ x pb   (column tile)
+    // tile mode 3: operands by rows from the panel workspace behind the front (Li: <= 256 x ASAM_LDW, Lj: <= 64 x ASAM_LDW)
+    const bool v3 = a.tile_mode == 3;
+    double *Wbase = F + (size_t) ld * m;
+    auto Wbuf = [&](int panel_index) { return Wbase + (size_t) (panel_index & 1) * (m + 2) * ASAM_LDW; };
+    double *Lj3 = Li + ASAM_TROWS * ASAM_LDW;
     double *dinv = a.dinv + 3 * (size_t) d.first;
     int *crew_bar = a.tbar + 2 * (size_t) s + 1; // flag: index (1-based) of the last published panel
 
@@ -924,6 +1047,17 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
     // (Dout != nullptr: the tile is the diagonal block of the next panel; its values also go straight
     // into the shared-memory block that diag_factor works on, saving the round trip through L2)
     auto tile = [&](int k0, int pb, int cb0, int ncol, int rb0, int nrow, double *Dout) {
+        if (v3) { // operands from the row-major workspace of the panel at k0; Dout: the next panel's diagonal block
+            const double *Wk = Wbuf(k0 / ASAM_TPB);
+            const int pb4 = (pb + 3) & ~3;
+            if (Dout)
+                tile_rm<1>(F, ld, Wk, pb4, cb0, ncol, rb0, nrow, 1, Dout, Li, Lj3, mbar, mb_parity);
+            else if (nrow <= 128)
+                tile_rm<2>(F, ld, Wk, pb4, cb0, ncol, rb0, nrow, 0, nullptr, Li, Lj3, mbar, mb_parity);
+            else
+                tile_rm<4>(F, ld, Wk, pb4, cb0, ncol, rb0, nrow, 0, nullptr, Li, Lj3, mbar, mb_parity);
+            return;
+        }
         if (a.tile_mode != 0) { // FP64 tensor pipe (1: operands staged by the threads, 2: by bulk asynchronous copies)
             const int bulk = a.tile_mode == 2;
             if (nrow <= 64)
@@ -1033,9 +1167,12 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
             for (int j = 0; j < pb; j++)
                 Li[tid + j * ASAM_TROWS] = __ldcg(&F[i + (size_t) (k0 + j) * ld]);
         __syncthreads();
-        diag_factor(D, pb, rdv, s, err);
+        if (v3)
+            diag_factor_rl(D, pb, rdv, s, err);
+        else
+            diag_factor(D, pb, rdv, s, err);
         if (row)
-            trsm_row(Li, D, rdv, pb, F + i + (size_t) k0 * ld, ld);
+            trsm_row(Li, D, rdv, pb, F + i + (size_t) k0 * ld, ld, v3 ? Wbuf(0) + (size_t) i * ASAM_LDW : nullptr);
     };
     auto writeback = [&](int k0, int pb) { // worker 0, after a team barrier: nobody reads the raw block any more
         for (int e = tid; e < pb * pb; e += nt) {
@@ -1051,7 +1188,10 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
     // factored ONCE and published -- L11 into the front, 1/diag into dinv, then the flag
     auto diag_publish = [&](int k0, int pb, int seq) {
         __syncthreads(); // D was zeroed before, and filled by, the tile that updated this block
-        diag_factor(D, pb, rdv, s, err);
+        if (v3)
+            diag_factor_rl(D, pb, rdv, s, err);
+        else
+            diag_factor(D, pb, rdv, s, err);
         writeback(k0, pb);
         __syncthreads();
         if (tid == 0) {
@@ -1061,11 +1201,11 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
     };
     // the other crew workers: rows [rb0, rb0+ASAM_CROWS) of the panel are fetched while worker 0 factors the
     // block, then solved against the published L11
-    auto rows_solve = [&](int k0, int pb, int rb0, int seq) {
+    auto rows_solve = [&](int k0, int pb, int rb0, int seq, double *Wnext) {
         __syncthreads();
         const int i = rb0 + tid;
         const bool row = tid < ASAM_CROWS && i <= m;
-        if (row)
+        if (row && !Wnext) // (tile mode 3: the tile left the updated rows in Li already)
             for (int j = 0; j < pb; j++)
                 Li[tid + j * ASAM_TROWS] = __ldcg(&F[i + (size_t) (k0 + j) * ld]);
         if (tid == 0) {
@@ -1093,7 +1233,7 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
             rdv[e] = e < pb ? __ldcg(&dinv[k0 + e]) : 0.0;
         __syncthreads();
         if (row)
-            trsm_row(Li, D, rdv, pb, F + i + (size_t) k0 * ld, ld);
+            trsm_row(Li, D, rdv, pb, F + i + (size_t) k0 * ld, ld, Wnext ? Wnext + (size_t) i * ASAM_LDW : nullptr);
         return true;
     };
 
@@ -1150,16 +1290,31 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
                 if (pt)
                     pt[2] = d_now();
             }
-            for (int it = (w == 0 ? G : w); it < ncrew; it += G) {
-                const int rb0 = kn0 + pbn + (it - 1) * ASAM_CROWS;
-                tile(k0, pb, kn0, pbn, rb0, min(ASAM_CROWS, m - rb0 + 1), nullptr);
-            }
-            if (pt && w > 0)
-                pt[1] = d_now();
-            for (int it = (w == 0 ? G : w); it < ncrew; it += G) {
-                const int rb0 = kn0 + pbn + (it - 1) * ASAM_CROWS;
-                if (!rows_solve(kn0, pbn, rb0, seq))
-                    return false;
+            if (v3) {
+                // fused crew item: the updated rows go from the tensor-pipe accumulators straight into shared
+                // memory (no round trip through the front), are solved there against the published L11 and
+                // leave once -- to the front (final L) and to the next panel's row-major workspace
+                for (int it = (w == 0 ? G : w); it < ncrew; it += G) {
+                    const int rb0 = kn0 + pbn + (it - 1) * ASAM_CROWS;
+                    tile_rm<2>(F, ld, Wbuf(k0 / ASAM_TPB), (pb + 3) & ~3, kn0, pbn, rb0, min(ASAM_CROWS, m - rb0 + 1), 2, Li, Li,
+                               Lj3, mbar, mb_parity);
+                    if (pt && w > 0 && it == w)
+                        pt[1] = d_now();
+                    if (!rows_solve(kn0, pbn, rb0, seq, Wbuf(kn0 / ASAM_TPB)))
+                        return false;
+                }
+            } else {
+                for (int it = (w == 0 ? G : w); it < ncrew; it += G) {
+                    const int rb0 = kn0 + pbn + (it - 1) * ASAM_CROWS;
+                    tile(k0, pb, kn0, pbn, rb0, min(ASAM_CROWS, m - rb0 + 1), nullptr);
+                }
+                if (pt && w > 0)
+                    pt[1] = d_now();
+                for (int it = (w == 0 ? G : w); it < ncrew; it += G) {
+                    const int rb0 = kn0 + pbn + (it - 1) * ASAM_CROWS;
+                    if (!rows_solve(kn0, pbn, rb0, seq, nullptr))
+                        return false;
+                }
             }
             if (pt && w > 0)
                 pt[2] = d_now();

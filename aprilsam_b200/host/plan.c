@@ -372,10 +372,12 @@ static inline int pack_nwait(int nw, int w, int G)
 
 static int plan_team_cap(const plan_t *pl) { return pl->max_team > 0 ? pl->max_team : 120; }
 
+/* doubles of the arena a front of mb block rows occupies: the front itself and, for fronts that do not fit
+ * in shared memory (team path), the two row-major panel buffers behind it (asam_kernels.cuh, ASAM_LDW) */
 static int64_t front_doubles(int mb)
 {
     int64_t m = 3 * (int64_t) mb;
-    return (int64_t) ASAM_LD(m) * m;
+    return (int64_t) ASAM_LD(m) * m + (front_fits_smem(mb) ? 0 : 2 * (m + 2) * 52);
 }
 
 /* ---- schedule: task lists of one batch solve ------------------------------------------------

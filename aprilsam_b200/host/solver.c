@@ -1052,6 +1052,9 @@ ASAM_API void april_graph_cholesky_inc(april_graph_t *graph, april_graph_cholesk
                     }
                     qbase = 0;
                     g_prof[18] += 1;
+                    g_prof[19] += ntasks;
+                    g_prof[20] += nbt;
+                    g_prof[21] += xd;
                 } else if (rs == 2) {
                     small = 0;
                 } else {

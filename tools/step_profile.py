@@ -35,7 +35,7 @@ def main():
         for k in range(2, min(args.steps, d.n_nodes) + 1):
             _, ms, info = h.replay_to(k, want_chi2=False)
             L.asam_dbg_profile(prof, 1)
-            rows.append([ms[0] * 1e3, info[0, 0]] + [prof[i] * 1e3 for i in range(7)] + [prof[18], prof[10]])
+            rows.append([ms[0] * 1e3, info[0, 0]] + [prof[i] * 1e3 for i in range(7)] + [prof[18], prof[10], prof[19], prof[20], prof[21]])
         dev = L.asam_dbg_dev_of_graph(h.graph_ptr())
         L.asam_small_steps.argtypes = [C.c_void_p]
         L.asam_small_steps.restype = C.c_int64
@@ -54,7 +54,9 @@ def main():
         x = r[sel]
         if not len(x):
             continue
-        print(f"{name}: {len(x)} steps, call median {np.median(x[:, 0]):.1f} us, mean {x[:, 0].mean():.1f} us")
+        print(f"{name}: {len(x)} steps, call median {np.median(x[:, 0]):.1f} us, mean {x[:, 0].mean():.1f} us"
+              + (f"; fronts re-factored mean {x[:, 11].mean():.2f}, supernodes back-solved mean {x[:, 12].mean():.2f}, x doubles mean {x[:, 13].mean():.1f}"
+                 if x[:, 9].sum() > 0 else ""))
         for i, nm in enumerate(NAMES):
             print(f"    {nm:40s} median {np.median(x[:, 2 + i]):7.2f}  mean {x[:, 2 + i].mean():7.2f} us")
 
