@@ -73,7 +73,7 @@ struct asam_dev {
     Buf Adiag, Aoff, Bq, y, x, dinv;
     // plan
     Buf sn, ipool, arena;
-    Buf arrive, xdone, tbar;
+    Buf arrive, xdone, tbar, xblk;
     // task lists
     Buf tasks_full, nwait_full, btasks_full;
     int ntasks_full = 0;
@@ -117,7 +117,8 @@ struct asam_dev {
     struct Pending *pend = nullptr;
     int npend = 0;
     int step_seq = 0;  // sequence number of the last k_step launch (completion flag in pin_down)
-    int tile_mode = 2; // ASAM_TILE_MODE: 0 DFMA tiles, 1 mma.sync f64, 2 mma.sync f64 + bulk async copies (team path)
+    int tile_mode = 3; // ASAM_TILE_MODE (team path tiles): 0 DFMA, 1 mma.sync f64, 2 + bulk async copy per panel column,
+                       // 3 mma.sync f64, operands by rows from the panel workspace (two bulk copies per tile), fused crew items
     int solo_pb = 48;  // ASAM_SOLO_PB: staged panel width of single-CTA fronts that live in HBM
     int small_ok = 1;  // ASAM_SMALL_STEP=0 disables the fused small-step kernel (A/B measurements)
     int64_t n_small = 0;
@@ -604,7 +605,7 @@ ASAM_EXPORT void asam_dev_destroy(asam_dev_t *d)
     cudaStreamSynchronize(d->stream);
     Buf *all[] = { &d->f_type, &d->f_a, &d->f_b, &d->f_z, &d->f_W, &d->f_slot, &d->lp, &d->st, &d->node2q, &d->q2node,
                    &d->Adiag, &d->Aoff, &d->Bq, &d->y, &d->x, &d->dinv, &d->sn, &d->ipool, &d->arena, &d->arrive,
-                   &d->xdone, &d->tbar, &d->tasks_full, &d->nwait_full, &d->btasks_full, &d->tasks_tmp, &d->nwait_tmp,
+                   &d->xdone, &d->xblk, &d->tbar, &d->tasks_full, &d->nwait_full, &d->btasks_full, &d->tasks_tmp, &d->nwait_tmp,
                    &d->btasks_tmp, &d->keep_tmp, &d->leaf_tasks, &d->top_tasks, &d->top_nwait, &d->ctrl, &d->partial, &d->patch_ids, &d->patch_desc, &d->pts, &d->flush, &d->trace_fac, &d->trace_bs, &d->ptrace };
     for (int i = 0; i < 2; i++)
         if (d->tev[i])
@@ -656,6 +657,7 @@ ASAM_EXPORT int asam_reserve(asam_dev_t *d, int n_nodes, int n_factors, int n_sl
     rc |= buf_reserve(d, d->sn, SN * sizeof(asam_sn_desc_t), true, false);
     rc |= buf_reserve(d, d->arrive, SN * sizeof(int), true, true);
     rc |= buf_reserve(d, d->xdone, SN * sizeof(int), true, true);
+    rc |= buf_reserve(d, d->xblk, SN * sizeof(int), true, true);
     rc |= buf_reserve(d, d->tbar, 2 * SN * sizeof(int), true, true);
     rc |= buf_reserve(d, d->ipool, (size_t) ipool_ints * sizeof(int), true, false);
     rc |= buf_reserve(d, d->arena, (size_t) arena_doubles * sizeof(double), true, false);
@@ -894,6 +896,7 @@ static int launch_backsolve(asam_dev *d, int ntasks, const int *btasks_dev, int 
     a.dinv = (const double *) d->dinv.p;
     a.x = (double *) d->x.p;
     a.xdone = (int *) d->xdone.p;
+    a.xblk = (int *) d->xblk.p;
     a.btasks = btasks_dev;
     a.bfirst = bfirst_dev;
     a.ntasks = ntasks;

@@ -1677,7 +1677,7 @@ __global__ void __launch_bounds__(256, 1) k_factor(FacArgs a)
         const int nwp = a.nwait[t];
         const int nw = nwp & 0xffff, tw = (nwp >> 16) & 0xff, tG = (nwp >> 24) & 0x7f;
         const asam_sn_desc_t d = a.sn[s];
-        if (tG > 1) { // one worker of a multi-CTA team
+        if (tG >= 1) { // one worker of a CTA team (a team of one runs the same panel code alone)
             unsigned long long *trow = (a.trace && tw == 0) ? a.trace + 8 * (size_t) t : nullptr;
             if (trow && tid == 0) {
                 trow[0] = tr0; trow[1] = tr0;
@@ -1901,6 +1901,7 @@ struct BsArgs {
     int *xdone;
     const int *btasks;
     const int *bfirst; // optional, per task: first wanted pose of the supernode (see cta_backsolve, jcol)
+    int *xblk;         // per supernode: (epoch << 8) | finished blocks (tasks that solve one block, see ASAM_BT_*)
     int ntasks;
     int *ctrl; // [2] ticket, [1] err
     int epoch;
@@ -1919,6 +1920,9 @@ struct BsArgs {
 // panel of the first block when it fits in shared memory) is fetched BEFORE waiting on the
 // parent's flag.
 #define ASAM_BSW 96
+// back-solve task word: bits 0-23 supernode, bits 24-30 (one ASAM_BSW-column block of it) + 1, 0 = all of it
+#define ASAM_BT_SN(e) ((e) & 0xffffff)
+#define ASAM_BT_BLK(e) ((((e) >> 24) & 0x7f) - 1)
 
 template <int U>
 __device__ __forceinline__ double bs_dot(const double *lk, const double *xs, int n, int lane)
@@ -1947,7 +1951,14 @@ __device__ __forceinline__ double bs_dot(const double *lk, const double *xs, int
 // jcol > 0 (incremental steps with the reference's pruned traversal, aprilsam.c:752-772): only x of the
 // columns [jcol, c) is wanted -- back-substitution inside a supernode runs from its last column down, so it
 // simply stops there (the columns before depend on these, not the other way round).
-__device__ bool cta_backsolve(const BsArgs &a, const int t, const int s, double *sm, int *s_abort, const int jcol = 0)
+// blk_only >= 0 (wide supernodes of a batch solve, host: build_schedule): this task solves ONE ASAM_BSW-column
+// block of the supernode; the blocks of a supernode are separate tasks (last block first) that run on
+// different CTAs: every block first subtracts the ancestors' part (rows below the supernode) -- all blocks at
+// once, as soon as the parent's flag is up -- and then the parts of the later blocks AS THEY FINISH
+// (a.xblk[s] counts finished blocks, tagged with the launch epoch), so that the dependent chain per block is
+// one 96 x 96 matrix-vector product and one triangular solve instead of a pass over everything below.
+__device__ bool cta_backsolve(const BsArgs &a, const int t, const int s, double *sm, int *s_abort, const int jcol = 0,
+                              const int blk_only = -1)
 {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
@@ -1972,7 +1983,8 @@ __device__ bool cta_backsolve(const BsArgs &a, const int t, const int s, double 
     const long long room = (long long) a.smem_doubles - (m + 2 * bwmax);
     const int nblk = (c + ASAM_BSW - 1) / ASAM_BSW;
 
-    for (int blk = nblk - 1; blk >= 0; --blk) {
+    const int blk_hi = blk_only >= 0 ? blk_only : nblk - 1, blk_lo = blk_only >= 0 ? blk_only : 0;
+    for (int blk = blk_hi; blk >= blk_lo; --blk) {
         const int b0 = blk * ASAM_BSW, bw = min(ASAM_BSW, c - b0), be = b0 + bw, hb = m - b0;
         // staging mode: 2 = whole panel of the block (rows b0..m-1, ld lm), 1 = its diagonal
         // block only (ld lc), 0 = none.  Staged leading dimensions are ODD: the triangular
@@ -1983,7 +1995,7 @@ __device__ bool cta_backsolve(const BsArgs &a, const int t, const int s, double 
         const int lm = hb | 1, lc = bw | 1;
         const int mode = ((long long) lm * bw <= room) ? 2 : (((long long) lc * bw <= room) ? 1 : 0);
         const int ll = mode == 2 ? lm : (mode == 1 ? lc : ld);
-        if (blk != nblk - 1)
+        if (blk != blk_hi)
             __syncthreads(); // the previous block is done with w / rd / Ls
         if (mode == 2) {
             for (int k = kmin + warp; k < bw; k += nwarps)
@@ -2000,7 +2012,7 @@ __device__ bool cta_backsolve(const BsArgs &a, const int t, const int s, double 
         }
         const double *L11 = mode ? Ls : (Lg + b0 + (size_t) b0 * ld); // (row, col) at L11[row + col*ll]
 
-        if (blk == nblk - 1) {
+        if (blk == blk_hi) {
             if (a.trace && tid == 0)
                 tr1 = d_now();
             if (d.parent >= 0 && tid == 0) {
@@ -2024,8 +2036,76 @@ __device__ bool cta_backsolve(const BsArgs &a, const int t, const int s, double 
                 xf[c + i] = __ldcg(&a.x[3 * (size_t) rows[d.cb + i / 3] + i % 3]);
         }
         __syncthreads();
+        if (blk_only >= 0) {
+            // (a) the ancestors' rows [c, m): available since the parent's flag
+            if (r > 0) {
+                for (int k = warp; k < bw; k += nwarps) {
+                    const double *lk = (mode == 2) ? (Ls + (size_t) k * lm + (c - b0)) : (Lg + (size_t) (b0 + k) * ld + c);
+                    const double acc = r > 512 ? bs_dot<16>(lk, xf + c, r, lane) : bs_dot<8>(lk, xf + c, r, lane);
+                    if (lane == 0)
+                        w[k] -= acc;
+                }
+            }
+            // (b) the later blocks of this supernode, in the order they finish
+            const int ep = a.epoch & 0xffffff;
+            for (int b2 = nblk - 1; b2 > blk; --b2) {
+                const int r0 = b2 * ASAM_BSW, n2 = min(ASAM_BSW, c - r0), need = nblk - b2;
+                if (tid == 0) {
+                    SpinClock spins;
+                    for (;;) {
+                        const int v = ld_volatile(&a.xblk[s]);
+                        if ((int) ((unsigned) v >> 8) == ep && (v & 0xff) >= need)
+                            break;
+                        __nanosleep(20);
+                        if (spin_over(spins, a.spin_limit) || ld_volatile(err) < 0) {
+                            atomicCAS(err, 0, -(1 + s));
+                            *s_abort = 1;
+                            break;
+                        }
+                    }
+                    __threadfence();
+                }
+                __syncthreads();
+                if (*s_abort)
+                    break;
+                for (int i = tid; i < n2; i += nt)
+                    xf[r0 + i] = __ldcg(&a.x[3 * (size_t) d.first + r0 + i]);
+                __syncthreads();
+                // 96 rows x up to 12 columns per warp, every load in flight at once (the chain of a block is this
+                // product + the triangular solve)
+                {
+                    double lv[12][3];
+#pragma unroll
+                    for (int j = 0; j < 12; j++) {
+                        const int k = warp + nwarps * j;
+                        const double *lk = (mode == 2) ? (Ls + (size_t) min(k, bw - 1) * lm + (r0 - b0))
+                                                       : (Lg + (size_t) (b0 + min(k, bw - 1)) * ld + r0);
+#pragma unroll
+                        for (int u = 0; u < 3; u++)
+                            lv[j][u] = (k < bw && lane + 32 * u < n2) ? lk[lane + 32 * u] : 0.0;
+                    }
+                    double xv[3];
+#pragma unroll
+                    for (int u = 0; u < 3; u++)
+                        xv[u] = lane + 32 * u < n2 ? xf[r0 + lane + 32 * u] : 0.0;
+#pragma unroll
+                    for (int j = 0; j < 12; j++) {
+                        double acc = lv[j][0] * xv[0] + lv[j][1] * xv[1] + lv[j][2] * xv[2];
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1)
+                            acc += __shfl_down_sync(0xffffffffu, acc, o);
+                        const int k = warp + nwarps * j;
+                        if (lane == 0 && k < bw)
+                            w[k] -= acc;
+                    }
+                }
+            }
+            __syncthreads();
+            if (*s_abort)
+                break;
+        }
         // w_k -= sum_{i >= be} L[i, b0+k] * xf[i]   (one warp per column)
-        const int nr = m - be;
+        const int nr = blk_only >= 0 ? 0 : m - be;
         if (nr > 0) {
             for (int k = kmin + warp; k < bw; k += nwarps) {
                 const double *lk = (mode == 2) ? (Ls + (size_t) k * lm + bw) : (Lg + (size_t) (b0 + k) * ld + be);
@@ -2072,7 +2152,10 @@ __device__ bool cta_backsolve(const BsArgs &a, const int t, const int s, double 
         return false;
     if (warp == 0 && lane == 0) {
         __threadfence();
-        atomicExch(&a.xdone[s], a.epoch);
+        if (blk_only >= 0)
+            atomicExch(&a.xblk[s], ((a.epoch & 0xffffff) << 8) | (nblk - blk_only));
+        if (blk_only <= 0)
+            atomicExch(&a.xdone[s], a.epoch);
         if (a.trace) {
             unsigned long long *tr = a.trace + 8 * (size_t) t;
             tr[0] = tr0; tr[1] = tr1; tr[2] = tr2; tr[3] = d_now();
@@ -2101,7 +2184,7 @@ __global__ void __launch_bounds__(256) k_backsolve(BsArgs a)
         const int t = s_task;
         if (t >= a.ntasks)
             break;
-        if (!cta_backsolve(a, t, a.btasks[t], sm, &s_abort, a.bfirst ? 3 * a.bfirst[t] : 0))
+        if (!cta_backsolve(a, t, ASAM_BT_SN(a.btasks[t]), sm, &s_abort, a.bfirst ? 3 * a.bfirst[t] : 0, ASAM_BT_BLK(a.btasks[t])))
             break;
     }
     ticket_release(&a.ctrl[2], &a.ctrl[4]);
@@ -2132,7 +2215,7 @@ __global__ void __launch_bounds__(32 * ASAM_BSL_WARPS) k_backsolve_leaf(BsArgs a
         t = __shfl_sync(0xffffffffu, t, 0);
         if (t >= a.ntasks)
             break;
-        const int s = a.btasks[t];
+        const int s = ASAM_BT_SN(a.btasks[t]);
         const asam_sn_desc_t d = a.sn[s];
         const int m = 3 * d.mb, c = 3 * d.cb, r = m - c, ld = ASAM_LD(m);
         if (r > ASAM_BSL_XS || c > 64) { // host error: not a leaf-set supernode
@@ -2349,7 +2432,7 @@ __global__ void __launch_bounds__(256, 1) k_step(StepArgs a)
         if (tid == 0)
             s_abort = 0;
         __syncthreads();
-        ok = cta_backsolve(a.bs, t, a.bs.btasks[t], sm, &s_abort, a.bs.bfirst ? 3 * a.bs.bfirst[t] : 0);
+        ok = cta_backsolve(a.bs, t, ASAM_BT_SN(a.bs.btasks[t]), sm, &s_abort, a.bs.bfirst ? 3 * a.bs.bfirst[t] : 0);
     }
     __syncthreads();
 
@@ -2360,7 +2443,7 @@ __global__ void __launch_bounds__(256, 1) k_step(StepArgs a)
     if (ok) {
         int off = 0;
         for (int t = 0; t < a.bs.ntasks; ++t) {
-            const int s = a.bs.btasks[t];
+            const int s = ASAM_BT_SN(a.bs.btasks[t]);
             const int first = a.bs.sn[s].first, c = 3 * a.bs.sn[s].cb;
             for (int k = tid; k < c; k += nt)
                 a.x_out[off + k] = __ldcg(&a.bs.x[3 * (size_t) first + k]);

@@ -46,7 +46,7 @@ void asam_dbg_build_profile(double *out, int reset)
 
 #define RELAX_Z 2     /* relaxed amalgamation: missing block rows tolerated per merge */
 #define RELAX_FILL 24 /* ... and explicit zero blocks (3x3) added per merge */
-#define ASAM_TEAM_ROOM 120       /* CTAs that the team fronts of one tree level may claim together */
+#define ASAM_TEAM_ROOM 100       /* CTAs that the team fronts of one tree level may claim together (swept: 100 / 120 / 148 / 220) */
 #define ASAM_BSLEAF_MAX 64       /* = ASAM_BSL_XS of k_backsolve_leaf: own columns / rows below */
 #define ASAM_BSLEAF_MIN_COUNT 4096 /* measured: no gain on M3500-sized trees (the kernel boundary eats it) */
 #define ASAM_LEAF_MAX_M 48       /* = ASAM_LEAF_M of k_factor_leaf */
@@ -417,6 +417,19 @@ void plan_work(const plan_t *pl, const int *tasks, int ntasks, double *step_work
     *batch_fronts = pl->nsn;
 }
 
+typedef struct {
+    double key;
+    int id;
+} sn_key_t;
+
+static int cmp_key_desc(const void *a, const void *b)
+{
+    const sn_key_t *x = a, *y = b;
+    if (x->key != y->key)
+        return x->key > y->key ? -1 : 1;
+    return (x->id > y->id) - (x->id < y->id); /* deterministic */
+}
+
 static void build_schedule(plan_t *pl)
 {
     const int nsn = pl->nsn, W = pl->world > 1 ? pl->world : 1, me = pl->world > 1 ? pl->rank : 0;
@@ -554,16 +567,50 @@ static void build_schedule(plan_t *pl)
         pl->bs_leaf[s] = (char) ok;
     }
 
-    /* counting sort by level, ids ascending inside a level */
+    /* Task order.  The persistent kernels hand out tasks in list order, so the list IS the schedule.  Plain
+     * level order (every front of level l before any of level l+1) starts the deepest chain of the tree last
+     * among its level-mates and leaves its top to run alone at the end (measured on the 100 k world: all SMs
+     * busy until 3.3 ms, then a 3.3 ms tail with most of them spinning; on M3500 the critical chain's
+     * level-2 front got its CTA at 50 us of 457).  Critical-path-first instead: fronts are listed by
+     * DESCENDING length of the dependent chain from them up to the root (their own modelled latency
+     * included), which is still a topological order -- a child's chain is its parent's plus its own -- so a
+     * waiting CTA only ever waits for tasks that were handed out before its own.  ASAM_TASK_ORDER=level keeps
+     * the level order (A/B). */
     int *byl = malloc(sizeof(int) * (size_t) (nsn + 1));
-    int *cnt = calloc((size_t) pl->n_levels + 2, sizeof(int));
-    for (int s = 0; s < nsn; s++)
-        cnt[pl->desc[s].level + 1]++;
-    for (int l = 0; l < pl->n_levels; l++)
-        cnt[l + 1] += cnt[l];
-    for (int s = 0; s < nsn; s++)
-        byl[cnt[pl->desc[s].level]++] = s;
-    free(cnt);
+    {
+        const char *eo = getenv("ASAM_TASK_ORDER");
+        if (eo && strcmp(eo, "level") == 0) {
+            int *cnt = calloc((size_t) pl->n_levels + 2, sizeof(int));
+            for (int s = 0; s < nsn; s++)
+                cnt[pl->desc[s].level + 1]++;
+            for (int l = 0; l < pl->n_levels; l++)
+                cnt[l + 1] += cnt[l];
+            for (int s = 0; s < nsn; s++)
+                byl[cnt[pl->desc[s].level]++] = s;
+            free(cnt);
+        } else {
+            sn_key_t *keys = malloc(sizeof(sn_key_t) * (size_t) (nsn + 1));
+            double *up = malloc(sizeof(double) * (size_t) (nsn + 1));
+            for (int s = nsn - 1; s >= 0; s--) { /* parents have larger ids */
+                const double m = 3.0 * pl->desc[s].mb, c = 3.0 * pl->desc[s].cb;
+                double lat; /* microseconds, fitted to traces of the kernels (tools/panel_trace.py --dump-trace) */
+                if (m <= ASAM_LEAF_MAX_M)
+                    lat = 2.0 + 0.1 * c;
+                else if (front_fits_smem(pl->desc[s].mb))
+                    lat = 6.0 + 0.07 * m + c * (0.25 + 0.0028 * m);
+                else
+                    lat = 40.0 + 31.0 * ceil(c / 48.0);
+                up[s] = lat + (pl->desc[s].parent >= 0 ? up[pl->desc[s].parent] : 0.0);
+                keys[s].key = up[s];
+                keys[s].id = s;
+            }
+            qsort(keys, (size_t) nsn, sizeof(sn_key_t), cmp_key_desc);
+            for (int k = 0; k < nsn; k++)
+                byl[k] = keys[k].id;
+            free(keys);
+            free(up);
+        }
+    }
 
     /* team sizes.  A front's team is bound by latency, not throughput (team_size()), so where one tree
      * level holds more team fronts than the 148 SMs can seat side by side, smaller teams finish the
@@ -581,18 +628,38 @@ static void build_schedule(plan_t *pl)
         const char *er = getenv("ASAM_TEAM_ROOM"); /* tuning knob (tools only) */
         if (er && atoi(er) > 0)
             room = atoi(er);
+        /* smallest team: 1 (ASAM_TEAM_MIN=2 for A/B): a "team" of one CTA runs the same panel code without
+         * partners -- no idle workers while the diagonal block is factored; pays where a level holds far more
+         * team fronts than SMs (the SM time per front is what limits the level, not its latency) */
+        int gmin = 1;
+        const char *em = getenv("ASAM_TEAM_MIN");
+        if (em && atoi(em) >= 1)
+            gmin = atoi(em);
         for (int s = 0; s < nsn; s++) {
             int64_t w = want[pl->desc[s].level];
             if (G_of[s] > 1 && w > room) {
                 int g = (int) ((int64_t) G_of[s] * room / w);
-                G_of[s] = g < 2 ? 2 : g;
+                G_of[s] = g < gmin ? gmin : g;
             }
+            if (G_of[s] == 1 && !leaf[s] && !front_fits_smem(pl->desc[s].mb) && 3 * pl->desc[s].mb > solo_max_m())
+                G_of[s] = -1; /* one CTA, team code path */
         }
         free(want);
     }
 
+    /* Back-solve entries of a supernode: one, or -- supernodes wider than one 96-column block (ASAM_BSW) in a
+     * batch schedule -- one per block, last block first, each solved by its own CTA (cta_backsolve, blk_only).
+     * Entry word: supernode | (block + 1) << 24.  ASAM_BS_SPLIT=0 switches the split off (A/B). */
+    int bs_split = 1;
+    {
+        const char *eb = getenv("ASAM_BS_SPLIT");
+        if (eb)
+            bs_split = atoi(eb) != 0;
+    }
+    pl->bt_split = 0;
+#define BS_NBLK(s_) ((bs_split && !pl->bs_leaf[s_] && 3 * pl->desc[s_].cb > 96 && pl->nsn < (1 << 24)) ? (3 * pl->desc[s_].cb + 95) / 96 : 1)
     int64_t n_local = 0, n_top = 0;
-    int n_leaf = 0, n_main_sn = 0, n_top_sn = 0, n_bsl = 0;
+    int n_leaf = 0, n_main_sn = 0, n_top_sn = 0, n_bsl = 0, n_top_bt = 0;
     for (int s = 0; s < nsn; s++)
         n_bsl += owner[s] == me && pl->bs_leaf[s];
     if (n_bsl < ASAM_BSLEAF_MIN_COUNT) {
@@ -604,12 +671,13 @@ static void build_schedule(plan_t *pl)
             if (leaf[s])
                 n_leaf++;
             else
-                n_local += G_of[s];
+                n_local += G_of[s] < 0 ? 1 : G_of[s];
             if (!pl->bs_leaf[s])
-                n_main_sn++;
+                n_main_sn += BS_NBLK(s);
         } else if (owner[s] == -1) {
-            n_top += G_of[s];
+            n_top += G_of[s] < 0 ? 1 : G_of[s];
             n_top_sn++;
+            n_top_bt += BS_NBLK(s);
         }
     }
     pl->ntasks = (int) n_local;
@@ -622,42 +690,52 @@ static void build_schedule(plan_t *pl)
     pl->top_tasks = malloc(sizeof(int) * (size_t) (n_top + 1));
     pl->top_nwait = malloc(sizeof(int) * (size_t) (n_top + 1));
     pl->n_bs_leaf = n_bsl;
-    pl->n_btasks = n_top_sn + n_main_sn + n_bsl;
+    pl->n_btasks = n_top_bt + n_main_sn + n_bsl;
     pl->btasks = malloc(sizeof(int) * (size_t) (pl->n_btasks + 1));
     /* back-solve list, parents first: [top | own shards outside the back-solve leaf set | that set] */
     int t = 0, tl = 0, tt = 0;
-    int bt = n_top_sn - 1, bm = n_top_sn + n_main_sn - 1, bl = pl->n_btasks - 1;
+    int bt = n_top_bt - 1, bm = n_top_bt + n_main_sn - 1, bl = pl->n_btasks - 1;
     for (int k = 0; k < nsn; k++) {
         int s = byl[k];
         if (owner[s] == -1) {
-            pl->btasks[bt--] = s;
+            {
+                const int nb = BS_NBLK(s); /* filled backwards: block 0 lands last, the last block first */
+                for (int b = 0; b < nb; b++)
+                    pl->btasks[bt--] = nb > 1 ? (s | ((b + 1) << 24)) : s;
+                pl->bt_split |= nb > 1;
+            }
             int nw = 0; /* children above the cut: the others were exchanged before this launch */
             for (int c = 0; c < pl->snh[s].children.n; c++)
                 nw += owner[pl->snh[s].children.p[c]] == -1;
-            int G = G_of[s];
+            int G = G_of[s] < 0 ? 1 : G_of[s];
             for (int w = 0; w < G; w++, tt++) {
                 pl->top_tasks[tt] = s;
-                pl->top_nwait[tt] = pack_nwait(nw, w, G > 1 ? G : 0);
+                pl->top_nwait[tt] = pack_nwait(nw, w, G > 1 ? G : (G_of[s] < 0 ? 1 : 0));
             }
             continue;
         }
         if (owner[s] != me)
             continue;
-        if (pl->bs_leaf[s])
+        if (pl->bs_leaf[s]) {
             pl->btasks[bl--] = s;
-        else
-            pl->btasks[bm--] = s;
+        } else {
+            const int nb = BS_NBLK(s);
+            for (int b = 0; b < nb; b++)
+                pl->btasks[bm--] = nb > 1 ? (s | ((b + 1) << 24)) : s;
+            pl->bt_split |= nb > 1;
+        }
         if (leaf[s]) {
             pl->leaf_tasks[tl++] = s;
             continue;
         }
         /* nwait counts ALL children: those of the leaf set arrived in the earlier launch */
-        int G = G_of[s];
+        int G = G_of[s] < 0 ? 1 : G_of[s];
         for (int w = 0; w < G; w++, t++) {
             pl->tasks[t] = s;
-            pl->nwait[t] = pack_nwait(pl->desc[s].ch_cnt, w, G > 1 ? G : 0);
+            pl->nwait[t] = pack_nwait(pl->desc[s].ch_cnt, w, G > 1 ? G : (G_of[s] < 0 ? 1 : 0));
         }
     }
+#undef BS_NBLK
     free(G_of);
     free(byl);
     free(leaf);
@@ -1090,6 +1168,21 @@ int plan_append(plan_t *pl, asam_dev_t *dev, int N, int n_factors, const int *ft
     if (pl->world > 1) {
         asam_set_error("a batch solve sharded over %d GPUs cannot be continued incrementally (replicas only)", pl->world);
         return 1;
+    }
+    /* incremental steps grow supernodes: the per-block entries of the batch schedule's back-solve list are
+     * replaced by one entry per supernode (parents first = descending id) once, at the first append */
+    if (pl->bt_split) {
+        int *plain = malloc(sizeof(int) * (size_t) (nsn0 + 1));
+        for (int sx = 0; sx < nsn0; sx++)
+            plain[sx] = nsn0 - 1 - sx;
+        free(pl->btasks);
+        pl->btasks = plain;
+        pl->n_btasks = nsn0;
+        pl->bt_split = 0;
+        pl->n_bs_leaf = 0;
+        if (dev && (asam_set_full_tasks(dev, pl->ntasks, pl->tasks, pl->nwait, pl->n_btasks, pl->btasks) ||
+                    asam_set_bs_leaf_count(dev, 0)))
+            return 1;
     }
     /* incremental steps run the whole schedule through k_factor / k_backsolve */
     if (pl->n_leaf > 0) {

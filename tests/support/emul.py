@@ -209,10 +209,14 @@ def factor(fr: Fronts, H: Hessian, desc, ipool, q2node, tasks, nwait=None, check
 
 
 def backsolve(fr: Fronts, desc, ipool, btasks):
-    """k_backsolve: parents first; list must be closed under ancestors."""
+    """k_backsolve: parents first; list must be closed under ancestors.  An entry is a supernode id, or -- wide
+    supernodes of a batch schedule -- supernode | (block + 1) << 24: one 96-column block per entry, the blocks of
+    a supernode consecutive, last block first (cta_backsolve, blk_only)."""
     done = set()
-    for s in btasks:
-        s = int(s)
+    blocks_seen = {}
+    for e in btasks:
+        e = int(e)
+        s, blk = e & 0xffffff, ((e >> 24) & 0x7f) - 1
         P = int(desc["parent"][s])
         assert P < 0 or P in done, f"parent {P} of {s} not solved first"
         rows, *_ = seg_views(desc, ipool, s)
@@ -220,8 +224,19 @@ def backsolve(fr: Fronts, desc, ipool, btasks):
         c = 3 * cb
         L = fr.F[int(desc["f_off"][s])]
         xs = np.concatenate([fr.x[3 * int(r):3 * int(r) + 3] for r in rows[cb:]]) if mb > cb else np.zeros(0)
-        w = fr.y[3 * first:3 * first + c] - L[c:, :c].T @ xs
-        L11 = np.tril(L[:c, :c])
-        x1 = np.linalg.solve(L11.T, w)
-        fr.x[3 * first:3 * first + c] = x1
-        done.add(s)
+        if blk < 0:
+            w = fr.y[3 * first:3 * first + c] - L[c:, :c].T @ xs
+            L11 = np.tril(L[:c, :c])
+            fr.x[3 * first:3 * first + c] = np.linalg.solve(L11.T, w)
+            done.add(s)
+            continue
+        nblk = (c + 95) // 96
+        assert c > 96 and 0 <= blk < nblk
+        assert blocks_seen.get(s, nblk) == blk + 1, f"blocks of supernode {s} must come last block first, consecutively"
+        blocks_seen[s] = blk
+        b0, be = 96 * blk, min(96 * blk + 96, c)
+        xlater = fr.x[3 * first + be:3 * first + c]  # the later blocks of this supernode: solved by earlier entries
+        w = fr.y[3 * first + b0:3 * first + be] - L[c:, b0:be].T @ xs - L[be:c, b0:be].T @ xlater
+        fr.x[3 * first + b0:3 * first + be] = np.linalg.solve(np.tril(L[b0:be, b0:be]).T, w)
+        if blk == 0:
+            done.add(s)
