@@ -2071,32 +2071,35 @@ __device__ bool cta_backsolve(const BsArgs &a, const int t, const int s, double 
                 for (int i = tid; i < n2; i += nt)
                     xf[r0 + i] = __ldcg(&a.x[3 * (size_t) d.first + r0 + i]);
                 __syncthreads();
-                // 96 rows x up to 12 columns per warp, every load in flight at once (the chain of a block is this
-                // product + the triangular solve)
+                // 96 rows x up to 12 columns per warp in two rounds of six: 18 loads in flight per lane (the
+                // chain of a block is this product + the triangular solve)
                 {
-                    double lv[12][3];
-#pragma unroll
-                    for (int j = 0; j < 12; j++) {
-                        const int k = warp + nwarps * j;
-                        const double *lk = (mode == 2) ? (Ls + (size_t) min(k, bw - 1) * lm + (r0 - b0))
-                                                       : (Lg + (size_t) (b0 + min(k, bw - 1)) * ld + r0);
-#pragma unroll
-                        for (int u = 0; u < 3; u++)
-                            lv[j][u] = (k < bw && lane + 32 * u < n2) ? lk[lane + 32 * u] : 0.0;
-                    }
                     double xv[3];
 #pragma unroll
                     for (int u = 0; u < 3; u++)
                         xv[u] = lane + 32 * u < n2 ? xf[r0 + lane + 32 * u] : 0.0;
+#pragma unroll 1
+                    for (int j0 = 0; j0 < 12; j0 += 6) {
+                        double lv[6][3];
 #pragma unroll
-                    for (int j = 0; j < 12; j++) {
-                        double acc = lv[j][0] * xv[0] + lv[j][1] * xv[1] + lv[j][2] * xv[2];
+                        for (int j = 0; j < 6; j++) {
+                            const int k = warp + nwarps * (j0 + j);
+                            const double *lk = (mode == 2) ? (Ls + (size_t) min(k, bw - 1) * lm + (r0 - b0))
+                                                           : (Lg + (size_t) (b0 + min(k, bw - 1)) * ld + r0);
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1)
-                            acc += __shfl_down_sync(0xffffffffu, acc, o);
-                        const int k = warp + nwarps * j;
-                        if (lane == 0 && k < bw)
-                            w[k] -= acc;
+                            for (int u = 0; u < 3; u++)
+                                lv[j][u] = (k < bw && lane + 32 * u < n2) ? lk[lane + 32 * u] : 0.0;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 6; j++) {
+                            double acc = lv[j][0] * xv[0] + lv[j][1] * xv[1] + lv[j][2] * xv[2];
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1)
+                                acc += __shfl_down_sync(0xffffffffu, acc, o);
+                            const int k = warp + nwarps * (j0 + j);
+                            if (lane == 0 && k < bw)
+                                w[k] -= acc;
+                        }
                     }
                 }
             }
@@ -2167,7 +2170,7 @@ __device__ bool cta_backsolve(const BsArgs &a, const int t, const int s, double 
     return true;
 }
 
-__global__ void __launch_bounds__(256) k_backsolve(BsArgs a)
+__global__ void __launch_bounds__(256, 2) k_backsolve(BsArgs a)
 {
     extern __shared__ __align__(16) double sm[]; // xf[m] | w[bw] | rd[bw] | staged L (panel or L11 of one block)
     __shared__ int s_task, s_abort;

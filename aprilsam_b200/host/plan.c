@@ -430,6 +430,103 @@ static int cmp_key_desc(const void *a, const void *b)
     return (x->id > y->id) - (x->id < y->id); /* deterministic */
 }
 
+/* ---- static list schedule --------------------------------------------------------------------------
+ * The ticket order of k_factor decides when a front's CTAs are taken: a team whose tickets come up while
+ * its children are still running spins on all its CTAs (measured on the 100 k world: the nine fronts of
+ * order > 1000 held ~50 CTAs each for 218 us before they could start -- an eighth of the kernel's SM time).
+ * So the order is taken from a SIMULATION of the kernel: P resident CTAs, every front with its modelled
+ * duration and team size, ready fronts started by priority (length of the dependent chain above them) as
+ * CTAs become free; the order in which the simulation STARTS the fronts is the ticket order.  Children finish
+ * before their parent starts in the simulation, so the order is topological; where the model is off the
+ * kernel merely waits as it would have.  in[s] != 0: s is a task of this launch (others count as done). */
+typedef struct {
+    double key;
+    int id;
+} hp_t;
+
+static void hp_push(hp_t *h, int *n, double key, int id, int maxheap)
+{
+    int i = (*n)++;
+    h[i].key = key;
+    h[i].id = id;
+    while (i > 0) {
+        int p = (i - 1) / 2;
+        int better = maxheap ? (h[i].key > h[p].key || (h[i].key == h[p].key && h[i].id < h[p].id))
+                             : (h[i].key < h[p].key || (h[i].key == h[p].key && h[i].id < h[p].id));
+        if (!better)
+            break;
+        hp_t t = h[p]; h[p] = h[i]; h[i] = t;
+        i = p;
+    }
+}
+
+static hp_t hp_pop(hp_t *h, int *n, int maxheap)
+{
+    hp_t top = h[0];
+    h[0] = h[--(*n)];
+    int i = 0;
+    for (;;) {
+        int l = 2 * i + 1, r = l + 1, b = i;
+        for (int c = l; c <= r; c++) {
+            if (c >= *n)
+                break;
+            int better = maxheap ? (h[c].key > h[b].key || (h[c].key == h[b].key && h[c].id < h[b].id))
+                                 : (h[c].key < h[b].key || (h[c].key == h[b].key && h[c].id < h[b].id));
+            if (better)
+                b = c;
+        }
+        if (b == i)
+            break;
+        hp_t t = h[b]; h[b] = h[i]; h[i] = t;
+        i = b;
+    }
+    return top;
+}
+
+/* returns the number of entries written to out[] (= tasks with in[s] != 0) */
+static int sim_order(const plan_t *pl, const char *in, const int *G_of, const double *lat, const double *prio, int P, int *out)
+{
+    const int nsn = pl->nsn;
+    int *pending = calloc((size_t) nsn + 1, sizeof(int));
+    hp_t *ready = malloc(sizeof(hp_t) * (size_t) (nsn + 1)), *events = malloc(sizeof(hp_t) * (size_t) (nsn + 1));
+    int nready = 0, nev = 0, nout = 0, free_cta = P;
+    for (int s = 0; s < nsn; s++)
+        if (in[s] && pl->desc[s].parent >= 0 && in[pl->desc[s].parent])
+            pending[pl->desc[s].parent]++;
+    for (int s = 0; s < nsn; s++)
+        if (in[s] && pending[s] == 0)
+            hp_push(ready, &nready, prio[s], s, 1);
+    double now = 0.0;
+    for (;;) {
+        while (nready > 0) {
+            int s = ready[0].id, g = G_of[s] < 0 ? 1 : (G_of[s] > P ? P : G_of[s]);
+            if (g > free_cta && nev > 0)
+                break; /* tickets are strictly ordered: nothing overtakes a team that is gathering its CTAs */
+            hp_pop(ready, &nready, 1);
+            out[nout++] = s;
+            free_cta -= g < free_cta ? g : free_cta;
+            hp_push(events, &nev, now + lat[s], s, 0);
+        }
+        if (nev == 0)
+            break;
+        hp_t e = hp_pop(events, &nev, 0);
+        now = e.key;
+        {
+            int s = e.id, g = G_of[s] < 0 ? 1 : (G_of[s] > P ? P : G_of[s]);
+            free_cta += g;
+            if (free_cta > P)
+                free_cta = P;
+            int par = pl->desc[s].parent;
+            if (par >= 0 && in[par] && --pending[par] == 0)
+                hp_push(ready, &nready, prio[par], par, 1);
+        }
+    }
+    free(pending);
+    free(ready);
+    free(events);
+    return nout;
+}
+
 static void build_schedule(plan_t *pl)
 {
     const int nsn = pl->nsn, W = pl->world > 1 ? pl->world : 1, me = pl->world > 1 ? pl->rank : 0;
@@ -577,20 +674,28 @@ static void build_schedule(plan_t *pl)
      * waiting CTA only ever waits for tasks that were handed out before its own.  ASAM_TASK_ORDER=level keeps
      * the level order (A/B). */
     int *byl = malloc(sizeof(int) * (size_t) (nsn + 1));
+    double *lat_us = NULL, *up_us = NULL; /* modelled duration / chain length above, microseconds (order modes cp, sim) */
+    int order_sim = 0;
+    int *bylv = malloc(sizeof(int) * (size_t) (nsn + 1)); /* plain level order: the back-substitution list (measured:
+                                                            * 1.15 ms against 1.42 ms with the reversed chain order) */
+    {
+        int *cnt = calloc((size_t) pl->n_levels + 2, sizeof(int));
+        for (int s = 0; s < nsn; s++)
+            cnt[pl->desc[s].level + 1]++;
+        for (int l = 0; l < pl->n_levels; l++)
+            cnt[l + 1] += cnt[l];
+        for (int s = 0; s < nsn; s++)
+            bylv[cnt[pl->desc[s].level]++] = s;
+        free(cnt);
+    }
     {
         const char *eo = getenv("ASAM_TASK_ORDER");
         if (eo && strcmp(eo, "level") == 0) {
-            int *cnt = calloc((size_t) pl->n_levels + 2, sizeof(int));
-            for (int s = 0; s < nsn; s++)
-                cnt[pl->desc[s].level + 1]++;
-            for (int l = 0; l < pl->n_levels; l++)
-                cnt[l + 1] += cnt[l];
-            for (int s = 0; s < nsn; s++)
-                byl[cnt[pl->desc[s].level]++] = s;
-            free(cnt);
+            memcpy(byl, bylv, sizeof(int) * (size_t) nsn);
         } else {
             sn_key_t *keys = malloc(sizeof(sn_key_t) * (size_t) (nsn + 1));
             double *up = malloc(sizeof(double) * (size_t) (nsn + 1));
+            lat_us = malloc(sizeof(double) * (size_t) (nsn + 1));
             for (int s = nsn - 1; s >= 0; s--) { /* parents have larger ids */
                 const double m = 3.0 * pl->desc[s].mb, c = 3.0 * pl->desc[s].cb;
                 double lat; /* microseconds, fitted to traces of the kernels (tools/panel_trace.py --dump-trace) */
@@ -600,6 +705,7 @@ static void build_schedule(plan_t *pl)
                     lat = 6.0 + 0.07 * m + c * (0.25 + 0.0028 * m);
                 else
                     lat = 40.0 + 31.0 * ceil(c / 48.0);
+                lat_us[s] = lat;
                 up[s] = lat + (pl->desc[s].parent >= 0 ? up[pl->desc[s].parent] : 0.0);
                 keys[s].key = up[s];
                 keys[s].id = s;
@@ -608,7 +714,8 @@ static void build_schedule(plan_t *pl)
             for (int k = 0; k < nsn; k++)
                 byl[k] = keys[k].id;
             free(keys);
-            free(up);
+            up_us = up;
+            order_sim = !(eo && strcmp(eo, "cp") == 0);
         }
     }
 
@@ -646,6 +753,40 @@ static void build_schedule(plan_t *pl)
         }
         free(want);
     }
+
+    if (order_sim) {
+        /* ticket order of k_factor = start order of the simulated schedule; the main list (own fronts outside
+         * the leaf set) and the part above a multi-GPU cut are separate launches, simulated separately; the leaf
+         * set keeps the chain-length order (warp-sized tasks: nothing to gather) */
+        char *in = calloc((size_t) nsn + 1, 1);
+        int *ord = malloc(sizeof(int) * (size_t) (nsn + 1)), *pos_of = malloc(sizeof(int) * (size_t) (nsn + 1));
+        const int P = pl->n_cta > 0 ? pl->n_cta : 148;
+        int n1, n2;
+        for (int s = 0; s < nsn; s++)
+            in[s] = owner[s] == me && !leaf[s];
+        n1 = sim_order(pl, in, G_of, lat_us, up_us, P, ord);
+        for (int s = 0; s < nsn; s++)
+            in[s] = owner[s] == -1;
+        n2 = sim_order(pl, in, G_of, lat_us, up_us, P, ord + n1);
+        for (int s = 0; s < nsn; s++)
+            pos_of[s] = -1;
+        for (int k = 0; k < n1 + n2; k++)
+            pos_of[ord[k]] = k;
+        /* byl: simulated tasks in start order, everything else (leaf set, other ranks) after them in the old order */
+        int *nb = malloc(sizeof(int) * (size_t) (nsn + 1)), k2 = 0;
+        for (int k = 0; k < n1 + n2; k++)
+            nb[k2++] = ord[k];
+        for (int k = 0; k < nsn; k++)
+            if (pos_of[byl[k]] < 0)
+                nb[k2++] = byl[k];
+        memcpy(byl, nb, sizeof(int) * (size_t) nsn);
+        free(nb);
+        free(in);
+        free(ord);
+        free(pos_of);
+    }
+    free(lat_us);
+    free(up_us);
 
     /* Back-solve entries of a supernode: one, or -- supernodes wider than one 96-column block (ASAM_BSW) in a
      * batch schedule -- one per block, last block first, each solved by its own CTA (cta_backsolve, blk_only).
@@ -695,15 +836,27 @@ static void build_schedule(plan_t *pl)
     /* back-solve list, parents first: [top | own shards outside the back-solve leaf set | that set] */
     int t = 0, tl = 0, tt = 0;
     int bt = n_top_bt - 1, bm = n_top_bt + n_main_sn - 1, bl = pl->n_btasks - 1;
-    for (int k = 0; k < nsn; k++) {
-        int s = byl[k];
+    for (int k = 0; k < nsn; k++) { /* back-solve entries, filled backwards: parents first */
+        int s = bylv[k];
         if (owner[s] == -1) {
-            {
-                const int nb = BS_NBLK(s); /* filled backwards: block 0 lands last, the last block first */
+            const int nb = BS_NBLK(s); /* block 0 lands last, the last block first */
+            for (int b = 0; b < nb; b++)
+                pl->btasks[bt--] = nb > 1 ? (s | ((b + 1) << 24)) : s;
+            pl->bt_split |= nb > 1;
+        } else if (owner[s] == me) {
+            if (pl->bs_leaf[s]) {
+                pl->btasks[bl--] = s;
+            } else {
+                const int nb = BS_NBLK(s);
                 for (int b = 0; b < nb; b++)
-                    pl->btasks[bt--] = nb > 1 ? (s | ((b + 1) << 24)) : s;
+                    pl->btasks[bm--] = nb > 1 ? (s | ((b + 1) << 24)) : s;
                 pl->bt_split |= nb > 1;
             }
+        }
+    }
+    for (int k = 0; k < nsn; k++) { /* factorisation tasks, children first */
+        int s = byl[k];
+        if (owner[s] == -1) {
             int nw = 0; /* children above the cut: the others were exchanged before this launch */
             for (int c = 0; c < pl->snh[s].children.n; c++)
                 nw += owner[pl->snh[s].children.p[c]] == -1;
@@ -716,14 +869,6 @@ static void build_schedule(plan_t *pl)
         }
         if (owner[s] != me)
             continue;
-        if (pl->bs_leaf[s]) {
-            pl->btasks[bl--] = s;
-        } else {
-            const int nb = BS_NBLK(s);
-            for (int b = 0; b < nb; b++)
-                pl->btasks[bm--] = nb > 1 ? (s | ((b + 1) << 24)) : s;
-            pl->bt_split |= nb > 1;
-        }
         if (leaf[s]) {
             pl->leaf_tasks[tl++] = s;
             continue;
@@ -738,6 +883,7 @@ static void build_schedule(plan_t *pl)
 #undef BS_NBLK
     free(G_of);
     free(byl);
+    free(bylv);
     free(leaf);
     free(owner);
 }
@@ -747,16 +893,17 @@ static int plan_build_impl(plan_t *pl, asam_dev_t *dev, int N, int n_factors, co
                            const int *fb, const int *order_keep, int N_keep)
 {
     uint64_t keep_hash = pl->struct_hash;
-    int keep_world = pl->world, keep_rank = pl->rank, keep_team = pl->max_team;
+    int keep_world = pl->world, keep_rank = pl->rank, keep_team = pl->max_team, keep_cta = pl->n_cta;
     plan_free(pl);
     pl->struct_hash = keep_hash;
     pl->world = keep_world;
     pl->rank = keep_rank;
     pl->max_team = keep_team;
+    pl->n_cta = keep_cta;
     if (dev) { /* teams are sized for the CTAs this device actually seats (MIG slice, smaller part, ...) */
         int n_sm = 0, fac_grid = 0, fac_smem = 0, bs_grid = 0;
         if (asam_device_info(dev, &n_sm, &fac_grid, &fac_smem, &bs_grid) == 0 && fac_grid > 0)
-            pl->max_team = fac_grid < 120 ? fac_grid : 120;
+            pl->max_team = fac_grid < 120 ? fac_grid : 120, pl->n_cta = fac_grid;
     }
     if (N <= 0)
         return 0;
