@@ -52,6 +52,7 @@ void asam_dbg_build_profile(double *out, int reset)
 #define ASAM_LEAF_MAX_M 48       /* = ASAM_LEAF_M of k_factor_leaf */
 #define ASAM_LEAF_MIN_COUNT 4096 /* below this one k_factor launch does it all */
 #define ASAM_SOLO_MAX_M_DEFAULT 0 /* see solo_max_m() */
+#define ASAM_TILES_PER_WORKER 1   /* trailing-update tiles per worker and panel that team_size() plans for */
 #define MAX_SN_COLS 32 /* block columns per supernode: L11 (96x96) fits k_backsolve shared memory */
 
 /* ---- pair map ---------------------------------------------------------------------------- */
@@ -347,7 +348,15 @@ static int team_size(int mb, int cb, int cap)
     for (int64_t cb0 = j0; cb0 < m; cb0 += 64)
         tiles += (m - cb0 + 1 + 255) / 256;
     int64_t chunks = 1 + (m - j0 + 1 + 127) / 128; /* look-ahead crew: the diagonal block + the 128-row chunks (ASAM_CROWS) */
-    int G = (int) (tiles + chunks); /* the look-ahead crew (one CTA per chunk) takes no tiles */
+    /* A panel step lasts ~30 us (diagonal block + row solves + barrier: the dependent chain), a tensor-pipe tile
+     * ~4-5 us: a worker outside the crew gets through several tiles per step, and a worker that has none left only
+     * holds an SM that another front could use.  ASAM_TILES_PER_WORKER overrides (tuning). */
+    static int tpw = 0;
+    if (tpw == 0) {
+        const char *e = getenv("ASAM_TILES_PER_WORKER");
+        tpw = e && atoi(e) > 0 ? atoi(e) : ASAM_TILES_PER_WORKER;
+    }
+    int G = (int) ((tiles + tpw - 1) / tpw + chunks); /* the look-ahead crew (one CTA per chunk) takes no tiles */
     /* every worker of a team must be resident at the same time (spin barriers in a persistent,
      * non-cooperative launch): never more workers than the device seats CTAs of k_factor */
     if (cap < 2)
@@ -674,8 +683,7 @@ static void build_schedule(plan_t *pl)
      * waiting CTA only ever waits for tasks that were handed out before its own.  ASAM_TASK_ORDER=level keeps
      * the level order (A/B). */
     int *byl = malloc(sizeof(int) * (size_t) (nsn + 1));
-    double *lat_us = NULL, *up_us = NULL; /* modelled duration / chain length above, microseconds (order modes cp, sim) */
-    int order_sim = 0;
+    int order_mode = 0; /* 0 level, 1 chain length ("cp"), 2 simulated schedule ("sim"), 3 auto: cp or sim by load */
     int *bylv = malloc(sizeof(int) * (size_t) (nsn + 1)); /* plain level order: the back-substitution list (measured:
                                                             * 1.15 ms against 1.42 ms with the reversed chain order) */
     {
@@ -693,29 +701,7 @@ static void build_schedule(plan_t *pl)
         if (eo && strcmp(eo, "level") == 0) {
             memcpy(byl, bylv, sizeof(int) * (size_t) nsn);
         } else {
-            sn_key_t *keys = malloc(sizeof(sn_key_t) * (size_t) (nsn + 1));
-            double *up = malloc(sizeof(double) * (size_t) (nsn + 1));
-            lat_us = malloc(sizeof(double) * (size_t) (nsn + 1));
-            for (int s = nsn - 1; s >= 0; s--) { /* parents have larger ids */
-                const double m = 3.0 * pl->desc[s].mb, c = 3.0 * pl->desc[s].cb;
-                double lat; /* microseconds, fitted to traces of the kernels (tools/panel_trace.py --dump-trace) */
-                if (m <= ASAM_LEAF_MAX_M)
-                    lat = 2.0 + 0.1 * c;
-                else if (front_fits_smem(pl->desc[s].mb))
-                    lat = 6.0 + 0.07 * m + c * (0.25 + 0.0028 * m);
-                else
-                    lat = 40.0 + 31.0 * ceil(c / 48.0);
-                lat_us[s] = lat;
-                up[s] = lat + (pl->desc[s].parent >= 0 ? up[pl->desc[s].parent] : 0.0);
-                keys[s].key = up[s];
-                keys[s].id = s;
-            }
-            qsort(keys, (size_t) nsn, sizeof(sn_key_t), cmp_key_desc);
-            for (int k = 0; k < nsn; k++)
-                byl[k] = keys[k].id;
-            free(keys);
-            up_us = up;
-            order_sim = !(eo && strcmp(eo, "cp") == 0);
+            order_mode = (eo && strcmp(eo, "cp") == 0) ? 1 : ((eo && strcmp(eo, "sim") == 0) ? 2 : 3);
         }
     }
 
@@ -754,39 +740,86 @@ static void build_schedule(plan_t *pl)
         free(want);
     }
 
-    if (order_sim) {
-        /* ticket order of k_factor = start order of the simulated schedule; the main list (own fronts outside
-         * the leaf set) and the part above a multi-GPU cut are separate launches, simulated separately; the leaf
-         * set keeps the chain-length order (warp-sized tasks: nothing to gather) */
-        char *in = calloc((size_t) nsn + 1, 1);
-        int *ord = malloc(sizeof(int) * (size_t) (nsn + 1)), *pos_of = malloc(sizeof(int) * (size_t) (nsn + 1));
+    if (order_mode != 0) {
+        /* modelled duration of every front once its children are done (microseconds; least-squares fit to device
+         * traces of the 100 k world, tools/panel_trace.py --dump-trace: median error 8 % for shared-memory fronts,
+         * 9 % for teams) and the length of the dependent chain from a front up to the root */
+        double *lat_us = malloc(sizeof(double) * (size_t) (nsn + 1)), *up_us = malloc(sizeof(double) * (size_t) (nsn + 1));
+        double work = 0.0, chain = 0.0;
+        for (int s = nsn - 1; s >= 0; s--) { /* parents have larger ids */
+            const double m = 3.0 * pl->desc[s].mb, c = 3.0 * pl->desc[s].cb;
+            const int g = G_of[s] < 0 ? 1 : G_of[s];
+            double lat;
+            if (m <= ASAM_LEAF_MAX_M) {
+                lat = 2.0 + 0.1 * c;
+            } else if (front_fits_smem(pl->desc[s].mb) || g < 1) {
+                lat = 3.8 + 0.121 * m + 0.105 * c + 0.00508 * c * m;
+            } else {
+                double tiles = 0.0, crew = 0.0;
+                const int npan = (int) ceil(c / 48.0);
+                for (int k = 0; k < npan; k++) {
+                    const double r = m - 48.0 * (k + 1) > 0 ? m - 48.0 * (k + 1) : 0.0;
+                    tiles += r * r / 2.0 / (256.0 * 64.0);
+                    crew += 1.0 + ceil(r / 128.0);
+                }
+                lat = 21.5 * npan + 24.4 * tiles / g + 11.6 * crew / g + 0.041 * m;
+            }
+            lat_us[s] = lat;
+            up_us[s] = lat + (pl->desc[s].parent >= 0 ? up_us[pl->desc[s].parent] : 0.0);
+            if ((owner[s] == me || owner[s] == -1) && !leaf[s])
+                work += lat * g;
+            if (up_us[s] > chain)
+                chain = up_us[s];
+        }
         const int P = pl->n_cta > 0 ? pl->n_cta : 148;
-        int n1, n2;
-        for (int s = 0; s < nsn; s++)
-            in[s] = owner[s] == me && !leaf[s];
-        n1 = sim_order(pl, in, G_of, lat_us, up_us, P, ord);
-        for (int s = 0; s < nsn; s++)
-            in[s] = owner[s] == -1;
-        n2 = sim_order(pl, in, G_of, lat_us, up_us, P, ord + n1);
-        for (int s = 0; s < nsn; s++)
-            pos_of[s] = -1;
-        for (int k = 0; k < n1 + n2; k++)
-            pos_of[ord[k]] = k;
-        /* byl: simulated tasks in start order, everything else (leaf set, other ranks) after them in the old order */
-        int *nb = malloc(sizeof(int) * (size_t) (nsn + 1)), k2 = 0;
-        for (int k = 0; k < n1 + n2; k++)
-            nb[k2++] = ord[k];
-        for (int k = 0; k < nsn; k++)
-            if (pos_of[byl[k]] < 0)
-                nb[k2++] = byl[k];
-        memcpy(byl, nb, sizeof(int) * (size_t) nsn);
-        free(nb);
-        free(in);
-        free(ord);
-        free(pos_of);
+        /* auto: where the SMs are far from saturated (M3500: 11 of 67 CTA-ms busy) spinning costs nothing and the
+         * eager chain-length order starts parents soonest; where they are saturated, a team must not take its
+         * CTAs before it can use them */
+        const int use_sim = order_mode == 2 || (order_mode == 3 && work / P > 0.5 * chain);
+        {
+            sn_key_t *keys = malloc(sizeof(sn_key_t) * (size_t) (nsn + 1));
+            for (int s = 0; s < nsn; s++) {
+                keys[s].key = up_us[s];
+                keys[s].id = s;
+            }
+            qsort(keys, (size_t) nsn, sizeof(sn_key_t), cmp_key_desc);
+            for (int k = 0; k < nsn; k++)
+                byl[k] = keys[k].id;
+            free(keys);
+        }
+        if (use_sim) {
+            /* ticket order of k_factor = start order of the simulated schedule; the main list (own fronts outside
+             * the leaf set) and the part above a multi-GPU cut are separate launches, simulated separately; the
+             * leaf set keeps the chain-length order (warp-sized tasks: nothing to gather) */
+            char *in = calloc((size_t) nsn + 1, 1);
+            int *ord = malloc(sizeof(int) * (size_t) (nsn + 1)), *pos_of = malloc(sizeof(int) * (size_t) (nsn + 1));
+            int n1, n2;
+            for (int s = 0; s < nsn; s++)
+                in[s] = owner[s] == me && !leaf[s];
+            n1 = sim_order(pl, in, G_of, lat_us, up_us, P, ord);
+            for (int s = 0; s < nsn; s++)
+                in[s] = owner[s] == -1;
+            n2 = sim_order(pl, in, G_of, lat_us, up_us, P, ord + n1);
+            for (int s = 0; s < nsn; s++)
+                pos_of[s] = -1;
+            for (int k = 0; k < n1 + n2; k++)
+                pos_of[ord[k]] = k;
+            /* byl: simulated tasks in start order, everything else (leaf set, other ranks) after them in the old order */
+            int *nb = malloc(sizeof(int) * (size_t) (nsn + 1)), k2 = 0;
+            for (int k = 0; k < n1 + n2; k++)
+                nb[k2++] = ord[k];
+            for (int k = 0; k < nsn; k++)
+                if (pos_of[byl[k]] < 0)
+                    nb[k2++] = byl[k];
+            memcpy(byl, nb, sizeof(int) * (size_t) nsn);
+            free(nb);
+            free(in);
+            free(ord);
+            free(pos_of);
+        }
+        free(lat_us);
+        free(up_us);
     }
-    free(lat_us);
-    free(up_us);
 
     /* Back-solve entries of a supernode: one, or -- supernodes wider than one 96-column block (ASAM_BSW) in a
      * batch schedule -- one per block, last block first, each solved by its own CTA (cta_backsolve, blk_only).
