@@ -54,6 +54,10 @@ def lib() -> C.CDLL:
     L.asam_comm_info.argtypes = [_ip, _ip, _ip]
     L.asam_comm_set_sharding.argtypes = [C.c_int]
     L.asam_measure_fp64_peak.argtypes = [C.c_void_p, _dp]
+    L.asam_small_steps.argtypes = [C.c_void_p]
+    L.asam_small_steps.restype = C.c_int64
+    L.asam_small_step_profile.argtypes = [C.c_void_p, _dp, C.c_int]
+    L.asam_small_step_profile.restype = None
     L.asam_dbg_profile.argtypes = [_dp, C.c_int]
     L.asam_dbg_profile.restype = None
     _lib = L

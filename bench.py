@@ -483,8 +483,13 @@ def bench_replay(ctx: Ctx, name: str, d, label: str, K: int, W: int, with_cpu: b
     h.replay_to(s0 + W, want_chi2=False)
     barrier_max(dist, local, 0.0)
     launches0, h2d0, d2h0 = capi.counters(dev)
+    small0 = int(L.asam_small_steps(dev))
+    sp = (C.c_double * 7)()
+    L.asam_small_step_profile(dev, sp, 1)
     _, ms, info = h.replay_to(s0 + W + K, want_chi2=False)
     launches1, h2d1, d2h1 = capi.counters(dev)
+    n_small = int(L.asam_small_steps(dev)) - small0
+    L.asam_small_step_profile(dev, sp, 0)
     chi2_end = h.chi2()
     end_states = h.states()
     h.close()
@@ -497,6 +502,12 @@ def bench_replay(ctx: Ctx, name: str, d, label: str, K: int, W: int, with_cpu: b
                    "d2h_bytes_per_step": (d2h1 - d2h0) // n},
            "gpu_launches": int(launches1 - launches0),
            "latency_by_bucket": bucket_latency(ms, info),
+           "fused_small_steps": {"count": n_small,
+                                 "note": "steps with naffected <= 5 run as ONE launch (k_step): uploads fetched over PCIe by the kernel, "
+                                         "linearize + partial re-factorisation + pruned back-substitution, results through pinned memory",
+                                 "mean_us": ({k: sp[i] / n_small for i, k in enumerate(
+                                     ("fetch_scatter", "linearize", "factor", "backsolve", "write_results", "host_launch_call", "host_flag_wait"))}
+                                             if n_small else None)},
            "roofline_kernels": None,
            "roofline_note": "incremental steps re-factor a handful of fronts (median naffected <= 5): launch + dependency latency, "
                             "not bytes; the per-bucket latencies above are the measure"}
@@ -596,6 +607,7 @@ def run_b200(args, names, world, rank, local, dist):
 
 
 def main():
+    os.environ.setdefault("NCCL_DEBUG", "WARN")  # (NCCL's version banner would otherwise share stdout with the JSON line)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
