@@ -854,45 +854,51 @@ __device__ __forceinline__ void diag_factor_rl(double *D, int pb, double *rdv, i
 // the 12x12 triangle fully unrolled.  Results go back to Li and to the front in HBM.
 // Wrow != nullptr: the solved row also goes to the row-major panel workspace (Wrow[0..pb), zero up to the next
 // multiple of 4), where the next iteration's tiles fetch it as part of one contiguous block.
-__device__ __forceinline__ void trsm_row(double *Li, const double *D, const double *rdv, int pb, double *Frow, int ld,
-                                         double *Wrow = nullptr)
+// one 12-column block [b0, b0+nb) of the row solve (needs x of the columns before b0 in Li and rows b0.. of the
+// columns [0, b0+nb) of L11 in D)
+__device__ __forceinline__ void trsm_row_block(double *Li, const double *D, const double *rdv, const int b0, const int nb,
+                                               double *Frow, int ld, double *Wrow)
 {
     const int tid = threadIdx.x;
     constexpr int LDD = ASAM_TPB;
-    for (int b0 = 0; b0 < pb; b0 += 12) {
-        const int nb = min(12, pb - b0);
-        double r[12];
+    double r[12];
 #pragma unroll
-        for (int q = 0; q < 12; q++)
-            r[q] = (q < nb) ? Li[tid + (b0 + q) * ASAM_TROWS] : 0.0;
-        for (int p = 0; p < b0; p++) {
-            const double xp = Li[tid + p * ASAM_TROWS];
-            const double2 *Dp = reinterpret_cast<const double2 *>(D + p * LDD + b0);
+    for (int q = 0; q < 12; q++)
+        r[q] = (q < nb) ? Li[tid + (b0 + q) * ASAM_TROWS] : 0.0;
+    for (int p = 0; p < b0; p++) {
+        const double xp = Li[tid + p * ASAM_TROWS];
+        const double2 *Dp = reinterpret_cast<const double2 *>(D + p * LDD + b0);
 #pragma unroll
-            for (int q2 = 0; q2 < 6; q2++) {
-                const double2 v = Dp[q2];
-                r[2 * q2] -= xp * v.x;
-                r[2 * q2 + 1] -= xp * v.y;
-            }
+        for (int q2 = 0; q2 < 6; q2++) {
+            const double2 v = Dp[q2];
+            r[2 * q2] -= xp * v.x;
+            r[2 * q2 + 1] -= xp * v.y;
         }
-#pragma unroll
-        for (int q = 0; q < 12; q++) {
-            if (q < nb) {
-                r[q] *= rdv[b0 + q];
-#pragma unroll
-                for (int q2 = q + 1; q2 < 12; q2++)
-                    r[q2] -= r[q] * D[(b0 + q2) + (b0 + q) * LDD];
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < 12; q++)
-            if (q < nb) {
-                Li[tid + (b0 + q) * ASAM_TROWS] = r[q];
-                Frow[(size_t) (b0 + q) * ld] = r[q];
-                if (Wrow)
-                    Wrow[b0 + q] = r[q];
-            }
     }
+#pragma unroll
+    for (int q = 0; q < 12; q++) {
+        if (q < nb) {
+            r[q] *= rdv[b0 + q];
+#pragma unroll
+            for (int q2 = q + 1; q2 < 12; q2++)
+                r[q2] -= r[q] * D[(b0 + q2) + (b0 + q) * LDD];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 12; q++)
+        if (q < nb) {
+            Li[tid + (b0 + q) * ASAM_TROWS] = r[q];
+            Frow[(size_t) (b0 + q) * ld] = r[q];
+            if (Wrow)
+                Wrow[b0 + q] = r[q];
+        }
+}
+
+__device__ __forceinline__ void trsm_row(double *Li, const double *D, const double *rdv, int pb, double *Frow, int ld,
+                                         double *Wrow = nullptr)
+{
+    for (int b0 = 0; b0 < pb; b0 += 12)
+        trsm_row_block(Li, D, rdv, b0, min(12, pb - b0), Frow, ld, Wrow);
     if (Wrow)
         for (int q = pb; q < ((pb + 3) & ~3); q++)
             Wrow[q] = 0.0;
@@ -1188,16 +1194,84 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
     // factored ONCE and published -- L11 into the front, 1/diag into dinv, then the flag
     auto diag_publish = [&](int k0, int pb, int seq) {
         __syncthreads(); // D was zeroed before, and filled by, the tile that updated this block
-        if (v3)
-            diag_factor_rl(D, pb, rdv, s, err);
-        else
-            diag_factor(D, pb, rdv, s, err);
+        if (v3) {
+            // blocked right-looking, PUBLISHED IN STAGES: after each 12-column sub-panel its columns of L11 are final
+            // and go to the front + the flag (8 * seq + stage); the crew solves the matching 12 columns of its rows
+            // while the next sub-panel is being factored, instead of starting when all 48 are done
+            constexpr int LDD = ASAM_TPB;
+            int stage = 0;
+            for (int k1 = 0; k1 < pb; k1 += ASAM_PB) {
+                const int pbb = min(ASAM_PB, pb - k1);
+                panel_factor(D + (size_t) k1 * LDD, LDD, k1, pbb, pb - 1, s, err, rdv);
+                for (int e = tid; e < pbb * pb; e += nt) {
+                    const int j = k1 + e / pb, i = e % pb;
+                    if (i >= j)
+                        F[(k0 + i) + (size_t) (k0 + j) * ld] = D[i + j * LDD];
+                }
+                for (int e = tid; e < pbb; e += nt)
+                    dinv[k0 + k1 + e] = rdv[k1 + e];
+                __syncthreads();
+                if (tid == 0) {
+                    __threadfence();
+                    atomicExch(crew_bar, 8 * seq + (++stage));
+                }
+                if (k1 + pbb < pb) {
+                    trailing_update<1, 4>(D, LDD, D + (size_t) k1 * LDD, LDD, pbb, k1 + pbb, pb, pb - 1);
+                    __syncthreads();
+                }
+            }
+            return;
+        }
+        diag_factor(D, pb, rdv, s, err);
         writeback(k0, pb);
         __syncthreads();
         if (tid == 0) {
             __threadfence();
             atomicExch(crew_bar, seq);
         }
+    };
+    // tile mode 3: the crew's rows (already updated, in Li) are solved 12 columns at a time, each stage as soon as
+    // worker 0 has published the matching columns of L11
+    auto rows_solve_staged = [&](int k0, int pb, int rb0, int seq, double *Wnext) {
+        constexpr int LDD = ASAM_TPB;
+        __syncthreads();
+        const int i = rb0 + tid;
+        const bool row = tid < ASAM_CROWS && i <= m;
+        int stage = 0;
+        for (int b0 = 0; b0 < pb; b0 += ASAM_PB) {
+            const int nb = min(ASAM_PB, pb - b0);
+            ++stage;
+            if (tid == 0) {
+                SpinClock spins;
+                int ok = 1;
+                while (ld_volatile(crew_bar) < 8 * seq + stage) {
+                    __nanosleep(20);
+                    if (spin_over(spins, a.spin_limit) || ld_volatile(err) < 0) {
+                        atomicCAS(err, 0, -(1 + s));
+                        ok = 0;
+                        break;
+                    }
+                }
+                __threadfence();
+                *s_flag = ok;
+            }
+            __syncthreads();
+            if (!*s_flag)
+                return false;
+            for (int e = tid; e < nb * ASAM_TPB; e += nt) {
+                const int j = b0 + e / ASAM_TPB, ii = e % ASAM_TPB;
+                D[ii + j * LDD] = (ii >= j && ii < pb) ? __ldcg(&F[(k0 + ii) + (size_t) (k0 + j) * ld]) : 0.0;
+            }
+            for (int e = tid; e < nb; e += nt)
+                rdv[b0 + e] = __ldcg(&dinv[k0 + b0 + e]);
+            __syncthreads();
+            if (row)
+                trsm_row_block(Li, D, rdv, b0, nb, F + i + (size_t) k0 * ld, ld, Wnext + (size_t) i * ASAM_LDW);
+        }
+        if (row)
+            for (int q = pb; q < ((pb + 3) & ~3); q++)
+                Wnext[(size_t) i * ASAM_LDW + q] = 0.0;
+        return true;
     };
     // the other crew workers: rows [rb0, rb0+ASAM_CROWS) of the panel are fetched while worker 0 factors the
     // block, then solved against the published L11
@@ -1300,7 +1374,7 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
                                Lj3, mbar, mb_parity);
                     if (pt && w > 0 && it == w)
                         pt[1] = d_now();
-                    if (!rows_solve(kn0, pbn, rb0, seq, Wbuf(kn0 / ASAM_TPB)))
+                    if (!rows_solve_staged(kn0, pbn, rb0, seq, Wbuf(kn0 / ASAM_TPB)))
                         return false;
                 }
             } else {
