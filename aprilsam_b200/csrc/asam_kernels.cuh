@@ -313,6 +313,7 @@ struct FacArgs {
     int smem_doubles;
     long long spin_limit;
     unsigned long long *trace; // optional: 8 words per task
+    int staged;    // tile mode 3: publish L11 in 12-column stages (0: all at once)
     int tile_mode; // trailing-update tiles of the team path: 0 DFMA, 1 mma.sync f64, 2 mma.sync f64 + bulk async copies
     int solo_pb; // widest staged panel of a front that one CTA handles out of HBM (multiple of ASAM_PB)
     unsigned long long *ptrace; // optional: panel-step stamps of supernode ptrace_sn, [panel][worker < 8][8]
@@ -1203,21 +1204,32 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
             for (int k1 = 0; k1 < pb; k1 += ASAM_PB) {
                 const int pbb = min(ASAM_PB, pb - k1);
                 panel_factor(D + (size_t) k1 * LDD, LDD, k1, pbb, pb - 1, s, err, rdv);
-                for (int e = tid; e < pbb * pb; e += nt) {
-                    const int j = k1 + e / pb, i = e % pb;
-                    if (i >= j)
-                        F[(k0 + i) + (size_t) (k0 + j) * ld] = D[i + j * LDD];
-                }
-                for (int e = tid; e < pbb; e += nt)
-                    dinv[k0 + k1 + e] = rdv[k1 + e];
-                __syncthreads();
-                if (tid == 0) {
-                    __threadfence();
-                    atomicExch(crew_bar, 8 * seq + (++stage));
+                ++stage;
+                if (a.staged) {
+                    for (int e = tid; e < pbb * pb; e += nt) {
+                        const int j = k1 + e / pb, i = e % pb;
+                        if (i >= j)
+                            F[(k0 + i) + (size_t) (k0 + j) * ld] = D[i + j * LDD];
+                    }
+                    for (int e = tid; e < pbb; e += nt)
+                        dinv[k0 + k1 + e] = rdv[k1 + e];
+                    __syncthreads();
+                    if (tid == 0) {
+                        __threadfence();
+                        atomicExch(crew_bar, 8 * seq + stage);
+                    }
                 }
                 if (k1 + pbb < pb) {
                     trailing_update<1, 4>(D, LDD, D + (size_t) k1 * LDD, LDD, pbb, k1 + pbb, pb, pb - 1);
                     __syncthreads();
+                }
+            }
+            if (!a.staged) { // (ASAM_STAGED=0, A/B: everything at once, as before)
+                writeback(k0, pb);
+                __syncthreads();
+                if (tid == 0) {
+                    __threadfence();
+                    atomicExch(crew_bar, 8 * seq + stage);
                 }
             }
             return;
