@@ -79,8 +79,6 @@ struct asam_dev {
     int ntasks_full = 0;
     Buf leaf_tasks; // supernodes handled by k_factor_leaf before k_factor (batch solves of large graphs)
     int n_leaf = 0;
-    Buf mid_tasks, mid_nwait; // ... and by k_factor_mid (two fronts per SM) between the two
-    int n_mid = 0, mid_grid = 0;
     int leaf_grid = 0, leaf_smem = 0;
     int bt_nleaf = 0; // the last bt_nleaf entries of btasks_full are back-solved by k_backsolve_leaf
     // multi-GPU shard schedule (asam_set_shard_schedule)
@@ -350,18 +348,6 @@ static int run_factor(asam_dev *d, const FacArgs &a, int grid, int with_leaves =
         d->n_launch++;
         CK(cudaGetLastError());
     }
-    if (with_leaves && d->n_mid > 0) {
-        FacArgs mda = a;
-        mda.tasks = (const int *) d->mid_tasks.p;
-        mda.nwait = (const int *) d->mid_nwait.p;
-        mda.keep = nullptr;
-        mda.ntasks = d->n_mid;
-        mda.smem_doubles = ASAM_MID_SMEM_BYTES / (int) sizeof(double);
-        mda.trace = nullptr;
-        k_factor_mid<<<d->n_mid < d->mid_grid ? d->n_mid : d->mid_grid, 256, ASAM_MID_SMEM_BYTES, d->stream>>>(mda);
-        d->n_launch++;
-        CK(cudaGetLastError());
-    }
     if (grid > 0) {
         k_factor<<<grid, d->fac_threads, d->fac_smem, d->stream>>>(a);
         d->n_launch++;
@@ -583,12 +569,6 @@ ASAM_EXPORT int asam_dev_create(asam_dev_t **out)
         return set_err("k_factor_leaf does not fit on an SM");
     d->leaf_grid = occ * d->n_sm;
 
-    CK(cudaFuncSetAttribute(k_factor_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, ASAM_MID_SMEM_BYTES));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_factor_mid, 256, ASAM_MID_SMEM_BYTES));
-    if (occ < 1)
-        return set_err("k_factor_mid does not fit on an SM");
-    d->mid_grid = occ * d->n_sm;
-
     d->bsl_smem = ASAM_BSL_WARPS * ASAM_BSL_STRIDE * (int) sizeof(double);
     CK(cudaFuncSetAttribute(k_backsolve_leaf, cudaFuncAttributeMaxDynamicSharedMemorySize, d->bsl_smem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_backsolve_leaf, 32 * ASAM_BSL_WARPS, d->bsl_smem));
@@ -629,7 +609,7 @@ ASAM_EXPORT void asam_dev_destroy(asam_dev_t *d)
     Buf *all[] = { &d->f_type, &d->f_a, &d->f_b, &d->f_z, &d->f_W, &d->f_slot, &d->lp, &d->st, &d->node2q, &d->q2node,
                    &d->Adiag, &d->Aoff, &d->Bq, &d->y, &d->x, &d->dinv, &d->sn, &d->ipool, &d->arena, &d->arrive,
                    &d->xdone, &d->xblk, &d->tbar, &d->tasks_full, &d->nwait_full, &d->btasks_full, &d->tasks_tmp, &d->nwait_tmp,
-                   &d->btasks_tmp, &d->keep_tmp, &d->leaf_tasks, &d->mid_tasks, &d->mid_nwait, &d->top_tasks, &d->top_nwait, &d->ctrl, &d->partial, &d->patch_ids, &d->patch_desc, &d->pts, &d->flush, &d->trace_fac, &d->trace_bs, &d->ptrace };
+                   &d->btasks_tmp, &d->keep_tmp, &d->leaf_tasks, &d->top_tasks, &d->top_nwait, &d->ctrl, &d->partial, &d->patch_ids, &d->patch_desc, &d->pts, &d->flush, &d->trace_fac, &d->trace_bs, &d->ptrace };
     for (int i = 0; i < 2; i++)
         if (d->tev[i])
             cudaEventDestroy(d->tev[i]);
@@ -859,7 +839,7 @@ ASAM_EXPORT int asam_linearize(asam_dev_t *d, int f_first, int f_count, const do
 static int launch_factor(asam_dev *d, int ntasks, const int *tasks_dev, const int *nwait_dev, int with_leaves = 0,
                          const int *keep_dev = nullptr)
 {
-    if (ntasks <= 0 && !(with_leaves && (d->n_leaf > 0 || d->n_mid > 0)))
+    if (ntasks <= 0 && !(with_leaves && d->n_leaf > 0))
         return 0;
     // ticket / team-barrier counters are left at zero by the previous launch (ticket_release,
     // team_leave); err is only ever non-zero on a fatal path (see clear_status)
@@ -960,7 +940,6 @@ ASAM_EXPORT int asam_set_full_tasks(asam_dev_t *d, int ntasks, const int32_t *ta
         return 1;
     d->ntasks_full = ntasks;
     d->n_leaf = 0;
-    d->n_mid = 0;
     d->bt_nleaf = 0;
     return 0;
 }
@@ -977,23 +956,6 @@ ASAM_EXPORT int asam_set_leaf_tasks(asam_dev_t *d, int n, const int32_t *tasks)
         upload(d, d->leaf_tasks.p, tasks, (size_t) n * sizeof(int)))
         return 1;
     d->n_leaf = n;
-    return 0;
-}
-
-// Supernodes k_factor_mid handles after the leaf kernel and before the list given to asam_set_full_tasks
-// (all of them single-CTA fronts of order <= ASAM_MID_MAX_M whose descendants are leaf or mid tasks); nwait =
-// number of children.  Call after asam_set_full_tasks.
-ASAM_EXPORT int asam_set_mid_tasks(asam_dev_t *d, int n, const int32_t *tasks, const int32_t *nwait)
-{
-    CK(cudaSetDevice(d->device));
-    d->n_mid = 0;
-    if (n <= 0)
-        return 0;
-    const size_t b = (size_t) n * sizeof(int);
-    if (buf_reserve(d, d->mid_tasks, b, false, false) || buf_reserve(d, d->mid_nwait, b, false, false) ||
-        upload(d, d->mid_tasks.p, tasks, b) || upload(d, d->mid_nwait.p, nwait, b))
-        return 1;
-    d->n_mid = n;
     return 0;
 }
 

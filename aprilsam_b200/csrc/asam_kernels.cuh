@@ -1791,41 +1791,6 @@ __global__ void __launch_bounds__(256, 1) k_factor(FacArgs a)
 }
 
 // ------------------------------------------------------------------------------------------
-// kernel 2b: the MID set.  Between the warp-sized leaves and the fronts that need a whole SM's shared memory
-// sit thousands of fronts of order 51..117 (100 k world: 8.7 k supernodes, a fifth of k_factor's SM time), each
-// a short chain of L2 round trips (descriptor, gather, children) and 12-column panel steps: one such CTA
-// leaves its SM idle most of the time.  The host hands the downward-closed set of them (all descendants in the
-// leaf set or in this set) to this kernel, launched between k_factor_leaf and k_factor with HALF the shared
-// memory and register budget: two fronts per SM, one's latency behind the other's arithmetic.  Same per-front
-// code as k_factor (cta_front), same counters.
-// ------------------------------------------------------------------------------------------
-#define ASAM_MID_MAX_M 117
-#define ASAM_MID_SMEM_BYTES (112 * 1024)
-
-__global__ void __launch_bounds__(256, 2) k_factor_mid(FacArgs a)
-{
-    extern __shared__ __align__(16) double sm[];
-    __shared__ int s_task, s_abort;
-    __shared__ asam_sn_desc_t s_cd[ASAM_MAX_CACHED_CHILDREN];
-    const int tid = threadIdx.x;
-    for (;;) {
-        if (tid == 0) {
-            s_task = atomicAdd(&a.ctrl[5], 1);
-            s_abort = 0;
-        }
-        __syncthreads();
-        const int t = s_task;
-        if (t >= a.ntasks)
-            break;
-        const int s = a.tasks[t];
-        const asam_sn_desc_t d = a.sn[s];
-        if (!cta_front(a, t, s, a.nwait[t] & 0xffff, d, sm, s_cd, &s_abort, 0ULL, 0))
-            break;
-    }
-    ticket_release(&a.ctrl[5], &a.ctrl[6]);
-}
-
-// ------------------------------------------------------------------------------------------
 // kernel 2a: the leaves.  Large graphs have tens of thousands of supernodes with tiny fronts
 // (100 k Manhattan: 36 k of 47 k have m < 49) at the bottom of the tree; one CTA per front
 // wastes the SM on them.  Here every WARP takes tickets on its own and factors a whole front

@@ -103,8 +103,6 @@ typedef struct {
     int ntasks;
     int *leaf_tasks; /* supernodes factored by k_factor_leaf before `tasks` (large graphs only) */
     int n_leaf;
-    int *mid_tasks, *mid_nwait; /* ... and by k_factor_mid (two fronts per SM) between the two */
-    int n_mid;
     int n_btasks;    /* entries of btasks (>= the supernodes in it: wide supernodes have one entry per 96-column block) */
     int bt_split;    /* btasks holds per-block entries (batch schedule only; undone by the first plan_append) */
     char *bs_leaf;   /* per supernode: back-solved by k_backsolve_leaf (last n_bs_leaf entries of btasks) */

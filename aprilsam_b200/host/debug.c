@@ -78,7 +78,7 @@ ASAM_API void asam_dbg_plan_info(void *p, int64_t *info, double *flops)
 
 /* which: 0 order 1 pos 2 node2q 3 q2node 4 parent_pos 5 fslot 6 sn_of_q 7 ipool 8 tasks 9 nwait
  * 10 btasks 11 desc (as int32 words, 12 per supernode) 12 leaf_tasks 13 top_tasks 14 top_nwait
- * 15 shard_owner 16 shard_q0 17 shard_qn 18 shard_off (int64 as 2 words) 19 shard_cnt (int64) 20 mid_tasks */
+ * 15 shard_owner 16 shard_q0 17 shard_qn 18 shard_off (int64 as 2 words) 19 shard_cnt (int64) */
 ASAM_API const int *asam_dbg_plan_array(void *p, int which, int64_t *count)
 {
     plan_t *pl = (plan_t *) p;
@@ -103,7 +103,6 @@ ASAM_API const int *asam_dbg_plan_array(void *p, int which, int64_t *count)
     case 17: *count = pl->shard_qn ? pl->n_shards : 0; return pl->shard_qn;
     case 18: *count = pl->shard_off ? 2 * (int64_t) pl->n_shards : 0; return (const int *) pl->shard_off;
     case 19: *count = pl->shard_cnt ? 2 * (int64_t) pl->n_shards : 0; return (const int *) pl->shard_cnt;
-    case 20: *count = pl->mid_tasks ? pl->n_mid : 0; return pl->mid_tasks;
     default: *count = 0; return NULL;
     }
 }

@@ -51,8 +51,6 @@ void asam_dbg_build_profile(double *out, int reset)
 #define ASAM_BSLEAF_MIN_COUNT 4096 /* measured: no gain on M3500-sized trees (the kernel boundary eats it) */
 #define ASAM_LEAF_MAX_M 48       /* = ASAM_LEAF_M of k_factor_leaf */
 #define ASAM_LEAF_MIN_COUNT 4096 /* below this one k_factor launch does it all */
-#define ASAM_MID_MAX_M_HOST 117  /* = ASAM_MID_MAX_M of k_factor_mid */
-#define ASAM_MID_MIN_COUNT 256
 #define ASAM_SOLO_MAX_M_DEFAULT 0 /* see solo_max_m() */
 #define ASAM_TILES_PER_WORKER 1   /* trailing-update tiles per worker and panel that team_size() plans for */
 #define MAX_SN_COLS 32 /* block columns per supernode: L11 (96x96) fits k_backsolve shared memory */
@@ -205,8 +203,6 @@ void plan_free(plan_t *pl)
     free(pl->nwait);
     free(pl->btasks);
     free(pl->leaf_tasks);
-    free(pl->mid_tasks);
-    free(pl->mid_nwait);
     free(pl->bs_leaf);
     free(pl->mark_idx);
     free(pl->top_tasks);
@@ -665,26 +661,6 @@ static void build_schedule(plan_t *pl)
     }
     if (n_leaf_all < ASAM_LEAF_MIN_COUNT)
         memset(leaf, 0, (size_t) nsn);
-    /* mid set: single-CTA fronts small enough for two per SM (k_factor_mid) whose descendants are all leaf or
-     * mid tasks; only where the leaf kernel runs at all (large graphs) and there are enough of them */
-    char *mid = calloc((size_t) nsn + 1, 1);
-    {
-        int n_mid_all = 0, on = 1;
-        const char *emid = getenv("ASAM_MID");
-        if (emid)
-            on = atoi(emid) != 0;
-        if (on && n_leaf_all >= ASAM_LEAF_MIN_COUNT) {
-            for (int s = 0; s < nsn; s++) {
-                int ok = !leaf[s] && 3 * pl->desc[s].mb <= ASAM_MID_MAX_M_HOST;
-                for (int c = 0; ok && c < pl->snh[s].children.n; c++)
-                    ok = leaf[pl->snh[s].children.p[c]] || mid[pl->snh[s].children.p[c]];
-                mid[s] = (char) ok;
-                n_mid_all += ok;
-            }
-            if (n_mid_all < ASAM_MID_MIN_COUNT)
-                memset(mid, 0, (size_t) nsn);
-        }
-    }
     /* the warp-per-supernode BACK-SOLVE takes any downward-closed set with <= 64 own columns and
      * <= 64 rows below (a superset of the factor leaf set); it pays from a few dozen supernodes on:
      * a warp per supernode has everything fetched before its parent's flag arrives */
@@ -790,7 +766,7 @@ static void build_schedule(plan_t *pl)
             }
             lat_us[s] = lat;
             up_us[s] = lat + (pl->desc[s].parent >= 0 ? up_us[pl->desc[s].parent] : 0.0);
-            if ((owner[s] == me || owner[s] == -1) && !leaf[s] && !mid[s])
+            if ((owner[s] == me || owner[s] == -1) && !leaf[s])
                 work += lat * g;
             if (up_us[s] > chain)
                 chain = up_us[s];
@@ -819,7 +795,7 @@ static void build_schedule(plan_t *pl)
             int *ord = malloc(sizeof(int) * (size_t) (nsn + 1)), *pos_of = malloc(sizeof(int) * (size_t) (nsn + 1));
             int n1, n2;
             for (int s = 0; s < nsn; s++)
-                in[s] = owner[s] == me && !leaf[s] && !mid[s];
+                in[s] = owner[s] == me && !leaf[s];
             n1 = sim_order(pl, in, G_of, lat_us, up_us, P, ord);
             for (int s = 0; s < nsn; s++)
                 in[s] = owner[s] == -1;
@@ -857,7 +833,7 @@ static void build_schedule(plan_t *pl)
     pl->bt_split = 0;
 #define BS_NBLK(s_) ((bs_split && !pl->bs_leaf[s_] && 3 * pl->desc[s_].cb > 96 && pl->nsn < (1 << 24)) ? (3 * pl->desc[s_].cb + 95) / 96 : 1)
     int64_t n_local = 0, n_top = 0;
-    int n_leaf = 0, n_mid = 0, n_main_sn = 0, n_top_sn = 0, n_bsl = 0, n_top_bt = 0;
+    int n_leaf = 0, n_main_sn = 0, n_top_sn = 0, n_bsl = 0, n_top_bt = 0;
     for (int s = 0; s < nsn; s++)
         n_bsl += owner[s] == me && pl->bs_leaf[s];
     if (n_bsl < ASAM_BSLEAF_MIN_COUNT) {
@@ -868,8 +844,6 @@ static void build_schedule(plan_t *pl)
         if (owner[s] == me) {
             if (leaf[s])
                 n_leaf++;
-            else if (mid[s])
-                n_mid++;
             else
                 n_local += G_of[s] < 0 ? 1 : G_of[s];
             if (!pl->bs_leaf[s])
@@ -885,11 +859,6 @@ static void build_schedule(plan_t *pl)
     pl->nwait = malloc(sizeof(int) * (size_t) (n_local + 1));
     pl->n_leaf = n_leaf;
     pl->leaf_tasks = malloc(sizeof(int) * (size_t) (n_leaf + 1));
-    free(pl->mid_tasks);
-    free(pl->mid_nwait);
-    pl->n_mid = n_mid;
-    pl->mid_tasks = malloc(sizeof(int) * (size_t) (n_mid + 1));
-    pl->mid_nwait = malloc(sizeof(int) * (size_t) (n_mid + 1));
     pl->n_top = (int) n_top;
     pl->n_top_sn = n_top_sn;
     pl->top_tasks = malloc(sizeof(int) * (size_t) (n_top + 1));
@@ -898,7 +867,7 @@ static void build_schedule(plan_t *pl)
     pl->n_btasks = n_top_bt + n_main_sn + n_bsl;
     pl->btasks = malloc(sizeof(int) * (size_t) (pl->n_btasks + 1));
     /* back-solve list, parents first: [top | own shards outside the back-solve leaf set | that set] */
-    int t = 0, tl = 0, tt = 0, tm = 0;
+    int t = 0, tl = 0, tt = 0;
     int bt = n_top_bt - 1, bm = n_top_bt + n_main_sn - 1, bl = pl->n_btasks - 1;
     for (int k = 0; k < nsn; k++) { /* back-solve entries, filled backwards: parents first */
         int s = bylv[k];
@@ -937,11 +906,6 @@ static void build_schedule(plan_t *pl)
             pl->leaf_tasks[tl++] = s;
             continue;
         }
-        if (mid[s]) {
-            pl->mid_tasks[tm] = s;
-            pl->mid_nwait[tm++] = pack_nwait(pl->desc[s].ch_cnt, 0, 0);
-            continue;
-        }
         /* nwait counts ALL children: those of the leaf set arrived in the earlier launch */
         int G = G_of[s] < 0 ? 1 : G_of[s];
         for (int w = 0; w < G; w++, t++) {
@@ -953,7 +917,6 @@ static void build_schedule(plan_t *pl)
     free(G_of);
     free(byl);
     free(bylv);
-    free(mid);
     free(leaf);
     free(owner);
 }
@@ -1314,7 +1277,6 @@ static int plan_build_impl(plan_t *pl, asam_dev_t *dev, int N, int n_factors, co
     rc |= asam_upload_fslot(dev, 0, n_factors, pl->fslot);
     rc |= asam_set_full_tasks(dev, pl->ntasks, pl->tasks, pl->nwait, pl->n_btasks, pl->btasks);
     rc |= asam_set_leaf_tasks(dev, pl->n_leaf, pl->leaf_tasks);
-    rc |= asam_set_mid_tasks(dev, pl->n_mid, pl->mid_tasks, pl->mid_nwait);
     rc |= asam_set_bs_leaf_count(dev, pl->n_bs_leaf);
     if (pl->world > 1) {
         asam_shard_sched_t sh;
@@ -1403,10 +1365,9 @@ int plan_append(plan_t *pl, asam_dev_t *dev, int N, int n_factors, const int *ft
             return 1;
     }
     /* incremental steps run the whole schedule through k_factor / k_backsolve */
-    if (pl->n_leaf > 0 || pl->n_mid > 0) {
+    if (pl->n_leaf > 0) {
         pl->n_leaf = 0;
-        pl->n_mid = 0;
-        if (dev && (asam_set_leaf_tasks(dev, 0, NULL) || asam_set_mid_tasks(dev, 0, NULL, NULL)))
+        if (dev && asam_set_leaf_tasks(dev, 0, NULL))
             return 1;
     }
 

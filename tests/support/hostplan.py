@@ -39,7 +39,7 @@ def _i(a):
 
 ARR = dict(order=0, pos=1, node2q=2, q2node=3, parent_pos=4, fslot=5, sn_of_q=6, ipool=7, tasks=8, nwait=9,
            btasks=10, desc=11, leaf_tasks=12, top_tasks=13, top_nwait=14, shard_owner=15,
-           shard_q0=16, shard_qn=17, shard_off=18, shard_cnt=19, mid_tasks=20)
+           shard_q0=16, shard_qn=17, shard_off=18, shard_cnt=19)
 TR_FLAG = 1 << 30
 
 

@@ -187,10 +187,7 @@ def emulate_batch(d):
     leaf = p.array("leaf_tasks")  # large graphs: k_factor_leaf runs these first (children first)
     if len(leaf):
         emul.factor(fr, Hs, desc, ipool, p.array("q2node"), leaf, None)
-    mid = p.array("mid_tasks")  # ... then k_factor_mid (two fronts per SM), then k_factor
-    if len(mid):
-        emul.factor(fr, Hs, desc, ipool, p.array("q2node"), mid, None, prior=leaf)
-    emul.factor(fr, Hs, desc, ipool, p.array("q2node"), p.array("tasks"), p.array("nwait"), prior=np.concatenate([leaf, mid]))
+    emul.factor(fr, Hs, desc, ipool, p.array("q2node"), p.array("tasks"), p.array("nwait"), prior=leaf)
     emul.backsolve(fr, desc, ipool, p.array("btasks"))
     x = np.stack([fr.x[3 * node2q[i]:3 * node2q[i] + 3] for i in range(n)])
     st = lp + x
@@ -225,17 +222,13 @@ def test_large_plan_leaf_set_and_merged_chains():
     ftype, fa, fb, fz, fW = factor_arrays(d)
     p = HostPlan().build(n, ftype, fa, fb)
     D = p.descs()
-    leaf, mid, tasks, nwait = p.array("leaf_tasks"), p.array("mid_tasks"), p.array("tasks"), p.array("nwait")
+    leaf, tasks, nwait = p.array("leaf_tasks"), p.array("tasks"), p.array("nwait")
     assert len(leaf) >= 4096 and (3 * D["mb"][leaf]).max() <= 48
     in_leaf = np.zeros(len(D["mb"]), bool)
     in_leaf[leaf] = True
     par = D["parent"]
     assert all(in_leaf[c] for c in range(len(par)) if par[c] >= 0 and in_leaf[par[c]]), "leaf set is downward closed"
-    in_lm = in_leaf.copy()
-    in_lm[mid] = True
-    assert len(mid) >= 256 and (3 * D["mb"][mid]).max() <= 117 and not (set(mid) & set(leaf))
-    assert all(in_lm[c] for c in range(len(par)) if par[c] >= 0 and in_lm[par[c]]), "leaf + mid set is downward closed"
-    assert sorted(set(leaf) | set(mid) | set(tasks)) == list(range(len(par))) and not ((set(leaf) | set(mid)) & set(tasks))
+    assert sorted(set(leaf) | set(tasks)) == list(range(len(par))) and not (set(leaf) & set(tasks))
     wide = D["cb"] > 32
     assert wide.any(), "fundamental chains of team-sized fronts are merged past the 32-pose cap"
     m = 3 * D["mb"][wide]
@@ -279,7 +272,7 @@ def test_sharded_schedule_emulated(world):
     top = set(int(t) for t in plans[0].array("top_tasks"))
     seen = set(top)
     for r, p in enumerate(plans):
-        mine = set(int(t) for t in p.array("tasks")) | set(int(t) for t in p.array("leaf_tasks")) | set(int(t) for t in p.array("mid_tasks"))
+        mine = set(int(t) for t in p.array("tasks")) | set(int(t) for t in p.array("leaf_tasks"))
         assert not (mine & seen), "shards are disjoint from each other and from the top"
         seen |= mine
         assert set(int(t) & 0xffffff for t in p.array("btasks")) == mine | top
@@ -303,12 +296,10 @@ def test_sharded_schedule_emulated(world):
     for r, p in enumerate(plans):  # phase 1: own shards
         fr = emul.Fronts()
         fr.ensure(n)
-        leaf, mid = p.array("leaf_tasks"), p.array("mid_tasks")
+        leaf = p.array("leaf_tasks")
         if len(leaf):
             emul.factor(fr, Hs, desc, ipool, q2node, leaf, None)
-        if len(mid):
-            emul.factor(fr, Hs, desc, ipool, q2node, mid, None, prior=leaf)
-        emul.factor(fr, Hs, desc, ipool, q2node, p.array("tasks"), p.array("nwait"), prior=np.concatenate([leaf, mid]))
+        emul.factor(fr, Hs, desc, ipool, q2node, p.array("tasks"), p.array("nwait"), prior=leaf)
         arenas.append(fr)
     for s_, i in root_of.items():  # exchange: root fronts of the shards
         o = int(desc["f_off"][s_])
