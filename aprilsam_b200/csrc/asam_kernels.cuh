@@ -101,6 +101,21 @@ __device__ __forceinline__ void d_xyt_eval(const double *pa, const double *pb, c
     r[2] = d_mod2pi(z[2] - zh2);
 }
 
+// 1/sqrt(a) for the Cholesky pivots: single-precision seed (MUFU.RSQ) + two Newton steps in double (relative
+// error 2^-22 -> 2^-43 -> below 2^-53; one to two ulp after rounding).  Three of these are CHAINED in every
+// 3x3 pivot block, i.e. they sit on the dependent chain of every panel of every front; the library rsqrt()
+// (MUFU.RSQ64H + a longer refinement with range fix-ups) costs about twice as much.  Pivots are O(1e-4 .. 1e7):
+// no range issue; a <= 0 gives NaN as before (and the pivot check flags it).
+__device__ __forceinline__ double d_rsqrt(const double a)
+{
+    double y = (double) rsqrtf((float) a);
+    double e = fma(-a * y, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    e = fma(-a * y, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    return y;
+}
+
 __device__ __forceinline__ int ld_volatile(const int *p) { return *((const volatile int *) p); }
 
 __device__ __forceinline__ unsigned long long d_now()
@@ -396,13 +411,13 @@ __device__ __forceinline__ void panel_factor(double *P, int ldp, int k0, int pb,
         __syncthreads(); // previous in-panel update (or trailing update) is complete
         const double a00 = p0[rb], a10 = p0[rb + 1], a20 = p0[rb + 2];
         const double a11 = p1[rb + 1], a21 = p1[rb + 2], a22 = p2[rb + 2];
-        const double r0 = rsqrt(a00);
+        const double r0 = d_rsqrt(a00);
         const double l10 = a10 * r0, l20 = a20 * r0;
         const double d1 = a11 - l10 * l10;
-        const double r1 = rsqrt(d1);
+        const double r1 = d_rsqrt(d1);
         const double l21 = (a21 - l20 * l10) * r1;
         const double d2 = a22 - l20 * l20 - l21 * l21;
-        const double r2 = rsqrt(d2);
+        const double r2 = d_rsqrt(d2);
         if (tid == 0 && !(a00 > 0.0 && d1 > 0.0 && d2 > 0.0))
             atomicCAS(err, 0, 1 + sn_id);
         // rows below the block: x = row * L11^-T  (the thread keeps x for the update below)
@@ -804,13 +819,13 @@ __device__ __forceinline__ void diag_factor(double *D, int pb, double *rdv, int 
         double *p0 = D + c0 * LDD, *p1 = p0 + LDD, *p2 = p1 + LDD;
         const double a00 = p0[c0], a10 = p0[c0 + 1], a20 = p0[c0 + 2];
         const double a11 = p1[c0 + 1], a21 = p1[c0 + 2], a22 = p2[c0 + 2];
-        const double r0 = rsqrt(a00);
+        const double r0 = d_rsqrt(a00);
         const double l10 = a10 * r0, l20 = a20 * r0;
         const double d1 = a11 - l10 * l10;
-        const double r1 = rsqrt(d1);
+        const double r1 = d_rsqrt(d1);
         const double l21 = (a21 - l20 * l10) * r1;
         const double d2 = a22 - l20 * l20 - l21 * l21;
-        const double r2 = rsqrt(d2);
+        const double r2 = d_rsqrt(d2);
         if (tid == 0 && !(a00 > 0.0 && d1 > 0.0 && d2 > 0.0))
             atomicCAS(err, 0, 1 + sn_id);
         const int i = c0 + 3 + tid;
@@ -1924,13 +1939,13 @@ __global__ void __launch_bounds__(32 * ASAM_LEAF_WARPS, 1) k_factor_leaf(LeafArg
             double *p0 = F + k * ld, *p1 = p0 + ld, *p2 = p1 + ld;
             const double a00 = p0[k], a10 = p0[k + 1], a20 = p0[k + 2];
             const double a11 = p1[k + 1], a21 = p1[k + 2], a22 = p2[k + 2];
-            const double r0 = rsqrt(a00);
+            const double r0 = d_rsqrt(a00);
             const double l10 = a10 * r0, l20 = a20 * r0;
             const double d1 = a11 - l10 * l10;
-            const double r1 = rsqrt(d1);
+            const double r1 = d_rsqrt(d1);
             const double l21 = (a21 - l20 * l10) * r1;
             const double d2 = a22 - l20 * l20 - l21 * l21;
-            const double r2 = rsqrt(d2);
+            const double r2 = d_rsqrt(d2);
             if (lane == 0 && !(a00 > 0.0 && d1 > 0.0 && d2 > 0.0))
                 atomicCAS(err, 0, 1 + s);
             __syncwarp(); // every lane has read the diagonal block

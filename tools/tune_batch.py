@@ -40,11 +40,16 @@ def main():
         dev = L.asam_dbg_dev_of_graph(h.graph_ptr())
         L.asam_set_timing(dev, 1)
         km, e2e = [], []
+        prof = (C.c_double * 24)()
+        L.asam_dbg_profile(prof, 1)
         for _ in range(args.iters):
             h.set_states(d.init)
             e2e.append(h.batch())
             km.append(capi.kernel_ms(dev))
         km = np.median(np.array(km), axis=0)
+        L.asam_dbg_profile(prof, 1)
+        host = " host ms/call: gather %.3f plan-check %.3f enqueue+verify %.3f wait+D2H %.3f tree+update %.3f" % tuple(
+            prof[i] / args.iters for i in (11, 12, 13, 14, 16))
     err = ""
     if args.save:
         np.save(args.save, st)
@@ -54,7 +59,7 @@ def main():
         dd[:, 2] = (dd[:, 2] + np.pi) % (2 * np.pi) - np.pi
         err = f" max_rel_vs_base {float(np.max(np.abs(dd) / np.maximum(1.0, np.abs(ref)))):.2e}"
     knobs = " ".join(f"{k}={v}" for k, v in sorted(os.environ.items()) if k.startswith("ASAM_"))
-    print(f"TUNE {args.tag or 'cfg'} [{knobs}] lin {km[0]:.3f} factor {km[1]:.3f} backsolve {km[2]:.3f} ms; e2e median {np.median(e2e):.3f} ms{err}", flush=True)
+    print(f"TUNE {args.tag or 'cfg'} [{knobs}] lin {km[0]:.3f} factor {km[1]:.3f} backsolve {km[2]:.3f} ms; e2e median {np.median(e2e):.3f} ms{err};{host}", flush=True)
 
 
 if __name__ == "__main__":
