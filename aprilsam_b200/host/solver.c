@@ -632,7 +632,6 @@ ASAM_API void april_graph_cholesky(april_graph_t *graph, april_graph_cholesky_pa
         asam_set_timing(dev, 1);
         stamp(&tp, "begin");
     }
-    check_nodes(graph, 0, N);
     int restarted = 0;
 restart:;
     const int F_mirrored = c->nf_dev < F ? c->nf_dev : F; /* already in HBM: checked while the kernels run */
@@ -642,12 +641,25 @@ restart:;
     /* (large graphs: the per-node loops of this function chase one pointer per pose into separately
      * malloc'd arrays -- they are split over a few host threads, SURVEY.md section 7 "host marshalling") */
     double *lp = gctx_stage(c, 3 * N);
-#pragma omp parallel for schedule(static) if (N >= ASAM_OMP_MIN_NODES) num_threads(ASAM_OMP_THREADS)
+    int bad_node = -1;
+#pragma omp parallel for schedule(static) reduction(max : bad_node) if (N >= ASAM_OMP_MIN_NODES) num_threads(ASAM_OMP_THREADS)
     for (int i = 0; i < N; i++) {
         april_graph_node_t *n = node_at(graph, i);
+        if (n->type != APRIL_GRAPH_NODE_XYT_TYPE || n->length != 3) {
+            bad_node = i > bad_node ? i : bad_node; /* reported below */
+            continue;
+        }
+        if (i + 16 < N) { /* every pose is three separate allocations: keep a few in flight */
+            const april_graph_node_t *nx = node_at(graph, i + 16);
+            __builtin_prefetch(nx);
+            __builtin_prefetch(node_at(graph, i + 8)->state);
+            __builtin_prefetch(node_at(graph, i + 8)->l_point, 1);
+        }
         memcpy(n->l_point, n->state, 3 * sizeof(double));
         memcpy(lp + 3 * (size_t) i, n->state, 3 * sizeof(double));
     }
+    if (bad_node >= 0)
+        check_nodes(graph, bad_node, bad_node + 1); /* aborts with the message */
 
     PROF_LAP(11);
     /* ordering + symbolic analysis: cached while the factor structure is unchanged */
@@ -707,16 +719,8 @@ restart:;
             DEV_OK(asam_backsolve_full(dev));
         }
     }
-    double *x = solver_x(s, N);
-    int fstatus = 0;
-    DEV_OK(asam_download_x_status(dev, 0, N, x, &fstatus));
-    PROF_LAP(14);
-    report_factor_status(s, fstatus, "april_graph_cholesky");
-    PROF_LAP(15);
-    if (param->show_timing)
-        stamp(&tp, "H2D, kernels, D2H of solution");
-
-    /* persistent state the incremental path continues from (:260-288) */
+    /* persistent state the incremental path continues from (:260-288) -- host-only work, done while the
+     * kernels are still in flight */
     if (plan_reused && s->tree_fresh && param->tr && param->tr->nnodes == N) {
         /* same structure as the previous batch: same tree; only the per-solve labels reset */
         search_tree_t *tr = param->tr;
@@ -745,10 +749,26 @@ restart:;
     param->nreordering = N;
     param->factor_num = F;
 
+    double *x = solver_x(s, N);
+    int fstatus = 0;
+    DEV_OK(asam_download_x_status(dev, 0, N, x, &fstatus));
+    PROF_LAP(14);
+    report_factor_status(s, fstatus, "april_graph_cholesky");
+    PROF_LAP(15);
+    if (param->show_timing)
+        stamp(&tp, "H2D, kernels, D2H of solution");
+
     /* state = l_point + x (:311-315) */
 #pragma omp parallel for schedule(static) if (N >= ASAM_OMP_MIN_NODES) num_threads(ASAM_OMP_THREADS)
-    for (int i = 0; i < N; i++)
+    for (int i = 0; i < N; i++) {
+        if (i + 16 < N) {
+            __builtin_prefetch(node_at(graph, i + 16));
+            __builtin_prefetch(node_at(graph, i + 8)->l_point);
+            __builtin_prefetch(node_at(graph, i + 8)->state, 1);
+            __builtin_prefetch(node_at(graph, i + 8)->delta_X, 1);
+        }
         apply_update(node_at(graph, i), x + 3 * (size_t) pl->node2q[i]);
+    }
     PROF_LAP(16);
     if (param->show_timing) {
         stamp(&tp, "tree, state update");
