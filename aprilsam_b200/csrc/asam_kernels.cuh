@@ -328,6 +328,7 @@ struct FacArgs {
     int smem_doubles;
     long long spin_limit;
     unsigned long long *trace; // optional: 8 words per task
+    int smem_mma;  // trailing update of shared-memory fronts on the FP64 tensor pipe (0: DFMA, A/B)
     int staged;    // tile mode 3: publish L11 in 12-column stages (0: all at once)
     int tile_mode; // trailing-update tiles of the team path: 0 DFMA, 1 mma.sync f64, 2 mma.sync f64 + bulk async copies
     int solo_pb; // widest staged panel of a front that one CTA handles out of HBM (multiple of ASAM_PB)
@@ -386,6 +387,56 @@ __device__ __forceinline__ void trailing_update(double *C, int ld, const double 
                     const int i = irow[r], j = tj + q;
                     if (i <= m && j < jend && i >= j)
                         C[i + (size_t) j * ld] -= acc[r][q];
+                }
+        }
+    }
+}
+
+// D(8x8) += A(8x4, row) * B(4x8, col) on the FP64 tensor pipe.  Fragments: lane = 4*g + t holds A[g][t], B[t][g],
+// D[g][2t], D[g][2t+1].
+__device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, const double a, const double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// The same trailing update on the FP64 tensor pipe, for fronts and panels in SHARED memory (any pb >= 1: the
+// k dimension is padded with zeros in the fragments).  Work items are (8-column block, 32-row block) pairs of the
+// lower trapezoid, dealt round-robin to the warps; per 4 panel columns 4 + 1 fragment loads feed 4 tensor
+// instructions of 256 multiply-adds (trailing_update<2,8>: 10 loads per 512).  Rows beyond m and columns beyond
+// jend are masked in the loads (no out-of-range reads) and at the store.
+__device__ __forceinline__ void trailing_update_mma(double *C, const int ld, const double *P, const int ldp, const int pb,
+                                                    const int j0, const int jend, const int m)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    int pair = 0;
+    for (int jb = j0; jb < jend; jb += 8) {
+        for (int ib = jb; ib <= m; ib += 32, ++pair) {
+            if (pair % nwarps != warp)
+                continue;
+            double acc[4][2];
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++)
+                acc[mt][0] = acc[mt][1] = 0.0;
+            const bool jok = jb + g < jend;
+            for (int kk = 0; kk < pb; kk += 4) {
+                const bool kok = kk + t < pb;
+                const size_t koff = (size_t) (kk + t) * ldp;
+                const double bv = (kok && jok) ? P[(jb + g) + koff] : 0.0;
+#pragma unroll
+                for (int mt = 0; mt < 4; mt++) {
+                    const int row = ib + 8 * mt + g;
+                    const double av = (kok && row <= m) ? -P[row + koff] : 0.0;
+                    dmma_8x8x4(acc[mt][0], acc[mt][1], av, bv);
+                }
+            }
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int i = ib + 8 * mt + g, j = jb + 2 * t + e;
+                    if (i <= m && j < jend && i >= j)
+                        C[i + (size_t) j * ld] += acc[mt][e];
                 }
         }
     }
@@ -518,11 +569,6 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
-}
-
-__device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, const double a, const double b)
-{
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
 // C[rb0.., cb0..] -= L[rb0.., k0..k0+pb) * L[cb0.., k0..k0+pb)'  (lower trapezoid of the front only) on the
@@ -1650,7 +1696,10 @@ __device__ bool cta_front(const FacArgs &a, const int t, const int s, const int 
                     nc[m] = oc[m_old];
             }
             __syncthreads();
-            trailing_update<2, 8>(F, ld, F, ld, keep, keep, m, m);
+            if (a.smem_mma)
+                trailing_update_mma(F, ld, F, ld, keep, keep, m, m);
+            else
+                trailing_update<2, 8>(F, ld, F, ld, keep, keep, m, m);
             __syncthreads();
             kstart = keep;
         }
@@ -1668,7 +1717,9 @@ __device__ bool cta_front(const FacArgs &a, const int t, const int s, const int 
                 accA += tb - ta;
             }
             const int n = m - (k0 + pb);
-            if (n > 48)
+            if (a.smem_mma && n > 0)
+                trailing_update_mma(F, ld, P, ld, pb, k0 + pb, m, m);
+            else if (n > 48)
                 trailing_update<2, 8>(F, ld, P, ld, pb, k0 + pb, m, m);
             else
                 trailing_update<1, 4>(F, ld, P, ld, pb, k0 + pb, m, m);
