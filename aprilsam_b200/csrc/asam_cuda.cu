@@ -119,7 +119,7 @@ struct asam_dev {
     int step_seq = 0;  // sequence number of the last k_step launch (completion flag in pin_down)
     int tile_mode = 3; // ASAM_TILE_MODE (team path tiles): 0 DFMA, 1 mma.sync f64, 2 + bulk async copy per panel column,
                        // 3 mma.sync f64, operands by rows from the panel workspace (two bulk copies per tile), fused crew items
-    int smem_mma = 1;  // ASAM_SMEM_MMA=0: DFMA trailing update for shared-memory fronts (A/B)
+    int smem_mma = 1;  // ASAM_SMEM_MMA: 0 DFMA only, 1 tensor pipe for the kept-columns update, 2 for every panel update
     int staged = 1;    // ASAM_STAGED=0: tile mode 3 publishes the diagonal block at once (A/B)
     int solo_pb = 48;  // ASAM_SOLO_PB: staged panel width of single-CTA fronts that live in HBM
     int small_ok = 1;  // ASAM_SMALL_STEP=0 disables the fused small-step kernel (A/B measurements)
@@ -589,7 +589,7 @@ ASAM_EXPORT int asam_dev_create(asam_dev_t **out)
     if (getenv("ASAM_SOLO_PB") && atoi(getenv("ASAM_SOLO_PB")) >= 12)
         d->solo_pb = atoi(getenv("ASAM_SOLO_PB")) / 12 * 12;
     if (getenv("ASAM_SMEM_MMA"))
-        d->smem_mma = atoi(getenv("ASAM_SMEM_MMA")) != 0;
+        d->smem_mma = atoi(getenv("ASAM_SMEM_MMA"));
     if (getenv("ASAM_STAGED"))
         d->staged = atoi(getenv("ASAM_STAGED")) != 0;
     if (getenv("ASAM_KEEP"))

@@ -328,7 +328,8 @@ struct FacArgs {
     int smem_doubles;
     long long spin_limit;
     unsigned long long *trace; // optional: 8 words per task
-    int smem_mma;  // trailing update of shared-memory fronts on the FP64 tensor pipe (0: DFMA, A/B)
+    int smem_mma;  // shared-memory fronts on the FP64 tensor pipe: 1 = the one wide update of kept columns (incremental
+                   // steps: k_step's factor phase 17.6 -> 15.0 us), 2 = also the 12-column panel updates, 0 = DFMA only
     int staged;    // tile mode 3: publish L11 in 12-column stages (0: all at once)
     int tile_mode; // trailing-update tiles of the team path: 0 DFMA, 1 mma.sync f64, 2 mma.sync f64 + bulk async copies
     int solo_pb; // widest staged panel of a front that one CTA handles out of HBM (multiple of ASAM_PB)
@@ -1717,7 +1718,7 @@ __device__ bool cta_front(const FacArgs &a, const int t, const int s, const int 
                 accA += tb - ta;
             }
             const int n = m - (k0 + pb);
-            if (a.smem_mma && n > 0)
+            if (a.smem_mma >= 2 && n > 0) // (measured: 12-column panels are faster on the DFMA tiles -- M3500 0.435 vs 0.459 ms)
                 trailing_update_mma(F, ld, P, ld, pb, k0 + pb, m, m);
             else if (n > 48)
                 trailing_update<2, 8>(F, ld, P, ld, pb, k0 + pb, m, m);
