@@ -1021,6 +1021,7 @@ static int g_world = 1, g_rank = 0, g_sharding = 0;
 #define ASAM_NCCL_FLOAT64 8
 #define ASAM_NCCL_INT32 2
 #define ASAM_NCCL_SUM 0
+#define ASAM_NCCL_MAX 2
 
 #define NCK(call)                                                                                  \
     do {                                                                                           \
@@ -1202,6 +1203,30 @@ static int shard_exchange(asam_dev *d, int which)
     return 0;
 }
 
+// Sharded solves: a pivot that fails in one rank's shard must fail the solve on EVERY rank (each rank owns a copy of
+// the caller's graph and takes the same action): ctrl[7] = "my status word is non-zero", all-reduced (max); a rank
+// whose own word is clean takes ASAM_STATUS_REMOTE.
+__global__ void k_status_flag(int *ctrl, int phase)
+{
+    if (phase == 0)
+        ctrl[7] = ctrl[1] != 0;
+    else if (ctrl[7] != 0 && ctrl[1] == 0)
+        ctrl[1] = ASAM_STATUS_REMOTE;
+}
+
+static int shard_status_agree(asam_dev *d)
+{
+    if (!d->sharded)
+        return 0;
+    int *ctrl = (int *) d->ctrl.p;
+    k_status_flag<<<1, 1, 0, d->stream>>>(ctrl, 0);
+    NCK(g_nccl.AllReduce(ctrl + 7, ctrl + 7, 1, ASAM_NCCL_INT32, ASAM_NCCL_MAX, g_comm, d->stream));
+    k_status_flag<<<1, 1, 0, d->stream>>>(ctrl, 1);
+    CK(cudaGetLastError());
+    d->n_launch += 3;
+    return 0;
+}
+
 ASAM_EXPORT int asam_factor_full(asam_dev_t *d)
 {
     CK(cudaSetDevice(d->device));
@@ -1260,6 +1285,8 @@ ASAM_EXPORT int asam_backsolve_full(asam_dev_t *d)
         if (d->defer)
             return set_err("sharded asam_backsolve_full inside asam_step_begin/asam_step_run");
         rc = shard_exchange(d, 1); // every rank ends up with the whole solution
+        if (!rc)
+            rc = shard_status_agree(d);
     }
     return rc;
 }

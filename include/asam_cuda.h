@@ -173,7 +173,9 @@ int asam_download_x_status(asam_dev_t *d, int q_first, int q_count, double *x3, 
 int asam_chi2(asam_dev_t *d, int n_factors, double *chi2_out);
 
 /* Status of the last factorisation: 0 ok, >0 = 1 + supernode id with a non-positive pivot,
- * <0 = internal dependency timeout. */
+ * <0 = internal dependency timeout; ASAM_STATUS_REMOTE = another rank of a sharded solve failed (the ranks agree
+ * on failure before the status is read, so that all of them take the same action). */
+#define ASAM_STATUS_REMOTE (-(1 << 28))
 int asam_factor_status(asam_dev_t *d, int *status_out);
 
 /* Debug / test access (not used on the solve path). */
