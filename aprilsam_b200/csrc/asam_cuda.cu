@@ -119,6 +119,7 @@ struct asam_dev {
     int step_seq = 0;  // sequence number of the last k_step launch (completion flag in pin_down)
     int tile_mode = 3; // ASAM_TILE_MODE (team path tiles): 0 DFMA, 1 mma.sync f64, 2 + bulk async copy per panel column,
                        // 3 mma.sync f64, operands by rows from the panel workspace (two bulk copies per tile), fused crew items
+    int pb_smem = 12;  // ASAM_PB_SMEM: panel width of shared-memory fronts
     int smem_mma = 1;  // ASAM_SMEM_MMA: 0 DFMA only, 1 tensor pipe for the kept-columns update, 2 for every panel update
     int staged = 1;    // ASAM_STAGED=0: tile mode 3 publishes the diagonal block at once (A/B)
     int solo_pb = 48;  // ASAM_SOLO_PB: staged panel width of single-CTA fronts that live in HBM
@@ -588,6 +589,8 @@ ASAM_EXPORT int asam_dev_create(asam_dev_t **out)
     CK(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, d->fac_smem));
     if (getenv("ASAM_SOLO_PB") && atoi(getenv("ASAM_SOLO_PB")) >= 12)
         d->solo_pb = atoi(getenv("ASAM_SOLO_PB")) / 12 * 12;
+    if (getenv("ASAM_PB_SMEM") && atoi(getenv("ASAM_PB_SMEM")) >= 3)
+        d->pb_smem = atoi(getenv("ASAM_PB_SMEM")) / 3 * 3;
     if (getenv("ASAM_SMEM_MMA"))
         d->smem_mma = atoi(getenv("ASAM_SMEM_MMA"));
     if (getenv("ASAM_STAGED"))
@@ -869,6 +872,7 @@ static int launch_factor(asam_dev *d, int ntasks, const int *tasks_dev, const in
     a.tile_mode = d->tile_mode;
     a.staged = d->staged;
     a.smem_mma = d->smem_mma;
+    a.pb_smem = d->pb_smem;
     a.trace = nullptr;
     if (d->trace_on) {
         if (buf_reserve(d, d->trace_fac, (size_t) ntasks * 8 * sizeof(unsigned long long), false, false))

@@ -328,6 +328,7 @@ struct FacArgs {
     int smem_doubles;
     long long spin_limit;
     unsigned long long *trace; // optional: 8 words per task
+    int pb_smem;   // panel width of shared-memory fronts (multiple of 3)
     int smem_mma;  // shared-memory fronts on the FP64 tensor pipe: 1 = the one wide update of kept columns (incremental
                    // steps: k_step's factor phase 17.6 -> 15.0 us), 2 = also the 12-column panel updates, 0 = DFMA only
     int staged;    // tile mode 3: publish L11 in 12-column stages (0: all at once)
@@ -345,10 +346,11 @@ struct FacArgs {
 // pipe, the limiter (2R + TN wavefronts feed R*TN warp-wide DFMAs per panel column).
 // Out-of-range rows/columns are clamped for the loads and masked at the store.
 template <int R, int TN>
-__device__ __forceinline__ void trailing_update(double *C, int ld, const double *P, int ldp, int pb, int j0, int jend, int m)
+__device__ __forceinline__ void trailing_update(double *C, int ld, const double *P, int ldp, int pb, int j0, int jend, int m,
+                                                const int sub_warps = 0)
 {
-    // columns [j0, jend) (jend <= m), rows [j, m]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    // columns [j0, jend) (jend <= m), rows [j, m]; sub_warps > 0: only that many warps take part
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = sub_warps ? sub_warps : (blockDim.x >> 5);
     for (int tj = j0 + TN * warp; tj < jend; tj += TN * nwarps) {
         int jc[TN];
 #pragma unroll
@@ -453,14 +455,26 @@ __device__ __forceinline__ void trailing_update_mma(double *C, const int ld, con
 // row TRSM (each thread owns rows) and the rank-3 update of the remaining panel columns.
 // Two block barriers per 3 columns; the code stays small (this kernel executes straight-line
 // code once per task, so instruction-cache footprint matters more than unrolling).
+// sub_nt > 0: only the first sub_nt threads of the CTA take part (they synchronise on named barrier 1; the
+// others must not call): a 48 x 48 block has work for two warps, and a barrier of two warps is far cheaper than one
+// of eight -- there are 9 of them per 12 columns on the dependent chain of every panel.
+__device__ __forceinline__ void bar_sub(const int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
+
 __device__ __forceinline__ void panel_factor(double *P, int ldp, int k0, int pb, int m, int sn_id, int *err,
-                                             double *dinv_out)
+                                             double *dinv_out, const int sub_nt = 0)
 {
-    const int tid = threadIdx.x, nt = blockDim.x;
+    const int tid = threadIdx.x, nt = sub_nt ? sub_nt : blockDim.x;
+#define PF_SYNC()            \
+    do {                     \
+        if (sub_nt)          \
+            bar_sub(sub_nt); \
+        else                 \
+            __syncthreads(); \
+    } while (0)
     for (int c0 = 0; c0 < pb; c0 += 3) {
         const int rb = k0 + c0; // front row of this 3x3 diagonal block
         double *p0 = P + (size_t) c0 * ldp, *p1 = p0 + ldp, *p2 = p1 + ldp;
-        __syncthreads(); // previous in-panel update (or trailing update) is complete
+        PF_SYNC(); // previous in-panel update (or trailing update) is complete
         const double a00 = p0[rb], a10 = p0[rb + 1], a20 = p0[rb + 2];
         const double a11 = p1[rb + 1], a21 = p1[rb + 2], a22 = p2[rb + 2];
         const double r0 = d_rsqrt(a00);
@@ -482,7 +496,7 @@ __device__ __forceinline__ void panel_factor(double *P, int ldp, int k0, int pb,
             p1[i] = x1;
             p2[i] = x2;
         }
-        __syncthreads(); // every thread has read the diagonal block; L rows are visible
+        PF_SYNC(); // every thread has read the diagonal block; L rows are visible
         if (tid == 0) {
             p0[rb] = a00 * r0; p0[rb + 1] = l10; p0[rb + 2] = l20;
             p1[rb + 1] = d1 * r1; p1[rb + 2] = l21;
@@ -505,7 +519,8 @@ __device__ __forceinline__ void panel_factor(double *P, int ldp, int k0, int pb,
             }
         }
     }
-    __syncthreads();
+    PF_SYNC();
+#undef PF_SYNC
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1262,30 +1277,36 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
             // and go to the front + the flag (8 * seq + stage); the crew solves the matching 12 columns of its rows
             // while the next sub-panel is being factored, instead of starting when all 48 are done
             constexpr int LDD = ASAM_TPB;
+            constexpr int SUB = 64; // two warps factor the block; the other six wait at the barrier below
             int stage = 0;
-            for (int k1 = 0; k1 < pb; k1 += ASAM_PB) {
-                const int pbb = min(ASAM_PB, pb - k1);
-                panel_factor(D + (size_t) k1 * LDD, LDD, k1, pbb, pb - 1, s, err, rdv);
-                ++stage;
-                if (a.staged) {
-                    for (int e = tid; e < pbb * pb; e += nt) {
-                        const int j = k1 + e / pb, i = e % pb;
-                        if (i >= j)
-                            F[(k0 + i) + (size_t) (k0 + j) * ld] = D[i + j * LDD];
+            if (tid < SUB) {
+                for (int k1 = 0; k1 < pb; k1 += ASAM_PB) {
+                    const int pbb = min(ASAM_PB, pb - k1);
+                    panel_factor(D + (size_t) k1 * LDD, LDD, k1, pbb, pb - 1, s, err, rdv, SUB);
+                    ++stage;
+                    if (a.staged) {
+                        for (int e = tid; e < pbb * pb; e += SUB) {
+                            const int j = k1 + e / pb, i = e % pb;
+                            if (i >= j)
+                                F[(k0 + i) + (size_t) (k0 + j) * ld] = D[i + j * LDD];
+                        }
+                        for (int e = tid; e < pbb; e += SUB)
+                            dinv[k0 + k1 + e] = rdv[k1 + e];
+                        bar_sub(SUB);
+                        if (tid == 0) {
+                            __threadfence();
+                            atomicExch(crew_bar, 8 * seq + stage);
+                        }
                     }
-                    for (int e = tid; e < pbb; e += nt)
-                        dinv[k0 + k1 + e] = rdv[k1 + e];
-                    __syncthreads();
-                    if (tid == 0) {
-                        __threadfence();
-                        atomicExch(crew_bar, 8 * seq + stage);
+                    if (k1 + pbb < pb) {
+                        trailing_update<1, 4>(D, LDD, D + (size_t) k1 * LDD, LDD, pbb, k1 + pbb, pb, pb - 1, SUB / 32);
+                        bar_sub(SUB);
                     }
                 }
-                if (k1 + pbb < pb) {
-                    trailing_update<1, 4>(D, LDD, D + (size_t) k1 * LDD, LDD, pbb, k1 + pbb, pb, pb - 1);
-                    __syncthreads();
-                }
+            } else {
+                stage = (pb + ASAM_PB - 1) / ASAM_PB;
             }
+            __syncthreads();
             if (!a.staged) { // (ASAM_STAGED=0, A/B: everything at once, as before)
                 writeback(k0, pb);
                 __syncthreads();
@@ -1706,8 +1727,9 @@ __device__ bool cta_front(const FacArgs &a, const int t, const int s, const int 
         }
     }
     if (use_sm) {
-        for (int k0 = kstart; k0 < c; k0 += ASAM_PB) {
-            const int pb = min(ASAM_PB, c - k0);
+        const int pbw = a.pb_smem; // panel width of shared-memory fronts (12; ASAM_PB_SMEM=24 for A/B)
+        for (int k0 = kstart; k0 < c; k0 += pbw) {
+            const int pb = min(pbw, c - k0);
             double *P = F + (size_t) k0 * ld; // panel columns live inside the front
             unsigned long long ta = 0, tb = 0;
             if (a.trace && tid == 0)
