@@ -913,17 +913,22 @@ __device__ __forceinline__ void diag_factor(double *D, int pb, double *rdv, int 
 // Same result, right-looking and blocked: 12-column sub-panels of closed-form 3x3 steps (panel_factor: every
 // thread of the CTA takes part in the row solves and the in-panel rank-3 updates) followed by a register-tiled
 // update of the rest of the block -- no dot products of growing length on the dependent chain.
+// Ends with a CTA-wide barrier.
 __device__ __forceinline__ void diag_factor_rl(double *D, int pb, double *rdv, int sn_id, int *err)
 {
     constexpr int LDD = ASAM_TPB;
-    for (int k1 = 0; k1 < pb; k1 += ASAM_PB) {
-        const int pbb = min(ASAM_PB, pb - k1);
-        panel_factor(D + (size_t) k1 * LDD, LDD, k1, pbb, pb - 1, sn_id, err, rdv);
-        if (k1 + pbb < pb) {
-            trailing_update<1, 4>(D, LDD, D + (size_t) k1 * LDD, LDD, pbb, k1 + pbb, pb, pb - 1);
-            __syncthreads();
+    constexpr int SUB = 256; // (64 = two warps on a named barrier was measured slower, see diag_publish)
+    if (threadIdx.x < SUB) {
+        for (int k1 = 0; k1 < pb; k1 += ASAM_PB) {
+            const int pbb = min(ASAM_PB, pb - k1);
+            panel_factor(D + (size_t) k1 * LDD, LDD, k1, pbb, pb - 1, sn_id, err, rdv, SUB);
+            if (k1 + pbb < pb) {
+                trailing_update<1, 4>(D, LDD, D + (size_t) k1 * LDD, LDD, pbb, k1 + pbb, pb, pb - 1, SUB / 32);
+                bar_sub(SUB);
+            }
         }
     }
+    __syncthreads();
 }
 
 // One row of the panel per thread: x = row * L11^-T.  The row lives in Li (column p at
@@ -1277,7 +1282,8 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
             // and go to the front + the flag (8 * seq + stage); the crew solves the matching 12 columns of its rows
             // while the next sub-panel is being factored, instead of starting when all 48 are done
             constexpr int LDD = ASAM_TPB;
-            constexpr int SUB = 64; // two warps factor the block; the other six wait at the barrier below
+            constexpr int SUB = 256; // threads that factor the block (measured: 64 threads on a two-warp barrier are SLOWER,
+                                     // 20.3 vs 15.7 us per block: the publish / update loops want the threads more than the barriers cost)
             int stage = 0;
             if (tid < SUB) {
                 for (int k1 = 0; k1 < pb; k1 += ASAM_PB) {
