@@ -78,8 +78,7 @@ struct asam_dev {
     Buf tasks_full, nwait_full, btasks_full;
     int ntasks_full = 0;
     Buf leaf_tasks; // supernodes handled by k_factor_leaf before k_factor (batch solves of large graphs)
-    int n_leaf = 0, n_leaf_tiny = 0; // the first n_leaf_tiny entries: order <= ASAM_LEAF_TINY_M, downward closed
-    int leaft_grid = 0, leaft_smem = 0;
+    int n_leaf = 0;
     int leaf_grid = 0, leaf_smem = 0;
     int bt_nleaf = 0; // the last bt_nleaf entries of btasks_full are back-solved by k_backsolve_leaf
     // multi-GPU shard schedule (asam_set_shard_schedule)
@@ -346,24 +345,10 @@ static int run_factor(asam_dev *d, const FacArgs &a, int grid, int with_leaves =
         l.ntasks = d->n_leaf;
         l.ctrl = a.ctrl;
         l.spin_limit = a.spin_limit;
-        if (d->n_leaf_tiny > 0) { // the small ones first: twice the warps per SM
-            LeafArgs lt = l;
-            lt.ntasks = d->n_leaf_tiny;
-            const int want = (lt.ntasks + ASAM_LEAF_TINY_WARPS - 1) / ASAM_LEAF_TINY_WARPS;
-            k_factor_leaf<ASAM_LEAF_TINY_M, ASAM_LEAF_TINY_WARPS>
-                <<<want < d->leaft_grid ? want : d->leaft_grid, 32 * ASAM_LEAF_TINY_WARPS, d->leaft_smem, d->stream>>>(lt);
-            d->n_launch++;
-            CK(cudaGetLastError());
-        }
-        if (d->n_leaf > d->n_leaf_tiny) {
-            l.tasks += d->n_leaf_tiny;
-            l.ntasks = d->n_leaf - d->n_leaf_tiny;
-            const int want = (l.ntasks + ASAM_LEAF_WARPS - 1) / ASAM_LEAF_WARPS;
-            k_factor_leaf<ASAM_LEAF_M, ASAM_LEAF_WARPS>
-                <<<want < d->leaf_grid ? want : d->leaf_grid, 32 * ASAM_LEAF_WARPS, d->leaf_smem, d->stream>>>(l);
-            d->n_launch++;
-            CK(cudaGetLastError());
-        }
+        const int want = (d->n_leaf + ASAM_LEAF_WARPS - 1) / ASAM_LEAF_WARPS;
+        k_factor_leaf<<<want < d->leaf_grid ? want : d->leaf_grid, 32 * ASAM_LEAF_WARPS, d->leaf_smem, d->stream>>>(l);
+        d->n_launch++;
+        CK(cudaGetLastError());
     }
     if (grid > 0) {
         k_factor<<<grid, d->fac_threads, d->fac_smem, d->stream>>>(a);
@@ -580,20 +565,11 @@ ASAM_EXPORT int asam_dev_create(asam_dev_t **out)
     d->fac_grid = occ * d->n_sm;
 
     d->leaf_smem = ASAM_LEAF_WARPS * ASAM_LEAF_STRIDE * (int) sizeof(double);
-    CK(cudaFuncSetAttribute(k_factor_leaf<ASAM_LEAF_M, ASAM_LEAF_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, d->leaf_smem));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_factor_leaf<ASAM_LEAF_M, ASAM_LEAF_WARPS>, 32 * ASAM_LEAF_WARPS,
-                                                     d->leaf_smem));
+    CK(cudaFuncSetAttribute(k_factor_leaf, cudaFuncAttributeMaxDynamicSharedMemorySize, d->leaf_smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_factor_leaf, 32 * ASAM_LEAF_WARPS, d->leaf_smem));
     if (occ < 1)
         return set_err("k_factor_leaf does not fit on an SM");
     d->leaf_grid = occ * d->n_sm;
-    d->leaft_smem = ASAM_LEAF_TINY_WARPS * ASAM_LEAF_STRIDE_OF(ASAM_LEAF_TINY_M) * (int) sizeof(double);
-    CK(cudaFuncSetAttribute(k_factor_leaf<ASAM_LEAF_TINY_M, ASAM_LEAF_TINY_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            d->leaft_smem));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_factor_leaf<ASAM_LEAF_TINY_M, ASAM_LEAF_TINY_WARPS>,
-                                                     32 * ASAM_LEAF_TINY_WARPS, d->leaft_smem));
-    if (occ < 1)
-        return set_err("k_factor_leaf (tiny) does not fit on an SM");
-    d->leaft_grid = occ * d->n_sm;
 
     d->bsl_smem = ASAM_BSL_WARPS * ASAM_BSL_STRIDE * (int) sizeof(double);
     CK(cudaFuncSetAttribute(k_backsolve_leaf, cudaFuncAttributeMaxDynamicSharedMemorySize, d->bsl_smem));
@@ -972,7 +948,6 @@ ASAM_EXPORT int asam_set_full_tasks(asam_dev_t *d, int ntasks, const int32_t *ta
         return 1;
     d->ntasks_full = ntasks;
     d->n_leaf = 0;
-    d->n_leaf_tiny = 0;
     d->bt_nleaf = 0;
     return 0;
 }
@@ -983,24 +958,12 @@ ASAM_EXPORT int asam_set_leaf_tasks(asam_dev_t *d, int n, const int32_t *tasks)
 {
     CK(cudaSetDevice(d->device));
     d->n_leaf = 0;
-    d->n_leaf_tiny = 0;
     if (n <= 0)
         return 0;
     if (buf_reserve(d, d->leaf_tasks, (size_t) n * sizeof(int), false, false) ||
         upload(d, d->leaf_tasks.p, tasks, (size_t) n * sizeof(int)))
         return 1;
     d->n_leaf = n;
-    d->n_leaf_tiny = 0;
-    return 0;
-}
-
-// The first n entries of the leaf list (asam_set_leaf_tasks) are fronts of order <= 30 whose descendants are in that
-// prefix too: they run through the instantiation of k_factor_leaf with twice the warps per SM.
-ASAM_EXPORT int asam_set_leaf_tiny_count(asam_dev_t *d, int n)
-{
-    if (n < 0 || n > d->n_leaf)
-        return set_err("asam_set_leaf_tiny_count: %d of %d", n, d->n_leaf);
-    d->n_leaf_tiny = getenv("ASAM_LEAF_TINY") && atoi(getenv("ASAM_LEAF_TINY")) == 0 ? 0 : n;
     return 0;
 }
 

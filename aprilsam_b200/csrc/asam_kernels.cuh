@@ -1896,13 +1896,7 @@ __global__ void __launch_bounds__(256, 1) k_factor(FacArgs a)
 // ------------------------------------------------------------------------------------------
 #define ASAM_LEAF_M 48
 #define ASAM_LEAF_WARPS 8
-// Most leaves are much smaller than 48 (100 k world: 71 % have order <= 30): the downward-closed set of those goes
-// through a second instantiation with a third of the shared memory per warp and twice the warps per SM -- a warp
-// spends its time waiting for L2 (descriptor, gather, children), so fronts in flight is what counts.
-#define ASAM_LEAF_TINY_M 30
-#define ASAM_LEAF_TINY_WARPS 16
-#define ASAM_LEAF_STRIDE_OF(LM) ((ASAM_LD(LM) * (LM) + (LM) / 2 + 3) & ~1) // doubles per warp (even)
-#define ASAM_LEAF_STRIDE ASAM_LEAF_STRIDE_OF(ASAM_LEAF_M)
+#define ASAM_LEAF_STRIDE (ASAM_LD(ASAM_LEAF_M) * ASAM_LEAF_M + ASAM_LEAF_M / 2 + 2) // doubles per warp (even)
 
 struct LeafArgs {
     const asam_sn_desc_t *sn;
@@ -1919,13 +1913,12 @@ struct LeafArgs {
     long long spin_limit;
 };
 
-template <int LM, int NW>
-__global__ void __launch_bounds__(32 * NW, 1) k_factor_leaf(LeafArgs a)
+__global__ void __launch_bounds__(32 * ASAM_LEAF_WARPS, 1) k_factor_leaf(LeafArgs a)
 {
     extern __shared__ __align__(16) double sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *F = sm + (size_t) warp * ASAM_LEAF_STRIDE_OF(LM);
-    int *dmap = (int *) (F + ASAM_LD(LM) * LM);
+    double *F = sm + (size_t) warp * ASAM_LEAF_STRIDE;
+    int *dmap = (int *) (F + ASAM_LD(ASAM_LEAF_M) * ASAM_LEAF_M);
     int *err = a.ctrl + 1;
     for (;;) {
         int t = 0;
@@ -1937,7 +1930,7 @@ __global__ void __launch_bounds__(32 * NW, 1) k_factor_leaf(LeafArgs a)
         const int s = a.tasks[t];
         const asam_sn_desc_t d = a.sn[s];
         const int m = 3 * d.mb, c = 3 * d.cb, ld = ASAM_LD(m);
-        if (m > LM) { // host error
+        if (m > ASAM_LEAF_M) { // host error
             if (lane == 0)
                 atomicCAS(err, 0, -(1 + s));
             break;

@@ -103,7 +103,6 @@ typedef struct {
     int ntasks;
     int *leaf_tasks; /* supernodes factored by k_factor_leaf before `tasks` (large graphs only) */
     int n_leaf;
-    int n_leaf_tiny; /* the first n_leaf_tiny of them: order <= 30, downward closed */
     int n_btasks;    /* entries of btasks (>= the supernodes in it: wide supernodes have one entry per 96-column block) */
     int bt_split;    /* btasks holds per-block entries (batch schedule only; undone by the first plan_append) */
     char *bs_leaf;   /* per supernode: back-solved by k_backsolve_leaf (last n_bs_leaf entries of btasks) */

@@ -857,18 +857,7 @@ static void build_schedule(plan_t *pl)
     pl->ntasks = (int) n_local;
     pl->tasks = malloc(sizeof(int) * (size_t) (n_local + 1));
     pl->nwait = malloc(sizeof(int) * (size_t) (n_local + 1));
-    /* tiny leaves (order <= 30, all descendants tiny): listed first, factored by the wide-occupancy instantiation */
-    char *tiny = calloc((size_t) nsn + 1, 1);
-    int n_leaf_tiny = 0;
-    for (int s = 0; s < nsn; s++) {
-        int ok = leaf[s] && owner[s] == me && 3 * pl->desc[s].mb <= 30;
-        for (int c = 0; ok && c < pl->snh[s].children.n; c++)
-            ok = tiny[pl->snh[s].children.p[c]];
-        tiny[s] = (char) ok;
-        n_leaf_tiny += ok;
-    }
     pl->n_leaf = n_leaf;
-    pl->n_leaf_tiny = n_leaf_tiny;
     pl->leaf_tasks = malloc(sizeof(int) * (size_t) (n_leaf + 1));
     pl->n_top = (int) n_top;
     pl->n_top_sn = n_top_sn;
@@ -878,7 +867,7 @@ static void build_schedule(plan_t *pl)
     pl->n_btasks = n_top_bt + n_main_sn + n_bsl;
     pl->btasks = malloc(sizeof(int) * (size_t) (pl->n_btasks + 1));
     /* back-solve list, parents first: [top | own shards outside the back-solve leaf set | that set] */
-    int t = 0, tl = 0, tt = 0, tlt = 0;
+    int t = 0, tl = 0, tt = 0;
     int bt = n_top_bt - 1, bm = n_top_bt + n_main_sn - 1, bl = pl->n_btasks - 1;
     for (int k = 0; k < nsn; k++) { /* back-solve entries, filled backwards: parents first */
         int s = bylv[k];
@@ -914,10 +903,7 @@ static void build_schedule(plan_t *pl)
         if (owner[s] != me)
             continue;
         if (leaf[s]) {
-            if (tiny[s])
-                pl->leaf_tasks[tlt++] = s; /* prefix: the tiny ones */
-            else
-                pl->leaf_tasks[n_leaf_tiny + tl++] = s;
+            pl->leaf_tasks[tl++] = s;
             continue;
         }
         /* nwait counts ALL children: those of the leaf set arrived in the earlier launch */
@@ -928,7 +914,6 @@ static void build_schedule(plan_t *pl)
         }
     }
 #undef BS_NBLK
-    free(tiny);
     free(G_of);
     free(byl);
     free(bylv);
@@ -1146,11 +1131,6 @@ static int plan_build_impl(plan_t *pl, asam_dev_t *dev, int N, int n_factors, co
      * child's structure is the node's structure plus itself (fundamental), or misses at most
      * RELAX_Z block rows of it (relaxed amalgamation: a few explicit zero blocks buy fewer, fatter
      * fronts and a shorter dependency chain); width capped at MAX_SN_COLS. */
-    int relax_z = RELAX_Z, relax_fill = RELAX_FILL; /* ASAM_RELAX_Z / ASAM_RELAX_FILL override (tuning) */
-    if (getenv("ASAM_RELAX_Z"))
-        relax_z = atoi(getenv("ASAM_RELAX_Z"));
-    if (getenv("ASAM_RELAX_FILL"))
-        relax_fill = atoi(getenv("ASAM_RELAX_FILL"));
     pl->nsn = 0;
     pl->nnz_l_blocks = 0;
     pl->flops = 0.0;
@@ -1169,7 +1149,7 @@ static int plan_build_impl(plan_t *pl, asam_dev_t *dev, int N, int n_factors, co
             int z = nb + 1 - nbp; /* block rows of {p} + below(p) missing from below(pp); >= 0 */
             int gcb = pl->desc[pl->nsn - 1].cb;
             if (parent[pp] == p && gcb < MAX_SN_COLS &&
-                (z == 0 || (z <= relax_z && (int64_t) z * gcb <= relax_fill)))
+                (z == 0 || (z <= RELAX_Z && (int64_t) z * gcb <= RELAX_FILL)))
                 merge = 1;
             /* a fundamental chain whose front is processed by a CTA team anyway (it does not fit
              * in shared memory) is not capped: splitting it only adds levels and one full copy of
@@ -1297,7 +1277,6 @@ static int plan_build_impl(plan_t *pl, asam_dev_t *dev, int N, int n_factors, co
     rc |= asam_upload_fslot(dev, 0, n_factors, pl->fslot);
     rc |= asam_set_full_tasks(dev, pl->ntasks, pl->tasks, pl->nwait, pl->n_btasks, pl->btasks);
     rc |= asam_set_leaf_tasks(dev, pl->n_leaf, pl->leaf_tasks);
-    rc |= asam_set_leaf_tiny_count(dev, pl->n_leaf_tiny);
     rc |= asam_set_bs_leaf_count(dev, pl->n_bs_leaf);
     if (pl->world > 1) {
         asam_shard_sched_t sh;

@@ -101,8 +101,6 @@ int asam_set_full_tasks(asam_dev_t *d, int ntasks, const int32_t *tasks, const i
  * subtree is of that kind are factored by a warp-per-front kernel launched right before the list
  * above by asam_factor_full.  Call after asam_set_full_tasks; n = 0 disables. */
 int asam_set_leaf_tasks(asam_dev_t *d, int n, const int32_t *tasks);
-/* the first n of them: order <= 30 and downward closed (run with twice the warps per SM) */
-int asam_set_leaf_tiny_count(asam_dev_t *d, int n);
 /* Back-substitution: the LAST n entries of the btasks list given to asam_set_full_tasks (a
  * downward-closed set of supernodes with <= 64 own columns and <= 64 rows below, parents first) are
  * solved by a warp-per-supernode kernel right after k_backsolve has done the rest.  n = 0: the whole
