@@ -1131,6 +1131,11 @@ static int plan_build_impl(plan_t *pl, asam_dev_t *dev, int N, int n_factors, co
      * child's structure is the node's structure plus itself (fundamental), or misses at most
      * RELAX_Z block rows of it (relaxed amalgamation: a few explicit zero blocks buy fewer, fatter
      * fronts and a shorter dependency chain); width capped at MAX_SN_COLS. */
+    int relax_z = RELAX_Z, relax_fill = RELAX_FILL; /* ASAM_RELAX_Z / ASAM_RELAX_FILL override (tuning) */
+    if (getenv("ASAM_RELAX_Z"))
+        relax_z = atoi(getenv("ASAM_RELAX_Z"));
+    if (getenv("ASAM_RELAX_FILL"))
+        relax_fill = atoi(getenv("ASAM_RELAX_FILL"));
     pl->nsn = 0;
     pl->nnz_l_blocks = 0;
     pl->flops = 0.0;
@@ -1149,7 +1154,7 @@ static int plan_build_impl(plan_t *pl, asam_dev_t *dev, int N, int n_factors, co
             int z = nb + 1 - nbp; /* block rows of {p} + below(p) missing from below(pp); >= 0 */
             int gcb = pl->desc[pl->nsn - 1].cb;
             if (parent[pp] == p && gcb < MAX_SN_COLS &&
-                (z == 0 || (z <= RELAX_Z && (int64_t) z * gcb <= RELAX_FILL)))
+                (z == 0 || (z <= relax_z && (int64_t) z * gcb <= relax_fill)))
                 merge = 1;
             /* a fundamental chain whose front is processed by a CTA team anyway (it does not fit
              * in shared memory) is not capped: splitting it only adds levels and one full copy of
