@@ -460,6 +460,8 @@ __device__ __forceinline__ void trailing_update_mma(double *C, const int ld, con
 // of eight -- there are 9 of them per 12 columns on the dependent chain of every panel.
 __device__ __forceinline__ void bar_sub(const int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 
+__device__ int g_pf_groups = 1; // ASAM_PF_GROUPS=0: one thread per row in the in-panel update of panel_factor (A/B)
+
 __device__ __forceinline__ void panel_factor(double *P, int ldp, int k0, int pb, int m, int sn_id, int *err,
                                              double *dinv_out, const int sub_nt = 0)
 {
@@ -507,14 +509,33 @@ __device__ __forceinline__ void panel_factor(double *P, int ldp, int k0, int pb,
         }
         // rank-3 update of the remaining panel columns jc in (c0+2, pb): rows i >= k0 + jc
         const int nrem = pb - (c0 + 3);
-        if (nrem > 0) {
-            for (int i = i_first; i <= m; i += nt) {
-                const double x0 = p0[i], x1 = p1[i], x2 = p2[i];
-                const int jmax = min(nrem, i - (rb + 3) + 1); // columns whose diagonal row <= i
-                for (int jj = 0; jj < jmax; jj++) {
-                    const int jr = rb + 3 + jj; // front row (= column) of panel column c0+3+jj
-                    double *pj = P + (size_t) (c0 + 3 + jj) * ldp;
-                    pj[i] -= x0 * p0[jr] + x1 * p1[jr] + x2 * p2[jr];
+        const int nrow = m - (rb + 3) + 1; // rows below the 3x3 block (the rhs row included)
+        if (nrem > 0 && nrow > 0) {
+            // fewer rows than threads (diagonal blocks of team fronts, small fronts): the spare threads share the
+            // columns of a row -- thread = (row, column group) -- instead of one thread walking all <= 9 of them
+            int ng = g_pf_groups ? nt / nrow : 1;
+            ng = ng > nrem ? nrem : ng;
+            if (ng > 1) {
+                const int gi = tid / nrow, ri = tid - gi * nrow;
+                if (gi < ng) {
+                    const int i = rb + 3 + ri;
+                    const double x0 = p0[i], x1 = p1[i], x2 = p2[i];
+                    const int jmax = min(nrem, ri + 1);
+                    for (int jj = gi; jj < jmax; jj += ng) {
+                        const int jr = rb + 3 + jj;
+                        double *pj = P + (size_t) (c0 + 3 + jj) * ldp;
+                        pj[i] -= x0 * p0[jr] + x1 * p1[jr] + x2 * p2[jr];
+                    }
+                }
+            } else {
+                for (int i = i_first; i <= m; i += nt) {
+                    const double x0 = p0[i], x1 = p1[i], x2 = p2[i];
+                    const int jmax = min(nrem, i - (rb + 3) + 1); // columns whose diagonal row <= i
+                    for (int jj = 0; jj < jmax; jj++) {
+                        const int jr = rb + 3 + jj; // front row (= column) of panel column c0+3+jj
+                        double *pj = P + (size_t) (c0 + 3 + jj) * ldp;
+                        pj[i] -= x0 * p0[jr] + x1 * p1[jr] + x2 * p2[jr];
+                    }
                 }
             }
         }
@@ -1285,6 +1306,45 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
             constexpr int SUB = 256; // threads that factor the block (measured: 64 threads on a two-warp barrier are SLOWER,
                                      // 20.3 vs 15.7 us per block: the publish / update loops want the threads more than the barriers cost)
             int stage = 0;
+            if (a.staged >= 2 && nt == 256) {
+                // warps 0-6 factor; WARP 7 PUBLISHES: it picks every finished sub-panel up on a named barrier of its
+                // own (2 + stage: the factoring warps only arrive, they never wait for it) and does the stores to the
+                // front, the fence and the flag while the others are already in the next sub-panel -- the ~1 us of
+                // stores + membar per stage leave the dependent chain of the diagonal block
+                constexpr int NCW = 7, CT = 32 * NCW;
+                if (warp < NCW) {
+                    for (int k1 = 0; k1 < pb; k1 += ASAM_PB) {
+                        const int pbb = min(ASAM_PB, pb - k1);
+                        panel_factor(D + (size_t) k1 * LDD, LDD, k1, pbb, pb - 1, s, err, rdv, CT);
+                        asm volatile("bar.arrive %0, 256;" ::"r"(2 + stage) : "memory");
+                        ++stage;
+                        if (k1 + pbb < pb) {
+                            trailing_update<1, 4>(D, LDD, D + (size_t) k1 * LDD, LDD, pbb, k1 + pbb, pb, pb - 1, NCW);
+                            bar_sub(CT);
+                        }
+                    }
+                } else {
+                    for (int k1 = 0; k1 < pb; k1 += ASAM_PB) {
+                        const int pbb = min(ASAM_PB, pb - k1);
+                        asm volatile("bar.sync %0, 256;" ::"r"(2 + stage) : "memory");
+                        ++stage;
+                        for (int e = lane; e < pbb * pb; e += 32) {
+                            const int j = k1 + e / pb, i = e % pb;
+                            if (i >= j)
+                                F[(k0 + i) + (size_t) (k0 + j) * ld] = D[i + j * LDD];
+                        }
+                        if (lane < pbb)
+                            dinv[k0 + k1 + lane] = rdv[k1 + lane];
+                        __syncwarp();
+                        if (lane == 0) {
+                            __threadfence();
+                            atomicExch(crew_bar, 8 * seq + stage);
+                        }
+                    }
+                }
+                __syncthreads();
+                return;
+            }
             if (tid < SUB) {
                 for (int k1 = 0; k1 < pb; k1 += ASAM_PB) {
                     const int pbb = min(ASAM_PB, pb - k1);

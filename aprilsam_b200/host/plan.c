@@ -46,6 +46,8 @@ void asam_dbg_build_profile(double *out, int reset)
 
 #define RELAX_Z 2     /* relaxed amalgamation: missing block rows tolerated per merge */
 #define RELAX_FILL 24 /* ... and explicit zero blocks (3x3) added per merge */
+#define TEAM_MERGE_PCT 0      /* team-sized fronts: extra rows tolerated per merge, % of the front (0: off) */
+#define TEAM_MERGE_MFLOP 400.0 /* ... and extra flops per merge (millions) */
 #define ASAM_TEAM_ROOM 100       /* CTAs that the team fronts of one tree level may claim together (swept: 100 / 120 / 148 / 220) */
 #define ASAM_BSLEAF_MAX 64       /* = ASAM_BSL_XS of k_backsolve_leaf: own columns / rows below */
 #define ASAM_BSLEAF_MIN_COUNT 4096 /* measured: no gain on M3500-sized trees (the kernel boundary eats it) */
@@ -439,6 +441,39 @@ static int cmp_key_desc(const void *a, const void *b)
     return (x->id > y->id) - (x->id < y->id); /* deterministic */
 }
 
+/* Modelled duration (microseconds) of front s once its children are done, factored by g CTAs (least-squares
+ * fits to device traces of the 100 k world, tools/panel_trace.py --dump-trace).  ASAM_TEAM_MODEL="a,b,c,d,e"
+ * overrides the team coefficients (tuning). */
+static double team_model[5] = { 21.5, 24.4, 11.6, 0.041, 0.0 };
+static void team_model_init(void)
+{
+    static int done = 0;
+    if (done)
+        return;
+    done = 1;
+    const char *e = getenv("ASAM_TEAM_MODEL");
+    if (e)
+        sscanf(e, "%lf,%lf,%lf,%lf,%lf", &team_model[0], &team_model[1], &team_model[2], &team_model[3], &team_model[4]);
+}
+
+static double front_lat_us(const plan_t *pl, int s, int g)
+{
+    const double m = 3.0 * pl->desc[s].mb, c = 3.0 * pl->desc[s].cb;
+    if (m <= ASAM_LEAF_MAX_M)
+        return 2.0 + 0.1 * c;
+    if (front_fits_smem(pl->desc[s].mb) || g < 1)
+        return 3.8 + 0.121 * m + 0.105 * c + 0.00508 * c * m;
+    double tiles = 0.0, crew = 0.0;
+    const int npan = (int) ceil(c / 48.0);
+    for (int k = 0; k < npan; k++) {
+        const double r = m - 48.0 * (k + 1) > 0 ? m - 48.0 * (k + 1) : 0.0;
+        tiles += r * r / 2.0 / (256.0 * 64.0);
+        crew += 1.0 + ceil(r / 128.0);
+    }
+    return team_model[0] * npan + team_model[1] * tiles / g + team_model[2] * crew / g + team_model[3] * m +
+           team_model[4] * m * m / 1024.0 / g;
+}
+
 /* ---- static list schedule --------------------------------------------------------------------------
  * The ticket order of k_factor decides when a front's CTAs are taken: a team whose tickets come up while
  * its children are still running spins on all its CTAs (measured on the 100 k world: the nine fronts of
@@ -739,31 +774,16 @@ static void build_schedule(plan_t *pl)
         }
         free(want);
     }
-
     if (order_mode != 0) {
         /* modelled duration of every front once its children are done (microseconds; least-squares fit to device
          * traces of the 100 k world, tools/panel_trace.py --dump-trace: median error 8 % for shared-memory fronts,
          * 9 % for teams) and the length of the dependent chain from a front up to the root */
         double *lat_us = malloc(sizeof(double) * (size_t) (nsn + 1)), *up_us = malloc(sizeof(double) * (size_t) (nsn + 1));
         double work = 0.0, chain = 0.0;
+        team_model_init();
         for (int s = nsn - 1; s >= 0; s--) { /* parents have larger ids */
-            const double m = 3.0 * pl->desc[s].mb, c = 3.0 * pl->desc[s].cb;
             const int g = G_of[s] < 0 ? 1 : G_of[s];
-            double lat;
-            if (m <= ASAM_LEAF_MAX_M) {
-                lat = 2.0 + 0.1 * c;
-            } else if (front_fits_smem(pl->desc[s].mb) || g < 1) {
-                lat = 3.8 + 0.121 * m + 0.105 * c + 0.00508 * c * m;
-            } else {
-                double tiles = 0.0, crew = 0.0;
-                const int npan = (int) ceil(c / 48.0);
-                for (int k = 0; k < npan; k++) {
-                    const double r = m - 48.0 * (k + 1) > 0 ? m - 48.0 * (k + 1) : 0.0;
-                    tiles += r * r / 2.0 / (256.0 * 64.0);
-                    crew += 1.0 + ceil(r / 128.0);
-                }
-                lat = 21.5 * npan + 24.4 * tiles / g + 11.6 * crew / g + 0.041 * m;
-            }
+            const double lat = front_lat_us(pl, s, g);
             lat_us[s] = lat;
             up_us[s] = lat + (pl->desc[s].parent >= 0 ? up_us[pl->desc[s].parent] : 0.0);
             if ((owner[s] == me || owner[s] == -1) && !leaf[s])
@@ -1136,6 +1156,12 @@ static int plan_build_impl(plan_t *pl, asam_dev_t *dev, int N, int n_factors, co
         relax_z = atoi(getenv("ASAM_RELAX_Z"));
     if (getenv("ASAM_RELAX_FILL"))
         relax_fill = atoi(getenv("ASAM_RELAX_FILL"));
+    int team_merge_pct = TEAM_MERGE_PCT;
+    double team_merge_mflop = TEAM_MERGE_MFLOP;
+    if (getenv("ASAM_TEAM_MERGE_PCT"))
+        team_merge_pct = atoi(getenv("ASAM_TEAM_MERGE_PCT"));
+    if (getenv("ASAM_TEAM_MERGE_MFLOP"))
+        team_merge_mflop = atof(getenv("ASAM_TEAM_MERGE_MFLOP"));
     pl->nsn = 0;
     pl->nnz_l_blocks = 0;
     pl->flops = 0.0;
@@ -1160,6 +1186,14 @@ static int plan_build_impl(plan_t *pl, asam_dev_t *dev, int N, int n_factors, co
              * in shared memory) is not capped: splitting it only adds levels and one full copy of
              * the update matrix per link */
             if (!merge && parent[pp] == p && z == 0 && !front_fits_smem(gcb + nbp))
+                merge = 1;
+            /* team-sized fronts along a chain: every front boundary costs the chain an extend-add pass, a
+             * first panel without look-ahead, a ticket and a partly filled last panel (~80 us together), the
+             * explicit zeros of a merge only tensor-pipe tiles spread over the whole team.  Merge while the
+             * extra rows stay below team_merge_pct % of the front and the extra flops below team_merge_mflop. */
+            if (!merge && parent[pp] == p && team_merge_pct > 0 && !front_fits_smem(gcb + nbp) &&
+                (int64_t) z * 100 <= (int64_t) team_merge_pct * (gcb + nbp) &&
+                27.0 * gcb * z * (2.0 * (gcb + nbp) + z) <= 1e6 * team_merge_mflop)
                 merge = 1;
         }
         if (merge) {
