@@ -408,9 +408,9 @@ __device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, const double 
 // instructions of 256 multiply-adds (trailing_update<2,8>: 10 loads per 512).  Rows beyond m and columns beyond
 // jend are masked in the loads (no out-of-range reads) and at the store.
 __device__ __forceinline__ void trailing_update_mma(double *C, const int ld, const double *P, const int ldp, const int pb,
-                                                    const int j0, const int jend, const int m)
+                                                    const int j0, const int jend, const int m, const int sub_warps = 0)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = sub_warps ? sub_warps : (blockDim.x >> 5);
     const int g = lane >> 2, t = lane & 3;
     int pair = 0;
     for (int jb = j0; jb < jend; jb += 8) {
@@ -461,6 +461,8 @@ __device__ __forceinline__ void trailing_update_mma(double *C, const int ld, con
 __device__ __forceinline__ void bar_sub(const int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 
 __device__ int g_pf_groups = 1; // ASAM_PF_GROUPS=0: one thread per row in the in-panel update of panel_factor (A/B)
+__device__ int g_dmap_ahead = 1; // ASAM_DMAP_AHEAD=0: destination maps child by child inside the extend-add loop (A/B)
+__device__ int g_diag_mma = 1;  // ASAM_DIAG_MMA=0: DFMA update inside the 48 x 48 diagonal block of the team path (A/B)
 
 __device__ __forceinline__ void panel_factor(double *P, int ldp, int k0, int pb, int m, int sn_id, int *err,
                                              double *dinv_out, const int sub_nt = 0)
@@ -944,7 +946,10 @@ __device__ __forceinline__ void diag_factor_rl(double *D, int pb, double *rdv, i
             const int pbb = min(ASAM_PB, pb - k1);
             panel_factor(D + (size_t) k1 * LDD, LDD, k1, pbb, pb - 1, sn_id, err, rdv, SUB);
             if (k1 + pbb < pb) {
-                trailing_update<1, 4>(D, LDD, D + (size_t) k1 * LDD, LDD, pbb, k1 + pbb, pb, pb - 1, SUB / 32);
+                if (g_diag_mma)
+                    trailing_update_mma(D, LDD, D + (size_t) k1 * LDD, LDD, pbb, k1 + pbb, pb, pb - 1, SUB / 32);
+                else
+                    trailing_update<1, 4>(D, LDD, D + (size_t) k1 * LDD, LDD, pbb, k1 + pbb, pb, pb - 1, SUB / 32);
                 bar_sub(SUB);
             }
         }
@@ -1306,45 +1311,6 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
             constexpr int SUB = 256; // threads that factor the block (measured: 64 threads on a two-warp barrier are SLOWER,
                                      // 20.3 vs 15.7 us per block: the publish / update loops want the threads more than the barriers cost)
             int stage = 0;
-            if (a.staged >= 2 && nt == 256) {
-                // warps 0-6 factor; WARP 7 PUBLISHES: it picks every finished sub-panel up on a named barrier of its
-                // own (2 + stage: the factoring warps only arrive, they never wait for it) and does the stores to the
-                // front, the fence and the flag while the others are already in the next sub-panel -- the ~1 us of
-                // stores + membar per stage leave the dependent chain of the diagonal block
-                constexpr int NCW = 7, CT = 32 * NCW;
-                if (warp < NCW) {
-                    for (int k1 = 0; k1 < pb; k1 += ASAM_PB) {
-                        const int pbb = min(ASAM_PB, pb - k1);
-                        panel_factor(D + (size_t) k1 * LDD, LDD, k1, pbb, pb - 1, s, err, rdv, CT);
-                        asm volatile("bar.arrive %0, 256;" ::"r"(2 + stage) : "memory");
-                        ++stage;
-                        if (k1 + pbb < pb) {
-                            trailing_update<1, 4>(D, LDD, D + (size_t) k1 * LDD, LDD, pbb, k1 + pbb, pb, pb - 1, NCW);
-                            bar_sub(CT);
-                        }
-                    }
-                } else {
-                    for (int k1 = 0; k1 < pb; k1 += ASAM_PB) {
-                        const int pbb = min(ASAM_PB, pb - k1);
-                        asm volatile("bar.sync %0, 256;" ::"r"(2 + stage) : "memory");
-                        ++stage;
-                        for (int e = lane; e < pbb * pb; e += 32) {
-                            const int j = k1 + e / pb, i = e % pb;
-                            if (i >= j)
-                                F[(k0 + i) + (size_t) (k0 + j) * ld] = D[i + j * LDD];
-                        }
-                        if (lane < pbb)
-                            dinv[k0 + k1 + lane] = rdv[k1 + lane];
-                        __syncwarp();
-                        if (lane == 0) {
-                            __threadfence();
-                            atomicExch(crew_bar, 8 * seq + stage);
-                        }
-                    }
-                }
-                __syncthreads();
-                return;
-            }
             if (tid < SUB) {
                 for (int k1 = 0; k1 < pb; k1 += ASAM_PB) {
                     const int pbb = min(ASAM_PB, pb - k1);
@@ -1365,7 +1331,10 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
                         }
                     }
                     if (k1 + pbb < pb) {
-                        trailing_update<1, 4>(D, LDD, D + (size_t) k1 * LDD, LDD, pbb, k1 + pbb, pb, pb - 1, SUB / 32);
+                        if (g_diag_mma)
+                            trailing_update_mma(D, LDD, D + (size_t) k1 * LDD, LDD, pbb, k1 + pbb, pb, pb - 1, SUB / 32);
+                        else
+                            trailing_update<1, 4>(D, LDD, D + (size_t) k1 * LDD, LDD, pbb, k1 + pbb, pb, pb - 1, SUB / 32);
                         bar_sub(SUB);
                     }
                 }
@@ -1661,6 +1630,31 @@ __device__ bool cta_front(const FacArgs &a, const int t, const int s, const int 
     for (int e = tid; e < d.ch_cnt && e < ASAM_MAX_CACHED_CHILDREN; e += nt)
         s_cd[e] = a.sn[children[e]];
     __syncthreads();
+    // Destination maps of ALL children now (they are plan data, not results): their loads share the round trip of
+    // the Hessian gather below and overlap the wait for the children, instead of costing every child one L2
+    // round trip of its own on the dependent chain.  Needs room behind the front for sum(rows + 1) ints.
+    __shared__ int s_doff[ASAM_MAX_CACHED_CHILDREN + 1];
+    bool dmap_ahead = false;
+    if (use_sm && g_dmap_ahead && d.ch_cnt > 0 && d.ch_cnt <= ASAM_MAX_CACHED_CHILDREN) {
+        if (tid == 0) {
+            int o = 0;
+            for (int e = 0; e < d.ch_cnt; e++) {
+                s_doff[e] = o;
+                o += 3 * (s_cd[e].mb - s_cd[e].cb) + 1;
+            }
+            s_doff[d.ch_cnt] = o;
+        }
+        __syncthreads();
+        dmap_ahead = (long long) s_doff[d.ch_cnt] <= 2 * ((long long) a.smem_doubles - fsz) - 2;
+        if (dmap_ahead)
+            for (int ci = 0; ci < d.ch_cnt; ++ci) {
+                const int cc = 3 * s_cd[ci].cb, cr = 3 * s_cd[ci].mb - cc;
+                const int *crel = a.ipool + s_cd[ci].seg + s_cd[ci].mb;
+                int *dm = dmap + s_doff[ci];
+                for (int i = tid; i <= cr; i += nt)
+                    dm[i] = (i < cr) ? 3 * crel[(cc + i) / 3] + (cc + i) % 3 : m;
+            }
+    }
     for (int e = tid; e < d.cb * 9; e += nt) {
         int k = e / 9, p = (e % 9) / 3, q = e % 3; // F[row 3k+p, col 3k+q], p >= q
         if (p >= q)
@@ -1707,9 +1701,13 @@ __device__ bool cta_front(const FacArgs &a, const int t, const int s, const int 
         const double *CF = a.arena + cd.f_off;
         const int *crel = a.ipool + cd.seg + cd.mb; // rel[]
         // destination row of child row cc+i (i in [0,cr]); the child's rhs row -> ours
-        for (int i = tid; i <= cr; i += nt)
-            dmap[i] = (i < cr) ? 3 * crel[(cc + i) / 3] + (cc + i) % 3 : m;
-        __syncthreads();
+        if (dmap_ahead) {
+            dmap = (int *) (sm + fsz) + s_doff[ci];
+        } else {
+            for (int i = tid; i <= cr; i += nt)
+                dmap[i] = (i < cr) ? 3 * crel[(cc + i) / 3] + (cc + i) % 3 : m;
+            __syncthreads();
+        }
         if (use_sm && cr <= 159) {
             // the whole update matrix in few round trips: four columns per warp and pass, up to
             // 160 rows each -> 20 independent loads in flight per lane (the critical path of a

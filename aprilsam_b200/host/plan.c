@@ -886,7 +886,35 @@ static void build_schedule(plan_t *pl)
     pl->n_bs_leaf = n_bsl;
     pl->n_btasks = n_top_bt + n_main_sn + n_bsl;
     pl->btasks = malloc(sizeof(int) * (size_t) (pl->n_btasks + 1));
-    /* back-solve list, parents first: [top | own shards outside the back-solve leaf set | that set] */
+    /* back-solve list, parents first: [top | own shards outside the back-solve leaf set | that set].
+     * Order inside a segment: by the modelled TIME of the longest chain below a supernode (its own solve included),
+     * longest first -- a parent's chain is longer than any child's, so the order is topological, and the deep
+     * chains do not queue behind the thousands of supernodes that merely share their height (level order: the
+     * bottom of the longest chain of the 100 k world got its tickets 20 us late per link).  ASAM_BS_ORDER=level
+     * keeps the height order (A/B). */
+    {
+        const char *eb = getenv("ASAM_BS_ORDER");
+        if (!(eb && strcmp(eb, "level") == 0) && nsn > 0) {
+            double *down = calloc((size_t) nsn, sizeof(double));
+            sn_key_t *keys = malloc(sizeof(sn_key_t) * (size_t) nsn);
+            for (int s = 0; s < nsn; s++) { /* children have smaller ids: down[s] holds max over children here */
+                if (!pl->bs_leaf[s]) /* (the warp-per-supernode set runs in a launch of its own, afterwards) */
+                    down[s] += 5.0 + 0.17 * 3.0 * pl->desc[s].cb + 0.01 * 3.0 * pl->desc[s].mb;
+                else
+                    down[s] += 1e-3 * (pl->desc[s].level + 1);
+                const int par = pl->desc[s].parent;
+                if (par >= 0 && down[s] > down[par])
+                    down[par] = down[s];
+                keys[s].key = down[s];
+                keys[s].id = s;
+            }
+            qsort(keys, (size_t) nsn, sizeof(sn_key_t), cmp_key_desc);
+            for (int k = 0; k < nsn; k++)
+                bylv[nsn - 1 - k] = keys[k].id; /* ascending: the list below is filled backwards */
+            free(keys);
+            free(down);
+        }
+    }
     int t = 0, tl = 0, tt = 0;
     int bt = n_top_bt - 1, bm = n_top_bt + n_main_sn - 1, bl = pl->n_btasks - 1;
     for (int k = 0; k < nsn; k++) { /* back-solve entries, filled backwards: parents first */
