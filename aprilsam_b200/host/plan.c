@@ -46,7 +46,7 @@ void asam_dbg_build_profile(double *out, int reset)
 
 #define RELAX_Z 2     /* relaxed amalgamation: missing block rows tolerated per merge */
 #define RELAX_FILL 24 /* ... and explicit zero blocks (3x3) added per merge */
-#define TEAM_MERGE_PCT 0      /* team-sized fronts: extra rows tolerated per merge, % of the front (0: off) */
+#define TEAM_MERGE_PCT 20     /* team-sized fronts: extra rows tolerated per merge, % of the front (0: off; swept 10 .. 60) */
 #define TEAM_MERGE_MFLOP 400.0 /* ... and extra flops per merge (millions) */
 #define ASAM_TEAM_ROOM 100       /* CTAs that the team fronts of one tree level may claim together (swept: 100 / 120 / 148 / 220) */
 #define ASAM_BSLEAF_MAX 64       /* = ASAM_BSL_XS of k_backsolve_leaf: own columns / rows below */
