@@ -460,9 +460,11 @@ __device__ __forceinline__ void trailing_update_mma(double *C, const int ld, con
 // of eight -- there are 9 of them per 12 columns on the dependent chain of every panel.
 __device__ __forceinline__ void bar_sub(const int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 
-__device__ int g_pf_groups = 1; // ASAM_PF_GROUPS=0: one thread per row in the in-panel update of panel_factor (A/B)
-__device__ int g_dmap_ahead = 1; // ASAM_DMAP_AHEAD=0: destination maps child by child inside the extend-add loop (A/B)
-__device__ int g_diag_mma = 1;  // ASAM_DIAG_MMA=0: DFMA update inside the 48 x 48 diagonal block of the team path (A/B)
+// (tuning switches live in CONSTANT memory: a __device__ global read inside panel_factor is a global load on the
+// dependent chain of every 3x3 step -- measured +2.3 us per 48 x 48 diagonal block)
+__constant__ int g_pf_groups = 1; // ASAM_PF_GROUPS=0: one thread per row in the in-panel update of panel_factor (A/B)
+__constant__ int g_dmap_ahead = 1; // ASAM_DMAP_AHEAD=0: destination maps child by child inside the extend-add loop (A/B)
+__constant__ int g_diag_mma = 1;  // ASAM_DIAG_MMA=0: DFMA update inside the 48 x 48 diagonal block of the team path (A/B)
 
 __device__ __forceinline__ void panel_factor(double *P, int ldp, int k0, int pb, int m, int sn_id, int *err,
                                              double *dinv_out, const int sub_nt = 0)
@@ -1364,6 +1366,57 @@ __device__ bool team_front(const FacArgs &a, const asam_sn_desc_t &d, int s, int
     // worker 0 has published the matching columns of L11
     auto rows_solve_staged = [&](int k0, int pb, int rb0, int seq, double *Wnext) {
         constexpr int LDD = ASAM_TPB;
+        if (a.staged >= 2 && nt == 256) {
+            // Two groups of four warps.  LOADERS (warps 4-7): wait for the flag of stage s, fetch its 12 columns of L11
+            // (one L2 round trip) into D and hand them over on named barrier 3 + s (they only arrive).  SOLVERS (warps
+            // 0-3, one row each): pick the columns up and solve.  The loaders are already polling for stage s + 1 while
+            // the solvers work on s: a stage costs the crew max(poll + fetch, solve) instead of their sum -- measured
+            // before: 5 us per stage against a block published every 3.9 us, the row chunks finished 9 us after the
+            // last publish and the whole team waited for them.
+            if (tid == 0)
+                *s_flag = 1;
+            __syncthreads();
+            const int i = rb0 + tid;
+            const bool row = tid < ASAM_CROWS && i <= m;
+            int stage = 0;
+            for (int b0 = 0; b0 < pb; b0 += ASAM_PB, ++stage) {
+                const int nb = min(ASAM_PB, pb - b0);
+                if (warp >= 4) {
+                    if (tid == 128 && *s_flag) {
+                        SpinClock spins;
+                        while (ld_volatile(crew_bar) < 8 * seq + stage + 1) {
+                            __nanosleep(20);
+                            if (spin_over(spins, a.spin_limit) || ld_volatile(err) < 0) {
+                                atomicCAS(err, 0, -(1 + s));
+                                *s_flag = 0;
+                                break;
+                            }
+                        }
+                        __threadfence();
+                    }
+                    asm volatile("bar.sync 2, 128;" ::: "memory");
+                    if (*s_flag) {
+                        for (int e = tid - 128; e < nb * ASAM_TPB; e += 128) {
+                            const int j = b0 + e / ASAM_TPB, ii = e % ASAM_TPB;
+                            D[ii + j * LDD] = (ii >= j && ii < pb) ? __ldcg(&F[(k0 + ii) + (size_t) (k0 + j) * ld]) : 0.0;
+                        }
+                        if (tid - 128 < nb)
+                            rdv[b0 + tid - 128] = __ldcg(&dinv[k0 + b0 + tid - 128]);
+                    }
+                    __threadfence_block();
+                    asm volatile("bar.arrive %0, 256;" ::"r"(3 + stage) : "memory");
+                } else {
+                    asm volatile("bar.sync %0, 256;" ::"r"(3 + stage) : "memory");
+                    if (row && *s_flag)
+                        trsm_row_block(Li, D, rdv, b0, nb, F + i + (size_t) k0 * ld, ld, Wnext + (size_t) i * ASAM_LDW);
+                }
+            }
+            if (row && *s_flag)
+                for (int q = pb; q < ((pb + 3) & ~3); q++)
+                    Wnext[(size_t) i * ASAM_LDW + q] = 0.0;
+            __syncthreads();
+            return *s_flag != 0;
+        }
         __syncthreads();
         const int i = rb0 + tid;
         const bool row = tid < ASAM_CROWS && i <= m;
