@@ -58,7 +58,8 @@ as it evolved); `r1*` / `r2*` files are round 1's.  `tools/round_evidence.sh` re
 | `{R}_sass_excerpt.txt` | `cuobjdump -sass` of the built library: instruction counts per kernel + excerpt (`DMMA.8x8x4`, `UBLKCP.S.G`, `SYNCS.ARRIVE.TRANS64`, `SYNCS.PHASECHK…TRYWAIT`) |
 | `{R}_memcheck.log` | `compute-sanitizer --tool memcheck` over M3500 batch, 60 replay steps (k_step) and a 12 k-pose synthetic world (leaf kernels, team path with bulk copies): 0 errors |
 | `{R}_tune_*.log` | the A/B sweeps behind the defaults (tile modes, staged publish, task order, team sizes, back-solve split, tensor-pipe variants) — same box within a file |
-| `rd2_*_panel_trace.log` | per-panel device stamps of the root front (m 1383, 24 panels): 32.3 µs/panel at the start of the round → 26.7 µs |
+| `rd2_*_panel_trace.log`, `{R}_panel_trace.log`, `rd2_panel_trace_final_ab.log` | per-panel device stamps of the root front: 32.3 µs/panel at the start of the round → 26.2 µs (final build: `{R}_panel_trace.log`) |
+| `{R}_step_profile.log` | device stamps of `k_step` (the one-launch small incremental step) over the M3500 replay + host-side phases |
 """)
 if b1 and ref:
     print("## Headline numbers (one box, both arms back to back; reference = unmodified AprilSAM, 1 thread — it has none)\n")
@@ -104,6 +105,15 @@ if b1 and ref:
             print(f"| {name} | `{e['kernel'].split(' ')[0]}` | {e['algorithmic_bytes_per_launch'] / 1e6:.1f} MB | {e['avg_launch_ms'] * 1e3:.0f} µs | "
                   f"{e['achieved']:.1f} GB/s | {100 * e['frac']:.2f} % | {tr} | {fp} |")
     print()
+w10, w90 = load(f"{R}_replay_from10k.json"), load(f"{R}_replay_from90k.json")
+if b1 and w10 and w90:
+    print("### Sparse 100 k replay by window (solves/s over the timed steps, escalations included)\n")
+    print("| first timed pose | aprilsam_b200 |")
+    print("|---|---|")
+    print(f"| 10 000 | {w10['value']:.0f} |")
+    print(f"| 50 000 (default line) | {b1['workloads']['manhattan_replay']['value']:.0f} |")
+    print(f"| 90 000 | {w90['value']:.0f} |")
+    print()
 sc = [(1, b1)] + [(n, bn[n]) for n in (2, 4, 8) if bn[n]]
 if len(sc) > 1:
     print("## 100 k batch sharded over the GPUs of one box (strong scaling; device-resident value = solves / max rank time)\n")
@@ -140,10 +150,13 @@ print("""## Reading the numbers
 
 * **The factorisation is bound by dependent chains and SM occupancy, not by bytes or flops** (DRAM busy 3 %, FP64 pipe
   active 2 % at 100 k).  Device traces (`tools/panel_trace.py --dump-trace`, analysed in DESIGN.md §4/§6): with the
-  simulated ticket order the 148 CTAs are saturated for ≈ 4 ms — every front is a short chain of L2 round trips and
-  barrier-separated panel steps, one CTA per SM — followed by a ≈ 1 ms tail that is ONE chain: the root separator's 24
-  panel steps (26.7 µs each: diagonal tile 3.2 + staged 48×48 factorisation 15.7 + last row-solve stage and barrier 7.8)
-  and the four small fronts around it.
+  simulated ticket order the 148 CTAs are saturated for ≈ 4.2 ms — every front is a short chain of L2 round trips and
+  barrier-separated panel steps, one CTA per SM (CTA-time by class at 100 k: shared-memory fronts 27 %, one-CTA team
+  fronts 14 %, teams of 2-15 22 %, larger teams 37 %) — followed by a ≈ 0.9 ms tail that is ONE chain: the merged root
+  front's 30 panel steps (26.2 µs each: diagonal tile 3.2 + staged 48×48 factorisation 16.4 + the crew's last row-solve
+  stage and the team barrier 6.6).  The 48×48 block itself (micro-benchmark `tools/ubench/diag_block.cu`, 11.4 µs
+  alone) is 48 chained reciprocal square roots of 131 cycles with two block barriers and three shared-memory round
+  trips per 3×3 step: neither a publisher warp nor register-resident 12×12 blocks shortened it (DESIGN.md §4).
 * DRAM traffic of `k_factor` is ≈ 3× the algorithmic bytes: a multifrontal method writes every update matrix (Schur
   complement) once and reads it once (1.5 GB of fronts at 100 k against 474 MB of L + A), plus the zero-fill of the
   fronts and the row-major panel workspace of the team path.  It is not the limiter.
@@ -151,7 +164,10 @@ print("""## Reading the numbers
   team fronts 60-75 → 38-42 µs, k_factor 7.2 → 6.6 ms), tensor-pipe tiles with two bulk copies per tile (256×64×48 tile
   14.3 → 4.2 µs; alone: no change of the total, the panel chain hides it), staged publish of the diagonal block
   (6.08 → 5.70 ms), simulated ticket order (30 k: 3.67 → 3.08 ms; M3500: chain-length order 0.457 → 0.426 ms),
-  back-substitution one block per CTA for wide supernodes (1.39 → 1.02 ms).  Tried and dropped with numbers: one CTA per
+  back-substitution one block per CTA for wide supernodes (1.39 → 1.02 ms) and tickets by modelled chain time
+  (1.018 → 0.987 ms), team-sized chain fronts merged up to 20 % extra rows (5.85 → 5.71 ms), destination maps of all
+  children built while a front waits (M3500 0.441 → 0.432 ms), tuning switches moved from `__device__` globals to
+  constant memory (a global load sat on the 3×3 step chain: diagonal block 18.0 → 16.4 µs).  Tried and dropped with numbers: one CTA per
   mid-size front out of HBM (worse from m > 240), a separate two-CTAs-per-SM kernel for fronts ≤ 117 (+0.3 ms: the extra
   launch boundary), several tiles per team worker (6.4 → 6.6-7.0 ms), tensor-pipe update for 12-column shared-memory
   panels (M3500 0.435 → 0.459 ms), nested-dissection ordering (CPU study, DESIGN.md §1).""")
