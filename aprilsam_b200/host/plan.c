@@ -54,6 +54,7 @@ void asam_dbg_build_profile(double *out, int reset)
 #define ASAM_LEAF_MAX_M 48       /* = ASAM_LEAF_M of k_factor_leaf */
 #define ASAM_LEAF_MIN_COUNT 4096 /* below this one k_factor launch does it all */
 #define ASAM_SOLO_MAX_M_DEFAULT 0 /* see solo_max_m() */
+#define ASAM_SHARD_TOL_DEFAULT 1.10 /* multi-GPU cut: heaviest rank's load / mean at which the splitting stops */
 #define ASAM_TILES_PER_WORKER 1   /* trailing-update tiles per worker and panel that team_size() plans for */
 #define MAX_SN_COLS 32 /* block columns per supernode: L11 (96x96) fits k_backsolve shared memory */
 
@@ -603,6 +604,9 @@ static void build_schedule(plan_t *pl)
         for (int s = 0; s < nsn; s++)
             owner[s] = -2; /* undecided */
         const int max_shards = 16 * W;
+        /* ASAM_SHARD_TOL: imbalance at which the splitting stops (tuning).  Every split moves one more front of the
+         * dependent chain above the cut, where all ranks repeat it */
+        const double shard_tol = getenv("ASAM_SHARD_TOL") ? atof(getenv("ASAM_SHARD_TOL")) : ASAM_SHARD_TOL_DEFAULT;
         double *load = malloc(sizeof(double) * (size_t) W);
         for (;;) {
             /* heaviest-first dealing (LPT) of the current frontier */
@@ -632,7 +636,7 @@ static void build_schedule(plan_t *pl)
             /* stop when balanced within 10 %, when there are plenty of shards, or when the heaviest
              * shard cannot be split (no children) */
             int h = fr[0];
-            if (nfr >= W && mx <= 1.10 * shard_sum / W)
+            if (nfr >= W && mx <= shard_tol * shard_sum / W)
                 break;
             if (nfr >= max_shards || pl->snh[h].children.n == 0)
                 break;

@@ -386,10 +386,14 @@ def bench_batch(ctx: Ctx, name: str, d, label: str, K: int, W: int, sharded: boo
     e2e_ms, kern = [], []
     launches0 = h2d0 = d2h0 = 0
     for i in range(W + K):
-        h.set_states(init)
+        h.set_states(init)  # scaffolding (the same first Gauss-Newton iteration every step), not timed
         if i == W:
             barrier_max(dist, local, 0.0)
             launches0, h2d0, d2h0 = capi.counters(dev)
+        elif sharded:
+            # the ranks of a sharded solve meet inside the call (NCCL exchange): without this, a rank's timed call would
+            # also wait for the slowest rank's set_states() above
+            barrier_max(dist, local, 0.0)
         t = h.batch()
         if i >= W:
             e2e_ms.append(t)

@@ -43,6 +43,9 @@ def main():
             dev = L.asam_dbg_dev_of_graph(h.graph_ptr())
             L.asam_set_timing(dev, 1)
             ms, km = [], []
+            import ctypes as C
+            prof = (C.c_double * 24)()
+            L.asam_dbg_profile(prof, 1)  # reset the host-side phase timers
             for _ in range(args.iters):
                 h.set_states(d.init)
                 dist.barrier()
@@ -51,6 +54,11 @@ def main():
                 h.batch()
                 ms.append((time.perf_counter() - t0) * 1e3)
                 km.append(capi.kernel_ms(dev))
+            L.asam_dbg_profile(prof, 1)
+            if rank == 0:
+                print(("sharded" if shard else "single ") + " host ms/call (rank 0): gather %.3f plan-check %.3f enqueue+verify %.3f wait+D2H %.3f "
+                      "tree+update %.3f; cpus %d (affinity %d)" % (*[prof[i] / args.iters for i in (11, 12, 13, 14, 16)], os.cpu_count(),
+                                                                  len(os.sched_getaffinity(0))), flush=True)
             return h.states(), h.chi2(), float(np.median(ms)), np.median(np.array(km), axis=0)
 
     s1, c1, t1, k1 = run(False)
