@@ -54,6 +54,8 @@ void asam_dbg_build_profile(double *out, int reset)
 #define ASAM_LEAF_MAX_M 48       /* = ASAM_LEAF_M of k_factor_leaf */
 #define ASAM_LEAF_MIN_COUNT 4096 /* below this one k_factor launch does it all */
 #define ASAM_SOLO_MAX_M_DEFAULT 0 /* see solo_max_m() */
+#define PLAN_OMP_MIN_SN 8192 /* below this many supernodes the symbolic loops stay on one thread */
+#define PLAN_OMP_THREADS 8 /* ASAM_PLAN_THREADS overrides (1: serial) */
 #define ASAM_SHARD_TOL_DEFAULT 1.10 /* multi-GPU cut: heaviest rank's load / mean at which the splitting stops */
 #define ASAM_TILES_PER_WORKER 1   /* trailing-update tiles per worker and panel that team_size() plans for */
 #define MAX_SN_COLS 32 /* block columns per supernode: L11 (96x96) fits k_backsolve shared memory */
@@ -265,6 +267,16 @@ static void fslot_reserve(plan_t *pl, int n)
 }
 
 /* rel[k] for k >= cb: index of the child's row in the parent's row list */
+static int plan_threads(void)
+{
+    static int v = 0;
+    if (v == 0) {
+        const char *e = getenv("ASAM_PLAN_THREADS");
+        v = e && atoi(e) > 0 ? atoi(e) : PLAN_OMP_THREADS;
+    }
+    return v;
+}
+
 static int compute_rel(plan_t *pl, int s)
 {
     sn_host_t *h = &pl->snh[s];
@@ -1099,9 +1111,14 @@ static int plan_build_impl(plan_t *pl, asam_dev_t *dev, int N, int n_factors, co
                 }
             }
         }
-        sort_ints(bl.p + start, bl.n - start);
+        /* (the lists stay unsorted: only their sizes, their union and their minimum -- the parent -- are used; the
+         * rows of a supernode are sorted once, in numeric positions, in step 7) */
         bptr[p + 1] = bl.n;
-        parent[p] = bl.n > start ? bl.p[start] : -1;
+        int pmin = -1;
+        for (int e = start; e < bl.n; e++)
+            if (pmin < 0 || bl.p[e] < pmin)
+                pmin = bl.p[e];
+        parent[p] = pmin;
         if (parent[p] >= 0) {
             int P = parent[p];
             if (tail[P] < 0)
@@ -1245,6 +1262,9 @@ static int plan_build_impl(plan_t *pl, asam_dev_t *dev, int N, int n_factors, co
     BUILD_LAP(3); /* post-order + supernodes */
     /* 7. row lists, parents, children, levels */
     pl->max_m = 0;
+    int max_m = 0;
+    /* (per-supernode work, independent: split over a few host threads on large graphs, like the pose loops of solver.c) */
+#pragma omp parallel for schedule(static, 256) reduction(max : max_m) if (pl->nsn >= PLAN_OMP_MIN_SN) num_threads(plan_threads())
     for (int s = 0; s < pl->nsn; s++) {
         asam_sn_desc_t *d = &pl->desc[s];
         sn_host_t *h = &pl->snh[s];
@@ -1258,10 +1278,11 @@ static int plan_build_impl(plan_t *pl, asam_dev_t *dev, int N, int n_factors, co
         /* positions on a root path are ordered alike in both numberings; be safe anyway */
         sort_ints(h->rows.p + d->cb, nb);
         d->mb = h->rows.n;
-        if (3 * d->mb > pl->max_m)
-            pl->max_m = 3 * d->mb;
+        if (3 * d->mb > max_m)
+            max_m = 3 * d->mb;
         d->parent = nb > 0 ? pl->sn_of_q[h->rows.p[d->cb]] : -1;
     }
+    pl->max_m = max_m;
     for (int s = 0; s < pl->nsn; s++) {
         int P = pl->desc[s].parent;
         if (P >= 0) {
@@ -1272,11 +1293,17 @@ static int plan_build_impl(plan_t *pl, asam_dev_t *dev, int N, int n_factors, co
         }
     }
     pl->n_levels = 0;
-    for (int s = 0; s < pl->nsn; s++) {
-        if (compute_rel(pl, s))
+    {
+        int rel_bad = 0, n_levels = 0;
+#pragma omp parallel for schedule(static, 256) reduction(| : rel_bad) reduction(max : n_levels) if (pl->nsn >= PLAN_OMP_MIN_SN) num_threads(plan_threads())
+        for (int s = 0; s < pl->nsn; s++) {
+            rel_bad |= compute_rel(pl, s);
+            if (pl->desc[s].level + 1 > n_levels)
+                n_levels = pl->desc[s].level + 1;
+        }
+        if (rel_bad)
             return 1;
-        if (pl->desc[s].level + 1 > pl->n_levels)
-            pl->n_levels = pl->desc[s].level + 1;
+        pl->n_levels = n_levels;
     }
     free(bptr);
     ivec_free(&bl);
@@ -1288,21 +1315,42 @@ static int plan_build_impl(plan_t *pl, asam_dev_t *dev, int N, int n_factors, co
     free(pofq);
 
     BUILD_LAP(4); /* row lists, rel */
-    /* 8. Hessian gather lists */
-    for (int sl = 0; sl < S; sl++) {
-        int lo = plo.p[sl], hi = phi.p[sl];
-        int qlo = pl->node2q[lo], qhi = pl->node2q[hi];
-        int qe = qlo < qhi ? qlo : qhi, ql = qlo < qhi ? qhi : qlo;
-        int s = pl->sn_of_q[qe];
-        sn_host_t *h = &pl->snh[s];
-        int rb = find_sorted(h->rows.p, h->rows.n, ql);
-        if (rb < 0) {
-            asam_set_error("plan: Hessian block (%d,%d) not in the structure of supernode %d", lo, hi, s);
+    /* 8. Hessian gather lists: the searches in parallel, the lists filled in slot order */
+    {
+        int *g_sn = malloc(sizeof(int) * (size_t) (S + 1)), *g_rb = malloc(sizeof(int) * (size_t) (S + 1)),
+            *g_cb = malloc(sizeof(int) * (size_t) (S + 1));
+        int bad_slot = -1;
+#pragma omp parallel for schedule(static, 4096) reduction(max : bad_slot) if (S >= 8 * PLAN_OMP_MIN_SN) num_threads(plan_threads())
+        for (int sl = 0; sl < S; sl++) {
+            int lo = plo.p[sl], hi = phi.p[sl];
+            int qlo = pl->node2q[lo], qhi = pl->node2q[hi];
+            int qe = qlo < qhi ? qlo : qhi, ql = qlo < qhi ? qhi : qlo;
+            int s = pl->sn_of_q[qe];
+            const sn_host_t *h = &pl->snh[s];
+            int rb = find_sorted(h->rows.p, h->rows.n, ql);
+            if (rb < 0 && sl > bad_slot)
+                bad_slot = sl;
+            g_sn[sl] = s;
+            g_rb[sl] = rb | (qe == qlo ? 0 : ASAM_TR_FLAG);
+            g_cb[sl] = qe - pl->desc[s].first;
+        }
+        if (bad_slot >= 0) {
+            asam_set_error("plan: Hessian block (%d,%d) not in the structure of supernode %d", plo.p[bad_slot], phi.p[bad_slot],
+                           g_sn[bad_slot]);
+            free(g_sn);
+            free(g_rb);
+            free(g_cb);
             return 1;
         }
-        ivec_push(&h->a_slot, sl);
-        ivec_push(&h->a_rb, rb | (qe == qlo ? 0 : ASAM_TR_FLAG));
-        ivec_push(&h->a_cb, qe - pl->desc[s].first);
+        for (int sl = 0; sl < S; sl++) {
+            sn_host_t *h = &pl->snh[g_sn[sl]];
+            ivec_push(&h->a_slot, sl);
+            ivec_push(&h->a_rb, g_rb[sl]);
+            ivec_push(&h->a_cb, g_cb[sl]);
+        }
+        free(g_sn);
+        free(g_rb);
+        free(g_cb);
     }
     ivec_free(&plo);
     ivec_free(&phi);
