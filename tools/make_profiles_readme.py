@@ -51,6 +51,7 @@ as it evolved); `r1*` / `r2*` files are round 1's.  `tools/round_evidence.sh` re
 | file | what |
 |---|---|
 | `{R}_bench_n1.json`, `{R}_bench_n1_reference.json` | the default `bench.py` line (ALL FOUR workloads, 100 k batch as headline) of both arms on one box, `--steps 20 --warmup 5` |
+| `{R}_bench_n1_after_plan_changes.json`, `{R}_plan_profile.log` | the b200 arm again after the last host-side changes (cold plan build), and the phases of the plan build on the GPU box's host with 1 / 8 / 16 threads |
 | `{R}_bench_n2.json`, `{R}_bench_n4.json`, `{R}_bench_n8.json` | the same line under `torchrun` on 2 / 4 / 8 GPUs: the 100 k batch solve SHARDED over the GPUs (in-line parity against the single-GPU solve), the other workloads as replicas |
 | `{R}_replay_from10k.json`, `{R}_replay_from90k.json` | sparse 100 k replay windows starting at pose 10 000 / 90 000 (the default line has the 50 000 window) |
 | `{R}_m3500_batch_launches.csv`, `{R}_100k_batch_launches.csv`, `{R}_m3500_replay_launches.csv` | every kernel launch with its device time (`ncu --metrics gpu__time_duration.sum`, cold cache, serialised: shares, not absolutes) |
@@ -73,6 +74,13 @@ if b1 and ref:
         print(f"| {name} | {r['value']:.3f} solves/s | **{w['e2e']['value']:.1f} solves/s** ({w['e2e'].get('ms_per_step', 1e3 / w['e2e']['value']):.3f} ms) | "
               f"{w['value']:.1f} solves/s ({w['ms_per_step']:.3f} ms) | {w['e2e']['value'] / r['value']:.1f}× | "
               + (f"{unc['value']:.2f} solves/s ({unc['ms_per_step']:.1f} ms, plan {unc['plan_build_ms_per_call']:.1f} ms) → {unc['value'] / r['value']:.1f}×" if unc else "—") + " |")
+    b1b = load(f"{R}_bench_n1_after_plan_changes.json")
+    if b1b and b1b.get("e2e_uncached"):
+        u0, u1 = b1["e2e_uncached"], b1b["e2e_uncached"]
+        print(f"\nAfter the last host-side changes of the round (cold plan: no per-column sort, symbolic loops on host threads) "
+              f"the same line on another box (`{R}_bench_n1_after_plan_changes.json`): plan {u0['plan_build_ms_per_call']:.0f} → "
+              f"{u1['plan_build_ms_per_call']:.0f} ms per uncached call, uncached 100 k batch {u0['value']:.2f} → {u1['value']:.2f} solves/s; "
+              f"device-resident {b1b['value']:.1f} solves/s, e2e {b1b['e2e']['value']:.1f} solves/s (unchanged within box-to-box spread).")
     print()
     print("Round 1 → round 2, same workloads (device-resident step): 100 k batch 8.67 → "
           f"{b1['ms_per_step']:.2f} ms (k_factor 7.21 → {b1['kernel_ms']['k_factor']:.2f}, k_backsolve 1.37 → {b1['kernel_ms']['k_backsolve']:.2f}); "
