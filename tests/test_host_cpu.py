@@ -250,6 +250,37 @@ def test_large_plan_leaf_set_and_merged_chains():
     assert np.abs(st - want).max() < 1e-6 * max(1.0, np.abs(want).max())
 
 
+def test_team_front_merge_and_backsolve_order(monkeypatch):
+    """Team-sized fronts absorb their chain parent while the explicit zero rows stay below ASAM_TEAM_MERGE_PCT per cent
+    (plan.c, supernode formation): fewer, wider supernodes, the same solution.  The back-substitution list (ordered by
+    modelled chain time) must stay parents-first, blocks of a wide supernode last block first."""
+    d = datasets.manhattan_dense(9000, seed=11)
+    n = d.n_nodes
+    ftype, fa, fb, fz, fW = factor_arrays(d)
+    monkeypatch.setenv("ASAM_TEAM_MERGE_PCT", "0")
+    p0 = HostPlan().build(n, ftype, fa, fb)
+    st0 = emulate_batch(d)
+    monkeypatch.setenv("ASAM_TEAM_MERGE_PCT", "40")
+    p1 = HostPlan().build(n, ftype, fa, fb)
+    st1 = emulate_batch(d)
+    D0, D1 = p0.descs(), p1.descs()
+    assert len(D1["mb"]) < len(D0["mb"]), "merging removes supernodes"
+    assert np.array_equal(p0.array("node2q"), p1.array("node2q")), "the elimination order is untouched"
+    lblocks = lambda D: int((D["cb"].astype(np.int64) * D["mb"] - D["cb"].astype(np.int64) * (D["cb"] - 1) // 2).sum())
+    assert lblocks(D1) > lblocks(D0), "explicit zero blocks were added to L"
+    assert np.abs(st1 - st0).max() < 1e-9 * max(1.0, np.abs(st0).max())
+    for p in (p0, p1):
+        bt, par = p.array("btasks"), p.descs()["parent"]
+        sn, blk = bt & 0xFFFFFF, bt >> 24
+        first = {}
+        for k, s in enumerate(sn):
+            first.setdefault(int(s), k)
+        assert all(par[s] < 0 or first[int(par[s])] < first[s] for s in first), "parents first"
+        for s in set(int(x) for x in sn[blk > 0]):
+            b = blk[sn == s]
+            assert (np.diff(b) < 0).all(), "last block first"
+
+
 @pytest.mark.parametrize("world", [2, 3, 8])
 def test_sharded_schedule_emulated(world):
     """Multi-GPU schedule: every rank factors its shards, the shard roots' trailing
