@@ -2005,8 +2005,8 @@ __global__ void __launch_bounds__(256, 1) k_factor(FacArgs a)
 // the rest afterwards.  Same arithmetic as k_factor's shared-memory path (3-column closed-form
 // steps, right-looking), same front layout, same arrival counters.
 // ------------------------------------------------------------------------------------------
-#define ASAM_LEAF_M 48
-#define ASAM_LEAF_WARPS 8
+#define ASAM_LEAF_M 63   // (host: ASAM_LEAF_MAX_M_DEFAULT; 7 warps x 32.5 KB of shared memory)
+#define ASAM_LEAF_WARPS 7
 #define ASAM_LEAF_STRIDE (ASAM_LD(ASAM_LEAF_M) * ASAM_LEAF_M + ASAM_LEAF_M / 2 + 2) // doubles per warp (even)
 
 struct LeafArgs {

@@ -51,7 +51,7 @@ void asam_dbg_build_profile(double *out, int reset)
 #define ASAM_TEAM_ROOM 100       /* CTAs that the team fronts of one tree level may claim together (swept: 100 / 120 / 148 / 220) */
 #define ASAM_BSLEAF_MAX 64       /* = ASAM_BSL_XS of k_backsolve_leaf: own columns / rows below */
 #define ASAM_BSLEAF_MIN_COUNT 4096 /* measured: no gain on M3500-sized trees (the kernel boundary eats it) */
-#define ASAM_LEAF_MAX_M 48       /* = ASAM_LEAF_M of k_factor_leaf */
+#define ASAM_LEAF_MAX_M_DEFAULT 63 /* <= ASAM_LEAF_M of k_factor_leaf (ASAM_LEAF_MAX_M overrides downwards, tuning) */
 #define ASAM_LEAF_MIN_COUNT 4096 /* below this one k_factor launch does it all */
 #define ASAM_SOLO_MAX_M_DEFAULT 0 /* see solo_max_m() */
 #define PLAN_OMP_MIN_SN 8192 /* below this many supernodes the symbolic loops stay on one thread */
@@ -267,6 +267,19 @@ static void fslot_reserve(plan_t *pl, int n)
 }
 
 /* rel[k] for k >= cb: index of the child's row in the parent's row list */
+/* Largest front of the warp-per-front kernel.  Big trees are bound by CTA-time (every front the leaf kernel takes frees an
+ * SM for 10-15 us: 100 k dense world 5.64 -> 5.49 ms with 63 instead of 48), small ones by their dependent chain, where
+ * a longer leaf launch ahead of k_factor only adds to it (30 k world 2.99 -> 3.07 ms): the wider limit from
+ * ASAM_LEAF_WIDE_MIN_SN supernodes on.  ASAM_LEAF_MAX_M overrides (tuning). */
+#define ASAM_LEAF_WIDE_MIN_SN 30000
+static int leaf_max_m_for(int nsn)
+{
+    const char *e = getenv("ASAM_LEAF_MAX_M");
+    if (e && atoi(e) >= 3 && atoi(e) <= ASAM_LEAF_MAX_M_DEFAULT)
+        return atoi(e);
+    return nsn >= ASAM_LEAF_WIDE_MIN_SN ? ASAM_LEAF_MAX_M_DEFAULT : 48;
+}
+
 static int plan_threads(void)
 {
     static int v = 0;
@@ -472,7 +485,7 @@ static void team_model_init(void)
 static double front_lat_us(const plan_t *pl, int s, int g)
 {
     const double m = 3.0 * pl->desc[s].mb, c = 3.0 * pl->desc[s].cb;
-    if (m <= ASAM_LEAF_MAX_M)
+    if (m <= 48) /* (fitted on fronts of the leaf kernel when its limit was 48) */
         return 2.0 + 0.1 * c;
     if (front_fits_smem(pl->desc[s].mb) || g < 1)
         return 3.8 + 0.121 * m + 0.105 * c + 0.00508 * c * m;
@@ -703,8 +716,9 @@ static void build_schedule(plan_t *pl)
      * there are thousands of them. */
     char *leaf = calloc((size_t) nsn + 1, 1);
     int n_leaf_all = 0;
+    const int leaf_max = leaf_max_m_for(nsn);
     for (int s = 0; s < nsn; s++) {
-        int ok = 3 * pl->desc[s].mb <= ASAM_LEAF_MAX_M;
+        int ok = 3 * pl->desc[s].mb <= leaf_max;
         for (int c = 0; ok && c < pl->snh[s].children.n; c++)
             ok = leaf[pl->snh[s].children.p[c]];
         leaf[s] = (char) ok;

@@ -223,7 +223,7 @@ def test_large_plan_leaf_set_and_merged_chains():
     p = HostPlan().build(n, ftype, fa, fb)
     D = p.descs()
     leaf, tasks, nwait = p.array("leaf_tasks"), p.array("tasks"), p.array("nwait")
-    assert len(leaf) >= 4096 and (3 * D["mb"][leaf]).max() <= 48
+    assert len(leaf) >= 4096 and (3 * D["mb"][leaf]).max() <= 63
     in_leaf = np.zeros(len(D["mb"]), bool)
     in_leaf[leaf] = True
     par = D["parent"]

@@ -22,7 +22,7 @@ from aprilsam_b200 import harness as H  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--poses", type=int, default=100000)
-    ap.add_argument("--workload", default="dense", choices=["dense", "m3500"])
+    ap.add_argument("--workload", default="dense", choices=["dense", "sparse", "m3500"])
     ap.add_argument("--iters", type=int, default=8)
     ap.add_argument("--tag", default="")
     ap.add_argument("--save", default="")
@@ -31,6 +31,8 @@ def main():
     L = capi.lib()
     if args.workload == "m3500":
         d = H.PoseGraphData.load(os.path.join(ROOT, "tests", "golden", "m3500.npz"))
+    elif args.workload == "sparse":
+        d = datasets.manhattan_sparse(args.poses, seed=1)
     else:
         d = datasets.manhattan_dense(args.poses, seed=1)
     with H.Harness("b200") as h:
