@@ -124,7 +124,7 @@ def seg_views(desc, ipool, s):
 
 
 def factor(fr: Fronts, H: Hessian, desc, ipool, q2node, tasks, nwait=None, check_order=True, prior=(), keep=None,
-           count_prior=True):
+           count_prior=True, panel=0, syrk=None):
     """k_factor: assemble + eliminate the listed supernodes (children first).  `prior` = supernodes
     factored by an earlier launch of the same solve; count_prior: their arrivals are part of nwait
     (k_factor_leaf before k_factor) or not (arrival counters zeroed in between: the multi-GPU top)."""
@@ -177,7 +177,27 @@ def factor(fr: Fronts, H: Hessian, desc, ipool, q2node, tasks, nwait=None, check
         if nwait is not None:
             assert nw == (int(nwait[ti]) & 0xffff), f"nwait mismatch for supernode {s}: {nw} vs {nwait[ti]}"
         # partial Cholesky of the first c columns (right-looking, lower triangle only)
-        for k in range(c):
+        if panel > 0:
+            # blocked like the kernels: a panel of `panel` columns in double precision, then ONE product for the
+            # trailing matrix, computed by syrk(P) ~ P P' (tools/ozaki_study.py plugs reduced-precision products in)
+            for k0 in range(0, c, panel):
+                k1 = min(c, k0 + panel)
+                for k in range(k0, k1):
+                    d = F[k, k]
+                    if not d > 0:
+                        raise np.linalg.LinAlgError(f"pivot <= 0 in supernode {s}")
+                    piv = np.sqrt(d)
+                    F[k, k] = piv
+                    F[k + 1:, k] /= piv
+                    rhs[k] /= piv
+                    lk = F[k + 1:, k]
+                    F[k + 1:, k + 1:k1] -= np.outer(lk, lk[:k1 - k - 1])  # the panel's own columns only
+                    rhs[k + 1:] -= lk * rhs[k]
+                if k1 < m:
+                    P = F[k1:, k0:k1]
+                    F[k1:, k1:] -= np.tril(syrk(P) if syrk is not None else P @ P.T)
+                F[:, :] = np.tril(F)
+        for k in range(c if panel <= 0 else 0):
             d = F[k, k]
             if not d > 0:
                 raise np.linalg.LinAlgError(f"pivot <= 0 in supernode {s}")

@@ -57,6 +57,7 @@ as it evolved); `r1*` / `r2*` files are round 1's.  `tools/round_evidence.sh` re
 | `{R}_m3500_batch_launches.csv`, `{R}_100k_batch_launches.csv`, `{R}_m3500_replay_launches.csv` | every kernel launch with its device time (`ncu --metrics gpu__time_duration.sum`, cold cache, serialised: shares, not absolutes) |
 | `{R}_m3500_batch_prof_raw.csv`, `{R}_100k_batch_prof_raw.csv` | `--page raw` export of one `ncu --set full` capture of every solve kernel of one step; `ncu_traffic.json` = their DRAM bytes per launch (`tools/ncu_extract.py`), which `bench.py` copies into `roofline_kernels[].traffic` |
 | `{R}_sass_excerpt.txt` | `cuobjdump -sass` of the built library: instruction counts per kernel + excerpt (`DMMA.8x8x4`, `UBLKCP.S.G`, `SYNCS.ARRIVE.TRANS64`, `SYNCS.PHASECHK…TRYWAIT`) |
+| `{R}_ozaki_study.log` | host-side numerical study (`tools/ozaki_study.py`): node-state error of the batch step when every trailing product is assembled from s int8 slices — 1e-6 needs 6 slices (21 products) on M3500, 7 (28) on an 8000-pose dense world |
 | `{R}_memcheck.log` | `compute-sanitizer --tool memcheck` over M3500 batch, 60 replay steps (k_step) and a 12 k-pose synthetic world (leaf kernels, team path with bulk copies): 0 errors |
 | `{R}_tune_*.log` | the A/B sweeps behind the defaults (tile modes, staged publish, task order, team sizes, back-solve split, tensor-pipe variants) — same box within a file |
 | `rd2_*_panel_trace.log`, `{R}_panel_trace.log`, `rd2_panel_trace_final_ab.log` | per-panel device stamps of the root front: 32.3 µs/panel at the start of the round → 26.2 µs (final build: `{R}_panel_trace.log`) |
