@@ -55,6 +55,11 @@ void pairmap_free(pairmap_t *m);
 /* returns the slot of (lo,hi); *created = 1 if it was inserted with value `next_slot` */
 int pairmap_get_or_add(pairmap_t *m, int lo, int hi, int next_slot, int *created);
 
+/* Host threads for the symbolic loops: ASAM_PLAN_THREADS (default 8, capped at 16), or 1 when a short calibration at first
+ * use finds that threads do not actually run side by side here (CPU quota of a container: eight threads on one core
+ * made the plan build of the 100 k world four times SLOWER). */
+int asam_host_threads(void);
+
 /* ---- ordering (ordering.c) ----------------------------------------------------------- */
 /* Reference-equivalent elimination order; adj lists ascending, no self loops.
  * Returns malloc'd order[pos] = node. */

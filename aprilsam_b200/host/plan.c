@@ -280,15 +280,53 @@ static int leaf_max_m_for(int nsn)
     return nsn >= ASAM_LEAF_WIDE_MIN_SN ? ASAM_LEAF_MAX_M_DEFAULT : 48;
 }
 
-static int plan_threads(void)
+static double host_now_ms(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+static double host_spin(int iters)
+{
+    volatile double x = 1.0;
+    for (int i = 0; i < iters; i++)
+        x = x * 1.0000001 + 1e-9;
+    return x;
+}
+
+int asam_host_threads(void)
 {
     static int v = 0;
     if (v == 0) {
         const char *e = getenv("ASAM_PLAN_THREADS");
-        v = e && atoi(e) > 0 ? atoi(e) : PLAN_OMP_THREADS;
+        int want = e && atoi(e) > 0 ? atoi(e) : PLAN_OMP_THREADS;
+        want = want > 16 ? 16 : want;
+        if (want > 1) {
+            /* two threads spinning for ~0.1 ms each: side by side that takes as long as one of them */
+            const int iters = 40000;
+            double t0 = host_now_ms();
+            host_spin(iters);
+            const double t1 = host_now_ms() - t0;
+            double tp = 1e30;
+            for (int rep = 0; rep < 3 && tp > 2.5 * t1 + 0.05; rep++) { /* (the first region also creates the threads) */
+                t0 = host_now_ms();
+#pragma omp parallel num_threads(2)
+                host_spin(iters);
+                const double t = host_now_ms() - t0;
+                tp = t < tp ? t : tp;
+            }
+            if (tp > 2.5 * t1 + 0.05)
+                want = 1;
+            if (getenv("ASAM_PLAN_VERBOSE"))
+                fprintf(stderr, "plan: host threads %d (one thread %.3f ms, two side by side %.3f ms)\n", want, t1, tp);
+        }
+        v = want;
     }
     return v;
 }
+
+static int plan_threads(void) { return asam_host_threads(); }
 
 static int compute_rel(plan_t *pl, int s)
 {
