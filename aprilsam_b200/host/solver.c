@@ -83,7 +83,7 @@ ASAM_API void asam_dbg_profile(double *out, int reset)
 #define ASAM_SMALL_MAX_BS 64
 
 #define ASAM_OMP_MIN_NODES 16384
-#define ASAM_OMP_THREADS 8
+/* (thread count of the per-pose loops: asam_host_threads(), plan.c) */
 
 #define DEV_OK(call)                                                                       \
     do {                                                                                   \
@@ -277,7 +277,7 @@ static int gctx_verify_factors(gctx_t *c, april_graph_t *g, int upto)
     int changed = 0, structural = 0;
     int lo = upto, hi = -1;
 #pragma omp parallel for schedule(static) reduction(| : changed, structural) reduction(min : lo) reduction(max : hi) \
-    if (upto >= 4 * ASAM_OMP_MIN_NODES) num_threads(ASAM_OMP_THREADS)
+    if (upto >= 4 * ASAM_OMP_MIN_NODES) num_threads(asam_host_threads())
     for (int i = 0; i < upto; i++) {
         const april_graph_factor_t *f = factor_at(g, i);
         const matd_t *Wm = f->u.common.W;
@@ -645,7 +645,7 @@ restart:;
      * malloc'd arrays -- they are split over a few host threads, SURVEY.md section 7 "host marshalling") */
     double *lp = gctx_stage(c, 3 * N);
     int bad_node = -1;
-#pragma omp parallel for schedule(static) reduction(max : bad_node) if (N >= ASAM_OMP_MIN_NODES) num_threads(ASAM_OMP_THREADS)
+#pragma omp parallel for schedule(static) reduction(max : bad_node) if (N >= ASAM_OMP_MIN_NODES) num_threads(asam_host_threads())
     for (int i = 0; i < N; i++) {
         april_graph_node_t *n = node_at(graph, i);
         if (n->type != APRIL_GRAPH_NODE_XYT_TYPE || n->length != 3) {
@@ -727,7 +727,7 @@ restart:;
     if (plan_reused && s->tree_fresh && param->tr && param->tr->nnodes == N) {
         /* same structure as the previous batch: same tree; only the per-solve labels reset */
         search_tree_t *tr = param->tr;
-#pragma omp parallel for schedule(static) if (N >= ASAM_OMP_MIN_NODES) num_threads(ASAM_OMP_THREADS)
+#pragma omp parallel for schedule(static) if (N >= ASAM_OMP_MIN_NODES) num_threads(asam_host_threads())
         for (int i = 0; i < N; i++) {
             tr->nodes[i].label_changed = 0;
             tr->nodes[i].label_relinearized = 0;
@@ -762,7 +762,7 @@ restart:;
         stamp(&tp, "H2D, kernels, D2H of solution");
 
     /* state = l_point + x (:311-315) */
-#pragma omp parallel for schedule(static) if (N >= ASAM_OMP_MIN_NODES) num_threads(ASAM_OMP_THREADS)
+#pragma omp parallel for schedule(static) if (N >= ASAM_OMP_MIN_NODES) num_threads(asam_host_threads())
     for (int i = 0; i < N; i++) {
         if (i + 16 < N) {
             __builtin_prefetch(node_at(graph, i + 16));
