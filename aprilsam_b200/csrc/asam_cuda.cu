@@ -156,9 +156,11 @@ static int buf_reserve(asam_dev *d, Buf &b, size_t bytes, bool keep, bool zero_n
         return 0;
     if (flush_uploads(d)) // queued items may point into the buffer that is about to move
         return 1;
-    size_t want = b.cap ? b.cap : 4096;
+    // growth in powers of two from 1 MiB: a replay grows ~25 buffers pose by pose, and every move costs a cudaMalloc, a stream
+    // synchronisation and a cudaFree (with 4 KiB x 1.5 the M3500 replay moved a buffer ~350 times on its way to 3500 poses)
+    size_t want = b.cap ? b.cap : ((size_t) 1 << 20);
     while (want < bytes)
-        want = want + want / 2 + 4096;
+        want *= 2;
     void *np = nullptr;
     CK(cudaMalloc(&np, want));
     if (zero_new)
